@@ -1,0 +1,71 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (build container only).
+
+    python oracle/gen_golden.py            # rewrites tests/golden/{schema_*.json, case_*.npz}
+
+Each case loads a deterministic weight set (oracle/weights.py) into the real reference ``Network`` with
+``strict=True``, runs ``forward`` on seeded synthetic frames on CPU fp32, and stores the frames' seed
+and the reference outputs.  Tests then compare the oracle (and, on the GPU, the CUDA path) with these.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import refshim  # noqa: E402
+import weights  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+# name, kind, variant, B, H, W, global, frames
+CASES = [
+    ("lite_default_off_96x128", "lite", "default", 1, 96, 128, False, "noise"),
+    ("lite_stress_on_128x192", "lite", "stress", 1, 128, 192, True, "texture"),
+    ("base_default_on_128x192", "base", "default", 1, 128, 192, True, "noise"),
+    ("base_stress_on_b2_64x96", "base", "stress", 2, 64, 96, True, "texture"),
+    ("lite_stress_off_b2_72x104", "lite", "stress", 2, 72, 104, False, "texture"),
+]
+
+
+def run_case(name, kind, variant, b, h, w, glob, frames):
+    Net = refshim.load_reference_network(kind)
+    P = weights.make_weights(kind, variant)
+    net = Net(global_motion=glob).eval()
+    net.load_state_dict(P, strict=True)
+    im0, im1 = weights.synthetic_frames(b, h, w, kind=frames)
+    with torch.no_grad():
+        out = net(im0, im1)
+    rec = {"I_t": out["I_t"], "opt_flow_0": out["opt_flow_0"], "opt_flow_1": out["opt_flow_1"],
+           "occ_mask1": out["occ_mask1"], "I_t_0": out["I_t_0"], "I_t_1": out["I_t_1"]}
+    for i, t in enumerate(out["im_t_list"]):
+        rec[f"im_t_list_{i}"] = t
+    rec["coarse_im0_warped"] = out["im0_warped_list"][-1]
+    rec["coarse_im1_warped"] = out["im1_warped_list"][-1]
+    np.savez_compressed(os.path.join(GOLDEN, f"case_{name}.npz"),
+                        meta=json.dumps(dict(kind=kind, variant=variant, B=b, H=h, W=w, global_motion=glob, frames=frames)),
+                        **{k: v.numpy().astype(np.float32) for k, v in rec.items()})
+    f0 = out["opt_flow_0"]
+    print(f"{name}: I_t mean {out['I_t'].mean():.4f} std {out['I_t'].std():.4f} clamp% "
+          f"{((out['I_t']==0)|(out['I_t']==1)).float().mean()*100:.1f} | flow0 absmax {f0.abs().max():.3f} std {f0.std():.3f} "
+          f"| occ [{out['occ_mask1'].min():.3f},{out['occ_mask1'].max():.3f}]")
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    for kind in ("base", "lite"):
+        Net = refshim.load_reference_network(kind)
+        torch.manual_seed(0)
+        sd = Net().state_dict()
+        with open(os.path.join(GOLDEN, f"schema_{kind}.json"), "w") as f:
+            json.dump({k: list(v.shape) for k, v in sd.items()}, f, indent=0)
+    only = sys.argv[1:]
+    for c in CASES:
+        if not only or c[0] in only:
+            run_case(*c)
+
+
+if __name__ == "__main__":
+    main()
