@@ -1,0 +1,106 @@
+"""ctypes binding of libatmvfi_b200.so (C ABI declared in include/atmvfi.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no fallback: if
+the shared object is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libatmvfi_b200.so")
+
+MAX_SRC = 4
+FP32, TF32 = 0, 1
+OUT_PIXEL, OUT_SHUFFLE2, OUT_WINDOW_REV = 0, 1, 2
+
+
+class AtmvfiError(RuntimeError):
+    pass
+
+
+class WindowGeom(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("B2", "H", "W", "ws", "shift", "Hp", "Wp", "pad_top", "pad_left")]
+
+
+class Src(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("C", C.c_int32), ("pitch", C.c_int32)]
+
+
+class GemmConvDesc(C.Structure):
+    _fields_ = [
+        ("nsrc", C.c_int32),
+        ("src", Src * MAX_SRC),
+        ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32),
+        ("ksize", C.c_int32), ("stride", C.c_int32), ("dil", C.c_int32),
+        ("Hout", C.c_int32), ("Wout", C.c_int32), ("Cout", C.c_int32),
+        ("weight", C.c_void_p), ("ldw", C.c_int32),
+        ("bias", C.c_void_p), ("prelu", C.c_void_p),
+        ("residual", C.c_void_p), ("res_pitch", C.c_int32),
+        ("out", C.c_void_p), ("out_pitch", C.c_int32),
+        ("out2", C.c_void_p), ("prelu2", C.c_void_p), ("out2_pitch", C.c_int32),
+        ("out_mode", C.c_int32),
+        ("win", WindowGeom),
+        ("precision", C.c_int32),
+        ("tma_host", C.c_void_p),
+    ]
+
+
+_P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
+_GP, _DP = C.POINTER(WindowGeom), C.POINTER(GemmConvDesc)
+
+# name -> argtypes; every function returns int (0 = ok) unless listed in _SPECIAL
+PROTOTYPES = {
+    "atmvfi_gemm_conv": [_DP, _P],
+    "atmvfi_gemm_conv_plan": [_DP, _P],
+    "atmvfi_layernorm": [_P, _I, _P, _I, _L, _I, _P, _P, _F, _P],
+    "atmvfi_window_gather_ln": [_P, _I, _P, _I, _I, _GP, _P, _P, _F, _P],
+    "atmvfi_window_attention": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
+    "atmvfi_dwconv3x3_gelu": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "atmvfi_flow_warp_nchw": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "atmvfi_flow_warp_nhwc": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
+    "atmvfi_warp_blend": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
+    "atmvfi_resize_bilinear_ac": [_P, _P, _I, _I, _I, _I, _I, _F, _P],
+    "atmvfi_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_residual_finish": [_P, _I, _P, _P, _P, _I, _I, _I, _P],
+    "atmvfi_u8_to_planar": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_planar_to_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+}
+_SPECIAL = {
+    "atmvfi_last_error": ([], C.c_char_p),
+    "atmvfi_abi_version": ([], C.c_int),
+    "atmvfi_device_info": ([_I, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+    "atmvfi_gemm_conv_plan_bytes": ([], C.c_int),
+}
+ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared object (once).  Raises AtmvfiError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AtmvfiError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "There is no CPU or PyTorch fallback for the ATM-VFI kernels.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argt in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argt, C.c_int
+    for name, (argt, rest) in _SPECIAL.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = argt, rest
+    if lib.atmvfi_abi_version() != 1:
+        raise AtmvfiError("libatmvfi_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        msg = load().atmvfi_last_error().decode("utf-8", "replace")
+        raise AtmvfiError(f"{what} failed (status {status}): {msg}")

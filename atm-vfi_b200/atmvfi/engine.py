@@ -1,0 +1,333 @@
+"""Host orchestration of the ATM-VFI forward on the sm_100a kernels.
+
+``PackedModel`` holds the GEMM operands packed from a reference-schema state-dict.  ``Plan`` is the
+launch list for one (batch, height, width, global_motion) shape: all buffers are allocated and all
+descriptors are built once; running it is a sequence of C-ABI calls on one stream (optionally replayed
+as a CUDA graph).  The dataflow follows network_base.py:433-546 (forward_normal); the layout is
+channels-last so tokens [2B, HW, C] and feature maps [2B, H, W, C] are the same bytes and every
+cat / slice / einops.rearrange of the reference is a pointer offset.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import pack
+from .arch import Arch, ENHANCE_WINDOW, MOTION_OUT, NUM_HEADS
+from .ops import Map, WinGeom
+
+Params = Dict[str, torch.Tensor]
+
+
+class _Block:
+    pass
+
+
+class PackedModel:
+    def __init__(self, arch: Arch, P: Params, local_ws: int, global_ws: int, with_global: bool = True):
+        self.arch, self.local_ws, self.global_ws = arch, local_ws, global_ws
+        a = arch
+        f32 = lambda n: P[n].detach().float().contiguous()
+        self.enc = [(pack.pack_convp(P, f"feat_extracts.{i}.0"), pack.pack_convp(P, f"feat_extracts.{i}.1")) for i in range(4)]
+
+        def fusion(n, fine, mid, coarse):
+            return dict(l0=pack.pack_conv(P, n + ".layers.0"), l1=pack.pack_conv(P, n + ".layers.1"), l2=pack.pack_conv(P, n + ".layers.2"),
+                        proj=pack.pack_conv(P, n + ".proj", split=[mid, fine, fine, coarse]),
+                        gamma=f32(n + ".norm.weight"), beta=f32(n + ".norm.bias"))
+
+        def block(n, atm):
+            b = _Block()
+            b.g1, b.b1, b.g2, b.b2 = f32(n + ".norm1.weight"), f32(n + ".norm1.bias"), f32(n + ".norm2.weight"), f32(n + ".norm2.bias")
+            b.qkv = pack.pack_linear(P, [n + ".attn.q", n + ".attn.kv"] if atm else [n + ".attn.qkv"])
+            b.proj = pack.pack_linear(P, [n + ".attn.proj"])
+            b.fc1, b.fc2 = pack.pack_linear(P, [n + ".mlp.fc1"]), pack.pack_linear(P, [n + ".mlp.fc2"])
+            b.dw_w, b.dw_b = pack.pack_dw(P, n + ".mlp.dwconv.dwconv")
+            b.atm = atm
+            if atm:
+                rc = f32(n + ".attn.relative_coord")
+                b.rc = rc.reshape(2, rc.shape[-2], rc.shape[-1]).contiguous()
+                b.mix = (f32(n + ".attn.mlp.0.weight"), f32(n + ".attn.mlp.0.bias"),
+                         f32(n + ".attn.mlp.2.weight").reshape(-1).contiguous(), f32(n + ".attn.mlp.2.bias"))
+            return b
+
+        def head(n, c):
+            return (pack.pack_convp(P, n + ".0", split=[NUM_HEADS, c, c]), pack.pack_convp(P, n + ".1"), pack.pack_conv(P, n + ".2"))
+
+        self.fuse_local = fusion("cross_scale_feature_fusion", a.enc[1], a.enc[2], a.enc[3])
+        self.enhance = [block(f"feat_enhance_transformer.{k}", False) for k in range(2)]
+        self.local_blocks = [block(f"local_motion_atmformer.{k}", True) for k in range(2)]
+        self.local_head = head("local_motion_mlp", a.C)
+        self.with_global = with_global
+        if with_global:
+            self.last = (pack.pack_convp(P, "last_feat_extract.0"), pack.pack_convp(P, "last_feat_extract.1"))
+            self.fuse_global = fusion("global_feature_fusion", a.enc[2], a.enc[3], a.last)
+            self.global_blocks = [block(f"global_motion_atmformer.{k}", True) for k in range(2)]
+            self.global_head = head("global_motion_mlp", a.GC)
+        d = a.dec
+        self.pyramid = []
+        for i in range(3):
+            n, j = f"upsample_pyramid.{i}", (0 if i == 0 else 1)
+            up = pack.pack_deconvp(P, f"{n}.{j}", split=[a.C, a.C, MOTION_OUT] if i == 0 else None)
+            c1 = pack.pack_convp(P, f"{n}.{j + 1}")
+            c2 = pack.pack_conv(P, f"{n}.{j + 2}")
+            nxt = f32(f"upsample_pyramid.{i + 1}.0.weight") if i < 2 else None
+            self.pyramid.append((up, c1, c2, nxt))
+        r = a.refine
+        self.proj = pack.pack_convp(P, "proj", split=[d[3], 15])
+        self.down1 = pack.pack_convp(P, "down1.0")
+        self.down2 = (pack.pack_convp(P, "down2.0", split=[r, d[2] - MOTION_OUT]), pack.pack_convp(P, "down2.1"))
+        self.down3 = (pack.pack_convp(P, "down3.0", split=[2 * r, d[1] - MOTION_OUT]), pack.pack_convp(P, "down3.1"), pack.pack_convp(P, "down3.2"))
+        self.up1 = (pack.pack_deconvp(P, "up1.0"), pack.pack_convp(P, "up1.1"))
+        self.up2 = (pack.pack_deconvp(P, "up2.0", split=[2 * r, 2 * r]), pack.pack_convp(P, "up2.1"))
+        self.up3 = pack.pack_deconvp(P, "up3.0", split=[r, r])
+        self.head = (pack.pack_convp(P, "refine_head.0", split=[r, r]), pack.pack_convp(P, "refine_head.1"))
+
+
+# ------------------------------------------------------------------------------------------------
+# building blocks (recorded through ``ops``)
+# ------------------------------------------------------------------------------------------------
+def transformer_block(ops, blk, tok: Map, g: WinGeom, motion: Optional[Map] = None, motion_off: int = 0) -> Map:
+    """ATMFormer / RefineBottleneck forward (attention.py:265-334, 433-495) on tokens [B2,H,W,C]."""
+    C = tok.C
+    hidden = blk.fc1.Cout
+    xw = ops.new_map(1, 1, g.rows, C)
+    ops.window_gather_ln(tok, xw, g, blk.g1, blk.b1)                       # pad + roll + partition + norm1
+    qkv = ops.new_map(1, 1, g.rows, 3 * C)
+    ops.gemm_conv([xw], blk.qkv, qkv, act=False)
+    ao = ops.new_map(1, 1, g.rows, C)
+    if blk.atm and motion is not None:
+        scratch = torch.empty(g.rows * NUM_HEADS * 2, device=xw.t.device, dtype=torch.float32)
+        ops.window_attention(qkv, ao, g, NUM_HEADS, True, blk.rc, blk.mix, motion, motion_off, scratch)
+    else:
+        ops.window_attention(qkv, ao, g, NUM_HEADS, blk.atm)
+    t2 = ops.new_map(tok.B, tok.H, tok.W, C)
+    ops.gemm_conv([ao], blk.proj, t2, act=False, residual=xw, win=g)       # proj + residual on the NORMED tokens, window reverse
+    t3 = ops.new_map(tok.B, tok.H, tok.W, C)
+    ops.layernorm(t2, t3, blk.g2, blk.b2)
+    h1 = ops.new_map(tok.B, tok.H, tok.W, hidden)
+    ops.gemm_conv([t3.rows()], blk.fc1, h1.rows(), act=False)
+    h2 = ops.new_map(tok.B, tok.H, tok.W, hidden)
+    ops.dwconv_gelu(h1, h2, blk.dw_w, blk.dw_b)
+    out = ops.new_map(tok.B, tok.H, tok.W, C)
+    ops.gemm_conv([h2.rows()], blk.fc2, out.rows(), act=False, residual=t2.rows())
+    return out
+
+
+def fusion(ops, f, fine: Map, mid: Map, coarse: Map) -> Map:
+    """CrossScaleFeatureFusion.forward (network_base.py:73-85): tokens [2B, H, W, Ccat] after LayerNorm."""
+    B, H, W = coarse.B, coarse.H, coarse.W
+    y0 = ops.new_map(B, H, W, mid.C)
+    ops.gemm_conv([mid], f["l0"], y0, stride=2, act=False)
+    y1 = ops.new_map(B, H, W, fine.C)
+    ops.gemm_conv([fine], f["l1"], y1, stride=4, dil=1, act=False)
+    y2 = ops.new_map(B, H, W, fine.C)
+    ops.gemm_conv([fine], f["l2"], y2, stride=4, dil=2, act=False)
+    z = ops.new_map(B, H, W, f["proj"].Cout)
+    ops.gemm_conv([y0, y1, y2, coarse], f["proj"], z, act=False)
+    tok = ops.new_map(B, H, W, z.C)
+    ops.layernorm(z, tok, f["gamma"], f["beta"])
+    return tok
+
+
+def motion_branch(ops, blocks, head, tok: Map, ws: int) -> Tuple[Map, Map]:
+    """Two ATMFormer blocks (shift 0, ws//2) and the conv motion head (network_base.py:367-415).
+    Returns (tokens after the blocks [2B,H,W,C], head [B,H,W,5])."""
+    B2, H, W = tok.B, tok.H, tok.W
+    B = B2 // 2
+    motion = ops.new_map(B, H, W, 2 * 4)
+    for k, shift in enumerate((0, ws // 2)):
+        tok = transformer_block(ops, blocks[k], tok, WinGeom(B2, H, W, ws, shift), motion, 4 * k)
+    h0, h1, h2 = head
+    a = ops.new_map(B, H, W, h0.Cout)
+    ops.gemm_conv([motion, tok.batch(0, B), tok.batch(B, B)], h0, a)
+    b = ops.new_map(B, H, W, h1.Cout)
+    ops.gemm_conv([a], h1, b)
+    out = ops.new_map(B, H, W, MOTION_OUT)
+    ops.gemm_conv([b], h2, out, act=False)
+    return tok, out
+
+
+class Plan:
+    """Launch list + buffers for one input shape."""
+
+    def __init__(self, ops, model: PackedModel, B: int, H: int, W: int, global_motion: bool):
+        div = 16 if global_motion else 8
+        if H % div or W % div:
+            raise RuntimeError(f"ATM-VFI forward: input {H}x{W} must be a multiple of {div} (global_motion={global_motion}); "
+                               "pad with InputPadder as the reference does")
+        if global_motion and not model.with_global:
+            raise RuntimeError("global_motion requested but the global-motion weights were not packed")
+        self.ops, self.model, self.key = ops, model, (B, H, W, global_motion)
+        a = model.arch
+        ops.recording = rec = []
+        try:
+            self._build(ops, model, a, B, H, W, global_motion)
+        finally:
+            ops.recording = None
+        self.records = rec
+        self.graph = None
+
+    # .............................................................................................
+    def _build(self, ops, m: PackedModel, a: Arch, B: int, H: int, W: int, glob: bool):
+        P = ops.new_planar
+        self.im0, self.im1 = P(B, 3, H, W), P(B, 3, H, W)
+        pyr0, pyr1 = [self.im0], [self.im1]
+        for l in range(1, 4):
+            pyr0.append(P(B, 3, H >> l, W >> l)); pyr1.append(P(B, 3, H >> l, W >> l))
+            ops.resize(pyr0[l - 1], pyr0[l]); ops.resize(pyr1[l - 1], pyr1[l])
+
+        # encoder on the two frames stacked on the batch axis (network_base.py:342-352, 451)
+        x = ops.new_map(2 * B, H, W, 3)
+        ops.nchw_to_nhwc(self.im0, x.batch(0, B), zero_fill_to=x.pitch)
+        ops.nchw_to_nhwc(self.im1, x.batch(B, B), zero_fill_to=x.pitch)
+        levels = []
+        for l in range(4):
+            c0, c1 = m.enc[l]
+            h, w = H >> l, W >> l
+            y = ops.new_map(2 * B, h, w, c0.Cout)
+            ops.gemm_conv([x], c0, y, stride=1 if l == 0 else 2)
+            x = ops.new_map(2 * B, h, w, c1.Cout)
+            ops.gemm_conv([y], c1, x)
+            levels.append(x)
+        tok = fusion(ops, m.fuse_local, levels[1], levels[2], levels[3])     # [2B, H/8, W/8, C]
+        h8, w8 = H >> 3, W >> 3
+
+        it_list, w0_list, w1_list = [], [], []
+        if glob:
+            h16, w16 = H >> 4, W >> 4
+            l0, l1 = m.last
+            y = ops.new_map(2 * B, h16, w16, l0.Cout)
+            ops.gemm_conv([levels[3]], l0, y, stride=2)
+            z = ops.new_map(2 * B, h16, w16, l1.Cout)
+            ops.gemm_conv([y], l1, z)
+            gtok = fusion(ops, m.fuse_global, levels[2], levels[3], z)
+            _, ghead = motion_branch(ops, m.global_blocks, m.global_head, gtok, m.global_ws)
+            i0, i1 = P(B, 3, h16, w16), P(B, 3, h16, w16)
+            ops.resize(pyr0[3], i0); ops.resize(pyr1[3], i1)
+            a0, a1, it = P(B, 3, h16, w16), P(B, 3, h16, w16), P(B, 3, h16, w16)
+            f0, f1 = P(B, 2, h16, w16), P(B, 2, h16, w16)
+            ops.warp_blend(i0, i1, ghead, a0, a1, it, f0, f1)
+            it_list.insert(0, it); w0_list.insert(0, a0); w1_list.insert(0, a1)
+            # flows x2 up to 1/8, warp the fused tokens of each frame (network_base.py:471-478)
+            f0u, f1u = P(B, 2, h8, w8), P(B, 2, h8, w8)
+            ops.resize(f0, f0u, 2.0); ops.resize(f1, f1u, 2.0)
+            fl = ops.new_map(2 * B, h8, w8, 2)
+            ops.nchw_to_nhwc(f0u, fl.batch(0, B), zero_fill_to=fl.pitch)
+            ops.nchw_to_nhwc(f1u, fl.batch(B, B), zero_fill_to=fl.pitch)
+            tokw = ops.new_map(2 * B, h8, w8, tok.C)
+            ops.flow_warp_nhwc(tok, fl, 0, tokw)
+            tok = tokw
+            # warp every pyramid level with the global flow, coarse to fine (network_base.py:480-485)
+            f0, f1 = f0u, f1u
+            for l in (3, 2, 1, 0):
+                n0, n1 = P(*pyr0[l].shape), P(*pyr1[l].shape)
+                ops.flow_warp_nchw(pyr0[l], f0, n0); ops.flow_warp_nchw(pyr1[l], f1, n1)
+                pyr0[l], pyr1[l] = n0, n1
+                if l:
+                    g0, g1 = P(B, 2, H >> (l - 1), W >> (l - 1)), P(B, 2, H >> (l - 1), W >> (l - 1))
+                    ops.resize(f0, g0, 2.0); ops.resize(f1, g1, 2.0)
+                    f0, f1 = g0, g1
+
+        tok, lhead = motion_branch(ops, m.local_blocks, m.local_head, tok, m.local_ws)
+        for k, shift in enumerate((0, ENHANCE_WINDOW // 2)):
+            tok = transformer_block(ops, m.enhance[k], tok, WinGeom(2 * B, h8, w8, ENHANCE_WINDOW, shift))
+
+        a0, a1, it = P(B, 3, h8, w8), P(B, 3, h8, w8), P(B, 3, h8, w8)
+        ops.warp_blend(pyr0[3], pyr1[3], lhead, a0, a1, it)
+        it_list.insert(0, it); w0_list.insert(0, a0); w1_list.insert(0, a1)
+        # warp each frame's enhanced features once with the 1/8 flows (network_base.py:504-506)
+        fw = ops.new_map(2 * B, h8, w8, tok.C)
+        ops.flow_warp_nhwc(tok.batch(0, B), lhead, 0, fw.batch(0, B))
+        ops.flow_warp_nhwc(tok.batch(B, B), lhead, 2, fw.batch(B, B))
+
+        srcs = [fw.batch(0, B), fw.batch(B, B), lhead]
+        skips = []
+        flow0 = flow1 = occ1 = occ2 = None
+        raw = None
+        for i, l in enumerate((2, 1, 0)):
+            up, c1, c2, nxt = m.pyramid[i]
+            h, w = H >> l, W >> l
+            u = ops.new_map(B, h, w, up.Cout)
+            ops.gemm_conv(srcs, up, u)
+            v = ops.new_map(B, h, w, c1.Cout)
+            ops.gemm_conv([u], c1, v)
+            raw = ops.new_map(B, h, w, c2.Cout)
+            act = ops.new_map(B, h, w, c2.Cout) if nxt is not None else None
+            ops.gemm_conv([v], c2, raw, act=False, out2=act, prelu2=nxt)     # raw level output (+ PReLU'd copy for the next deconv)
+            hd = raw.chan(raw.C - MOTION_OUT, MOTION_OUT)
+            if l:
+                skips.append(raw.chan(0, raw.C - MOTION_OUT))
+            a0, a1, it = P(B, 3, h, w), P(B, 3, h, w), P(B, 3, h, w)
+            if l == 0:
+                flow0, flow1, occ1, occ2 = P(B, 2, h, w), P(B, 2, h, w), P(B, 1, h, w), P(B, 1, h, w)
+            ops.warp_blend(pyr0[l], pyr1[l], hd, a0, a1, it, flow0, flow1, occ1, occ2)
+            it_list.insert(0, it); w0_list.insert(0, a0); w1_list.insert(0, a1)
+            srcs = [act]
+
+        # residual-refinement U-Net (network_base.py:417-431); the ORIGINAL frames go in
+        r = a.refine
+        imgs = ops.new_map(B, H, W, 15)
+        for j, t in enumerate((self.im0, a0, self.im1, a1, it)):
+            ops.nchw_to_nhwc(t, imgs.chan(3 * j, 3), zero_fill_to=(imgs.pitch if j == 4 else 0))
+        r0 = ops.new_map(B, H, W, r)
+        ops.gemm_conv([raw, imgs], m.proj, r0)
+        r1 = ops.new_map(B, H >> 1, W >> 1, r)
+        ops.gemm_conv([r0], m.down1, r1, stride=2)
+        t = ops.new_map(B, H >> 2, W >> 2, 2 * r)
+        ops.gemm_conv([r1, skips.pop()], m.down2[0], t, stride=2)
+        r2 = ops.new_map(B, H >> 2, W >> 2, 2 * r)
+        ops.gemm_conv([t], m.down2[1], r2)
+        t = ops.new_map(B, h8, w8, 4 * r)
+        ops.gemm_conv([r2, skips.pop()], m.down3[0], t, stride=2)
+        t2 = ops.new_map(B, h8, w8, 4 * r)
+        ops.gemm_conv([t], m.down3[1], t2)
+        r3 = ops.new_map(B, h8, w8, 4 * r)
+        ops.gemm_conv([t2], m.down3[2], r3)
+        t = ops.new_map(B, H >> 2, W >> 2, 2 * r)
+        ops.gemm_conv([r3], m.up1[0], t)
+        u2 = ops.new_map(B, H >> 2, W >> 2, 2 * r)
+        ops.gemm_conv([t], m.up1[1], u2)
+        t = ops.new_map(B, H >> 1, W >> 1, 2 * r)
+        ops.gemm_conv([u2, r2], m.up2[0], t)
+        u1 = ops.new_map(B, H >> 1, W >> 1, r)
+        ops.gemm_conv([t], m.up2[1], u1)
+        u0 = ops.new_map(B, H, W, r)
+        ops.gemm_conv([u1, r1], m.up3, u0)
+        t = ops.new_map(B, H, W, r)
+        ops.gemm_conv([u0, r0], m.head[0], t)
+        res = ops.new_map(B, H, W, 3)
+        ops.gemm_conv([t], m.head[1], res)
+        it_sum, out = P(B, 3, H, W), P(B, 3, H, W)
+        ops.residual_finish(res, it, it_sum, out)
+        it_list[0] = it_sum      # the reference's in-place ``I_t += residual`` aliases im_t_list[0] (network_base.py:532)
+
+        self.outputs = {"I_t": out, "im_t_list": it_list, "im0_warped_list": w0_list, "im1_warped_list": w1_list,
+                        "opt_flow_0": flow0, "opt_flow_1": flow1, "I_t_0": a0, "I_t_1": a1, "occ_mask1": occ1, "occ_mask2": occ2}
+
+    # .............................................................................................
+    def launch(self, stream: Optional[int] = None) -> None:
+        """Enqueue every kernel of the forward on ``stream`` (default: torch's current stream)."""
+        self.ops.replay(self.records, stream)
+
+    def num_launches(self) -> int:
+        return self.ops.count_launches(self.records)
+
+    def run(self, im0: torch.Tensor, im1: torch.Tensor, use_graph: bool = False) -> Dict[str, object]:
+        self.im0.copy_(im0); self.im1.copy_(im1)
+        if use_graph:
+            if self.graph is None:
+                self.launch()                                    # warm-up outside capture (lazy module load, attributes)
+                torch.cuda.current_stream().synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.launch()
+                self.graph = g
+            self.graph.replay()
+        else:
+            self.launch()
+        return self.outputs
+
+
+def clone_outputs(out: Dict[str, object]) -> Dict[str, object]:
+    return {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in out.items()}

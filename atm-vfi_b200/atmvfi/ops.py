@@ -1,0 +1,271 @@
+"""Operator layer between the host orchestration (engine.py) and the C ABI (include/atmvfi.h).
+
+``Map`` describes a channels-last feature map (or a channel / batch slice of one) by tensor + offsets, so
+that every torch.cat / slice / rearrange of the reference becomes pointer arithmetic.  ``CudaOps``
+marshals those descriptions into C-ABI calls on the current CUDA stream; with ``recording`` set, calls
+are appended to a launch list instead (the engine replays the list, eagerly or under a CUDA graph).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class Map:
+    """NHWC fp32 view: tensor ``t`` of shape [B, H, W, pitch]; this view covers channels [c0, c0+C)."""
+
+    __slots__ = ("t", "c0", "C")
+
+    def __init__(self, t: torch.Tensor, c0: int = 0, C: Optional[int] = None):
+        assert t.dim() == 4 and t.dtype == torch.float32
+        assert t.stride(3) == 1 and t.stride(2) == t.shape[3] and t.stride(1) == t.shape[2] * t.shape[3]
+        self.t, self.c0 = t, c0
+        self.C = t.shape[3] - c0 if C is None else C
+        assert 0 <= c0 and c0 + self.C <= t.shape[3]
+
+    B = property(lambda s: s.t.shape[0])
+    H = property(lambda s: s.t.shape[1])
+    W = property(lambda s: s.t.shape[2])
+    pitch = property(lambda s: s.t.shape[3])
+
+    def chan(self, c0: int, C: int) -> "Map":
+        assert c0 + C <= self.C
+        return Map(self.t, self.c0 + c0, C)
+
+    def batch(self, b0: int, nb: int) -> "Map":
+        return Map(self.t[b0 : b0 + nb], self.c0, self.C)
+
+    def rows(self) -> "Map":
+        """Same memory seen as [1, 1, B*H*W, pitch] (token rows for the linear layers)."""
+        assert self.t.is_contiguous()
+        return Map(self.t.view(1, 1, -1, self.t.shape[3]), self.c0, self.C)
+
+    def grid(self, B: int, H: int, W: int) -> "Map":
+        assert self.t.is_contiguous() and B * H * W == self.t.shape[0] * self.t.shape[1] * self.t.shape[2]
+        return Map(self.t.view(B, H, W, self.t.shape[3]), self.c0, self.C)
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + 4 * self.c0
+
+    def view(self) -> torch.Tensor:
+        return self.t[..., self.c0 : self.c0 + self.C]
+
+    @property
+    def nrows(self) -> int:
+        return self.t.shape[0] * self.t.shape[1] * self.t.shape[2]
+
+
+@dataclass(frozen=True)
+class WinGeom:
+    B2: int
+    H: int
+    W: int
+    ws: int
+    shift: int
+
+    @property
+    def Hp(self) -> int:
+        return -(-self.H // self.ws) * self.ws
+
+    @property
+    def Wp(self) -> int:
+        return -(-self.W // self.ws) * self.ws
+
+    @property
+    def pad_top(self) -> int:
+        return (self.Hp - self.H) // 2
+
+    @property
+    def pad_left(self) -> int:
+        return (self.Wp - self.W) // 2
+
+    @property
+    def rows(self) -> int:
+        return self.B2 * self.Hp * self.Wp
+
+    def c(self) -> _lib.WindowGeom:
+        return _lib.WindowGeom(self.B2, self.H, self.W, self.ws, self.shift, self.Hp, self.Wp, self.pad_top, self.pad_left)
+
+
+@dataclass
+class PackedGemm:
+    """One GEMM-shaped layer after host-side packing (pack.py)."""
+    name: str
+    ksize: int
+    split: Sequence[int]              # channels per source, in order
+    Cout: int
+    shuffle: bool                     # ConvTranspose2d k2 s2
+    w32: torch.Tensor                 # [K, ldw] fp32, K = taps*sum(split)
+    bias: Optional[torch.Tensor]
+    prelu: Optional[torch.Tensor]
+    wtc: Optional[torch.Tensor] = None   # tcgen05 layout, filled by pack.py when the TF32 path is enabled
+    tc_meta: Optional[dict] = None
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class CudaOps:
+    """Launches the sm_100a kernels.  No fallback: construction fails without the library or a CUDA device."""
+
+    def __init__(self, device: torch.device, precision: int = _lib.FP32):
+        if device.type != "cuda":
+            raise _lib.AtmvfiError(
+                f"ATM-VFI B200 kernels need a CUDA device, got '{device}'. There is no CPU fallback; "
+                "use the reference implementation for CPU inference.")
+        self.lib = _lib.load()
+        self.device = device
+        self.precision = precision
+        self.recording: Optional[List] = None
+        self._keep: List = []
+        self.launches = 0
+
+    # -- memory -------------------------------------------------------------------------------
+    def new_map(self, B: int, H: int, W: int, C: int, zero: bool = False) -> Map:
+        pitch = round_up(C, 4)
+        f = torch.zeros if (zero or pitch != C) else torch.empty
+        return Map(f((B, H, W, pitch), device=self.device, dtype=torch.float32), 0, C)
+
+    def new_planar(self, *shape: int) -> torch.Tensor:
+        return torch.empty(shape, device=self.device, dtype=torch.float32)
+
+    # -- launch plumbing ----------------------------------------------------------------------
+    def _emit(self, name: str, args: tuple, keep=()):
+        fn = getattr(self.lib, name)
+        if self.recording is not None:
+            self.recording.append((name, fn, args, keep))
+        else:
+            _lib.check(fn(*args, torch.cuda.current_stream(self.device).cuda_stream), name)
+            self.launches += 1
+
+    def replay(self, records, stream: Optional[int] = None) -> None:
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        for name, fn, args, _ in records:
+            rc = fn(*args, st)
+            if rc:
+                _lib.check(rc, name)
+        self.launches += self.count_launches(records)
+
+    @staticmethod
+    def count_launches(records) -> int:
+        # one kernel per record, except attention-with-motion which also launches the head-mix kernel
+        return sum(2 if (name == "atmvfi_window_attention" and args[13] is not None) else 1 for name, _, args, _ in records)
+
+    # -- GEMM-shaped layers -------------------------------------------------------------------
+    def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride: int = 1, dil: int = 1,
+                  act: bool = True, residual: Optional[Map] = None, out2: Optional[Map] = None,
+                  prelu2: Optional[torch.Tensor] = None, win: Optional[WinGeom] = None,
+                  precision: Optional[int] = None):
+        assert [s.C for s in srcs] == list(w.split), (w.name, [s.C for s in srcs], w.split)
+        s0 = srcs[0]
+        for s in srcs:
+            assert (s.B, s.H, s.W) == (s0.B, s0.H, s0.W), w.name
+        pad = dil * (w.ksize - 1) // 2
+        Hout = (s0.H + 2 * pad - dil * (w.ksize - 1) - 1) // stride + 1
+        Wout = (s0.W + 2 * pad - dil * (w.ksize - 1) - 1) // stride + 1
+        d = _lib.GemmConvDesc()
+        d.nsrc = len(srcs)
+        for i, s in enumerate(srcs):
+            d.src[i] = _lib.Src(s.ptr, s.C, s.pitch)
+        d.B, d.Hin, d.Win = s0.B, s0.H, s0.W
+        d.ksize, d.stride, d.dil = w.ksize, stride, dil
+        d.Hout, d.Wout, d.Cout = Hout, Wout, w.Cout
+        d.weight, d.ldw = w.w32.data_ptr(), w.w32.shape[1]
+        d.bias = _p(w.bias)
+        d.prelu = _p(w.prelu) if act else None
+        if residual is not None:
+            assert residual.C == w.Cout
+            d.residual, d.res_pitch = residual.ptr, residual.pitch
+        d.out, d.out_pitch = out.ptr, out.pitch
+        assert out.C == w.Cout, (w.name, out.C, w.Cout)
+        if out2 is not None:
+            d.out2, d.prelu2, d.out2_pitch = out2.ptr, prelu2.data_ptr(), out2.pitch
+        if win is not None:
+            d.out_mode, d.win = _lib.OUT_WINDOW_REV, win.c()
+            assert s0.nrows == win.rows and out.nrows == win.B2 * win.H * win.W
+        elif w.shuffle:
+            d.out_mode = _lib.OUT_SHUFFLE2
+            assert (out.B, out.H, out.W) == (s0.B, 2 * Hout, 2 * Wout), w.name
+        else:
+            d.out_mode = _lib.OUT_PIXEL
+            assert out.nrows == s0.B * Hout * Wout, (w.name, out.t.shape, (s0.B, Hout, Wout))
+        d.precision = self.precision if precision is None else precision
+        self._emit("atmvfi_gemm_conv", (C.byref(d),), keep=(d, srcs, w, out, residual, out2, prelu2))
+
+    # -- transformer pieces -------------------------------------------------------------------
+    def layernorm(self, x: Map, out: Map, gamma: torch.Tensor, beta: torch.Tensor):
+        assert x.C == out.C == gamma.numel()
+        self._emit("atmvfi_layernorm", (x.ptr, x.pitch, out.ptr, out.pitch, x.nrows, x.C, gamma.data_ptr(), beta.data_ptr(), 1e-5),
+                   keep=(x, out, gamma, beta))
+
+    def window_gather_ln(self, tok: Map, win: Map, g: WinGeom, gamma: torch.Tensor, beta: torch.Tensor):
+        assert tok.nrows == g.B2 * g.H * g.W and win.nrows == g.rows and tok.C == win.C
+        gc = g.c()
+        self._emit("atmvfi_window_gather_ln", (tok.ptr, tok.pitch, win.ptr, win.pitch, tok.C, C.byref(gc), gamma.data_ptr(), beta.data_ptr(), 1e-5),
+                   keep=(tok, win, gc, gamma, beta))
+
+    def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads: int, cross: bool, rc: Optional[torch.Tensor] = None,
+                         mix: Optional[Sequence[torch.Tensor]] = None, motion: Optional[Map] = None, motion_off: int = 0,
+                         scratch: Optional[torch.Tensor] = None):
+        assert qkv.C == 3 * out.C and qkv.nrows == g.rows == out.nrows
+        gc = g.c()
+        m = [None] * 4 if mix is None else [t.data_ptr() for t in mix]
+        self._emit("atmvfi_window_attention",
+                   (qkv.ptr, qkv.pitch, out.ptr, out.pitch, out.C, heads, C.byref(gc), int(cross), _p(rc), m[0], m[1], m[2], m[3],
+                    None if motion is None else motion.ptr, 0 if motion is None else motion.pitch, motion_off, _p(scratch)),
+                   keep=(qkv, out, gc, rc, mix, motion, scratch))
+
+    def dwconv_gelu(self, x: Map, out: Map, w9c: torch.Tensor, bias: torch.Tensor):
+        assert x.c0 == 0 and out.c0 == 0 and x.pitch == out.pitch and x.C == out.C
+        self._emit("atmvfi_dwconv3x3_gelu", (x.ptr, out.ptr, x.B, x.H, x.W, x.C, x.pitch, w9c.data_ptr(), bias.data_ptr()),
+                   keep=(x, out, w9c, bias))
+
+    # -- warps, resampling, layout ------------------------------------------------------------
+    def flow_warp_nchw(self, img: torch.Tensor, flow: torch.Tensor, out: torch.Tensor):
+        b, c, h, w = img.shape
+        assert flow.shape == (b, 2, h, w) and img.is_contiguous() and flow.is_contiguous() and out.is_contiguous()
+        self._emit("atmvfi_flow_warp_nchw", (img.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w), keep=(img, flow, out))
+
+    def flow_warp_nhwc(self, src: Map, head: Map, flow_off: int, out: Map):
+        assert (src.B, src.H, src.W) == (head.B, head.H, head.W) == (out.B, out.H, out.W) and src.C == out.C
+        self._emit("atmvfi_flow_warp_nhwc", (src.ptr, src.pitch, head.ptr, head.pitch, flow_off, out.ptr, out.pitch, src.B, src.C, src.H, src.W),
+                   keep=(src, head, out))
+
+    def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None):
+        b, _, h, w = im0.shape
+        assert (head.B, head.H, head.W) == (b, h, w) and head.C >= 5
+        self._emit("atmvfi_warp_blend", (im0.data_ptr(), im1.data_ptr(), head.ptr, head.pitch, 0, w0.data_ptr(), w1.data_ptr(), it.data_ptr(),
+                                         _p(flow0), _p(flow1), _p(occ1), _p(occ2), b, h, w),
+                   keep=(im0, im1, head, w0, w1, it, flow0, flow1, occ1, occ2))
+
+    def resize(self, x: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+        assert x.is_contiguous() and out.is_contiguous() and x.shape[:2] == out.shape[:2]
+        self._emit("atmvfi_resize_bilinear_ac", (x.data_ptr(), out.data_ptr(), x.shape[0] * x.shape[1], x.shape[2], x.shape[3], out.shape[2], out.shape[3], float(scale)),
+                   keep=(x, out))
+
+    def nchw_to_nhwc(self, x: torch.Tensor, out: Map, zero_fill_to: int = 0):
+        b, c, h, w = x.shape
+        assert (out.B, out.H, out.W) == (b, h, w) and out.C >= c and x.is_contiguous()
+        self._emit("atmvfi_nchw_to_nhwc", (x.data_ptr(), out.t.data_ptr(), out.pitch, out.c0, b, c, h, w, zero_fill_to), keep=(x, out))
+
+    def residual_finish(self, res: Map, it, it_sum, it_clamped):
+        b, _, h, w = it.shape
+        self._emit("atmvfi_residual_finish", (res.ptr, res.pitch, it.data_ptr(), _p(it_sum), it_clamped.data_ptr(), b, h, w),
+                   keep=(res, it, it_sum, it_clamped))
+
+    def u8_to_planar(self, src_u8: torch.Tensor, out: torch.Tensor, H, W, Hp, Wp, top, left, bgr: bool):
+        self._emit("atmvfi_u8_to_planar", (src_u8.data_ptr(), out.data_ptr(), H, W, Hp, Wp, top, left, int(bgr)), keep=(src_u8, out))
+
+    def planar_to_u8(self, src: torch.Tensor, out_u8: torch.Tensor, H, W, Hp, Wp, top, left, bgr: bool):
+        self._emit("atmvfi_planar_to_u8", (src.data_ptr(), out_u8.data_ptr(), H, W, Hp, Wp, top, left, int(bgr)), keep=(src, out_u8))

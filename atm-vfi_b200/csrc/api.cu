@@ -1,0 +1,54 @@
+// C-ABI plumbing of libatmvfi_b200.so: error reporting, device probe, precision dispatch.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void atmvfi_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int atmvfi_gemm_conv_simt(const atmvfi_gemm_conv_desc* d, cudaStream_t st);
+int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st);
+
+extern "C" {
+
+const char* atmvfi_last_error(void) { return g_err; }
+int atmvfi_abi_version(void) { return ATMVFI_ABI_VERSION; }
+
+int atmvfi_device_info(int device, char* name, int* cc_major, int* cc_minor) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    atmvfi_set_error("device_info: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  if (name) { strncpy(name, prop.name, 255); name[255] = 0; }
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  if (prop.major != 10) {
+    atmvfi_set_error("device_info: %s is sm_%d%d; this library only carries sm_100a code", prop.name, prop.major, prop.minor);
+    return -1;
+  }
+  return prop.multiProcessorCount;
+}
+
+int atmvfi_gemm_conv(const atmvfi_gemm_conv_desc* d, void* stream) {
+  ATMVFI_REQUIRE(d != nullptr, "gemm_conv: null descriptor");
+  ATMVFI_REQUIRE(d->nsrc >= 1 && d->nsrc <= ATMVFI_MAX_SRC, "gemm_conv: nsrc=%d out of range", d->nsrc);
+  ATMVFI_REQUIRE(d->ksize == 1 || d->ksize == 3, "gemm_conv: kernel size %d unsupported (1 or 3)", d->ksize);
+  ATMVFI_REQUIRE(d->stride >= 1 && d->dil >= 1, "gemm_conv: bad stride/dilation");
+  ATMVFI_REQUIRE(d->out_mode >= ATMVFI_OUT_PIXEL && d->out_mode <= ATMVFI_OUT_WINDOW_REV, "gemm_conv: bad out_mode %d", d->out_mode);
+  ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_SHUFFLE2 || (d->ksize == 1 && d->stride == 1), "gemm_conv: SHUFFLE2 needs ksize=1, stride=1");
+  ATMVFI_REQUIRE(!d->out2 || d->prelu2, "gemm_conv: out2 needs prelu2 slopes");
+  if (d->precision == ATMVFI_FP32) return atmvfi_gemm_conv_simt(d, (cudaStream_t)stream);
+  if (d->precision == ATMVFI_TF32) return atmvfi_gemm_conv_tc(d, (cudaStream_t)stream);
+  atmvfi_set_error("gemm_conv: unknown precision %d", d->precision);
+  return 2;
+}
+
+}  // extern "C"

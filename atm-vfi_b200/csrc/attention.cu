@@ -1,0 +1,194 @@
+// Window attention with the attention-to-motion reduction (attention.py:187-213, 370-390), fp32 SIMT.
+//
+// One CTA per (window, head); thread i owns query row i and streams the keys with an online softmax,
+// accumulating  P*V  and the motion expectation  sum_j P_ij * relative_coord[:, i, j]  in registers.
+// K and V of the (possibly other-frame) window live in shared memory and are read as warp broadcasts.
+// Windows are addressed in place: masks are evaluated from the geometry, never materialised.
+// A second tiny kernel applies the head-mix MLP (8 -> 4 -> GELU -> 1) and scatters the motion to the
+// token grid, undoing window partition / roll / centre padding.
+#include "common.cuh"
+
+namespace {
+
+template <int HD>
+__global__ void __launch_bounds__(256) window_attention_kernel(const float* __restrict__ qkv, int qkv_pitch,
+                                                               float* __restrict__ out, int out_pitch, int C, int heads,
+                                                               atmvfi_window_geom g, int cross,
+                                                               const float* __restrict__ rc, float* __restrict__ motion_raw) {
+  extern __shared__ float smem[];
+  const int N = g.ws * g.ws;
+  float* sk = smem;             // [N][HD]
+  float* sv = smem + N * HD;    // [N][HD]
+  int* slab = reinterpret_cast<int*>(smem + 2 * N * HD);   // [N] mask labels
+
+  const int h = blockIdx.y;
+  const int64_t win = blockIdx.x;
+  const int nW = (g.Hp / g.ws) * (g.Wp / g.ws);
+  const int64_t total_win = (int64_t)g.B2 * nW;
+  // the other frame's copy of this window sits half the window batch away (attention.py:318)
+  const int64_t kv_win = cross ? (win + total_win / 2) % total_win : win;
+
+  const float* kbase = qkv + kv_win * N * qkv_pitch + C + h * HD;
+  const float* vbase = kbase + C;
+  for (int i = threadIdx.x; i < N * (HD / 4); i += blockDim.x) {
+    int r = i / (HD / 4), c4 = i % (HD / 4);
+    reinterpret_cast<float4*>(sk + r * HD)[c4] = __ldg(reinterpret_cast<const float4*>(kbase + (int64_t)r * qkv_pitch) + c4);
+    reinterpret_cast<float4*>(sv + r * HD)[c4] = __ldg(reinterpret_cast<const float4*>(vbase + (int64_t)r * qkv_pitch) + c4);
+  }
+  const bool masked = (g.shift != 0) || g.Hp != g.H || g.Wp != g.W;
+  const int wy = (int)((win % nW) / (g.Wp / g.ws)), wx = (int)((win % nW) % (g.Wp / g.ws));
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    slab[i] = masked ? win_mask_label(g, wy * g.ws + i / g.ws, wx * g.ws + i % g.ws) : 0;
+  __syncthreads();
+
+  const int i = threadIdx.x;
+  if (i >= N) return;
+  const int64_t row = win * N + i;
+  float q[HD];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(qkv + row * qkv_pitch + h * HD);
+#pragma unroll
+    for (int d = 0; d < HD / 4; ++d) {
+      float4 t = __ldg(qp + d);
+      q[4 * d] = t.x; q[4 * d + 1] = t.y; q[4 * d + 2] = t.z; q[4 * d + 3] = t.w;
+    }
+  }
+  const float scale = (float)(1.0 / sqrt((double)HD));   // python: head_dim ** -0.5, folded at compile time
+  const int mylab = slab[i];
+  float acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f, mx = 0.f, my = 0.f;
+  const float* rcx = rc ? rc + (int64_t)i * N : nullptr;
+  const float* rcy = rc ? rc + (int64_t)N * N + (int64_t)i * N : nullptr;
+  for (int j = 0; j < N; ++j) {
+    const float4* kp = reinterpret_cast<const float4*>(sk + j * HD);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int d = 0; d < HD / 4; ++d) {
+      float4 k4 = kp[d];
+      s0 = fmaf(q[4 * d], k4.x, s0);
+      s1 = fmaf(q[4 * d + 1], k4.y, s1);
+      s2 = fmaf(q[4 * d + 2], k4.z, s2);
+      s3 = fmaf(q[4 * d + 3], k4.w, s3);
+    }
+    float s = ((s0 + s1) + (s2 + s3)) * scale;
+    if (slab[j] != mylab) s += -100.0f;           // additive mask, -100 not -inf (attention.py:55-57)
+    float mn = fmaxf(m, s);
+    float corr = expf(m - mn);                    // exp(-inf) = 0 on the first key
+    float p = expf(s - mn);
+    l = l * corr + p;
+    const float4* vp = reinterpret_cast<const float4*>(sv + j * HD);
+#pragma unroll
+    for (int d = 0; d < HD / 4; ++d) {
+      float4 v4 = vp[d];
+      acc[4 * d] = fmaf(p, v4.x, acc[4 * d] * corr);
+      acc[4 * d + 1] = fmaf(p, v4.y, acc[4 * d + 1] * corr);
+      acc[4 * d + 2] = fmaf(p, v4.z, acc[4 * d + 2] * corr);
+      acc[4 * d + 3] = fmaf(p, v4.w, acc[4 * d + 3] * corr);
+    }
+    if (rc) {
+      mx = fmaf(p, __ldg(rcx + j), mx * corr);
+      my = fmaf(p, __ldg(rcy + j), my * corr);
+    }
+    m = mn;
+  }
+  const float inv = 1.0f / l;
+  float4* op = reinterpret_cast<float4*>(out + row * out_pitch + h * HD);
+#pragma unroll
+  for (int d = 0; d < HD / 4; ++d)
+    op[d] = make_float4(acc[4 * d] * inv, acc[4 * d + 1] * inv, acc[4 * d + 2] * inv, acc[4 * d + 3] * inv);
+  if (motion_raw) {
+    motion_raw[(row * heads + h) * 2 + 0] = mx * inv;
+    motion_raw[(row * heads + h) * 2 + 1] = my * inv;
+  }
+}
+
+// motion[b, y, x, off + frame*2 + xy] = w2 . gelu(w0 . m_heads + b0) + b2     (attention.py:143-146, 209-211)
+__global__ void __launch_bounds__(256) motion_mix_kernel(const float* __restrict__ motion_raw, int heads,
+                                                         atmvfi_window_geom g, int64_t rows,
+                                                         const float* __restrict__ w0, const float* __restrict__ b0,
+                                                         const float* __restrict__ w2, const float* __restrict__ b2,
+                                                         float* __restrict__ motion, int motion_pitch, int motion_off) {
+  const int hid = heads / 2;
+  const int pairs = g.B2 / 2;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < rows * 2; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = t >> 1;
+    int xy = (int)(t & 1);
+    WinPos p = win_decode(g, r);
+    if (!p.real) continue;
+    float o = __ldg(b2);
+    for (int k = 0; k < hid; ++k) {
+      float a = __ldg(b0 + k);
+      for (int hh = 0; hh < heads; ++hh) a = fmaf(__ldg(w0 + k * heads + hh), __ldg(motion_raw + (r * heads + hh) * 2 + xy), a);
+      a = 0.5f * a * (1.f + erff(a * 0.70710678118654752440f));
+      o = fmaf(__ldg(w2 + k), a, o);
+    }
+    int frame = p.b >= pairs ? 1 : 0;
+    int pb = p.b - frame * pairs;
+    motion[((int64_t)(pb * g.H + p.y) * g.W + p.x) * motion_pitch + motion_off + frame * 2 + xy] = o;
+  }
+}
+
+template <int HD>
+int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                     const atmvfi_window_geom& g, int cross, const float* rc, float* motion_raw, cudaStream_t st) {
+  const int N = g.ws * g.ws;
+  const int64_t wins = (int64_t)g.B2 * (g.Hp / g.ws) * (g.Wp / g.ws);
+  size_t smem = (size_t)(2 * N * HD) * sizeof(float) + N * sizeof(int);
+  auto kern = window_attention_kernel<HD>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      atmvfi_set_error("window_attention: cannot reserve %zu B of shared memory: %s", smem, cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  dim3 grid((unsigned)wins, (unsigned)heads);
+  int threads = ((N + 31) / 32) * 32;
+  kern<<<grid, threads, smem, st>>>(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, rc, motion_raw);
+  ATMVFI_CHECK_LAUNCH("window_attention");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                                       const atmvfi_window_geom* g, int cross, const float* relative_coord,
+                                       const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
+                                       float* motion, int motion_pitch, int motion_off, float* scratch, void* stream) {
+  ATMVFI_REQUIRE(heads > 0 && C % heads == 0, "window_attention: dim %d should be divided by num_heads %d", C, heads);
+  const int hd = C / heads, N = g->ws * g->ws;
+  ATMVFI_REQUIRE(N <= 256, "window_attention: window %d too large (max 16)", g->ws);
+  ATMVFI_REQUIRE(g->Hp % g->ws == 0 && g->Wp % g->ws == 0 && g->shift >= 0 && g->shift < g->ws, "window_attention: bad geometry");
+  ATMVFI_REQUIRE(!cross || g->B2 % 2 == 0, "window_attention: cross attention needs an even batch");
+  ATMVFI_REQUIRE(qkv_pitch % 4 == 0 && out_pitch % 4 == 0 && hd % 4 == 0, "window_attention: pitches / head dim must be multiples of 4");
+  const bool want_motion = motion != nullptr;
+  ATMVFI_REQUIRE(!want_motion || (relative_coord && scratch && mix_w0 && mix_b0 && mix_w2 && mix_b2 && cross),
+                 "window_attention: motion output needs relative_coord, scratch and the head-mix MLP");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* raw = want_motion ? scratch : nullptr;
+  const float* rc = want_motion ? relative_coord : nullptr;
+  int rcode;
+  switch (hd) {
+    case 28: rcode = launch_attention<28>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
+    case 44: rcode = launch_attention<44>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
+    case 48: rcode = launch_attention<48>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
+    case 84: rcode = launch_attention<84>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
+    case 16: rcode = launch_attention<16>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
+    case 32: rcode = launch_attention<32>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
+    case 64: rcode = launch_attention<64>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
+    default:
+      atmvfi_set_error("window_attention: head dim %d not instantiated (have 16,28,32,44,48,64,84)", hd);
+      return 2;
+  }
+  if (rcode) return rcode;
+  if (want_motion) {
+    int64_t rows = (int64_t)g->B2 * g->Hp * g->Wp;
+    int blocks = (int)((rows * 2 + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    motion_mix_kernel<<<blocks, 256, 0, st>>>(raw, heads, *g, rows, mix_w0, mix_b0, mix_w2, mix_b2, motion, motion_pitch, motion_off);
+    ATMVFI_CHECK_LAUNCH("motion_mix");
+  }
+  return 0;
+}

@@ -1,0 +1,122 @@
+// Shared helpers for the sm_100a kernels of libatmvfi_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/atmvfi.h"
+
+void atmvfi_set_error(const char* fmt, ...);
+
+#define ATMVFI_CHECK_LAUNCH(what)                                                        \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      atmvfi_set_error("%s: launch failed: %s", what, cudaGetErrorString(e__));          \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define ATMVFI_REQUIRE(cond, ...)                                                        \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      atmvfi_set_error(__VA_ARGS__);                                                     \
+      return 2;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// Window bookkeeping (attention.py:8-71, 275-331) as index arithmetic.
+// A window-major row r enumerates (image b, window row wy, window col wx, token ty, tx) exactly like
+// window_partition() does on the centre-padded, cyclically shifted map.
+// ---------------------------------------------------------------------------------------------
+struct WinPos {
+  int b;        // image on the batch axis
+  int yr, xr;   // coordinates in the padded + rolled frame (what the window sees)
+  int y, x;     // coordinates in the un-padded token grid, valid only if `real`
+  bool real;    // false: a centre-padding token
+};
+
+__device__ __forceinline__ WinPos win_decode(const atmvfi_window_geom& g, int64_t r) {
+  const int N = g.ws * g.ws;
+  const int nwx = g.Wp / g.ws, nwy = g.Hp / g.ws;
+  int n = (int)(r % N);
+  int64_t w = r / N;
+  int wx = (int)(w % nwx);
+  w /= nwx;
+  int wy = (int)(w % nwy);
+  WinPos p;
+  p.b = (int)(w / nwy);
+  p.yr = wy * g.ws + n / g.ws;
+  p.xr = wx * g.ws + n % g.ws;
+  // torch.roll(x, -shift): rolled[i] = padded[(i + shift) mod size]
+  int yp = p.yr + g.shift;
+  if (yp >= g.Hp) yp -= g.Hp;
+  int xp = p.xr + g.shift;
+  if (xp >= g.Wp) xp -= g.Wp;
+  p.y = yp - g.pad_top;
+  p.x = xp - g.pad_left;
+  p.real = (p.y >= 0) && (p.y < g.H) && (p.x >= 0) && (p.x < g.W);
+  return p;
+}
+
+// Region labels of the two additive -100 masks.  The reference builds the centre-padding mask on the
+// UN-rolled padded frame and applies it to the rolled windows (attention.py:273-303), so the padding
+// label is a function of the window-frame coordinates, not of where the token came from.
+__device__ __forceinline__ int win_pad_label(const atmvfi_window_geom& g, int yr, int xr) {
+  int ly = yr < g.pad_top ? 0 : (yr < g.pad_top + g.H ? 1 : 2);
+  int lx = xr < g.pad_left ? 0 : (xr < g.pad_left + g.W ? 1 : 2);
+  return ly * 3 + lx;
+}
+__device__ __forceinline__ int win_shift_label(const atmvfi_window_geom& g, int yr, int xr) {
+  int ly = yr < g.Hp - g.ws ? 0 : (yr < g.Hp - g.shift ? 1 : 2);
+  int lx = xr < g.Wp - g.ws ? 0 : (xr < g.Wp - g.shift ? 1 : 2);
+  return ly * 3 + lx;
+}
+// one packed label: differing labels <=> masked pair
+__device__ __forceinline__ int win_mask_label(const atmvfi_window_geom& g, int yr, int xr) {
+  int lab = 0;
+  if (g.Hp != g.H || g.Wp != g.W) lab = win_pad_label(g, yr, xr);
+  if (g.shift) lab = lab * 9 + win_shift_label(g, yr, xr);
+  return lab;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid_sample(bilinear, zeros, align_corners=True) coordinate arithmetic of flow_warp.py:35-40 replayed
+// operation by operation in fp32 (no FMA contraction): pixel + flow -> normalise -> un-normalise.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_src_coord(float pix, float flow, int size) {
+  float p = __fadd_rn(pix, flow);
+  float gsz = (float)(size - 1);
+  float g = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, p), gsz), -1.f);          // 2*x/(w-1) - 1
+  return __fmul_rn(__fadd_rn(g, 1.f), __fdiv_rn(gsz, 2.f));              // (g+1) * ((w-1)/2)
+}
+
+struct Bilin {
+  int x0, y0;
+  float wnw, wne, wsw, wse;
+  bool vx0, vx1, vy0, vy1;
+};
+
+__device__ __forceinline__ Bilin bilin_setup(float ix, float iy, int W, int H) {
+  Bilin s;
+  float fx = floorf(ix), fy = floorf(iy);
+  s.x0 = (int)fx;
+  s.y0 = (int)fy;
+  float tx = __fsub_rn(ix, fx), ty = __fsub_rn(iy, fy);
+  float ux = __fsub_rn(__fadd_rn(fx, 1.f), ix), uy = __fsub_rn(__fadd_rn(fy, 1.f), iy);
+  s.wnw = __fmul_rn(ux, uy);
+  s.wne = __fmul_rn(tx, uy);
+  s.wsw = __fmul_rn(ux, ty);
+  s.wse = __fmul_rn(tx, ty);
+  s.vx0 = s.x0 >= 0 && s.x0 < W;
+  s.vx1 = s.x0 + 1 >= 0 && s.x0 + 1 < W;
+  s.vy0 = s.y0 >= 0 && s.y0 < H;
+  s.vy1 = s.y0 + 1 >= 0 && s.y0 + 1 < H;
+  // non-finite coordinates (NaN flow) sample nothing, like ATen's bounds checks
+  if (!(ix > -2.0e9f && ix < 2.0e9f) || !(iy > -2.0e9f && iy < 2.0e9f)) s.vx0 = s.vx1 = s.vy0 = s.vy1 = false;
+  return s;
+}
+
+__device__ __forceinline__ float sigmoidf_exact(float x) { return 1.f / (1.f + expf(-x)); }

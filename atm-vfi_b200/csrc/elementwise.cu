@@ -1,0 +1,424 @@
+// HBM-bound kernels of the ATM-VFI forward: LayerNorm (plain and fused with the window gather),
+// depth-wise 3x3 + GELU, backward warps (+ occlusion blend), align_corners resize, layout packers.
+// Every kernel is a coalesced streaming pass; grids are sized in multiples of the SM count (148).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp normalises one row of C floats (C % 4 == 0); row kept in registers between the passes.
+template <int MAXV>   // float4 per lane
+__device__ __forceinline__ void ln_row(const float* __restrict__ src, float* __restrict__ dst, int C,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float eps, int lane) {
+  float4 v[MAXV];
+  const int nv = C >> 2;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int idx = lane + i * 32;
+    if (idx < nv) {
+      v[i] = __ldg(reinterpret_cast<const float4*>(src) + idx);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int idx = lane + i * 32;
+    if (idx < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int idx = lane + i * 32;
+    if (idx < nv) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+      float4 b = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + b.x;
+      o.y = (v[i].y - mean) * rstd * g.y + b.y;
+      o.z = (v[i].z - mean) * rstd * g.z + b.z;
+      o.w = (v[i].w - mean) * rstd * g.w + b.w;
+      reinterpret_cast<float4*>(dst)[idx] = o;
+    }
+  }
+}
+
+constexpr int kLnMaxV = 8;   // up to C = 1024
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, int in_pitch,
+                                                        float* __restrict__ out, int out_pitch, int64_t rows, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps)
+    ln_row<kLnMaxV>(in + r * in_pitch, out + r * out_pitch, C, gamma, beta, eps, lane);
+}
+
+__global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __restrict__ tok, int tok_pitch,
+                                                               float* __restrict__ win, int win_pitch, int C,
+                                                               atmvfi_window_geom g, int64_t rows,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+    WinPos p = win_decode(g, r);
+    float* dst = win + r * win_pitch;
+    if (p.real) {
+      const float* src = tok + ((int64_t)(p.b * g.H + p.y) * g.W + p.x) * tok_pitch;
+      ln_row<kLnMaxV>(src, dst, C, gamma, beta, eps, lane);
+    } else {
+      // LayerNorm of an all-zero token: (0-0)*rstd*gamma + beta = beta (attention.py:273,316)
+      for (int i = lane; i < (C >> 2); i += 32)
+        reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+    }
+  }
+}
+
+// depth-wise 3x3, pad 1, + bias + exact GELU.  One thread: one pixel x 4 channels.
+__global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
+                                                          int H, int W, int C, int pitch,
+                                                          const float* __restrict__ w9c, const float* __restrict__ bias) {
+  const int cv = C >> 2;
+  const int64_t total = (int64_t)B * H * W * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % cv);
+    int64_t pix = i / cv;
+    int x = (int)(pix % W);
+    int y = (int)((pix / W) % H);
+    int b = (int)(pix / ((int64_t)W * H));
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        float4 v = __ldg(reinterpret_cast<const float4*>(in + ((int64_t)(b * H + yy) * W + xx) * pitch) + c4);
+        float4 k = __ldg(reinterpret_cast<const float4*>(w9c + ((dy + 1) * 3 + (dx + 1)) * C) + c4);
+        acc.x = fmaf(v.x, k.x, acc.x);
+        acc.y = fmaf(v.y, k.y, acc.y);
+        acc.z = fmaf(v.z, k.z, acc.z);
+        acc.w = fmaf(v.w, k.w, acc.w);
+      }
+    }
+    const float r2 = 0.70710678118654752440f;
+    float4 o;
+    o.x = 0.5f * acc.x * (1.f + erff(acc.x * r2));
+    o.y = 0.5f * acc.y * (1.f + erff(acc.y * r2));
+    o.z = 0.5f * acc.z * (1.f + erff(acc.z * r2));
+    o.w = 0.5f * acc.w * (1.f + erff(acc.w * r2));
+    reinterpret_cast<float4*>(out + pix * pitch)[c4] = o;
+  }
+}
+
+__device__ __forceinline__ float sample_plane(const float* __restrict__ p, const Bilin& s, int W) {
+  float o = 0.f;
+  const float* r0 = p + (int64_t)s.y0 * W + s.x0;
+  if (s.vy0 && s.vx0) o = __fmul_rn(__ldg(r0), s.wnw);
+  if (s.vy0 && s.vx1) o = __fadd_rn(o, __fmul_rn(__ldg(r0 + 1), s.wne));
+  if (s.vy1 && s.vx0) o = __fadd_rn(o, __fmul_rn(__ldg(r0 + W), s.wsw));
+  if (s.vy1 && s.vx1) o = __fadd_rn(o, __fmul_rn(__ldg(r0 + W + 1), s.wse));
+  return o;
+}
+
+__global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __restrict__ img, const float* __restrict__ flow,
+                                                             float* __restrict__ out, int B, int C, int H, int W) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / hw);
+    int64_t rem = i - b * hw;
+    int y = (int)(rem / W), x = (int)(rem % W);
+    float ix = warp_src_coord((float)x, __ldg(flow + (int64_t)b * 2 * hw + rem), W);
+    float iy = warp_src_coord((float)y, __ldg(flow + ((int64_t)b * 2 + 1) * hw + rem), H);
+    Bilin s = bilin_setup(ix, iy, W, H);
+    for (int c = 0; c < C; ++c) out[((int64_t)b * C + c) * hw + rem] = sample_plane(img + ((int64_t)b * C + c) * hw, s, W);
+  }
+}
+
+// NHWC gather: a group of (C/4) lanes serves one output pixel, each lane moves one float4 per corner.
+__global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __restrict__ src, int src_pitch,
+                                                             const float* __restrict__ head, int head_pitch, int flow_off,
+                                                             float* __restrict__ out, int out_pitch, int B, int C, int H,
+                                                             int W) {
+  const int cv = C >> 2;
+  const int64_t total = (int64_t)B * H * W * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c4 = (int)(i % cv);
+    int64_t pix = i / cv;
+    int x = (int)(pix % W);
+    int y = (int)((pix / W) % H);
+    int b = (int)(pix / ((int64_t)W * H));
+    const float* hp = head + pix * head_pitch + flow_off;
+    float ix = warp_src_coord((float)x, __ldg(hp), W);
+    float iy = warp_src_coord((float)y, __ldg(hp + 1), H);
+    Bilin s = bilin_setup(ix, iy, W, H);
+    const float* base = src + (int64_t)b * H * W * src_pitch;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto corner = [&](int yy, int xx, float w, bool first) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)yy * W + xx) * src_pitch) + c4);
+      if (first) {
+        o.x = __fmul_rn(v.x, w); o.y = __fmul_rn(v.y, w); o.z = __fmul_rn(v.z, w); o.w = __fmul_rn(v.w, w);
+      } else {
+        o.x = __fadd_rn(o.x, __fmul_rn(v.x, w)); o.y = __fadd_rn(o.y, __fmul_rn(v.y, w));
+        o.z = __fadd_rn(o.z, __fmul_rn(v.z, w)); o.w = __fadd_rn(o.w, __fmul_rn(v.w, w));
+      }
+    };
+    if (s.vy0 && s.vx0) corner(s.y0, s.x0, s.wnw, false);
+    if (s.vy0 && s.vx1) corner(s.y0, s.x0 + 1, s.wne, false);
+    if (s.vy1 && s.vx0) corner(s.y0 + 1, s.x0, s.wsw, false);
+    if (s.vy1 && s.vx1) corner(s.y0 + 1, s.x0 + 1, s.wse, false);
+    reinterpret_cast<float4*>(out + pix * out_pitch)[c4] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256) warp_blend_kernel(const float* __restrict__ im0, const float* __restrict__ im1,
+                                                         const float* __restrict__ head, int head_pitch, int head_off,
+                                                         float* __restrict__ w0, float* __restrict__ w1,
+                                                         float* __restrict__ it, float* __restrict__ flow0,
+                                                         float* __restrict__ flow1, float* __restrict__ occ1,
+                                                         float* __restrict__ occ2, int B, int H, int W) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / hw);
+    int64_t rem = i - b * hw;
+    int y = (int)(rem / W), x = (int)(rem % W);
+    const float* hp = head + i * head_pitch + head_off;
+    float f0x = __ldg(hp), f0y = __ldg(hp + 1), f1x = __ldg(hp + 2), f1y = __ldg(hp + 3), lg = __ldg(hp + 4);
+    Bilin s0 = bilin_setup(warp_src_coord((float)x, f0x, W), warp_src_coord((float)y, f0y, H), W, H);
+    Bilin s1 = bilin_setup(warp_src_coord((float)x, f1x, W), warp_src_coord((float)y, f1y, H), W, H);
+    float m1 = sigmoidf_exact(lg);
+    float m2 = __fsub_rn(1.f, m1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int64_t o = ((int64_t)b * 3 + c) * hw;
+      float a = sample_plane(im0 + o, s0, W);
+      float bb = sample_plane(im1 + o, s1, W);
+      w0[o + rem] = a;
+      w1[o + rem] = bb;
+      it[o + rem] = __fadd_rn(__fmul_rn(m1, a), __fmul_rn(m2, bb));
+    }
+    if (flow0) {
+      flow0[(int64_t)b * 2 * hw + rem] = f0x;
+      flow0[((int64_t)b * 2 + 1) * hw + rem] = f0y;
+    }
+    if (flow1) {
+      flow1[(int64_t)b * 2 * hw + rem] = f1x;
+      flow1[((int64_t)b * 2 + 1) * hw + rem] = f1y;
+    }
+    if (occ1) occ1[i] = m1;
+    if (occ2) occ2[i] = m2;
+  }
+}
+
+// F.interpolate(bilinear, align_corners=True): src = dst * (in-1)/(out-1); ATen's weights w1 = src - floor, w0 = 1 - w1.
+__global__ void __launch_bounds__(256) resize_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int planes,
+                                                        int Hin, int Win, int Hout, int Wout, float sh, float sw,
+                                                        float scale) {
+  const int64_t total = (int64_t)planes * Hout * Wout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % Wout);
+    int y = (int)((i / Wout) % Hout);
+    int64_t p = i / ((int64_t)Wout * Hout);
+    float fy = __fmul_rn(sh, (float)y), fx = __fmul_rn(sw, (float)x);
+    int y0 = (int)fy, x0 = (int)fx;
+    int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+    float ly = __fsub_rn(fy, (float)y0), lx = __fsub_rn(fx, (float)x0);
+    float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+    const float* src = in + p * Hin * Win;
+    float v00 = __ldg(src + (int64_t)y0 * Win + x0), v01 = __ldg(src + (int64_t)y0 * Win + x1);
+    float v10 = __ldg(src + (int64_t)y1 * Win + x0), v11 = __ldg(src + (int64_t)y1 * Win + x1);
+    float top = __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01));
+    float bot = __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11));
+    float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+    out[i] = scale == 1.f ? v : __fmul_rn(v, scale);
+  }
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                           int out_pitch, int chan_off, int B, int C, int H, int W,
+                                                           int zero_to) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / hw);
+    int64_t rem = i - b * hw;
+    float* o = out + i * out_pitch + chan_off;
+    for (int c = 0; c < C; ++c) o[c] = __ldg(in + ((int64_t)b * C + c) * hw + rem);
+    for (int c = chan_off + C; c < zero_to; ++c) out[i * out_pitch + c] = 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) residual_finish_kernel(const float* __restrict__ res, int res_pitch,
+                                                              const float* __restrict__ it, float* __restrict__ it_sum,
+                                                              float* __restrict__ it_clamped, int B, int H, int W) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(i / hw);
+    int64_t rem = i - b * hw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int64_t o = ((int64_t)b * 3 + c) * hw + rem;
+      float r = __fsub_rn(__fmul_rn(2.f, sigmoidf_exact(__ldg(res + i * res_pitch + c))), 1.f);
+      float s = __fadd_rn(__ldg(it + o), r);
+      if (it_sum) it_sum[o] = s;
+      it_clamped[o] = fminf(fmaxf(s, 0.f), 1.f);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) u8_to_planar_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int H,
+                                                           int W, int Hp, int Wp, int top, int left, int bgr) {
+  const int64_t total = (int64_t)Hp * Wp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % Wp), y = (int)(i / Wp);
+    int sx = min(max(x - left, 0), W - 1), sy = min(max(y - top, 0), H - 1);   // replicate pad (utils.py:66-69)
+    const uint8_t* p = in + ((int64_t)sy * W + sx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) out[(int64_t)c * total + i] = __fdiv_rn((float)p[bgr ? 2 - c : c], 255.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) planar_to_u8_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int H,
+                                                           int W, int Hp, int Wp, int top, int left, int bgr) {
+  const int64_t total = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int x = (int)(i % W), y = (int)(i / W);
+    int64_t s = (int64_t)(y + top) * Wp + (x + left);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = rintf(__fmul_rn(__ldg(in + (int64_t)c * Hp * Wp + s), 255.f));   // np.round: half to even
+      out[i * 3 + (bgr ? 2 - c : c)] = (uint8_t)fminf(fmaxf(v, 0.f), 255.f);
+    }
+  }
+}
+
+inline int grid_for(int64_t work_items, int block) {
+  int64_t blocks = (work_items + block - 1) / block;
+  int64_t cap = (int64_t)kSMs * 16;   // 16 resident 256-thread CTAs/SM worth of grid-stride work
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+int atmvfi_layernorm(const float* in, int in_pitch, float* out, int out_pitch, int64_t rows, int C, const float* gamma,
+                     const float* beta, float eps, void* stream) {
+  ATMVFI_REQUIRE(C % 4 == 0 && C <= kLnMaxV * 128 && in_pitch % 4 == 0 && out_pitch % 4 == 0,
+                 "layernorm: C=%d pitches %d/%d unsupported (need C%%4==0, C<=%d)", C, in_pitch, out_pitch, kLnMaxV * 128);
+  if (rows <= 0) return 0;
+  layernorm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, C, gamma, beta, eps);
+  ATMVFI_CHECK_LAUNCH("layernorm");
+  return 0;
+}
+
+int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win_pitch, int C, const atmvfi_window_geom* g,
+                            const float* gamma, const float* beta, float eps, void* stream) {
+  ATMVFI_REQUIRE(C % 4 == 0 && C <= kLnMaxV * 128 && tok_pitch % 4 == 0 && win_pitch % 4 == 0, "window_gather_ln: C=%d unsupported", C);
+  ATMVFI_REQUIRE(g->Hp % g->ws == 0 && g->Wp % g->ws == 0 && g->shift >= 0 && g->shift < g->ws, "window_gather_ln: bad geometry");
+  int64_t rows = (int64_t)g->B2 * g->Hp * g->Wp;
+  if (rows <= 0) return 0;
+  window_gather_ln_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(tok, tok_pitch, win, win_pitch, C, *g, rows, gamma, beta, eps);
+  ATMVFI_CHECK_LAUNCH("window_gather_ln");
+  return 0;
+}
+
+int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch, const float* w9c,
+                          const float* bias, void* stream) {
+  ATMVFI_REQUIRE(C % 4 == 0 && pitch % 4 == 0, "dwconv3x3_gelu: C=%d pitch=%d must be multiples of 4", C, pitch);
+  int64_t n = (int64_t)B * H * W * (C / 4);
+  if (n <= 0) return 0;
+  dwconv_gelu_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias);
+  ATMVFI_CHECK_LAUNCH("dwconv3x3_gelu");
+  return 0;
+}
+
+int atmvfi_flow_warp_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream) {
+  int64_t n = (int64_t)B * H * W;
+  if (n <= 0 || C <= 0) return 0;
+  flow_warp_nchw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(img, flow, out, B, C, H, W);
+  ATMVFI_CHECK_LAUNCH("flow_warp_nchw");
+  return 0;
+}
+
+int atmvfi_flow_warp_nhwc(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off, float* out,
+                          int out_pitch, int B, int C, int H, int W, void* stream) {
+  ATMVFI_REQUIRE(C % 4 == 0 && src_pitch % 4 == 0 && out_pitch % 4 == 0, "flow_warp_nhwc: C=%d must be a multiple of 4", C);
+  int64_t n = (int64_t)B * H * W * (C / 4);
+  if (n <= 0) return 0;
+  flow_warp_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W);
+  ATMVFI_CHECK_LAUNCH("flow_warp_nhwc");
+  return 0;
+}
+
+int atmvfi_warp_blend(const float* im0, const float* im1, const float* head, int head_pitch, int head_off, float* w0,
+                      float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2, int B, int H, int W,
+                      void* stream) {
+  int64_t n = (int64_t)B * H * W;
+  if (n <= 0) return 0;
+  warp_blend_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(im0, im1, head, head_pitch, head_off, w0, w1, it, flow0, flow1, occ1, occ2, B, H, W);
+  ATMVFI_CHECK_LAUNCH("warp_blend");
+  return 0;
+}
+
+int atmvfi_resize_bilinear_ac(const float* in, float* out, int planes, int Hin, int Win, int Hout, int Wout, float scale,
+                              void* stream) {
+  int64_t n = (int64_t)planes * Hout * Wout;
+  if (n <= 0) return 0;
+  // ATen area_pixel_compute_scale(align_corners=True): (in-1)/(out-1), 0 when out == 1
+  float sh = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
+  float sw = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+  resize_ac_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hin, Win, Hout, Wout, sh, sw, scale);
+  ATMVFI_CHECK_LAUNCH("resize_bilinear_ac");
+  return 0;
+}
+
+int atmvfi_nchw_to_nhwc(const float* in, float* out, int out_pitch, int chan_off, int B, int C, int H, int W,
+                        int zero_fill_to, void* stream) {
+  int64_t n = (int64_t)B * H * W;
+  if (n <= 0) return 0;
+  nchw_to_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, out_pitch, chan_off, B, C, H, W, zero_fill_to);
+  ATMVFI_CHECK_LAUNCH("nchw_to_nhwc");
+  return 0;
+}
+
+int atmvfi_residual_finish(const float* res, int res_pitch, const float* it, float* it_sum, float* it_clamped, int B, int H,
+                           int W, void* stream) {
+  int64_t n = (int64_t)B * H * W;
+  if (n <= 0) return 0;
+  residual_finish_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(res, res_pitch, it, it_sum, it_clamped, B, H, W);
+  ATMVFI_CHECK_LAUNCH("residual_finish");
+  return 0;
+}
+
+int atmvfi_u8_to_planar(const uint8_t* in, float* out, int H, int W, int Hp, int Wp, int top, int left, int bgr, void* stream) {
+  u8_to_planar_kernel<<<grid_for((int64_t)Hp * Wp, 256), 256, 0, (cudaStream_t)stream>>>(in, out, H, W, Hp, Wp, top, left, bgr);
+  ATMVFI_CHECK_LAUNCH("u8_to_planar");
+  return 0;
+}
+
+int atmvfi_planar_to_u8(const float* in, uint8_t* out, int H, int W, int Hp, int Wp, int top, int left, int bgr, void* stream) {
+  planar_to_u8_kernel<<<grid_for((int64_t)H * W, 256), 256, 0, (cudaStream_t)stream>>>(in, out, H, W, Hp, Wp, top, left, bgr);
+  ATMVFI_CHECK_LAUNCH("planar_to_u8");
+  return 0;
+}
+
+}  // extern "C"

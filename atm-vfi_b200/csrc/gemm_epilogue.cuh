@@ -1,0 +1,54 @@
+// Fused epilogue shared by the FP32 (CUDA-core) and TF32 (tcgen05) implicit-GEMM kernels:
+// bias -> residual -> PReLU, output-row remapping (plain / ConvTranspose pixel-shuffle / window reverse),
+// optional second PReLU'd copy.
+#pragma once
+#include "common.cuh"
+
+struct EpiParams {
+  int Cout;
+  const float* bias;
+  const float* prelu;
+  const float* residual;
+  int res_pitch;
+  float* out;
+  int out_pitch;
+  float* out2;
+  const float* prelu2;
+  int out2_pitch;
+  int out_mode;
+  int Hout, Wout;          // GEMM rows enumerate (b, y, x) over this grid
+  atmvfi_window_geom win;
+};
+
+// Destination row of GEMM row m (and shuffle block q); -1 = discard (centre-padding token).
+__device__ __forceinline__ int64_t epi_out_row(const EpiParams& e, int64_t m, int q) {
+  if (e.out_mode == ATMVFI_OUT_PIXEL) return m;
+  if (e.out_mode == ATMVFI_OUT_SHUFFLE2) {
+    int x = (int)(m % e.Wout);
+    int64_t t = m / e.Wout;
+    int y = (int)(t % e.Hout);
+    int64_t b = t / e.Hout;
+    return (b * 2 * e.Hout + 2 * y + (q >> 1)) * (2 * (int64_t)e.Wout) + 2 * x + (q & 1);
+  }
+  WinPos p = win_decode(e.win, m);
+  if (!p.real) return -1;
+  return ((int64_t)p.b * e.win.H + p.y) * e.win.W + p.x;
+}
+
+// acc = A*W for (GEMM row m, output channel co); orow from epi_out_row.
+__device__ __forceinline__ void epi_store(const EpiParams& e, int64_t m, int64_t orow, int co, float acc) {
+  float v = acc;
+  if (e.bias) v += __ldg(e.bias + co);
+  if (e.residual) v += __ldg(e.residual + m * e.res_pitch + co);
+  if (e.prelu) v = v > 0.f ? v : v * __ldg(e.prelu + co);
+  e.out[orow * e.out_pitch + co] = v;
+  if (e.out2) e.out2[orow * e.out2_pitch + co] = v > 0.f ? v : v * __ldg(e.prelu2 + co);
+}
+
+static inline EpiParams make_epi(const atmvfi_gemm_conv_desc* d) {
+  EpiParams e;
+  e.Cout = d->Cout; e.bias = d->bias; e.prelu = d->prelu; e.residual = d->residual; e.res_pitch = d->res_pitch;
+  e.out = d->out; e.out_pitch = d->out_pitch; e.out2 = d->out2; e.prelu2 = d->prelu2; e.out2_pitch = d->out2_pitch;
+  e.out_mode = d->out_mode; e.Hout = d->Hout; e.Wout = d->Wout; e.win = d->win;
+  return e;
+}

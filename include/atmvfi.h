@@ -1,0 +1,174 @@
+/*
+ * atmvfi.h - C ABI of libatmvfi_b200.so: the B200 (sm_100a) kernels behind the ATM-VFI model forward.
+ *
+ * The reference (Gancheekim/ATM-VFI) has no FFI of its own: its "operator boundary" is the set of
+ * torch / torch.nn.functional calls made by network/network_base.py, network/attention.py and
+ * network/flow_warp.py.  Every entry point below replaces one family of those
+ * calls and cites it.  Conventions:
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *   - no hidden allocation: the caller owns every buffer;
+ *   - return 0 on success, non-zero on error; atmvfi_last_error() returns the message (thread-local);
+ *   - feature maps are channels-last ("NHWC": [B][H][W][pitch], pitch >= C floats, pitch % 4 == 0),
+ *     3-channel images, flows and masks are planar ("NCHW") like the reference's public tensors;
+ *   - fp32 storage everywhere; `precision` selects the multiply datapath of the GEMM-shaped ops:
+ *     ATMVFI_FP32 = CUDA-core FFMA, ATMVFI_TF32 = tcgen05.mma kind::tf32 (fp32 accumulate in TMEM).
+ *
+ * There is no CPU fallback behind any of these symbols.
+ */
+#ifndef ATMVFI_H_
+#define ATMVFI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATMVFI_ABI_VERSION 1
+#define ATMVFI_MAX_SRC 4
+
+enum { ATMVFI_FP32 = 0, ATMVFI_TF32 = 1 };
+
+/* output row mapping of atmvfi_gemm_conv */
+enum {
+  ATMVFI_OUT_PIXEL = 0,      /* output pixel (b,y,x) -> row of `out` (plain conv / linear)                      */
+  ATMVFI_OUT_SHUFFLE2 = 1,   /* ConvTranspose2d(k=2,s=2): column block q=(dy*2+dx) of pixel (y,x) -> (2y+dy,2x+dx) */
+  ATMVFI_OUT_WINDOW_REV = 2  /* rows are window-major tokens; undo partition / roll / centre pad (attention.py:17-25,65-71,323-331) */
+};
+
+/* window geometry shared by the transformer kernels (attention.py:28-62, 275-305) */
+typedef struct {
+  int32_t B2;        /* images on the batch axis (2 x pairs: frame-0 images first, network_base.py:451) */
+  int32_t H, W;      /* token grid                                                                    */
+  int32_t ws;        /* window side                                                                   */
+  int32_t shift;     /* cyclic shift (0 or ws/2)                                                      */
+  int32_t Hp, Wp;    /* grid after centre padding to a multiple of ws                                 */
+  int32_t pad_top, pad_left;
+} atmvfi_window_geom;
+
+typedef struct {
+  const float* ptr;  /* NHWC source                                                 */
+  int32_t C;         /* channels taken from this source                             */
+  int32_t pitch;     /* floats between consecutive pixels                           */
+} atmvfi_src;
+
+/*
+ * Implicit-GEMM convolution / linear layer with a fused epilogue.  Replaces
+ *   nn.Conv2d 3x3 / 1x1 (+PReLU)            network_base.py:20-25, 38-54, 155-159, 192-196, 203-260
+ *   nn.ConvTranspose2d k2 s2 (+PReLU)       network_base.py:27-32, 202-221, 243-255
+ *   nn.Linear (+bias, +residual)            attention.py:93-96, 138-141, 349-351
+ *   torch.cat on the channel axis of inputs network_base.py:81, 384, 410, 418-428, 506  (the sources are read in place)
+ * A[m][k]: m = output pixel, k = (tap, source, channel);  W: packed by the host (see atmvfi_pack.py).
+ * out = act( A*W + bias (+ residual) ), optionally also out2 = prelu(out, slope2).
+ */
+typedef struct {
+  int32_t nsrc;
+  atmvfi_src src[ATMVFI_MAX_SRC];
+  int32_t B, Hin, Win;           /* all sources share the spatial shape        */
+  int32_t ksize;                 /* 1 or 3 (deconv uses ksize=1 + SHUFFLE2)     */
+  int32_t stride, dil;           /* pad = dil*(ksize-1)/2                       */
+  int32_t Hout, Wout;            /* conv output grid (before SHUFFLE2)          */
+  int32_t Cout;                  /* true output channels (per shuffle block)    */
+  const float* weight;           /* packed weights, layout depends on precision */
+  int32_t ldw;                   /* FP32: floats per k-row (= padded N)         */
+  const float* bias;             /* [Cout] or NULL                              */
+  const float* prelu;            /* [Cout] slopes or NULL                       */
+  const float* residual;         /* added after bias, rows like `out`, or NULL  */
+  int32_t res_pitch;
+  float* out;
+  int32_t out_pitch;
+  float* out2;                   /* optional second output = prelu(out, prelu2) */
+  const float* prelu2;
+  int32_t out2_pitch;
+  int32_t out_mode;              /* ATMVFI_OUT_*                                */
+  atmvfi_window_geom win;        /* used by ATMVFI_OUT_WINDOW_REV               */
+  int32_t precision;             /* ATMVFI_FP32 / ATMVFI_TF32                   */
+  const void* tma_host;          /* TF32: host pointer to the plan made by atmvfi_gemm_conv_plan, else NULL */
+} atmvfi_gemm_conv_desc;
+
+const char* atmvfi_last_error(void);
+int atmvfi_abi_version(void);
+/* Fills name[] (<=255 chars) with the device name and returns the SM count, or -1 without a usable sm_100 device. */
+int atmvfi_device_info(int device, char* name, int* cc_major, int* cc_minor);
+
+int atmvfi_gemm_conv(const atmvfi_gemm_conv_desc* d, void* stream);
+/* TF32 path: build the TMA tensor maps once per (layer, shape).  plan_host must hold atmvfi_gemm_conv_plan_bytes() bytes. */
+int atmvfi_gemm_conv_plan_bytes(void);
+int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_host);
+
+/* LayerNorm over channels of `rows` tokens (nn.LayerNorm, network_base.py:55,84; attention.py:235,333). */
+int atmvfi_layernorm(const float* in, int in_pitch, float* out, int out_pitch, int64_t rows, int C,
+                     const float* gamma, const float* beta, float eps, void* stream);
+
+/*
+ * pad_if_needed + torch.roll + window_partition + norm1 in one pass (attention.py:273-316):
+ * reads tokens [B2][H][W][C] and writes window-major rows [B2*nW*ws*ws][C]; centre-pad tokens are
+ * LayerNorm(0) = beta, exactly as in the reference where padding precedes norm1.
+ */
+int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win_pitch, int C,
+                            const atmvfi_window_geom* g, const float* gamma, const float* beta, float eps,
+                            void* stream);
+
+/*
+ * Window attention with the attention-to-motion reduction (attention.py:187-213, 370-390).
+ * qkv: window-major rows [rows][3C] (q | k | v, head-major inside each).  cross != 0: queries of a window
+ * attend to the keys/values of the same window of the OTHER frame (attention.py:318).  The additive
+ * -100 masks of the centre padding and of the cyclic shift are evaluated from `g` on the fly.
+ * out: window-major [rows][C] = softmax(q k^T * hd^-0.5 + mask) v, heads concatenated.
+ * motion (cross only, may be NULL): NHWC [B2/2][H][W][motion_pitch]; this block's 4 channels
+ * (frame0 x,y, frame1 x,y) start at motion_off; values = head-mix MLP( sum_j attn_ij * relative_coord_ij ).
+ * relative_coord: [2][N][N] buffer from the state-dict (attention.py:150-157).
+ * scratch: rows*heads*2 floats of workspace for the per-head motion (needed only with motion).
+ */
+int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                            const atmvfi_window_geom* g, int cross, const float* relative_coord,
+                            const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
+                            float* motion, int motion_pitch, int motion_off, float* scratch, void* stream);
+
+/* Mlp middle: depth-wise 3x3 (pad 1) + bias + exact-erf GELU on NHWC tokens (attention.py:74-85,118-119). */
+int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch,
+                          const float* w9c /* [9][C] */, const float* bias, void* stream);
+
+/* flow_warp.flow_warp (flow_warp.py:50-60) on planar tensors: out[b,c] = bilinear(img[b,c], grid+flow[b]). */
+int atmvfi_flow_warp_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+
+/* Same sampling on an NHWC map; the flow is read from channels [flow_off, flow_off+2) of an NHWC head. */
+int atmvfi_flow_warp_nhwc(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off,
+                          float* out, int out_pitch, int B, int C, int H, int W, void* stream);
+
+/*
+ * Fused pair warp + occlusion blend (network_base.py:385-387, 464-466, 496-498, 514-525):
+ * head: NHWC 5 channels (flow0.xy, flow1.xy, occlusion logit) starting at head_off.
+ * w0 = warp(im0, flow0), w1 = warp(im1, flow1), it = sigmoid(l)*w0 + (1-sigmoid(l))*w1  (all planar [B,3,H,W]).
+ * Optional planar exports (NULL to skip): flow0/flow1 [B,2,H,W], occ1/occ2 [B,1,H,W].
+ */
+int atmvfi_warp_blend(const float* im0, const float* im1, const float* head, int head_pitch, int head_off,
+                      float* w0, float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2,
+                      int B, int H, int W, void* stream);
+
+/* F.interpolate(bilinear, align_corners=True) on `planes` planar images; values multiplied by `scale`
+ * (network_base.py:11-18 uses x2 with scale 2; :445-446 uses x0.5 with scale 1). */
+int atmvfi_resize_bilinear_ac(const float* in, float* out, int planes, int Hin, int Win, int Hout, int Wout,
+                              float scale, void* stream);
+
+/* planar [B][C][H][W] -> channels [chan_off, chan_off+C) of an NHWC buffer (replaces torch.cat with images). */
+int atmvfi_nchw_to_nhwc(const float* in, float* out, int out_pitch, int chan_off, int B, int C, int H, int W,
+                        int zero_fill_to /* also zero channels [chan_off+C, zero_fill_to) */, void* stream);
+
+/* I_t += 2*sigmoid(res)-1 ; clamp (network_base.py:429, 532-533).  res: NHWC 3 channels. */
+int atmvfi_residual_finish(const float* res, int res_pitch, const float* it, float* it_sum, float* it_clamped,
+                           int B, int H, int W, void* stream);
+
+/* demo_2x.inference_2frame host arithmetic on the device (demo_2x.py:64-75, 79-85):
+ * uint8 HWC (optionally BGR) -> fp32 planar RGB / 255, replicate-padded by (left, top) to Hp x Wp, and back
+ * with round-half-even (np.round) and clipping to [0,255]. */
+int atmvfi_u8_to_planar(const uint8_t* in, float* out, int H, int W, int Hp, int Wp, int top, int left,
+                        int bgr, void* stream);
+int atmvfi_planar_to_u8(const float* in, uint8_t* out, int H, int W, int Hp, int Wp, int top, int left,
+                        int bgr, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATMVFI_H_ */

@@ -1,0 +1,207 @@
+"""CPU emulation of the C-ABI operator CONTRACTS (include/atmvfi.h) - TEST INFRASTRUCTURE ONLY.
+
+It lets the CPU suite check the host logic of the product (weight packing in pack.py, buffer slicing
+and launch order in engine.py) against the oracle without a GPU: each op is re-expressed with stock
+torch CPU functions from the header's documentation, NOT from the CUDA sources.  Nothing under
+``atm-vfi_b200/`` imports this module; the product path has no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from atmvfi.ops import Map, PackedGemm, WinGeom, round_up
+
+
+def _partition(x, ws):
+    b, h, w, c = x.shape
+    return x.reshape(b, h // ws, ws, w // ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, c)
+
+
+def _unpartition(win, ws, b, h, w):
+    c = win.shape[-1]
+    return win.reshape(b, h // ws, w // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(b, h, w, c)
+
+
+def _win_forward(x, g: WinGeom):
+    """[B2,H,W,C] -> window-major rows [rows, C] (centre zero pad, roll, partition)."""
+    pt, pl = g.pad_top, g.pad_left
+    x = F.pad(x, (0, 0, pl, g.Wp - g.W - pl, pt, g.Hp - g.H - pt))
+    if g.shift:
+        x = torch.roll(x, (-g.shift, -g.shift), (1, 2))
+    return _partition(x, g.ws).reshape(g.rows, -1)
+
+
+def _win_reverse(rows, g: WinGeom):
+    x = _unpartition(rows.reshape(-1, g.ws * g.ws, rows.shape[-1]), g.ws, g.B2, g.Hp, g.Wp)
+    if g.shift:
+        x = torch.roll(x, (g.shift, g.shift), (1, 2))
+    return x[:, g.pad_top : g.pad_top + g.H, g.pad_left : g.pad_left + g.W]
+
+
+def _labels(g: WinGeom):
+    """per-row mask label in the window frame: (pad label on the UN-rolled frame, shift label)."""
+    ys = torch.arange(g.Hp)[:, None].expand(g.Hp, g.Wp)
+    xs = torch.arange(g.Wp)[None, :].expand(g.Hp, g.Wp)
+    lab = torch.zeros(g.Hp, g.Wp, dtype=torch.long)
+    if g.Hp != g.H or g.Wp != g.W:
+        ly = (ys >= g.pad_top).long() + (ys >= g.pad_top + g.H).long()
+        lx = (xs >= g.pad_left).long() + (xs >= g.pad_left + g.W).long()
+        lab = ly * 3 + lx
+    if g.shift:
+        ly = (ys >= g.Hp - g.ws).long() + (ys >= g.Hp - g.shift).long()
+        lx = (xs >= g.Wp - g.ws).long() + (xs >= g.Wp - g.shift).long()
+        lab = lab * 9 + ly * 3 + lx
+    return _partition(lab[None, :, :, None].float(), g.ws).squeeze(-1)      # [nW, N]
+
+
+def _warp(img, flow):
+    b, _, h, w = img.shape
+    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    px, py = xs.float() + flow[:, 0], ys.float() + flow[:, 1]
+    grid = torch.stack([2 * px / (w - 1) - 1, 2 * py / (h - 1) - 1], -1)
+    return F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+
+
+class EmulOps:
+    def __init__(self):
+        self.recording: Optional[List] = None
+        self.launches = 0
+
+    def new_map(self, B, H, W, C, zero=False):
+        return Map(torch.full((B, H, W, round_up(C, 4)), float("nan") if round_up(C, 4) == C and not zero else 0.0), 0, C)
+
+    def new_planar(self, *shape):
+        return torch.full(shape, float("nan"))
+
+    def _emit(self, fn):
+        if self.recording is not None:
+            self.recording.append(fn)
+        else:
+            fn()
+
+    def replay(self, records, stream=None):
+        for fn in records:
+            fn()
+
+    @staticmethod
+    def count_launches(records):
+        return len(records)
+
+    # ---------------------------------------------------------------------------------------------
+    def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride=1, dil=1, act=True, residual=None,
+                  out2=None, prelu2=None, win: Optional[WinGeom] = None, precision=None):
+        assert [s.C for s in srcs] == list(w.split)
+        k, ci = w.ksize, sum(w.split)
+        n_tot = 4 * w.Cout if w.shuffle else w.Cout
+        wk = w.w32[:, :n_tot]
+        assert wk.shape[0] == k * k * ci
+
+        def run():
+            x = torch.cat([s.view() for s in srcs], -1)                       # [B,H,W,Ci]
+            if w.shuffle:
+                wt = wk.reshape(ci, 2, 2, w.Cout).permute(0, 3, 1, 2)          # [Ci,Co,2,2]
+                y = F.conv_transpose2d(x.permute(0, 3, 1, 2), wt, w.bias, stride=2).permute(0, 2, 3, 1)
+            else:
+                wt = wk.reshape(k, k, ci, w.Cout).permute(3, 2, 0, 1)          # [Co,Ci,k,k]
+                y = F.conv2d(x.permute(0, 3, 1, 2), wt, w.bias, stride=stride, padding=dil * (k - 1) // 2, dilation=dil).permute(0, 2, 3, 1)
+            if residual is not None:
+                y = y + residual.view().reshape(y.shape)
+            if act and w.prelu is not None:
+                y = torch.where(y > 0, y, y * w.prelu)
+            if win is not None:
+                y = _win_reverse(y.reshape(win.rows, -1), win)
+            out.view().copy_(y.reshape(out.view().shape))
+            if out2 is not None:
+                out2.view().copy_(torch.where(y > 0, y, y * prelu2).reshape(out2.view().shape))
+
+        self._emit(run)
+
+    def layernorm(self, x: Map, out: Map, gamma, beta):
+        self._emit(lambda: out.view().copy_(F.layer_norm(x.view(), (x.C,), gamma, beta, 1e-5)))
+
+    def window_gather_ln(self, tok: Map, win: Map, g: WinGeom, gamma, beta):
+        def run():
+            rows = _win_forward(tok.view().reshape(g.B2, g.H, g.W, tok.C), g)
+            win.view().copy_(F.layer_norm(rows, (tok.C,), gamma, beta, 1e-5).reshape(win.view().shape))
+        self._emit(run)
+
+    def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads, cross, rc=None, mix=None, motion=None, motion_off=0, scratch=None):
+        def run():
+            C = out.C
+            N = g.ws * g.ws
+            hd = C // heads
+            x = qkv.view().reshape(-1, N, 3 * C)
+            q, k, v = x[..., :C], x[..., C : 2 * C], x[..., 2 * C :]
+            if cross:
+                half = x.shape[0] // 2
+                k, v = torch.cat([k[half:], k[:half]]), torch.cat([v[half:], v[:half]])
+            sp = lambda t: t.reshape(-1, N, heads, hd).permute(0, 2, 1, 3)
+            logits = (sp(q) @ sp(k).transpose(-1, -2)) * (hd ** -0.5)
+            if g.shift or g.Hp != g.H or g.Wp != g.W:
+                lab = _labels(g)                                               # [nW, N]
+                m = (lab[:, :, None] != lab[:, None, :]).float() * -100.0      # [nW, N, N]
+                nW = m.shape[0]
+                logits = (logits.reshape(-1, nW, heads, N, N) + m[None, :, None]).reshape(-1, heads, N, N)
+            p = logits.softmax(-1)
+            out.view().copy_((p @ sp(v)).transpose(1, 2).reshape(out.view().shape))
+            if motion is not None:
+                mo = (p[:, :, None] * rc[None, None]).sum(-1).permute(0, 2, 3, 1)          # [Bw,2,N,heads]
+                w0, b0, w2, b2 = mix
+                mo = F.gelu(mo @ w0.t() + b0) @ w2.reshape(-1, 1) + b2                      # [Bw,2,N,1]
+                mo = _win_reverse(mo.squeeze(-1).permute(0, 2, 1).reshape(g.rows, 2), g)    # [B2,H,W,2]
+                B = g.B2 // 2
+                mv = motion.view()
+                mv[..., motion_off : motion_off + 2] = mo[:B]
+                mv[..., motion_off + 2 : motion_off + 4] = mo[B:]
+        self._emit(run)
+
+    def dwconv_gelu(self, x: Map, out: Map, w9c, bias):
+        def run():
+            c = x.C
+            wt = w9c.t().reshape(c, 1, 3, 3)
+            y = F.conv2d(x.view().permute(0, 3, 1, 2), wt, bias, padding=1, groups=c)
+            out.view().copy_(F.gelu(y).permute(0, 2, 3, 1))
+        self._emit(run)
+
+    def flow_warp_nchw(self, img, flow, out):
+        self._emit(lambda: out.copy_(_warp(img, flow)))
+
+    def flow_warp_nhwc(self, src: Map, head: Map, flow_off, out: Map):
+        def run():
+            fl = head.view()[..., flow_off : flow_off + 2].permute(0, 3, 1, 2)
+            out.view().copy_(_warp(src.view().permute(0, 3, 1, 2), fl).permute(0, 2, 3, 1))
+        self._emit(run)
+
+    def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None):
+        def run():
+            hv = head.view().permute(0, 3, 1, 2)
+            a, b = _warp(im0, hv[:, 0:2]), _warp(im1, hv[:, 2:4])
+            m = torch.sigmoid(hv[:, 4:5])
+            w0.copy_(a); w1.copy_(b); it.copy_(m * a + (1 - m) * b)
+            if flow0 is not None: flow0.copy_(hv[:, 0:2])
+            if flow1 is not None: flow1.copy_(hv[:, 2:4])
+            if occ1 is not None: occ1.copy_(m)
+            if occ2 is not None: occ2.copy_(1 - m)
+        self._emit(run)
+
+    def resize(self, x, out, scale=1.0):
+        self._emit(lambda: out.copy_(F.interpolate(x, size=out.shape[-2:], mode="bilinear", align_corners=True) * scale))
+
+    def nchw_to_nhwc(self, x, out: Map, zero_fill_to=0):
+        def run():
+            c = x.shape[1]
+            out.t[..., out.c0 : out.c0 + c] = x.permute(0, 2, 3, 1)
+            if zero_fill_to > out.c0 + c:
+                out.t[..., out.c0 + c : zero_fill_to] = 0
+        self._emit(run)
+
+    def residual_finish(self, res: Map, it, it_sum, it_clamped):
+        def run():
+            s = it + (2 * torch.sigmoid(res.view()[..., :3].permute(0, 3, 1, 2)) - 1)
+            if it_sum is not None: it_sum.copy_(s)
+            it_clamped.copy_(s.clamp(0, 1))
+        self._emit(run)

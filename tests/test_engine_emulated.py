@@ -1,0 +1,44 @@
+"""Host-logic check (CPU): the product's packing (pack.py) and orchestration (engine.py), driven through
+the CPU emulation of the operator contracts (tests/emul_ops.py), must reproduce the oracle."""
+import pytest
+import torch
+
+import atmvfi_oracle as oracle
+import weights
+from atmvfi.arch import ARCHS
+from atmvfi.engine import PackedModel, Plan
+from emul_ops import EmulOps
+
+CASES = [
+    ("lite", "stress", 1, 64, 96, False),
+    ("lite", "stress", 1, 128, 192, True),      # 1/16 grid 8x12 -> padded 12x12: pad mask + shift mask
+    ("base", "stress", 2, 64, 96, True),
+    ("lite", "default", 2, 72, 104, False),     # 1/8 grid 9x13 -> padded 16x16
+]
+
+
+@pytest.mark.parametrize("kind,variant,B,H,W,glob", CASES)
+def test_plan_matches_oracle(kind, variant, B, H, W, glob):
+    P = weights.make_weights(kind, variant)
+    im0, im1 = weights.synthetic_frames(B, H, W, kind="texture")
+    ref = oracle.forward(P, im0, im1, glob)
+    model = PackedModel(ARCHS[kind], P, 8, 12, with_global=glob)
+    plan = Plan(EmulOps(), model, B, H, W, glob)
+    out = plan.run(im0, im1)
+    tol = 5e-3 if variant == "stress" else 2e-5
+    for key in ("I_t", "opt_flow_0", "opt_flow_1", "occ_mask1", "occ_mask2", "I_t_0", "I_t_1"):
+        assert out[key].shape == ref[key].shape, key
+        err = (out[key] - ref[key]).abs().max().item()
+        assert err <= tol, (key, err)
+    for name in ("im_t_list", "im0_warped_list", "im1_warped_list"):
+        assert len(out[name]) == len(ref[name]) == (5 if glob else 4)
+        for a, b in zip(out[name], ref[name]):
+            assert a.shape == b.shape
+            assert (a - b).abs().max().item() <= tol, name
+
+
+def test_bad_shape_raises():
+    P = weights.make_weights("lite", "default")
+    model = PackedModel(ARCHS["lite"], P, 8, 12)
+    with pytest.raises(RuntimeError):
+        Plan(EmulOps(), model, 1, 72, 104, True)    # not a multiple of 16 with global motion
