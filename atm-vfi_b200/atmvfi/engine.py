@@ -315,6 +315,10 @@ class Plan:
 
     def run(self, im0: torch.Tensor, im1: torch.Tensor, use_graph: bool = False) -> Dict[str, object]:
         self.im0.copy_(im0); self.im1.copy_(im1)
+        return self.run_inplace(use_graph)
+
+    def run_inplace(self, use_graph: bool = False) -> Dict[str, object]:
+        """Run on whatever ``self.im0`` / ``self.im1`` currently hold (filled by the caller on this stream)."""
         if use_graph:
             if self.graph is None:
                 self.launch()                                    # warm-up outside capture (lazy module load, attributes)

@@ -1,0 +1,65 @@
+"""Per-module engine cache: packs weights lazily, re-packs when parameters change, caches plans per shape."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .arch import Arch
+from .engine import PackedModel, Plan, clone_outputs
+from .ops import CudaOps
+
+PRECISIONS = {"fp32": _lib.FP32, "tf32": _lib.TF32}
+
+
+class Runtime:
+    def __init__(self, arch: Arch):
+        self.arch = arch
+        self._sig = None
+        self._model: Optional[PackedModel] = None
+        self._ops: Optional[CudaOps] = None
+        self._plans: Dict[Tuple, Plan] = {}
+        self._staging: Dict[Tuple, dict] = {}
+
+    def _signature(self, module: torch.nn.Module, extra) -> Tuple:
+        items = []
+        for n, t in list(module.named_parameters()) + list(module.named_buffers()):
+            items.append((n, t.data_ptr(), t._version, tuple(t.shape)))
+        return (tuple(items), extra)
+
+    def prepare(self, module: torch.nn.Module, device: torch.device, precision: str, local_ws: int, global_ws: int) -> None:
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}, got {precision!r}")
+        sig = self._signature(module, (str(device), precision, local_ws, global_ws))
+        if sig == self._sig:
+            return
+        self._ops = CudaOps(device, PRECISIONS[precision])          # raises without CUDA / the built library
+        sd = {k: v.detach() for k, v in module.state_dict().items()}
+        for k, v in sd.items():
+            if v.device != device:
+                raise RuntimeError(f"parameter {k} is on {v.device} but the inputs are on {device}")
+        self._model = PackedModel(self.arch, sd, local_ws, global_ws, with_global=True)
+        self._plans.clear()
+        self._sig = sig
+
+    def plan(self, B: int, H: int, W: int, global_motion: bool) -> Plan:
+        key = (B, H, W, bool(global_motion))
+        p = self._plans.get(key)
+        if p is None:
+            if len(self._plans) >= 4:            # plans own all activation buffers; keep the cache small
+                self._plans.pop(next(iter(self._plans)))
+            p = self._plans[key] = Plan(self._ops, self._model, B, H, W, bool(global_motion))
+        return p
+
+    def staging(self, H: int, W: int, device: torch.device) -> dict:
+        """Pinned host + device uint8 frame buffers for the fused uint8 path."""
+        key = (H, W, str(device))
+        st = self._staging.get(key)
+        if st is None:
+            if len(self._staging) >= 4:
+                self._staging.pop(next(iter(self._staging)))
+            mk_h = lambda: torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+            mk_d = lambda: torch.empty((H, W, 3), dtype=torch.uint8, device=device)
+            st = self._staging[key] = dict(h0=mk_h(), h1=mk_h(), hout=mk_h(), d0=mk_d(), d1=mk_d(), dout=mk_d())
+        return st

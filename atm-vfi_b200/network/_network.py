@@ -1,0 +1,153 @@
+"""Shared implementation of ``network_base.Network`` and ``network_lite.Network``.
+
+Same public surface as the reference classes (network/network_base.py:88-340): constructor arguments,
+the mutable ``global_motion`` / ``ensemble_global_motion`` attributes, the window-size setters, the
+freeze / finetune toggles, the 236-entry state-dict and the ``forward(im0, im1) -> dict`` contract.
+The forward itself is the sm_100a engine (atmvfi/engine.py); there is no PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _PKG_ROOT not in sys.path:
+    sys.path.insert(0, _PKG_ROOT)
+
+from atmvfi import arch as _arch                      # noqa: E402
+from atmvfi.engine import clone_outputs               # noqa: E402
+from atmvfi.modules import ParamTree, relative_coord_buffer   # noqa: E402
+from atmvfi.runtime import Runtime                    # noqa: E402
+
+_LOCAL_PARTS = ("feat_extracts", "cross_scale_feature_fusion", "local_motion_atmformer", "local_motion_mlp",
+                "feat_enhance_transformer", "upsample_pyramid", "proj", "down1", "down2", "down3", "up1", "up2", "up3",
+                "refine_head")
+_GLOBAL_PARTS = ("last_feat_extract", "global_feature_fusion", "global_motion_atmformer", "global_motion_mlp")
+_REFINE_PARTS = ("proj", "down1", "down2", "down3", "up1", "up2", "up3", "refine_head")
+
+
+class NetworkBase(ParamTree):
+    ARCH: _arch.Arch = None
+
+    def __init__(self, global_motion=True, ensemble_global_motion=False):
+        super().__init__()
+        a = self.ARCH
+        self.pyramid_level = 4
+        self.hidden_dims = list(a.enc)
+        self.global_motion = global_motion
+        self.ensemble_global_motion = ensemble_global_motion
+        self.local_motion_args = {"window_size": 8, "num_heads": _arch.NUM_HEADS, "patch_size": 1, "dim": a.C,
+                                  "enhance_window": _arch.ENHANCE_WINDOW}
+        self.global_motion_args = {"window_size": 12, "num_heads": _arch.NUM_HEADS, "patch_size": 1, "dim": a.GC}
+        if a.name == "lite":
+            self.local_motion_args["mlp_ratio"] = a.mlp_ratio
+            self.global_motion_args["mlp_ratio"] = a.mlp_ratio
+        self.fused_dim = 2 * a.C
+        self.motion_out_dim = _arch.MOTION_OUT
+        self.fused_dim1, self.fused_dim2, self.fused_dim3 = a.C, a.C // 2, a.C // 4
+        self.fused_dims = [self.fused_dim1, self.fused_dim2, self.fused_dim3, 2 * self.fused_dim1]
+        self.populate(_arch.param_schema(a))
+        # engine knobs (not part of the reference surface)
+        self.precision = os.environ.get("ATMVFI_PRECISION", "tf32")   # "tf32": tcgen05 kind::tf32; "fp32": CUDA-core FFMA
+        self.use_cuda_graph = os.environ.get("ATMVFI_CUDA_GRAPH", "1") != "0"
+        self.zero_copy_outputs = False
+        self._runtime = Runtime(a)
+
+    # ---- reference API: window sizes (network_base.py:262-270) -------------------------------------
+    def _set_ws(self, blocks: ParamTree, ws: int) -> None:
+        for k in ("0", "1"):
+            attn = blocks._modules[k]._modules["attn"]
+            dev = attn.relative_coord.device
+            attn.relative_coord = relative_coord_buffer(ws).to(dev)
+
+    def __set_local_window_size__(self, window_size):
+        self.local_motion_args["window_size"] = window_size
+        self._set_ws(self.local_motion_atmformer, window_size)
+
+    def __set_global_window_size__(self, window_size):
+        self.global_motion_args["window_size"] = window_size
+        self._set_ws(self.global_motion_atmformer, window_size)
+
+    # ---- reference API: training toggles (network_base.py:272-334); names kept so callers resolve ---
+    def _grad(self, parts, flag):
+        for p in parts:
+            getattr(self, p).requires_grad_(flag)
+
+    def __freeze_global_motion__(self):
+        self._grad(_GLOBAL_PARTS, False)
+
+    def __finetune_global_motion__(self):
+        self._grad(_GLOBAL_PARTS, True)
+
+    def __freeze_local_motion__(self):
+        self._grad(_LOCAL_PARTS, False)
+
+    def __finetune_local_motion__(self):
+        self._grad(_LOCAL_PARTS, True)
+
+    # ---- forward ------------------------------------------------------------------------------------
+    def forward(self, im0, im1):
+        if self.ensemble_global_motion:
+            return self.forward_global_ensemble(im0, im1)
+        return self.forward_normal(im0, im1)
+
+    def _check_inputs(self, im0, im1):
+        if im0.dim() != 4 or im0.shape[1] != 3 or im0.shape != im1.shape:
+            raise RuntimeError(f"expected two [B,3,H,W] tensors of equal shape, got {tuple(im0.shape)} and {tuple(im1.shape)}")
+        if im0.dtype != torch.float32 or im1.dtype != torch.float32:
+            raise RuntimeError("ATM-VFI forward expects float32 frames in [0,1]")
+        if im0.device != im1.device:
+            raise RuntimeError("im0 and im1 are on different devices")
+
+    def forward_normal(self, im0, im1):
+        """im0, im1: [B,3,H,W] float32 in [0,1] on the model's CUDA device -> the reference's 10-entry dict
+        (network_base.py:535-545).  Inference only: outputs carry no autograd graph."""
+        self._check_inputs(im0, im1)
+        rt = self._runtime
+        rt.prepare(self, im0.device, self.precision, self.local_motion_args["window_size"], self.global_motion_args["window_size"])
+        B, _, H, W = im0.shape
+        with torch.cuda.device(im0.device):
+            plan = rt.plan(B, H, W, bool(self.global_motion))
+            out = plan.run(im0, im1, use_graph=self.use_cuda_graph)
+            return out if self.zero_copy_outputs else clone_outputs(out)
+
+    # ---- fused uint8 path used by demo_2x.inference_2frame ---------------------------------------------
+    def interpolate_u8(self, img0, img1, isBGR=True, divisor=64):
+        """numpy HxWx3 uint8 pair -> numpy HxWx3 uint8 middle frame.  Same arithmetic as the reference's
+        inference_2frame (demo_2x.py:54-87) with the colour flip, /255, replicate padding, un-padding,
+        *255 + np.round and the cast done by two small kernels around the forward, so only 3 bytes per
+        pixel cross PCIe in each direction.  Pinned staging buffers are cached per shape."""
+        import numpy as np
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("inference needs the model on a CUDA device (model.to('cuda')); there is no CPU fallback")
+        if img0.shape != img1.shape or img0.ndim != 3 or img0.shape[2] != 3 or img0.dtype != np.uint8:
+            raise RuntimeError(f"expected two HxWx3 uint8 frames of equal shape, got {img0.shape} {img0.dtype} and {img1.shape} {img1.dtype}")
+        H, W = img0.shape[:2]
+        eh, ew = (-H) % divisor, (-W) % divisor
+        Hp, Wp, top, left = H + eh, W + ew, eh // 2, ew // 2
+        rt = self._runtime
+        rt.prepare(self, dev, self.precision, self.local_motion_args["window_size"], self.global_motion_args["window_size"])
+        with torch.cuda.device(dev):
+            plan = rt.plan(1, Hp, Wp, bool(self.global_motion))
+            st = rt.staging(H, W, dev)
+            st["h0"].numpy()[...] = img0
+            st["h1"].numpy()[...] = img1
+            st["d0"].copy_(st["h0"], non_blocking=True)
+            st["d1"].copy_(st["h1"], non_blocking=True)
+            ops = rt._ops
+            ops.u8_to_planar(st["d0"], plan.im0, H, W, Hp, Wp, top, left, isBGR)
+            ops.u8_to_planar(st["d1"], plan.im1, H, W, Hp, Wp, top, left, isBGR)
+            out = plan.run_inplace(use_graph=self.use_cuda_graph)
+            ops.planar_to_u8(out["I_t"], st["dout"], H, W, Hp, Wp, top, left, isBGR)
+            st["hout"].copy_(st["dout"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return st["hout"].numpy().copy()
+
+    def forward_global_ensemble(self, im0, im1):
+        raise NotImplementedError(
+            "multi-scale global-motion ensemble (network_base.py:564-712) is not built yet in the B200 engine; "
+            "it is off by default in every reference script (SURVEY.md 8a, row a16)")

@@ -53,8 +53,39 @@ def run_case(name, kind, variant, b, h, w, glob, frames):
           f"| occ [{out['occ_mask1'].min():.3f},{out['occ_mask1'].max():.3f}]")
 
 
+def run_config0():
+    """BASELINE.json configs[0]: Lite, 2x interpolation of asset/example_frame0/1.png, global motion off, CPU fp32,
+    through the reference's own InputPadder + forward + rounding (demo_2x.py:54-87 minus the .cuda() calls)."""
+    import cv2
+    import torch.nn.functional as F
+    Net = refshim.load_reference_network("lite")
+    net = Net(global_motion=False).eval()
+    net.load_state_dict(weights.make_weights("lite", "default"), strict=True)
+    a = cv2.imread(os.path.join(refshim.REF_ROOT, "asset", "example_frame0.png"))
+    b = cv2.imread(os.path.join(refshim.REF_ROOT, "asset", "example_frame1.png"))
+    sys.path.insert(0, refshim.REF_ROOT)
+    refshim.install()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_bench_utils", os.path.join(refshim.REF_ROOT, "benchmark", "utils.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    sys.path.pop(0)
+    t0 = (torch.tensor(a[:, :, ::-1].copy().transpose(2, 0, 1)) / 255.).unsqueeze(0)
+    t1 = (torch.tensor(b[:, :, ::-1].copy().transpose(2, 0, 1)) / 255.).unsqueeze(0)
+    padder = mod.InputPadder(t0.shape, divisor=64)
+    p0, p1 = padder.pad(t0, t1)
+    with torch.no_grad():
+        pred = padder.unpad(net(p0, p1)["I_t"][0])
+    pred = np.round(pred.numpy().transpose(1, 2, 0) * 255).astype(np.uint8)[:, :, ::-1].copy()
+    np.savez_compressed(os.path.join(GOLDEN, "case_config0_lite_example_frames.npz"),
+                        meta=json.dumps(dict(kind="lite", variant="default", B=1, H=a.shape[0], W=a.shape[1], global_motion=False, frames="asset")),
+                        pred_bgr=pred)
+    print("config0:", pred.shape, "mean", pred.mean())
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    if not sys.argv[1:] or "config0" in sys.argv[1:]:
+        run_config0()
     for kind in ("base", "lite"):
         Net = refshim.load_reference_network(kind)
         torch.manual_seed(0)

@@ -27,7 +27,10 @@ def install() -> None:
         timm.models, models.layers = models, layers
         sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers})
     for stub in ("imageio", "flow_vis"):
-        sys.modules.setdefault(stub, types.ModuleType(stub))
+        if stub not in sys.modules:
+            m = types.ModuleType(stub)
+            m.imread = m.imwrite = None          # names benchmark/utils.py:8 imports; never called on the forward path
+            sys.modules[stub] = m
 
 
 def load_reference_network(kind: str):

@@ -16,7 +16,7 @@ import atmvfi_oracle as oracle
 import weights
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-CASES = sorted(glob.glob(os.path.join(GOLDEN, "case_*.npz")))
+CASES = [p for p in sorted(glob.glob(os.path.join(GOLDEN, "case_*.npz"))) if "config0" not in p]
 
 
 def test_golden_present():
@@ -54,3 +54,15 @@ def test_oracle_matches_reference_output(path):
         err = np.abs(out["im_t_list"][i].numpy() - z[f"im_t_list_{i}"]).max()
         assert err <= tol, (i, err)
     assert np.abs(out["im0_warped_list"][-1].numpy() - z["coarse_im0_warped"]).max() <= tol
+
+
+def test_oracle_inference_2frame_config0():
+    """BASELINE config 0 through the oracle's restatement of demo_2x.inference_2frame, byte for byte."""
+    import cv2
+    a = cv2.imread(os.path.join(GOLDEN, "example_frame0.png"))
+    b = cv2.imread(os.path.join(GOLDEN, "example_frame1.png"))
+    z = np.load(os.path.join(GOLDEN, "case_config0_lite_example_frames.npz"))
+    P = weights.make_weights("lite", "default")
+    pred = oracle.inference_2frame(P, a, b, global_motion=False, is_bgr=True)
+    assert pred.shape == (600, 414, 3)
+    assert np.array_equal(pred, z["pred_bgr"])
