@@ -200,8 +200,31 @@ class CudaOps:
         else:
             d.out_mode = _lib.OUT_PIXEL
             assert out.nrows == s0.B * Hout * Wout, (w.name, out.t.shape, (s0.B, Hout, Wout))
-        d.precision = self.precision if precision is None else precision
-        self._emit("atmvfi_gemm_conv", (C.byref(d),), keep=(d, srcs, w, out, residual, out2, prelu2))
+        prec = self.precision if precision is None else precision
+        if prec == _lib.TF32 and not self._tc_eligible(srcs, w, out, out2):
+            prec = _lib.FP32
+        d.precision = prec
+        planbuf = None
+        if prec == _lib.TF32:
+            if w.wtc is None:
+                from .pack import pack_tc
+                w.wtc = pack_tc(w)
+            d.weight, d.ldw = w.wtc.data_ptr(), w.wtc.shape[1]
+            nbytes = self.lib.atmvfi_gemm_conv_plan_bytes()
+            planbuf = C.create_string_buffer(nbytes + 64)
+            addr = (C.addressof(planbuf) + 63) & ~63
+            _lib.check(self.lib.atmvfi_gemm_conv_plan(C.byref(d), addr), f"gemm_conv_plan({w.name})")
+            d.tma_host = addr
+        self._emit("atmvfi_gemm_conv", (C.byref(d),), keep=(d, srcs, w, out, residual, out2, prelu2, planbuf))
+
+    @staticmethod
+    def _tc_eligible(srcs, w, out, out2) -> bool:
+        """Layers the tcgen05 kernel takes: 16-byte aligned operands and enough input channels to fill a K chunk."""
+        if sum(w.split) < 16:
+            return False
+        if any(s.ptr % 16 for s in srcs) or out.ptr % 16 or (out2 is not None and out2.ptr % 16):
+            return False
+        return True
 
     # -- transformer pieces -------------------------------------------------------------------
     def layernorm(self, x: Map, out: Map, gamma: torch.Tensor, beta: torch.Tensor):

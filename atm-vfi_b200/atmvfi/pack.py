@@ -68,3 +68,52 @@ def pack_dw(P: Params, name: str):
     """depth-wise Conv2d weight [C,1,3,3] -> [9][C]."""
     w = P[name + ".weight"].detach().float()
     return w.reshape(w.shape[0], 9).t().contiguous(), _f32(P[name + ".bias"])
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 (TF32) operand layout - must agree with atmvfi_gemm_conv_plan() in csrc/gemm_conv_tc.cu
+# ------------------------------------------------------------------------------------------------
+TC_CHUNK = 32          # fp32 elements per K step (one 128-byte swizzle row)
+TC_MAX_N = 256
+
+
+def tc_layout(split: Sequence[int], ksize: int, cout: int, shuffle: bool) -> dict:
+    chunks = [-(-c // TC_CHUNK) for c in split]
+    ktc = ksize * ksize * sum(chunks) * TC_CHUNK
+    cq_pad = round_up(cout, 32)
+    n_need = 4 * cq_pad if shuffle else cq_pad
+    n_tiles = -(-n_need // TC_MAX_N)
+    block_n = round_up(-(-n_need // n_tiles), 32)
+    return dict(chunks=chunks, ktc=ktc, cq_pad=cq_pad, n_tiles=n_tiles, block_n=block_n, n_pad=n_tiles * block_n)
+
+
+def round_tf32(t: torch.Tensor) -> torch.Tensor:
+    """fp32 -> nearest TF32 value (10-bit mantissa), ties away from zero (cvt.rna.tf32.f32)."""
+    bits = t.contiguous().view(torch.int32)
+    bits = (bits + 0x1000) & ~0x1FFF
+    return bits.view(torch.float32)
+
+
+def pack_tc(w: PackedGemm) -> torch.Tensor:
+    """[K, ldw] fp32 GEMM operand -> [N_pad][K_tc] K-major: every (tap, source) block is padded to whole
+    32-channel chunks (TMA zero-fills the matching activation channels), ConvTranspose column blocks are
+    padded to a multiple of 32 columns; values pre-rounded to TF32."""
+    L = tc_layout(w.split, w.ksize, w.Cout, w.shuffle)
+    taps, ctot = w.ksize * w.ksize, sum(w.split)
+    n_true = 4 * w.Cout if w.shuffle else w.Cout
+    src = w.w32[:, :n_true].reshape(taps, ctot, n_true)
+    parts, c0 = [], 0
+    for c, ch in zip(w.split, L["chunks"]):
+        blk = src[:, c0 : c0 + c]
+        if ch * TC_CHUNK != c:
+            blk = torch.nn.functional.pad(blk, (0, 0, 0, ch * TC_CHUNK - c))
+        parts.append(blk)
+        c0 += c
+    kmat = torch.cat(parts, 1).reshape(L["ktc"], n_true)           # [K_tc, n_true]
+    out = torch.zeros(L["n_pad"], L["ktc"], dtype=torch.float32, device=w.w32.device)
+    if w.shuffle:
+        for q in range(4):
+            out[q * L["cq_pad"] : q * L["cq_pad"] + w.Cout] = kmat[:, q * w.Cout : (q + 1) * w.Cout].t()
+    else:
+        out[: w.Cout] = kmat.t()
+    return round_tf32(out)

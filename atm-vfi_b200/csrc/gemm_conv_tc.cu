@@ -1,8 +1,483 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// TF32 implicit-GEMM convolution / linear layer on the 5th-generation tensor cores (sm_100a).
+//
+//   D[128 pixels x BLOCK_N channels] (fp32, TMEM) += A[128 x 32] (smem, K-major, SW128) * B[BLOCK_N x 32]^T
+//
+// * A is never materialised: for every (tap, source, 32-channel chunk) one 4-D TMA box
+//   {32 ch, TW px, TH px, 1 image} of the NHWC source lands in shared memory as 128 rows of 128 B with the
+//   128-byte swizzle the UMMA descriptor expects.  The box origin is shifted by the tap offset; TMA zero-fills
+//   everything outside the image (= conv zero padding) and beyond the source's channel count; stride-2/4
+//   convolutions use the tensor map's element strides.  Channel concatenation of up to 4 inputs is just a
+//   loop over 4 tensor maps.
+// * B (weights) is packed on the host as [N_pad][K_tc] K-major fp32 (pre-rounded to TF32) and fetched with a
+//   2-D TMA box {32, BLOCK_N}.
+// * Warp roles (CTA = 256 threads, persistent, one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer
+//   (one elected lane, tcgen05.mma cta_group::1 kind::tf32, M=128, N=BLOCK_N, K=8), warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue (tcgen05.ld 32 lanes x 32 columns -> bias / residual / PReLU / row remap -> global).
+// * 4-stage smem ring (full/empty mbarriers), 2 TMEM accumulator stages (512 columns) so the epilogue of
+//   tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include <string.h>
 #include "gemm_epilogue.cuh"
-int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc*, cudaStream_t) {
-  atmvfi_set_error("gemm_conv(tf32): not built yet");
-  return 3;
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBlockM = 128;
+constexpr int kChunk = 32;                      // fp32 elements per K step = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * 128;          // 16 KB
+constexpr int kMaxBlockN = 256;
+constexpr int kBBytesMax = kMaxBlockN * 128;    // 32 KB
+constexpr int kStageBytes = kABytes + kBBytesMax;
+constexpr int kBarOff = kStages * kStageBytes;
+constexpr int kEpiOff = kBarOff + 256;                       // 4 warps x (32 x 33 floats) staging + per-row info
+constexpr int kEpiBytes = 4 * 32 * 33 * 4 + 4 * 64 * 8;
+constexpr int kSmemBytes = kEpiOff + kEpiBytes + 1024 /*align*/;
+constexpr int kThreads = 256;
+
+struct TcPlan {                                 // host-side, produced by atmvfi_gemm_conv_plan
+  CUtensorMap mapA[ATMVFI_MAX_SRC];
+  CUtensorMap mapB;
+  int nsrc;
+  int chunks[ATMVFI_MAX_SRC];                   // 32-channel chunks per source
+  int ntaps, ksize, stride, dil, pad;
+  int TW, TH, tiles_x, tiles_y, B;
+  int block_n, n_tiles, cq_pad;
+  int Hout, Wout;
+  uint32_t magic;
+};
+constexpr uint32_t kPlanMagic = 0xA7B20001u;
+
+struct TcParams {
+  CUtensorMap mapA[ATMVFI_MAX_SRC];
+  CUtensorMap mapB;
+  int nsrc;
+  int chunks[ATMVFI_MAX_SRC];
+  int ntaps, ksize, stride, dil, pad;
+  int TW, TH, tiles_x, tiles_y, B;
+  int block_n, n_tiles, cq_pad;
+  int total_tiles, k_iters;
+  EpiParams epi;
+};
+
+// ------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-extern "C" int atmvfi_gemm_conv_plan_bytes(void) { return 0; }
-extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc*, void*) { atmvfi_set_error("gemm_conv_plan: not built yet"); return 3; }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle: 8-row groups of 1024 B (SBO = 1024), LBO unused, descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (ignored for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version, bits [46,48)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B, bits [61,64)
+  return d;
+}
+
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                 // D format = F32
+  d |= 2u << 7;                 // A format = TF32
+  d |= 2u << 10;                // B format = TF32
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(kBlockM >> 4) << 24;
+  return d;
+}
+
+__device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& n_tile, int& b, int& oy0, int& ox0) {
+  n_tile = tile % p.n_tiles;
+  int mt = tile / p.n_tiles;
+  int tx = mt % p.tiles_x;
+  mt /= p.tiles_x;
+  int ty = mt % p.tiles_y;
+  b = mt / p.tiles_y;
+  oy0 = ty * p.TH;
+  ox0 = tx * p.TW;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + kStages;            // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;        // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 2) {   // whole warp: allocate all 512 TMEM columns (one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int n_tile, b, oy0, ox0;
+        tile_coords(p, tile, n_tile, b, oy0, ox0);
+        int kb = 0;                                           // K chunk index into the packed weights
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int ky = p.ksize == 3 ? tap / 3 : 0, kx = p.ksize == 3 ? tap % 3 : 0;
+          const int iy = oy0 * p.stride + ky * p.dil - p.pad;
+          const int ix = ox0 * p.stride + kx * p.dil - p.pad;
+          for (int s = 0; s < p.nsrc; ++s) {
+            const CUtensorMap* mapA = s == 0 ? &p.mapA[0] : (s == 1 ? &p.mapA[1] : (s == 2 ? &p.mapA[2] : &p.mapA[3]));
+            for (int c = 0; c < p.chunks[s]; ++c, ++kb, ++it) {
+              const int st = it % kStages;
+              const uint32_t ph = (it / kStages) & 1;
+              mbar_wait(&empty[st], ph ^ 1);
+              uint8_t* sa = smem + st * kStageBytes;
+              mbar_expect_tx(&full[st], kABytes + p.block_n * 128);
+              tma_load_4d(sa, mapA, &full[st], c * kChunk, ix, iy, b);
+              tma_load_2d(sa + kABytes, &p.mapB, &full[st], kb * kChunk, n_tile * p.block_n);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================= MMA issuer =========================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(p.block_n);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kMaxBlockN;
+        for (int k = 0; k < p.k_iters; ++k, ++it) {
+          const int st = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + st * kStageBytes);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
+            tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (k | j) != 0 ? 1u : 0u);
+          tc_commit(&empty[st]);          // frees the smem stage once these MMAs retire
+        }
+        tc_commit(&tfull[as]);            // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================================= epilogue ===========================================
+    // Each warp drains its own 32 TMEM lanes (= 32 output pixels): accumulators go through a padded
+    // per-warp smem tile so that global traffic is row-coalesced - 8 lanes x float4 cover 128 contiguous
+    // bytes of one output row, bias / PReLU slopes are fetched once per lane per 32-column chunk.
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+    float* stage = reinterpret_cast<float*>(smem + kEpiOff) + q * (32 * 33);
+    int64_t* s_orow = reinterpret_cast<int64_t*>(smem + kEpiOff + 4 * 32 * 33 * 4) + q * 64;
+    int64_t* s_m = s_orow + 32;
+    const int m_local = q * 32 + lane;
+    const int th = m_local / p.TW, tw = m_local % p.TW;
+    const int l8 = lane & 7, rsub = lane >> 3, col = 4 * l8;
+    const EpiParams& e = p.epi;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+      int n_tile, b, oy0, ox0;
+      tile_coords(p, tile, n_tile, b, oy0, ox0);
+      const int oy = oy0 + th, ox = ox0 + tw;
+      const bool row_ok = oy < e.Hout && ox < e.Wout;
+      const int64_t m = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * kMaxBlockN;
+      int last_q = -1;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const int n0 = n_tile * p.block_n + c0;               // first GEMM column of this chunk (warp-uniform)
+        int sq = 0, co0 = n0;
+        if (e.out_mode == ATMVFI_OUT_SHUFFLE2) { sq = n0 / p.cq_pad; co0 = n0 - sq * p.cq_pad; }
+        if (co0 >= e.Cout || sq > 3) continue;                // padding columns: nothing to store (uniform branch)
+        uint32_t r[32];
+        __syncwarp();
+        tc_ld32(trow + c0, r);
+        tc_wait_ld();
+        if (sq != last_q) {
+          s_orow[lane] = row_ok ? epi_out_row(e, m, sq) : -1;
+          s_m[lane] = m;
+          last_q = sq;
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) stage[lane * 33 + c] = __uint_as_float(r[c]);
+        __syncwarp();
+        const int nvalid = min(32, e.Cout - co0);
+        const bool full4 = col + 4 <= nvalid;
+        float bz[4] = {0.f, 0.f, 0.f, 0.f}, sl[4] = {1.f, 1.f, 1.f, 1.f}, sl2[4] = {1.f, 1.f, 1.f, 1.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (col + k < nvalid) {
+            if (e.bias) bz[k] = __ldg(e.bias + co0 + col + k);
+            if (e.prelu) sl[k] = __ldg(e.prelu + co0 + col + k);
+            if (e.out2) sl2[k] = __ldg(e.prelu2 + co0 + col + k);
+          }
+#pragma unroll 2
+        for (int rr = 0; rr < 8; ++rr) {
+          const int row = rr * 4 + rsub;
+          const int64_t orow = s_orow[row];
+          if (orow < 0 || col >= nvalid) continue;
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = stage[row * 33 + col + k] + bz[k];
+          if (e.residual) {
+            const float* rs = e.residual + s_m[row] * e.res_pitch + co0 + col;
+            if (full4) {
+              float4 t = __ldg(reinterpret_cast<const float4*>(rs));
+              v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (col + k < nvalid) v[k] += __ldg(rs + k);
+            }
+          }
+          if (e.prelu) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * sl[k];
+          }
+          float* o1 = e.out + orow * e.out_pitch + co0 + col;
+          if (full4) {
+            *reinterpret_cast<float4*>(o1) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (col + k < nvalid) o1[k] = v[k];
+          }
+          if (e.out2) {
+            float* o2 = e.out2 + orow * e.out2_pitch + co0 + col;
+            float w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[k] = v[k] > 0.f ? v[k] : v[k] * sl2[k];
+            if (full4) {
+              *reinterpret_cast<float4*>(o2) = make_float4(w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (col + k < nvalid) o2[k] = w[k];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);                 // 4 epilogue warps -> accumulator stage free
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+// Layout contract shared with atmvfi/pack.py (pack_tc): see tc_layout() there.
+extern "C" int atmvfi_gemm_conv_plan_bytes(void) { return (int)sizeof(TcPlan); }
+
+extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_host) {
+  ATMVFI_REQUIRE(d && plan_host, "gemm_conv_plan: null argument");
+  ATMVFI_REQUIRE(((uintptr_t)plan_host & 63) == 0, "gemm_conv_plan: plan buffer must be 64-byte aligned");
+  EncodeTiledFn enc = get_encode();
+  ATMVFI_REQUIRE(enc != nullptr, "gemm_conv_plan: cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  TcPlan* pl = reinterpret_cast<TcPlan*>(plan_host);
+  memset(pl, 0, sizeof(TcPlan));
+  pl->nsrc = d->nsrc;
+  pl->ksize = d->ksize; pl->ntaps = d->ksize * d->ksize; pl->stride = d->stride; pl->dil = d->dil;
+  pl->pad = d->dil * (d->ksize - 1) / 2;
+  pl->B = d->B; pl->Hout = d->Hout; pl->Wout = d->Wout;
+  ATMVFI_REQUIRE(d->stride == 1 || d->stride == 2 || d->stride == 4, "gemm_conv(tf32): stride %d unsupported", d->stride);
+
+  // pixel tile TW x TH = 128: least padding waste, then squarest; element-strided boxes are capped at 256
+  int best_tw = 0;
+  int64_t best_cost = -1;
+  const int cands[5] = {16, 32, 8, 64, 128};
+  for (int i = 0; i < 5; ++i) {
+    int tw = cands[i], th = 128 / tw;
+    if (tw * d->stride > 256 || th * d->stride > 256) continue;
+    int64_t cost = (int64_t)cdiv(d->Wout, tw) * cdiv(d->Hout, th);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
+  }
+  ATMVFI_REQUIRE(best_tw > 0, "gemm_conv(tf32): no tile shape for stride %d", d->stride);
+  pl->TW = best_tw; pl->TH = 128 / best_tw;
+  pl->tiles_x = cdiv(d->Wout, pl->TW); pl->tiles_y = cdiv(d->Hout, pl->TH);
+
+  const bool shuffle = d->out_mode == ATMVFI_OUT_SHUFFLE2;
+  pl->cq_pad = round_up_i(d->Cout, 32);
+  const int n_need = shuffle ? 4 * pl->cq_pad : pl->cq_pad;
+  pl->n_tiles = cdiv(n_need, kMaxBlockN);
+  pl->block_n = round_up_i(cdiv(n_need, pl->n_tiles), 32);
+  const int n_pad = pl->n_tiles * pl->block_n;
+
+  int ktc = 0;
+  for (int s = 0; s < d->nsrc; ++s) {
+    pl->chunks[s] = cdiv(d->src[s].C, kChunk);
+    ktc += pl->chunks[s] * kChunk;
+  }
+  ktc *= pl->ntaps;
+  ATMVFI_REQUIRE(d->ldw == ktc, "gemm_conv(tf32): packed weight row length %d != expected %d", d->ldw, ktc);
+
+  for (int s = 0; s < d->nsrc; ++s) {
+    const atmvfi_src& sr = d->src[s];
+    ATMVFI_REQUIRE(((uintptr_t)sr.ptr & 15) == 0 && sr.pitch % 4 == 0, "gemm_conv(tf32): source %d must be 16-byte aligned with pitch %% 4 == 0", s);
+    cuuint64_t gdim[4] = {(cuuint64_t)sr.C, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
+    cuuint64_t gstr[3] = {(cuuint64_t)sr.pitch * 4, (cuuint64_t)sr.pitch * 4 * d->Win, (cuuint64_t)sr.pitch * 4 * d->Win * d->Hin};
+    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)(pl->TW * d->stride), (cuuint32_t)(pl->TH * d->stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = enc(&pl->mapA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sr.ptr), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ATMVFI_REQUIRE(r == CUDA_SUCCESS, "gemm_conv(tf32): cuTensorMapEncodeTiled(A%d) failed with %d (C=%d W=%d H=%d B=%d pitch=%d stride=%d)", s,
+                   (int)r, sr.C, d->Win, d->Hin, d->B, sr.pitch, d->stride);
+  }
+  {
+    ATMVFI_REQUIRE(((uintptr_t)d->weight & 15) == 0, "gemm_conv(tf32): weights must be 16-byte aligned");
+    cuuint64_t gdim[2] = {(cuuint64_t)ktc, (cuuint64_t)n_pad};
+    cuuint64_t gstr[1] = {(cuuint64_t)ktc * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)pl->block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->weight), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ATMVFI_REQUIRE(r == CUDA_SUCCESS, "gemm_conv(tf32): cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  ATMVFI_REQUIRE(((uintptr_t)d->out & 15) == 0 && d->out_pitch % 4 == 0, "gemm_conv(tf32): output must be 16-byte aligned with pitch %% 4 == 0");
+  ATMVFI_REQUIRE(!d->out2 || (((uintptr_t)d->out2 & 15) == 0 && d->out2_pitch % 4 == 0), "gemm_conv(tf32): out2 must be 16-byte aligned");
+  pl->magic = kPlanMagic;
+  return 0;
+}
+
+int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
+  const TcPlan* pl = reinterpret_cast<const TcPlan*>(d->tma_host);
+  ATMVFI_REQUIRE(pl && pl->magic == kPlanMagic, "gemm_conv(tf32): missing plan (call atmvfi_gemm_conv_plan first)");
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(gemm_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) {
+      num_sms = 0;
+      atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
+      return 1;
+    }
+  }
+  TcParams p;
+  memcpy(p.mapA, pl->mapA, sizeof(p.mapA));
+  memcpy(&p.mapB, &pl->mapB, sizeof(p.mapB));
+  p.nsrc = pl->nsrc;
+  int ch = 0;
+  for (int s = 0; s < ATMVFI_MAX_SRC; ++s) { p.chunks[s] = pl->chunks[s]; ch += pl->chunks[s]; }
+  p.ntaps = pl->ntaps; p.ksize = pl->ksize; p.stride = pl->stride; p.dil = pl->dil; p.pad = pl->pad;
+  p.TW = pl->TW; p.TH = pl->TH; p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.B = pl->B;
+  p.block_n = pl->block_n; p.n_tiles = pl->n_tiles; p.cq_pad = pl->cq_pad;
+  p.total_tiles = pl->tiles_x * pl->tiles_y * pl->B * pl->n_tiles;
+  p.k_iters = ch * pl->ntaps;
+  p.epi = make_epi(d);
+  if (p.total_tiles <= 0) return 0;
+  int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  gemm_conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
+  ATMVFI_CHECK_LAUNCH("gemm_conv(tf32)");
+  return 0;
+}

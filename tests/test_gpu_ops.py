@@ -63,7 +63,8 @@ def test_gemm_conv_plain(ops, B, H, W, split, Co, k, stride, dil):
     cu.gemm_conv(to_gpu(srcs), _pg_to_gpu(w), out_g, stride=stride, dil=dil)
     assert max_err(out_g, out_c) < 2e-5
     # channels outside the written slice stay untouched
-    assert out_g.t.cpu()[..., : out_g.c0].abs().max() == 0
+    if out_g.c0:
+        assert out_g.t.cpu()[..., : out_g.c0].abs().max() == 0
 
 
 def test_gemm_conv_dual_output_and_residual(ops):
