@@ -2,34 +2,39 @@
 //
 //   D[128 pixels x BLOCK_N channels] (fp32, TMEM) += A[128 x 32] (smem, K-major, SW128) * B[BLOCK_N x 32]^T
 //
-// * A is never materialised: for every (tap, source, 32-channel chunk) one 4-D TMA box
-//   {32 ch, TW px, TH px, 1 image} of the NHWC source lands in shared memory as 128 rows of 128 B with the
-//   128-byte swizzle the UMMA descriptor expects.  The box origin is shifted by the tap offset; TMA zero-fills
-//   everything outside the image (= conv zero padding) and beyond the source's channel count; stride-2/4
-//   convolutions use the tensor map's element strides.  Channel concatenation of up to 4 inputs is just a
-//   loop over 4 tensor maps.
-// * B (weights) is packed on the host as [N_pad][K_tc] K-major fp32 (pre-rounded to TF32) and fetched with a
-//   2-D TMA box {32, BLOCK_N}.
+// * A is never materialised.  The NHWC source is a 4-D TMA tensor {C, W, H, B}; one box of 32 channels
+//   x (TW x TH pixels) lands in shared memory as 128-byte rows with the 128-byte swizzle the UMMA
+//   descriptor expects.  TMA zero-fills outside the image (= conv zero padding) and beyond the source's
+//   channel count; stride-2/4 convolutions use the tensor map's element strides; channel concatenation of
+//   up to 4 inputs is a loop over 4 tensor maps.
+// * 3x3 / stride 1 layers ("halo" mode) fetch, per 32-channel chunk and per horizontal tap kx, ONE box
+//   with a vertical halo {32, TW, TH+2}; the three vertical taps are UMMA descriptors offset by ky*TW rows
+//   (a multiple of the 1024-byte swizzle atom), so the activation traffic from L2 is 3 boxes instead of 9.
+// * B (weights) is packed on the host as [N_pad][K_tc] K-major fp32 (pre-rounded to TF32).  CTAs are
+//   launched in clusters of 2 along M: each CTA fetches half of the B tile and TMA-multicasts it to both,
+//   halving the weight traffic from L2 (the kernel is L2-bandwidth-bound otherwise).
 // * Warp roles (CTA = 256 threads, persistent, one CTA per SM): warp 0 = TMA producer, warp 1 = MMA issuer
 //   (one elected lane, tcgen05.mma cta_group::1 kind::tf32, M=128, N=BLOCK_N, K=8), warp 2 = TMEM allocator,
-//   warps 4-7 = epilogue (tcgen05.ld 32 lanes x 32 columns -> bias / residual / PReLU / row remap -> global).
-// * 4-stage smem ring (full/empty mbarriers), 2 TMEM accumulator stages (512 columns) so the epilogue of
-//   tile i overlaps the main loop of tile i+1.
+//   warps 4-7 = epilogue (tcgen05.ld -> smem transpose -> bias / residual / PReLU / row remap -> coalesced
+//   global stores).
+// * Separate smem rings for A (3 slots x 24 KB) and B (4 slots x 32 KB) with full/empty mbarriers, and
+//   2 TMEM accumulator stages (512 columns) so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "gemm_epilogue.cuh"
 
 namespace {
 
-constexpr int kStages = 4;
 constexpr int kBlockM = 128;
 constexpr int kChunk = 32;                      // fp32 elements per K step = one 128-byte swizzle row
-constexpr int kABytes = kBlockM * 128;          // 16 KB
+constexpr int kMaxASlots = 4;
+constexpr int kMaxBSlots = 12;
 constexpr int kMaxBlockN = 256;
-constexpr int kBBytesMax = kMaxBlockN * 128;    // 32 KB
-constexpr int kStageBytes = kABytes + kBBytesMax;
-constexpr int kBarOff = kStages * kStageBytes;
-constexpr int kEpiOff = kBarOff + 256;                       // 4 warps x (32 x 33 floats) staging + per-row info
+constexpr int kDataBytes = 200 * 1024;          // A ring + B ring, carved per layer (see atmvfi_gemm_conv_tc)
+constexpr int kMaxABoxBytes = 24 * 1024;        // up to 192 rows of 128 B (halo box), 128 rows otherwise
+constexpr int kBarOff = kDataBytes;
+constexpr int kEpiOff = kBarOff + 512;                       // 4 warps x (32 x 33 floats) staging + per-row info
 constexpr int kEpiBytes = 4 * 32 * 33 * 4 + 4 * 64 * 8;
 constexpr int kSmemBytes = kEpiOff + kEpiBytes + 1024 /*align*/;
 constexpr int kThreads = 256;
@@ -43,9 +48,11 @@ struct TcPlan {                                 // host-side, produced by atmvfi
   int TW, TH, tiles_x, tiles_y, B;
   int block_n, n_tiles, cq_pad;
   int Hout, Wout;
+  int halo;                                     // 1: 3x3 stride-1 layer, A boxes carry a vertical halo
+  int cluster;                                  // CTAs per cluster (B multicast), 1 or 2
   uint32_t magic;
 };
-constexpr uint32_t kPlanMagic = 0xA7B20001u;
+constexpr uint32_t kPlanMagic = 0xA7B20002u;
 
 struct TcParams {
   CUtensorMap mapA[ATMVFI_MAX_SRC];
@@ -55,7 +62,9 @@ struct TcParams {
   int ntaps, ksize, stride, dil, pad;
   int TW, TH, tiles_x, tiles_y, B;
   int block_n, n_tiles, cq_pad;
-  int total_tiles, k_iters;
+  int halo, a_bytes, sum_chunks, m_tiles;
+  int a_slots, a_slot_bytes, b_slots, b_slot_bytes;   // smem rings: A at offset 0, B right after
+  int total_ctiles;                             // cluster tiles: ceil(m_tiles / cluster) * n_tiles
   EpiParams epi;
 };
 
@@ -84,10 +93,25 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// non-blocking probe (try_wait may suspend the thread until a time-out when the phase is not complete)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
@@ -99,6 +123,44 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// One lane of a converged warp; the warp keeps executing uniformly, which lets ptxas hold descriptors and
+// coordinates in uniform registers (a whole role under `if (lane == 0)` compiles to ELECT/R2UR loops per MMA).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -151,32 +213,43 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
   return d;
 }
 
-__device__ __forceinline__ void tile_coords(const TcParams& p, int tile, int& n_tile, int& b, int& oy0, int& ox0) {
-  n_tile = tile % p.n_tiles;
-  int mt = tile / p.n_tiles;
+// cluster tile -> (n_tile, image, tile origin) for this CTA; m tiles beyond the last one are phantoms whose
+// coordinates fall outside the tensor (TMA zero-fills, the epilogue stores nothing).
+__device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs, int rank, int& n_tile, int& b, int& oy0, int& ox0) {
+  n_tile = ctile % p.n_tiles;
+  int mt = (ctile / p.n_tiles) * cs + rank;
   int tx = mt % p.tiles_x;
   mt /= p.tiles_x;
   int ty = mt % p.tiles_y;
-  b = mt / p.tiles_y;
+  b = mt / p.tiles_y;                      // may be >= B for a phantom tile
   oy0 = ty * p.TH;
   ox0 = tx * p.TW;
 }
 
+template <bool kHalo, int kCS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
-  uint64_t* full = bars;                       // [kStages]
-  uint64_t* empty = bars + kStages;            // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;        // [2]
-  uint64_t* tempty = bars + 2 * kStages + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* fullA = bars;                                  // [kMaxASlots]
+  uint64_t* emptyA = fullA + kMaxASlots;                   // [kMaxASlots]
+  uint64_t* fullB = emptyA + kMaxASlots;                   // [kMaxBSlots]
+  uint64_t* emptyB = fullB + kMaxBSlots;                   // [kMaxBSlots]
+  uint64_t* tfull = emptyB + kMaxBSlots;                   // [2]
+  uint64_t* tempty = tfull + 2;                            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 3);   // tempty[2] is a scratch barrier for experiments
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int cs = kCS;
+  const int rank = kCS > 1 ? (int)cluster_ctarank() : 0;
+  const int num_clusters = gridDim.x / cs, cluster_id = blockIdx.x / cs;
+  const uint16_t mc_mask = (uint16_t)((1u << cs) - 1);
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kMaxASlots; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], cs); }   // every CTA of the cluster releases a B slot
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    mbar_init(&tempty[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -186,59 +259,128 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();          // peers' barriers must exist before any multicast arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // K is walked as "A groups" (one activation box in smem) x "steps" (one weight tile, 4 MMAs each):
+  //   halo mode : group = (source, chunk, kx), steps ky = 0..2 reuse the box at row offset ky*TW
+  //   otherwise : group = (tap, source, chunk), a single step
+  constexpr int steps_per_group = kHalo ? 3 : 1;
+  const int b_rows = p.block_n / cs;                         // rows of the B tile this CTA fetches
+  const int kASlots = p.a_slots, kBSlots = p.b_slots;
+  uint8_t* const ringA = smem;
+  uint8_t* const ringB = smem + p.a_slots * p.a_slot_bytes;
+
   if (warp == 0) {
     // ======================================= TMA producer =======================================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    {
+      int as_ = 0, bs_ = 0;
+      uint32_t aph_ = 0, bph_ = 0;                            // ring slot + phase bit, advanced without div/mod
+      for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters) {
         int n_tile, b, oy0, ox0;
-        tile_coords(p, tile, n_tile, b, oy0, ox0);
-        int kb = 0;                                           // K chunk index into the packed weights
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int ky = p.ksize == 3 ? tap / 3 : 0, kx = p.ksize == 3 ? tap % 3 : 0;
-          const int iy = oy0 * p.stride + ky * p.dil - p.pad;
-          const int ix = ox0 * p.stride + kx * p.dil - p.pad;
+        tile_coords(p, ct, cs, rank, n_tile, b, oy0, ox0);
+        const int outer = kHalo ? 1 : p.ntaps;
+        for (int tap_o = 0; tap_o < outer; ++tap_o) {
+          int cbase = 0;
           for (int s = 0; s < p.nsrc; ++s) {
             const CUtensorMap* mapA = s == 0 ? &p.mapA[0] : (s == 1 ? &p.mapA[1] : (s == 2 ? &p.mapA[2] : &p.mapA[3]));
-            for (int c = 0; c < p.chunks[s]; ++c, ++kb, ++it) {
-              const int st = it % kStages;
-              const uint32_t ph = (it / kStages) & 1;
-              mbar_wait(&empty[st], ph ^ 1);
-              uint8_t* sa = smem + st * kStageBytes;
-              mbar_expect_tx(&full[st], kABytes + p.block_n * 128);
-              tma_load_4d(sa, mapA, &full[st], c * kChunk, ix, iy, b);
-              tma_load_2d(sa + kABytes, &p.mapB, &full[st], kb * kChunk, n_tile * p.block_n);
+            for (int c = 0; c < p.chunks[s]; ++c) {
+              constexpr int inner = kHalo ? 3 : 1;
+              for (int kx_i = 0; kx_i < inner; ++kx_i) {
+                int ix, iy;
+                if (kHalo) {
+                  ix = ox0 + kx_i - 1;
+                  iy = oy0 - 1;
+                } else {
+                  const int ky = p.ksize == 3 ? tap_o / 3 : 0, kx = p.ksize == 3 ? tap_o % 3 : 0;
+                  iy = oy0 * p.stride + ky * p.dil - p.pad;
+                  ix = ox0 * p.stride + kx * p.dil - p.pad;
+                }
+                mbar_wait(&emptyA[as_], aph_ ^ 1);
+                if (elect_one()) {
+                  mbar_expect_tx(&fullA[as_], p.a_bytes);
+                  tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                }
+                __syncwarp();
+                for (int st = 0; st < steps_per_group; ++st) {
+                  const int tap = kHalo ? st * 3 + kx_i : tap_o;
+                  const int kb = tap * p.sum_chunks + cbase + c;
+                  mbar_wait(&emptyB[bs_], bph_ ^ 1);
+                  if (elect_one()) {
+                    mbar_expect_tx(&fullB[bs_], p.block_n * 128);
+                    uint8_t* dst = ringB + bs_ * p.b_slot_bytes + rank * b_rows * 128;
+                    if (cs > 1)
+                      tma_load_2d_mc(dst, &p.mapB, &fullB[bs_], kb * kChunk, n_tile * p.block_n + rank * b_rows, mc_mask);
+                    else
+                      tma_load_2d(dst, &p.mapB, &fullB[bs_], kb * kChunk, n_tile * p.block_n);
+                  }
+                  __syncwarp();
+                  if (++bs_ == kBSlots) { bs_ = 0; bph_ ^= 1; }
+                }
+                if (++as_ == kASlots) { as_ = 0; aph_ ^= 1; }
+              }
             }
+            cbase += p.chunks[s];
           }
         }
       }
     }
   } else if (warp == 1) {
     // ======================================= MMA issuer =========================================
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_tf32(p.block_n);
-      uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const int groups = (kHalo ? 3 : p.ntaps) * p.sum_chunks;
+      const uint32_t a_step = kHalo ? (uint32_t)(p.TW * 128) >> 4 : 0;      // descriptor units of 16 B per vertical tap
+      uint32_t tcount = 0;
+      int as_ = 0, bs_ = 0;
+      uint32_t aph_ = 0, bph_ = 0;
+      for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
         const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kMaxBlockN;
-        for (int k = 0; k < p.k_iters; ++k, ++it) {
-          const int st = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + st * kStageBytes);
-          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + kABytes);
+        // The issuing warp stalls ~100 cycles on every mbarrier probe and the tensor pipe drains meanwhile, so
+        // the state of the NEXT step's barriers is probed before this step's MMAs are issued and only
+        // re-checked (normally already true) afterwards.
+        uint32_t first = 1;
+        mbar_wait(&fullA[as_], aph_);
+        mbar_wait(&fullB[bs_], bph_);
+        for (int g = 0; g < groups; ++g) {
+          const uint64_t adesc0 = make_smem_desc(smem_u32(ringA + as_ * p.a_slot_bytes));
+          int as_n = as_ + 1;
+          uint32_t aph_n = aph_;
+          if (as_n == kASlots) { as_n = 0; aph_n ^= 1; }
+          for (int st = 0; st < steps_per_group; ++st) {
+            int bs_n = bs_ + 1;
+            uint32_t bph_n = bph_;
+            if (bs_n == kBSlots) { bs_n = 0; bph_n ^= 1; }
+            const bool last_step = st == steps_per_group - 1;
+            const bool last_of_tile = last_step && g == groups - 1;
+            uint32_t okB = 1, okA = 1;
+            if (!last_of_tile) {
+              okB = mbar_test_wait(&fullB[bs_n], bph_n);
+              if (last_step) okA = mbar_test_wait(&fullA[as_n], aph_n);
+            }
+            tc_fence_after();
+            const uint64_t adesc = adesc0 + (uint64_t)(st * a_step);
+            const uint64_t bdesc = make_smem_desc(smem_u32(ringB + bs_ * p.b_slot_bytes));
+            if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
-            tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (k | j) != 0 ? 1u : 0u);
-          tc_commit(&empty[st]);          // frees the smem stage once these MMAs retire
+              for (int j = 0; j < 4; ++j)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
+                tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+              if (cs > 1) tc_commit_mc(&emptyB[bs_], mc_mask); else tc_commit(&emptyB[bs_]);
+              if (last_step) tc_commit(&emptyA[as_]);      // frees the activation box once its MMAs retire
+              if (last_of_tile) tc_commit(&tfull[as]);     // accumulator complete
+            }
+            __syncwarp();
+            first = 0;
+            bs_ = bs_n; bph_ = bph_n;
+            if (!okB) mbar_wait(&fullB[bs_], bph_);
+            if (last_step && !okA) mbar_wait(&fullA[as_n], aph_n);
+          }
+          as_ = as_n; aph_ = aph_n;
         }
-        tc_commit(&tfull[as]);            // accumulator complete
       }
     }
   } else if (warp >= 4) {
@@ -255,12 +397,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
     const int l8 = lane & 7, rsub = lane >> 3, col = 4 * l8;
     const EpiParams& e = p.epi;
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+    for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       int n_tile, b, oy0, ox0;
-      tile_coords(p, tile, n_tile, b, oy0, ox0);
+      tile_coords(p, ct, cs, rank, n_tile, b, oy0, ox0);
       const int oy = oy0 + th, ox = ox0 + tw;
-      const bool row_ok = oy < e.Hout && ox < e.Wout;
+      const bool row_ok = b < p.B && oy < e.Hout && ox < e.Wout;
       const int64_t m = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -347,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
 
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();          // no CTA may exit while a peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -389,19 +532,33 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   pl->B = d->B; pl->Hout = d->Hout; pl->Wout = d->Wout;
   ATMVFI_REQUIRE(d->stride == 1 || d->stride == 2 || d->stride == 4, "gemm_conv(tf32): stride %d unsupported", d->stride);
 
-  // pixel tile TW x TH = 128: least padding waste, then squarest; element-strided boxes are capped at 256
+  // 3x3 stride-1 layers fetch activation boxes with a vertical halo and reuse them for the 3 vertical taps
+  static int halo_ok = -1;
+  if (halo_ok < 0) { const char* ev = getenv("ATMVFI_TC_HALO"); halo_ok = ev ? atoi(ev) : 1; }
+  pl->halo = (halo_ok && d->ksize == 3 && d->stride == 1 && d->dil == 1) ? 1 : 0;
+  // pixel tile TW x TH = 128: least padding waste, then squarest.  Element-strided boxes are capped at 256
+  // per dimension; halo boxes need TW % 8 == 0 (vertical taps = whole swizzle atoms) and (TH+2)*TW <= 192 rows.
   int best_tw = 0;
   int64_t best_cost = -1;
   const int cands[5] = {16, 32, 8, 64, 128};
   for (int i = 0; i < 5; ++i) {
     int tw = cands[i], th = 128 / tw;
     if (tw * d->stride > 256 || th * d->stride > 256) continue;
+    if (pl->halo && (th + 2) * tw * 128 > kMaxABoxBytes) continue;
     int64_t cost = (int64_t)cdiv(d->Wout, tw) * cdiv(d->Hout, th);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
   }
   ATMVFI_REQUIRE(best_tw > 0, "gemm_conv(tf32): no tile shape for stride %d", d->stride);
   pl->TW = best_tw; pl->TH = 128 / best_tw;
   pl->tiles_x = cdiv(d->Wout, pl->TW); pl->tiles_y = cdiv(d->Hout, pl->TH);
+  {
+    // clusters of 2 CTAs along M share each weight tile through TMA multicast
+    static int forced = -1;
+    if (forced < 0) { const char* ev = getenv("ATMVFI_TC_CLUSTER"); forced = ev ? atoi(ev) : 0; }
+    const int64_t m_tiles = (int64_t)pl->tiles_x * pl->tiles_y * d->B;
+    pl->cluster = forced ? forced : (m_tiles >= 2 ? 2 : 1);
+    ATMVFI_REQUIRE(pl->cluster == 1 || pl->cluster == 2 || pl->cluster == 4, "gemm_conv(tf32): cluster size %d unsupported", pl->cluster);
+  }
 
   const bool shuffle = d->out_mode == ATMVFI_OUT_SHUFFLE2;
   pl->cq_pad = round_up_i(d->Cout, 32);
@@ -423,7 +580,7 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     ATMVFI_REQUIRE(((uintptr_t)sr.ptr & 15) == 0 && sr.pitch % 4 == 0, "gemm_conv(tf32): source %d must be 16-byte aligned with pitch %% 4 == 0", s);
     cuuint64_t gdim[4] = {(cuuint64_t)sr.C, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
     cuuint64_t gstr[3] = {(cuuint64_t)sr.pitch * 4, (cuuint64_t)sr.pitch * 4 * d->Win, (cuuint64_t)sr.pitch * 4 * d->Win * d->Hin};
-    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)(pl->TW * d->stride), (cuuint32_t)(pl->TH * d->stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)(pl->TW * d->stride), (cuuint32_t)((pl->halo ? pl->TH + 2 : pl->TH) * d->stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     CUresult r = enc(&pl->mapA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sr.ptr), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -435,7 +592,7 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     ATMVFI_REQUIRE(((uintptr_t)d->weight & 15) == 0, "gemm_conv(tf32): weights must be 16-byte aligned");
     cuuint64_t gdim[2] = {(cuuint64_t)ktc, (cuuint64_t)n_pad};
     cuuint64_t gstr[1] = {(cuuint64_t)ktc * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)pl->block_n};
+    cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)(pl->block_n / pl->cluster)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->weight), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -451,16 +608,24 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
 int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   const TcPlan* pl = reinterpret_cast<const TcPlan*>(d->tma_host);
   ATMVFI_REQUIRE(pl && pl->magic == kPlanMagic, "gemm_conv(tf32): missing plan (call atmvfi_gemm_conv_plan first)");
+  typedef void (*KernelFn)(TcParams);
+  KernelFn kern = nullptr;
+  if (pl->halo) kern = pl->cluster == 2 ? gemm_conv_tc_kernel<true, 2> : (pl->cluster == 4 ? gemm_conv_tc_kernel<true, 4> : gemm_conv_tc_kernel<true, 1>);
+  else kern = pl->cluster == 2 ? gemm_conv_tc_kernel<false, 2> : (pl->cluster == 4 ? gemm_conv_tc_kernel<false, 4> : gemm_conv_tc_kernel<false, 1>);
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(gemm_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) {
-      num_sms = 0;
-      atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
-      return 1;
+    KernelFn all[6] = {gemm_conv_tc_kernel<true, 1>, gemm_conv_tc_kernel<true, 2>, gemm_conv_tc_kernel<true, 4>,
+                       gemm_conv_tc_kernel<false, 1>, gemm_conv_tc_kernel<false, 2>, gemm_conv_tc_kernel<false, 4>};
+    for (int i = 0; i < 6; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      if (e != cudaSuccess) {
+        num_sms = 0;
+        atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
+        return 1;
+      }
     }
   }
   TcParams p;
@@ -472,12 +637,38 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   p.ntaps = pl->ntaps; p.ksize = pl->ksize; p.stride = pl->stride; p.dil = pl->dil; p.pad = pl->pad;
   p.TW = pl->TW; p.TH = pl->TH; p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.B = pl->B;
   p.block_n = pl->block_n; p.n_tiles = pl->n_tiles; p.cq_pad = pl->cq_pad;
-  p.total_tiles = pl->tiles_x * pl->tiles_y * pl->B * pl->n_tiles;
-  p.k_iters = ch * pl->ntaps;
+  p.halo = pl->halo;
+  p.a_bytes = (pl->halo ? (pl->TH + 2) * pl->TW : kBlockM) * 128;
+  p.sum_chunks = ch;
+  p.a_slots = pl->halo ? 3 : 4;
+  p.a_slot_bytes = (p.a_bytes + 1023) / 1024 * 1024;
+  p.b_slot_bytes = pl->block_n * 128;
+  p.b_slots = (kDataBytes - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+  if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
+  p.m_tiles = pl->tiles_x * pl->tiles_y * pl->B;
+  const int cs = pl->cluster;
+  p.total_ctiles = ((p.m_tiles + cs - 1) / cs) * pl->n_tiles;
   p.epi = make_epi(d);
-  if (p.total_tiles <= 0) return 0;
-  int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  gemm_conv_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(p);
-  ATMVFI_CHECK_LAUNCH("gemm_conv(tf32)");
+  if (p.total_ctiles <= 0) return 0;
+  int clusters = num_sms / cs;
+  if (p.total_ctiles < clusters) clusters = p.total_ctiles;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(clusters * cs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
+  if (le != cudaSuccess) {
+    atmvfi_set_error("gemm_conv(tf32): launch failed: %s", cudaGetErrorString(le));
+    return 1;
+  }
   return 0;
 }
