@@ -72,6 +72,7 @@ _SPECIAL = {
     "atmvfi_abi_version": ([], C.c_int),
     "atmvfi_device_info": ([_I, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     "atmvfi_gemm_conv_plan_bytes": ([], C.c_int),
+    "atmvfi_set_output_rounding": ([C.c_int], None),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))
 

@@ -146,11 +146,14 @@ class CudaOps:
         if self.recording is not None:
             self.recording.append((name, fn, args, keep))
         else:
+            self.lib.atmvfi_set_output_rounding(1 if self.precision == _lib.TF32 else 0)
             _lib.check(fn(*args, torch.cuda.current_stream(self.device).cuda_stream), name)
             self.launches += 1
 
     def replay(self, records, stream: Optional[int] = None) -> None:
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        # tcgen05 kind::tf32 truncates its operands: producers round feature maps to TF32 in that mode
+        self.lib.atmvfi_set_output_rounding(1 if self.precision == _lib.TF32 else 0)
         for name, fn, args, _ in records:
             rc = fn(*args, st)
             if rc:

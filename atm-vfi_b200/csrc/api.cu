@@ -4,6 +4,8 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+static thread_local int g_round = 0;
+int atmvfi_output_rounding() { return g_round; }
 
 void atmvfi_set_error(const char* fmt, ...) {
   va_list ap;
@@ -19,6 +21,7 @@ extern "C" {
 
 const char* atmvfi_last_error(void) { return g_err; }
 int atmvfi_abi_version(void) { return ATMVFI_ABI_VERSION; }
+void atmvfi_set_output_rounding(int on) { g_round = on ? 1 : 0; }
 
 int atmvfi_device_info(int device, char* name, int* cc_major, int* cc_minor) {
   cudaDeviceProp prop;

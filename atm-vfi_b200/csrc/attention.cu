@@ -14,7 +14,7 @@ template <int HD>
 __global__ void __launch_bounds__(256) window_attention_kernel(const float* __restrict__ qkv, int qkv_pitch,
                                                                float* __restrict__ out, int out_pitch, int C, int heads,
                                                                atmvfi_window_geom g, int cross,
-                                                               const float* __restrict__ rc, float* __restrict__ motion_raw) {
+                                                               const float* __restrict__ rc, float* __restrict__ motion_raw, bool rnd) {
   extern __shared__ float smem[];
   const int N = g.ws * g.ws;
   float* sk = smem;             // [N][HD]
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) window_attention_kernel(const float* __re
   float4* op = reinterpret_cast<float4*>(out + row * out_pitch + h * HD);
 #pragma unroll
   for (int d = 0; d < HD / 4; ++d)
-    op[d] = make_float4(acc[4 * d] * inv, acc[4 * d + 1] * inv, acc[4 * d + 2] * inv, acc[4 * d + 3] * inv);
+    op[d] = round_tf32_if(make_float4(acc[4 * d] * inv, acc[4 * d + 1] * inv, acc[4 * d + 2] * inv, acc[4 * d + 3] * inv), rnd);
   if (motion_raw) {
     motion_raw[(row * heads + h) * 2 + 0] = mx * inv;
     motion_raw[(row * heads + h) * 2 + 1] = my * inv;
@@ -146,7 +146,7 @@ int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch,
   }
   dim3 grid((unsigned)wins, (unsigned)heads);
   int threads = ((N + 31) / 32) * 32;
-  kern<<<grid, threads, smem, st>>>(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, rc, motion_raw);
+  kern<<<grid, threads, smem, st>>>(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, rc, motion_raw, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("window_attention");
   return 0;
 }

@@ -17,7 +17,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int MAXV>   // float4 per lane
 __device__ __forceinline__ void ln_row(const float* __restrict__ src, float* __restrict__ dst, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                       float eps, int lane) {
+                                       float eps, int lane, bool rnd) {
   float4 v[MAXV];
   const int nv = C >> 2;
   float s = 0.f;
@@ -51,7 +51,7 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ src, float* __r
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      reinterpret_cast<float4*>(dst)[idx] = o;
+      reinterpret_cast<float4*>(dst)[idx] = round_tf32_if(o, rnd);
     }
   }
 }
@@ -61,18 +61,18 @@ constexpr int kLnMaxV = 8;   // up to C = 1024
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, int in_pitch,
                                                         float* __restrict__ out, int out_pitch, int64_t rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float eps) {
+                                                        float eps, bool rnd) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps)
-    ln_row<kLnMaxV>(in + r * in_pitch, out + r * out_pitch, C, gamma, beta, eps, lane);
+    ln_row<kLnMaxV>(in + r * in_pitch, out + r * out_pitch, C, gamma, beta, eps, lane, rnd);
 }
 
 __global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __restrict__ tok, int tok_pitch,
                                                                float* __restrict__ win, int win_pitch, int C,
                                                                atmvfi_window_geom g, int64_t rows,
                                                                const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, float eps) {
+                                                               const float* __restrict__ beta, float eps, bool rnd) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
@@ -80,11 +80,11 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __re
     float* dst = win + r * win_pitch;
     if (p.real) {
       const float* src = tok + ((int64_t)(p.b * g.H + p.y) * g.W + p.x) * tok_pitch;
-      ln_row<kLnMaxV>(src, dst, C, gamma, beta, eps, lane);
+      ln_row<kLnMaxV>(src, dst, C, gamma, beta, eps, lane, rnd);
     } else {
       // LayerNorm of an all-zero token: (0-0)*rstd*gamma + beta = beta (attention.py:273,316)
       for (int i = lane; i < (C >> 2); i += 32)
-        reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(beta) + i);
+        reinterpret_cast<float4*>(dst)[i] = round_tf32_if(__ldg(reinterpret_cast<const float4*>(beta) + i), rnd);
     }
   }
 }
@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __re
 // depth-wise 3x3, pad 1, + bias + exact GELU.  One thread: one pixel x 4 channels.
 __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
                                                           int H, int W, int C, int pitch,
-                                                          const float* __restrict__ w9c, const float* __restrict__ bias) {
+                                                          const float* __restrict__ w9c, const float* __restrict__ bias,
+                                                          bool rnd) {
   const int cv = C >> 2;
   const int64_t total = (int64_t)B * H * W * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restric
     o.y = 0.5f * acc.y * (1.f + erff(acc.y * r2));
     o.z = 0.5f * acc.z * (1.f + erff(acc.z * r2));
     o.w = 0.5f * acc.w * (1.f + erff(acc.w * r2));
-    reinterpret_cast<float4*>(out + pix * pitch)[c4] = o;
+    reinterpret_cast<float4*>(out + pix * pitch)[c4] = round_tf32_if(o, rnd);
   }
 }
 
@@ -156,7 +157,7 @@ __global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __rest
 __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __restrict__ src, int src_pitch,
                                                              const float* __restrict__ head, int head_pitch, int flow_off,
                                                              float* __restrict__ out, int out_pitch, int B, int C, int H,
-                                                             int W) {
+                                                             int W, bool rnd) {
   const int cv = C >> 2;
   const int64_t total = (int64_t)B * H * W * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __rest
     if (s.vy0 && s.vx1) corner(s.y0, s.x0 + 1, s.wne, false);
     if (s.vy1 && s.vx0) corner(s.y0 + 1, s.x0, s.wsw, false);
     if (s.vy1 && s.vx1) corner(s.y0 + 1, s.x0 + 1, s.wse, false);
-    reinterpret_cast<float4*>(out + pix * out_pitch)[c4] = o;
+    reinterpret_cast<float4*>(out + pix * out_pitch)[c4] = round_tf32_if(o, rnd);
   }
 }
 
@@ -253,13 +254,13 @@ __global__ void __launch_bounds__(256) resize_ac_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                            int out_pitch, int chan_off, int B, int C, int H, int W,
-                                                           int zero_to) {
+                                                           int zero_to, bool rnd) {
   const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int b = (int)(i / hw);
     int64_t rem = i - b * hw;
     float* o = out + i * out_pitch + chan_off;
-    for (int c = 0; c < C; ++c) o[c] = __ldg(in + ((int64_t)b * C + c) * hw + rem);
+    for (int c = 0; c < C; ++c) o[c] = round_tf32_if(__ldg(in + ((int64_t)b * C + c) * hw + rem), rnd);
     for (int c = chan_off + C; c < zero_to; ++c) out[i * out_pitch + c] = 0.f;
   }
 }
@@ -325,7 +326,7 @@ int atmvfi_layernorm(const float* in, int in_pitch, float* out, int out_pitch, i
   ATMVFI_REQUIRE(C % 4 == 0 && C <= kLnMaxV * 128 && in_pitch % 4 == 0 && out_pitch % 4 == 0,
                  "layernorm: C=%d pitches %d/%d unsupported (need C%%4==0, C<=%d)", C, in_pitch, out_pitch, kLnMaxV * 128);
   if (rows <= 0) return 0;
-  layernorm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, C, gamma, beta, eps);
+  layernorm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, C, gamma, beta, eps, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("layernorm");
   return 0;
 }
@@ -336,7 +337,7 @@ int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win
   ATMVFI_REQUIRE(g->Hp % g->ws == 0 && g->Wp % g->ws == 0 && g->shift >= 0 && g->shift < g->ws, "window_gather_ln: bad geometry");
   int64_t rows = (int64_t)g->B2 * g->Hp * g->Wp;
   if (rows <= 0) return 0;
-  window_gather_ln_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(tok, tok_pitch, win, win_pitch, C, *g, rows, gamma, beta, eps);
+  window_gather_ln_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(tok, tok_pitch, win, win_pitch, C, *g, rows, gamma, beta, eps, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("window_gather_ln");
   return 0;
 }
@@ -346,7 +347,7 @@ int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int 
   ATMVFI_REQUIRE(C % 4 == 0 && pitch % 4 == 0, "dwconv3x3_gelu: C=%d pitch=%d must be multiples of 4", C, pitch);
   int64_t n = (int64_t)B * H * W * (C / 4);
   if (n <= 0) return 0;
-  dwconv_gelu_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias);
+  dwconv_gelu_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("dwconv3x3_gelu");
   return 0;
 }
@@ -364,7 +365,7 @@ int atmvfi_flow_warp_nhwc(const float* src, int src_pitch, const float* head, in
   ATMVFI_REQUIRE(C % 4 == 0 && src_pitch % 4 == 0 && out_pitch % 4 == 0, "flow_warp_nhwc: C=%d must be a multiple of 4", C);
   int64_t n = (int64_t)B * H * W * (C / 4);
   if (n <= 0) return 0;
-  flow_warp_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W);
+  flow_warp_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("flow_warp_nhwc");
   return 0;
 }
@@ -395,7 +396,7 @@ int atmvfi_nchw_to_nhwc(const float* in, float* out, int out_pitch, int chan_off
                         int zero_fill_to, void* stream) {
   int64_t n = (int64_t)B * H * W;
   if (n <= 0) return 0;
-  nchw_to_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, out_pitch, chan_off, B, C, H, W, zero_fill_to);
+  nchw_to_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, out_pitch, chan_off, B, C, H, W, zero_fill_to, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("nchw_to_nhwc");
   return 0;
 }

@@ -458,6 +458,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * sl[k];
           }
+          const bool rnd = e.round != 0;
+          float w[4];
+          if (e.out2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[k] = round_tf32_if(v[k] > 0.f ? v[k] : v[k] * sl2[k], rnd);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = round_tf32_if(v[k], rnd);
           float* o1 = e.out + orow * e.out_pitch + co0 + col;
           if (full4) {
             *reinterpret_cast<float4*>(o1) = make_float4(v[0], v[1], v[2], v[3]);
@@ -468,9 +476,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
           }
           if (e.out2) {
             float* o2 = e.out2 + orow * e.out2_pitch + co0 + col;
-            float w[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) w[k] = v[k] > 0.f ? v[k] : v[k] * sl2[k];
             if (full4) {
               *reinterpret_cast<float4*>(o2) = make_float4(w[0], w[1], w[2], w[3]);
             } else {

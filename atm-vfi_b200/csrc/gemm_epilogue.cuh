@@ -17,6 +17,7 @@ struct EpiParams {
   int out2_pitch;
   int out_mode;
   int Hout, Wout;          // GEMM rows enumerate (b, y, x) over this grid
+  int round;               // round stored values to TF32
   atmvfi_window_geom win;
 };
 
@@ -41,14 +42,14 @@ __device__ __forceinline__ void epi_store(const EpiParams& e, int64_t m, int64_t
   if (e.bias) v += __ldg(e.bias + co);
   if (e.residual) v += __ldg(e.residual + m * e.res_pitch + co);
   if (e.prelu) v = v > 0.f ? v : v * __ldg(e.prelu + co);
-  e.out[orow * e.out_pitch + co] = v;
-  if (e.out2) e.out2[orow * e.out2_pitch + co] = v > 0.f ? v : v * __ldg(e.prelu2 + co);
+  e.out[orow * e.out_pitch + co] = round_tf32_if(v, e.round);
+  if (e.out2) e.out2[orow * e.out2_pitch + co] = round_tf32_if(v > 0.f ? v : v * __ldg(e.prelu2 + co), e.round);
 }
 
 static inline EpiParams make_epi(const atmvfi_gemm_conv_desc* d) {
   EpiParams e;
   e.Cout = d->Cout; e.bias = d->bias; e.prelu = d->prelu; e.residual = d->residual; e.res_pitch = d->res_pitch;
   e.out = d->out; e.out_pitch = d->out_pitch; e.out2 = d->out2; e.prelu2 = d->prelu2; e.out2_pitch = d->out2_pitch;
-  e.out_mode = d->out_mode; e.Hout = d->Hout; e.Wout = d->Wout; e.win = d->win;
+  e.out_mode = d->out_mode; e.Hout = d->Hout; e.Wout = d->Wout; e.win = d->win; e.round = atmvfi_output_rounding();
   return e;
 }

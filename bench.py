@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""ATM-VFI forward benchmark (driver contract: python bench.py --gpus N --steps K --warmup W [--impl reference]).
+
+Metric (BASELINE.json): interpolated frames per second (= frame pairs per second).  One "step" = one forward of
+the hot path over one batch of synthetic frame pairs.  Default workload: Base network, 1080p (1920x1080 padded
+to 1088x1920 as demo_2x.inference_2frame does), global motion on, one pair per step.
+
+  value  : whole-job pairs/s with the frames already resident in HBM (CUDA events, CUDA-graph replay of the plan).
+  e2e    : the same through the reference-facing API demo_2x.inference_2frame: numpy uint8 HOST frames in,
+           numpy uint8 frame out; H2D/D2H copies, colour conversion, padding and rounding inside the timed region.
+  roofline / cpu_baseline: see DESIGN.md section "Measurement".
+
+N > 1 (torchrun, one rank per GPU): frame pairs are independent, so every rank interpolates its own pairs with no
+data-path collective (weak scaling); NCCL is used only for the barrier and the max-over-ranks of the elapsed time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "atm-vfi_b200"), os.path.join(ROOT, "atm-vfi_b200", "network")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (kind, B, H, W, global_motion, description)
+    "base_1080p": ("base", 1, 1080, 1920, True, "network_base Network, 1920x1080 synthetic frame pairs (padded to 1088x1920), global_motion on, 1 pair/step"),
+    "lite_1080p": ("lite", 1, 1080, 1920, True, "network_lite Network, 1920x1080 synthetic frame pairs, global_motion on, 1 pair/step"),
+    "base_vimeo_b32": ("base", 32, 256, 448, True, "network_base Network, Vimeo90K-shape 448x256 synthetic pairs, batch 32, local+global motion"),
+    "base_4k": ("base", 1, 2160, 4096, True, "network_base Network, 4096x2160 synthetic frame pairs (padded to 2176x4096), global_motion on, 1 pair/step"),
+    "lite_example": ("lite", 1, 600, 414, False, "network_lite Network, example-frame shape 414x600, global_motion off"),
+}
+TF32_PEAK_NOTE = "tf32 tensor peak taken as measured dense bf16 (MEASURED_PEAKS.json, sustained) / 2: kind::tf32 issues at half the bf16 MMA rate"
+
+
+def pad64(h, w):
+    return h + (-h) % 64, w + (-w) % 64
+
+
+class ClockSampler:
+    def __init__(self, device_index):
+        self.samples, self.reasons, self.proc = [], set(), None
+        self.idx = device_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append((int(f[0]), int(f[1])))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(n)
+
+    def reset(self):
+        self.samples, self.reasons = [], set()
+
+    def stop(self):
+        if self.proc:
+            self.proc.kill()
+        s = sorted(x[0] for x in self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.samples[0][1] if self.samples else None,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return pk["hbm_gbs"], pk["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def build_net(kind, device, precision):
+    import torch
+    from network_base import Network as NB
+    from network_lite import Network as NL
+    torch.manual_seed(0)
+    net = (NB if kind == "base" else NL)()          # random-init weights of the named architecture
+    net = net.to(device).eval()
+    net.precision = precision
+    return net
+
+
+def synthetic_u8(B, H, W, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    return [(rng.integers(0, 256, (H, W, 3), dtype=np.uint8), rng.integers(0, 256, (H, W, 3), dtype=np.uint8)) for _ in range(B)]
+
+
+def measure_kernels(plan, torch):
+    """Per-launch device time of every record of the plan (CUDA events on the launching stream), grouped by entry
+    point; returns (table, tc_summary) where tc_summary describes the dominant tcgen05 GEMM kernel."""
+    ops = plan.ops
+    recs = plan.records
+    ops.lib.atmvfi_set_output_rounding(1 if ops.precision == 1 else 0)
+    st = torch.cuda.current_stream().cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(recs) + 1)]
+    for rep in range(2):                      # first pass warms caches / clocks
+        ev[0].record()
+        for i, (name, fn, args, _) in enumerate(recs):
+            fn(*args, st)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+    per = {}
+    tc_flops = tc_ms = 0.0
+    tc_n = 0
+    for i, (name, fn, args, keep) in enumerate(recs):
+        ms = ev[i].elapsed_time(ev[i + 1])
+        key = name
+        if name == "atmvfi_gemm_conv":
+            d = keep[0]
+            key = "atmvfi_gemm_conv[tf32 tcgen05]" if d.precision == 1 else "atmvfi_gemm_conv[fp32 ffma]"
+            if d.precision == 1:
+                cin = sum(d.src[s].C for s in range(d.nsrc))
+                n = d.Cout * (4 if d.out_mode == 1 else 1)
+                tc_flops += 2.0 * d.B * d.Hout * d.Wout * cin * d.ksize * d.ksize * n
+                tc_ms += ms
+                tc_n += 1
+        a = per.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += ms
+    return per, (tc_flops, tc_ms, tc_n)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    kind, B, H, W, glob, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    net = build_net(kind, dev, args.precision)
+    net.global_motion = glob
+    Hp, Wp = pad64(H, W)
+
+    # ---------------- device-resident timing: value ----------------
+    g = torch.Generator().manual_seed(1234 + rank)
+    im0 = torch.rand(B, 3, Hp, Wp, generator=g).to(dev)
+    im1 = torch.rand(B, 3, Hp, Wp, generator=g).to(dev)
+    net.zero_copy_outputs = True
+    rt = net._runtime
+    rt.prepare(net, dev, net.precision, 8, 12)
+    plan = rt.plan(B, Hp, Wp, glob)
+    launches_per_step = plan.num_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        net(im0, im1)
+    t0 = time.time()
+    while time.time() - t0 < 1.5:          # let the SM clock ramp; part of warm-up, not timed
+        net(im0, im1)
+    barrier()
+    sampler.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        net(im0, im1)                      # inputs: 2 x 25 MB per pair at 1080p + ~19 GB of plan buffers >> 126 MB of L2
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.steps * B / (ms / 1e3)
+
+    # ---------------- end to end through the reference-facing API: e2e ----------------
+    from demo_2x import inference_2frame
+    pairs = synthetic_u8(B, H, W, 99 + rank)
+    for a, b in pairs[:1]:
+        for _ in range(3):
+            inference_2frame(a, b, net)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for a, b in pairs:
+            out = inference_2frame(a, b, net)          # pinned staging, H2D, kernels, D2H, sync: all inside
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * args.steps * B / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 2 * B * H * W * 3, "d2h_bytes_per_step": B * H * W * 3,
+           "api": "demo_2x.inference_2frame (uint8 HWC host frames in, uint8 host frame out)"}
+    if B > 1:
+        e2e["note"] = "inference_2frame is a batch-1 API: the B pairs of a step are interpolated one after the other"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---------------- roofline of the dominant kernel (rank 0) ----------------
+    hbm_gbs, bf16_tf, basis = load_peaks()
+    per, (tc_flops, tc_ms, tc_n) = measure_kernels(plan, torch)
+    total_ms = sum(v[1] for v in per.values())
+    roof = None
+    if tc_n:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_tc_dram_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.workload)
+            except Exception:
+                traffic = None
+        achieved = tc_flops / tc_n / (tc_ms / tc_n * 1e-3) / 1e12
+        roof = {"kernel": "gemm_conv_tc_kernel (tcgen05 kind::tf32 implicit-GEMM conv/linear)", "bound": "tensor", "achieved": round(achieved, 1),
+                "peak": round(bf16_tf / 2, 1), "unit": "TFLOP/s", "frac": round(achieved / (bf16_tf / 2), 3), "traffic": traffic,
+                "launches_per_step": tc_n, "flops_per_launch": tc_flops / tc_n, "avg_launch_ms": tc_ms / tc_n,
+                "share_of_step": round(tc_ms / total_ms, 3), "peak_basis": f"{basis}; {TF32_PEAK_NOTE}"}
+    kernels = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])}
+
+    # ---------------- CPU baseline: the oracle (port of the reference forward) on the host cores, N=1 only ----------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_baseline(kind, B, Hp, Wp, glob, steps=1)
+    line = {
+        "metric": "interpolated frames/sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
+        "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "pairs_per_step_per_gpu": B, "padded_shape": [Hp, Wp],
+                                        "parallelism": f"pairs sharded over {world} GPU(s), no data-path collective", "weights": "random-init",
+                                        "l2": "inputs+activations per step (>10 GB) exceed the 126 MB L2; no flush needed"},
+        "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roof, "kernels_ms_per_step": kernels,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(kind, B, Hp, Wp, glob, steps=1):
+    """Times the CPU oracle (oracle/atmvfi_oracle.py, a port of the reference forward) on a bounded sample."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import atmvfi_oracle as oracle
+    import weights
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # bounded sample: one pair of the workload's shape; on a small host (< 16 cores) and >= 1080p, a half-resolution
+    # pair of the same kind whose time is scaled by the pixel ratio (the forward is linear in pixels)
+    scale, h, w = 1, Hp, Wp
+    if cores < 16 and Hp * Wp >= 1088 * 1920:
+        h, w, scale = Hp // 2 // 64 * 64, Wp // 2 // 64 * 64, None
+        scale = (Hp * Wp) / float(h * w)
+    b = 1
+    P = weights.make_weights(kind, "default")
+    im0, im1 = weights.synthetic_frames(b, h, w)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle.forward(P, im0, im1, glob)
+    dt = (time.perf_counter() - t0) / steps
+    pairs_per_s = b / (dt * scale)
+    return {"value": round(pairs_per_s, 5), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"1 pair at {h}x{w} (of the {Hp}x{Wp} workload{', time scaled x%.2f by pixel count' % scale if scale > 1 else ''}), fp32, torch CPU threads={cores}, {dt:.1f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the CPU oracle (port), all host threads."""
+    kind, B, H, W, glob, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    Hp, Wp = pad64(H, W)
+    cpu = cpu_baseline(kind, B, Hp, Wp, glob, steps=max(1, min(args.steps, 2)))
+    line = {"impl": "reference", "metric": "interpolated frames/sec", "value": cpu["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1e3 * B / cpu["value"], 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "padded_shape": [Hp, Wp]},
+            "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="base_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if not os.path.exists(os.path.join(ROOT, "atm-vfi_b200", "atmvfi", "libatmvfi_b200.so")):
+            sys.path.insert(0, ROOT)
+            import __graft_entry__ as ge
+            ge.build()
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -89,6 +89,10 @@ typedef struct {
 
 const char* atmvfi_last_error(void);
 int atmvfi_abi_version(void);
+/* Thread-local mode for subsequent launches from this thread: when on, kernels that produce channels-last feature
+ * maps round their outputs to the nearest TF32 value (the tcgen05 tf32 datapath truncates operands otherwise).
+ * The host runtime turns it on for precision ATMVFI_TF32 and off for ATMVFI_FP32. */
+void atmvfi_set_output_rounding(int on);
 /* Fills name[] (<=255 chars) with the device name and returns the SM count, or -1 without a usable sm_100 device. */
 int atmvfi_device_info(int device, char* name, int* cc_major, int* cc_minor);
 

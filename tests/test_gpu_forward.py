@@ -16,13 +16,16 @@ import weights
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 CASES = [p for p in sorted(glob.glob(os.path.join(GOLDEN, "case_*.npz"))) if "config0" not in p]
 
-# Stated tolerances (max-abs on I_t in [0,1]; flows in pixels of the finest scale).
-#   fp32: CUDA-core FFMA datapath, differs from the CPU oracle only by summation order.
-#   tf32: tcgen05 kind::tf32 (10-bit mantissa operands, fp32 accumulate) - the datapath the reference itself
-#         gets from cuDNN by default on GPU.  The stress set multiplies every error by its gains (x100 on the
-#         motion heads), so it is a structural check with loose bounds.
-TOL = {("fp32", "default"): dict(img=1e-4, flow=1e-4), ("fp32", "stress"): dict(img=2e-2, flow=2e-2),
-       ("tf32", "default"): dict(img=5e-3, flow=1e-3), ("tf32", "stress"): dict(img=0.35, flow=0.5)}
+# Stated tolerances, calibrated on B200 (gpurun, profiles/parity_r01.md).  max-abs on images in [0,1], flows in px.
+#   fp32: CUDA-core FFMA datapath; differs from the CPU oracle by summation order only
+#         (measured: I_t <= 3.3e-5, flows <= 5.4e-6 on every case, stress set included).
+#   tf32: tcgen05 kind::tf32 (10-bit mantissa operands, fp32 accumulate; activations rounded to nearest TF32 by
+#         their producers) - the datapath the reference itself gets from cuDNN on a GPU (torch default allow_tf32).
+#         Measured on the default-init sets: I_t max 2.8e-3 / mean 3.7e-4, PSNR(new, ref) 66 dB (Base), flows 2.6e-5 px.
+#         The stress set multiplies every rounding error by its gains (x100 on the motion heads, x50 on the
+#         occlusion logit), so with tf32 it is checked on mean error and final outputs only.
+TOL = {("fp32", "default"): dict(img=1e-4, flow=1e-4, mean=1e-5), ("fp32", "stress"): dict(img=2e-3, flow=1e-4, mean=1e-4),
+       ("tf32", "default"): dict(img=8e-3, flow=2e-4, mean=1e-3), ("tf32", "stress"): dict(img=0.1, flow=0.1, mean=5e-3)}
 
 
 def _net(kind, P):
@@ -58,12 +61,15 @@ def test_forward_matches_reference_golden(path, precision):
     for key in ("opt_flow_0", "opt_flow_1"):
         err = np.abs(out[key].cpu().numpy() - z[key]).max()
         assert err <= tol["flow"], (key, err)
+    assert np.abs(out["I_t"].cpu().numpy() - z["I_t"]).mean() <= tol["mean"]
     n = 5 if meta["global_motion"] else 4
     assert len(out["im_t_list"]) == len(out["im0_warped_list"]) == len(out["im1_warped_list"]) == n
+    noisy = precision == "tf32" and meta["variant"] == "stress"     # amplified rounding noise: means only
     for i in range(n):
-        err = np.abs(out["im_t_list"][i].cpu().numpy() - z[f"im_t_list_{i}"]).max()
-        assert err <= tol["img"], (i, err)
-    assert np.abs(out["im0_warped_list"][-1].cpu().numpy() - z["coarse_im0_warped"]).max() <= tol["img"]
+        d = np.abs(out["im_t_list"][i].cpu().numpy() - z[f"im_t_list_{i}"])
+        assert (d.mean() <= 2e-2) if noisy else (d.max() <= tol["img"]), (i, d.max(), d.mean())
+    d = np.abs(out["im0_warped_list"][-1].cpu().numpy() - z["coarse_im0_warped"])
+    assert (d.mean() <= 2e-2) if noisy else (d.max() <= tol["img"])
     if meta["variant"] == "default":
         assert psnr(out["I_t"].cpu(), torch.from_numpy(z["I_t"])) >= (90 if precision == "fp32" else 60)
 
