@@ -178,15 +178,17 @@ class Plan:
             ops.resize(pyr0[l - 1], pyr0[l]); ops.resize(pyr1[l - 1], pyr1[l])
 
         # encoder on the two frames stacked on the batch axis (network_base.py:342-352, 451)
-        x = ops.new_map(2 * B, H, W, 3)
-        ops.nchw_to_nhwc(self.im0, x.batch(0, B), zero_fill_to=x.pitch)
-        ops.nchw_to_nhwc(self.im1, x.batch(B, B), zero_fill_to=x.pitch)
         levels = []
+        x = None
         for l in range(4):
             c0, c1 = m.enc[l]
             h, w = H >> l, W >> l
             y = ops.new_map(2 * B, h, w, c0.Cout)
-            ops.gemm_conv([x], c0, y, stride=1 if l == 0 else 2)
+            if l == 0:      # 3 -> C0 straight from the planar frames (no channels-last copy of the inputs)
+                ops.conv3x3_first(self.im0, c0, y.batch(0, B))
+                ops.conv3x3_first(self.im1, c0, y.batch(B, B))
+            else:
+                ops.gemm_conv([x], c0, y, stride=2)
             x = ops.new_map(2 * B, h, w, c1.Cout)
             ops.gemm_conv([y], c1, x)
             levels.append(x)
@@ -268,8 +270,7 @@ class Plan:
         # residual-refinement U-Net (network_base.py:417-431); the ORIGINAL frames go in
         r = a.refine
         imgs = ops.new_map(B, H, W, 15)
-        for j, t in enumerate((self.im0, a0, self.im1, a1, it)):
-            ops.nchw_to_nhwc(t, imgs.chan(3 * j, 3), zero_fill_to=(imgs.pitch if j == 4 else 0))
+        ops.pack5_planar((self.im0, a0, self.im1, a1, it), imgs)
         r0 = ops.new_map(B, H, W, r)
         ops.gemm_conv([raw, imgs], m.proj, r0)
         r1 = ops.new_map(B, H >> 1, W >> 1, r)

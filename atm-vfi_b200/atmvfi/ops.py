@@ -229,6 +229,18 @@ class CudaOps:
             return False
         return True
 
+    def conv3x3_first(self, img: torch.Tensor, w: PackedGemm, out: Map):
+        """feat_extracts.0.0 on a planar frame (3 channels) -> NHWC."""
+        b, c, h, wd = img.shape
+        assert c == 3 and w.ksize == 3 and list(w.split) == [3] and (out.B, out.H, out.W, out.C) == (b, h, wd, w.Cout) and out.c0 == 0
+        self._emit("atmvfi_conv3x3_first", (img.data_ptr(), w.w32.data_ptr(), w.w32.shape[1], _p(w.bias), _p(w.prelu), out.ptr, out.pitch, b, h, wd, w.Cout),
+                   keep=(img, w, out))
+
+    def pack5_planar(self, imgs: Sequence[torch.Tensor], out: Map):
+        b, _, h, wd = imgs[0].shape
+        assert len(imgs) == 5 and all(t.shape == (b, 3, h, wd) and t.is_contiguous() for t in imgs) and out.c0 == 0 and out.pitch >= 16
+        self._emit("atmvfi_pack5_planar", tuple(t.data_ptr() for t in imgs) + (out.ptr, out.pitch, b, h, wd), keep=(imgs, out))
+
     # -- transformer pieces -------------------------------------------------------------------
     def layernorm(self, x: Map, out: Map, gamma: torch.Tensor, beta: torch.Tensor):
         assert x.C == out.C == gamma.numel()

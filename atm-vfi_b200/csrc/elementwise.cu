@@ -89,43 +89,132 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __re
   }
 }
 
-// depth-wise 3x3, pad 1, + bias + exact GELU.  One thread: one pixel x 4 channels.
+// depth-wise 3x3, pad 1, + bias + exact GELU.  One thread owns (x, 4 channels) and walks down a strip of kDwRows
+// rows with a 3x3 register window, so every input row is fetched once per strip (3 loads per output instead of 9);
+// consecutive threads cover consecutive channel quads -> 512-byte coalesced segments per warp.
+constexpr int kDwRows = 8;
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+
 __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
                                                           int H, int W, int C, int pitch,
                                                           const float* __restrict__ w9c, const float* __restrict__ bias,
                                                           bool rnd) {
   const int cv = C >> 2;
-  const int64_t total = (int64_t)B * H * W * cv;
+  const int strips = (H + kDwRows - 1) / kDwRows;
+  const int64_t total = (int64_t)B * strips * W * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % cv);
-    int64_t pix = i / cv;
-    int x = (int)(pix % W);
-    int y = (int)((pix / W) % H);
-    int b = (int)(pix / ((int64_t)W * H));
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    const int c4 = (int)(i % cv);
+    int64_t t = i / cv;
+    const int x = (int)(t % W);
+    t /= W;
+    const int y0 = (int)(t % strips) * kDwRows;
+    const int b = (int)(t / strips);
+    float4 k[9];
 #pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      int yy = y + dy;
-      if (yy < 0 || yy >= H) continue;
+    for (int j = 0; j < 9; ++j) k[j] = __ldg(reinterpret_cast<const float4*>(w9c + j * C) + c4);
+    const float4 bz = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool xl = x > 0, xr = x + 1 < W;
+    auto load_row = [&](int yy, float4& l, float4& m, float4& r) {
+      if (yy < 0 || yy >= H) { l = m = r = zero; return; }
+      const float* rowp = in + ((int64_t)(b * H + yy) * W + x) * pitch;
+      m = __ldg(reinterpret_cast<const float4*>(rowp) + c4);
+      l = xl ? __ldg(reinterpret_cast<const float4*>(rowp - pitch) + c4) : zero;
+      r = xr ? __ldg(reinterpret_cast<const float4*>(rowp + pitch) + c4) : zero;
+    };
+    float4 a0, a1, a2, b0, b1, b2, c0, c1, c2;      // rows y-1, y, y+1
+    load_row(y0 - 1, a0, a1, a2);
+    load_row(y0, b0, b1, b2);
 #pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        int xx = x + dx;
-        if (xx < 0 || xx >= W) continue;
-        float4 v = __ldg(reinterpret_cast<const float4*>(in + ((int64_t)(b * H + yy) * W + xx) * pitch) + c4);
-        float4 k = __ldg(reinterpret_cast<const float4*>(w9c + ((dy + 1) * 3 + (dx + 1)) * C) + c4);
-        acc.x = fmaf(v.x, k.x, acc.x);
-        acc.y = fmaf(v.y, k.y, acc.y);
-        acc.z = fmaf(v.z, k.z, acc.z);
-        acc.w = fmaf(v.w, k.w, acc.w);
-      }
+    for (int dy = 0; dy < kDwRows; ++dy) {
+      const int y = y0 + dy;
+      if (y >= H) break;
+      load_row(y + 1, c0, c1, c2);
+      // same accumulation order as the per-pixel reference loop: taps row-major starting from the bias
+      float4 acc = bz;
+      acc = fma4(a0, k[0], acc); acc = fma4(a1, k[1], acc); acc = fma4(a2, k[2], acc);
+      acc = fma4(b0, k[3], acc); acc = fma4(b1, k[4], acc); acc = fma4(b2, k[5], acc);
+      acc = fma4(c0, k[6], acc); acc = fma4(c1, k[7], acc); acc = fma4(c2, k[8], acc);
+      float4 o = make_float4(gelu_exact(acc.x), gelu_exact(acc.y), gelu_exact(acc.z), gelu_exact(acc.w));
+      reinterpret_cast<float4*>(out + ((int64_t)(b * H + y) * W + x) * pitch)[c4] = round_tf32_if(o, rnd);
+      a0 = b0; a1 = b1; a2 = b2;
+      b0 = c0; b1 = c1; b2 = c2;
     }
-    const float r2 = 0.70710678118654752440f;
-    float4 o;
-    o.x = 0.5f * acc.x * (1.f + erff(acc.x * r2));
-    o.y = 0.5f * acc.y * (1.f + erff(acc.y * r2));
-    o.z = 0.5f * acc.z * (1.f + erff(acc.z * r2));
-    o.w = 0.5f * acc.w * (1.f + erff(acc.w * r2));
-    reinterpret_cast<float4*>(out + pix * pitch)[c4] = round_tf32_if(o, rnd);
+  }
+}
+
+// First encoder layer: 3x3 conv (pad 1) on a planar 3-channel image + bias + PReLU -> NHWC.  One thread computes all
+// COUT channels of one pixel from 27 cached planar loads; weights/bias/slopes sit in shared memory (broadcast reads).
+template <int COUT>
+__global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wk,
+                                                            int ldw, const float* __restrict__ bias,
+                                                            const float* __restrict__ prelu, float* __restrict__ out,
+                                                            int out_pitch, int B, int H, int W, bool rnd) {
+  __shared__ float sw[27 * COUT];
+  __shared__ float sb[COUT], sp[COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = wk[(i / COUT) * ldw + (i % COUT)];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sb[i] = bias[i]; sp[i] = prelu ? prelu[i] : 1.f; }
+  __syncthreads();
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const int64_t rem = i - b * hw;
+    const int y = (int)(rem / W), x = (int)(rem % W);
+    float v[27];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int yy = y + ky - 1, xx = x + kx - 1;
+        const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = ok ? __ldg(img + ((int64_t)b * 3 + c) * hw + (int64_t)yy * W + xx) : 0.f;
+      }
+    float* o = out + i * out_pitch;
+#pragma unroll
+    for (int co = 0; co < COUT; co += 4) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&sw[k * COUT + co]);
+        a[0] = fmaf(v[k], w4.x, a[0]); a[1] = fmaf(v[k], w4.y, a[1]); a[2] = fmaf(v[k], w4.z, a[2]); a[3] = fmaf(v[k], w4.w, a[3]);
+      }
+      float4 r;
+      float* rp = &r.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float t = a[e] + sb[co + e];
+        t = t > 0.f ? t : t * sp[co + e];
+        rp[e] = round_tf32_if(t, rnd);
+      }
+      *reinterpret_cast<float4*>(o + co) = r;
+    }
+  }
+}
+
+// Up to 5 planar 3-channel images -> 15 (+1 zero) consecutive channels of an NHWC buffer in one pass
+// (the image part of torch.cat([feat, im0, I_t_0, im1, I_t_1, I_t], 1), network_base.py:418).
+__global__ void __launch_bounds__(256) pack5_planar_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
+                                                           const float* __restrict__ s2, const float* __restrict__ s3,
+                                                           const float* __restrict__ s4, float* __restrict__ out,
+                                                           int out_pitch, int B, int H, int W, bool rnd) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+  const float* src[5] = {s0, s1, s2, s3, s4};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const int64_t rem = i - b * hw;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[j * 3 + c] = round_tf32_if(__ldg(src[j] + ((int64_t)b * 3 + c) * hw + rem), rnd);
+    v[15] = 0.f;
+    float4* o = reinterpret_cast<float4*>(out + i * out_pitch);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
 }
 
@@ -342,10 +431,40 @@ int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win
   return 0;
 }
 
+int atmvfi_conv3x3_first(const float* img, const float* wk, int ldw, const float* bias, const float* prelu, float* out,
+                         int out_pitch, int B, int H, int W, int Cout, void* stream) {
+  ATMVFI_REQUIRE(out_pitch % 4 == 0 && ((uintptr_t)out & 15) == 0, "conv3x3_first: output must be 16-byte aligned, pitch %% 4 == 0");
+  int64_t n = (int64_t)B * H * W;
+  if (n <= 0) return 0;
+  const bool rnd = atmvfi_output_rounding() != 0;
+  int grid = grid_for(n, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (Cout) {
+    case 16: conv3x3_first_kernel<16><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, rnd); break;
+    case 24: conv3x3_first_kernel<24><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, rnd); break;
+    case 32: conv3x3_first_kernel<32><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, rnd); break;
+    default:
+      atmvfi_set_error("conv3x3_first: Cout=%d not instantiated (16, 24, 32)", Cout);
+      return 2;
+  }
+  ATMVFI_CHECK_LAUNCH("conv3x3_first");
+  return 0;
+}
+
+int atmvfi_pack5_planar(const float* s0, const float* s1, const float* s2, const float* s3, const float* s4, float* out,
+                        int out_pitch, int B, int H, int W, void* stream) {
+  ATMVFI_REQUIRE(out_pitch >= 16 && out_pitch % 4 == 0 && ((uintptr_t)out & 15) == 0, "pack5_planar: output needs pitch >= 16 and 16-byte alignment");
+  int64_t n = (int64_t)B * H * W;
+  if (n <= 0) return 0;
+  pack5_planar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s0, s1, s2, s3, s4, out, out_pitch, B, H, W, atmvfi_output_rounding() != 0);
+  ATMVFI_CHECK_LAUNCH("pack5_planar");
+  return 0;
+}
+
 int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch, const float* w9c,
                           const float* bias, void* stream) {
   ATMVFI_REQUIRE(C % 4 == 0 && pitch % 4 == 0, "dwconv3x3_gelu: C=%d pitch=%d must be multiples of 4", C, pitch);
-  int64_t n = (int64_t)B * H * W * (C / 4);
+  int64_t n = (int64_t)B * ((H + kDwRows - 1) / kDwRows) * W * (C / 4);
   if (n <= 0) return 0;
   dwconv_gelu_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("dwconv3x3_gelu");

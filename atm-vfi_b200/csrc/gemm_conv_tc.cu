@@ -31,13 +31,16 @@ constexpr int kChunk = 32;                      // fp32 elements per K step = on
 constexpr int kMaxASlots = 4;
 constexpr int kMaxBSlots = 12;
 constexpr int kMaxBlockN = 256;
-constexpr int kDataBytes = 200 * 1024;          // A ring + B ring, carved per layer (see atmvfi_gemm_conv_tc)
+constexpr int kDataBytes = 184 * 1024;          // A ring + B ring, carved per layer (see atmvfi_gemm_conv_tc)
 constexpr int kMaxABoxBytes = 24 * 1024;        // up to 192 rows of 128 B (halo box), 128 rows otherwise
 constexpr int kBarOff = kDataBytes;
-constexpr int kEpiOff = kBarOff + 512;                       // 4 warps x (32 x 33 floats) staging + per-row info
-constexpr int kEpiBytes = 4 * 32 * 33 * 4 + 4 * 64 * 8;
-constexpr int kSmemBytes = kEpiOff + kEpiBytes + 1024 /*align*/;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;                                  // two warps per TMEM lane quarter, alternating column chunks
+constexpr int kEpiPitch = 36;                                 // floats per staged row: 16-byte aligned, conflict-free for 128-bit access
+constexpr int kEpiOff = kBarOff + 512;                        // per epilogue warp: 32 x 36 floats staging + 32 x int2 row info
+constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4 + 32 * 8;
+constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
+constexpr int kSmemBytes = kEpiOff + kEpiBytes;
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 
 struct TcPlan {                                 // host-side, produced by atmvfi_gemm_conv_plan
   CUtensorMap mapA[ATMVFI_MAX_SRC];
@@ -228,8 +231,8 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
 
 template <bool kHalo, int kCS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B atoms need a 1024-byte aligned base
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
   uint64_t* fullA = bars;                                  // [kMaxASlots]
   uint64_t* emptyA = fullA + kMaxASlots;                   // [kMaxASlots]
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxASlots; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], cs); }   // every CTA of the cluster releases a B slot
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
     mbar_init(&tempty[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -385,17 +388,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
     }
   } else if (warp >= 4) {
     // ======================================= epilogue ===========================================
-    // Each warp drains its own 32 TMEM lanes (= 32 output pixels): accumulators go through a padded
-    // per-warp smem tile so that global traffic is row-coalesced - 8 lanes x float4 cover 128 contiguous
-    // bytes of one output row, bias / PReLU slopes are fetched once per lane per 32-column chunk.
+    // Warp w drains TMEM lanes [32*(w%4), +32) (= 32 output pixels); the two warps of a quarter alternate over the
+    // 32-column chunks.  Accumulators pass through a padded per-warp smem tile so that global traffic is
+    // row-coalesced: 8 lanes x float4 cover 128 contiguous bytes of one output row; bias / PReLU slopes are
+    // fetched once per lane per chunk.
+    const int ew = warp - 4;                                  // 0..7
     const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-    float* stage = reinterpret_cast<float*>(smem + kEpiOff) + q * (32 * 33);
-    int64_t* s_orow = reinterpret_cast<int64_t*>(smem + kEpiOff + 4 * 32 * 33 * 4) + q * 64;
-    int64_t* s_m = s_orow + 32;
+    const int half = ew >> 2;                                 // which chunk parity this warp takes
+    float* stage = reinterpret_cast<float*>(smem + kEpiOff + ew * kEpiWarpBytes);
+    int2* s_row = reinterpret_cast<int2*>(smem + kEpiOff + ew * kEpiWarpBytes + 32 * kEpiPitch * 4);   // (orow, m) per row
     const int m_local = q * 32 + lane;
     const int th = m_local / p.TW, tw = m_local % p.TW;
     const int l8 = lane & 7, rsub = lane >> 3, col = 4 * l8;
     const EpiParams& e = p.epi;
+    const bool rnd = e.round != 0;
     uint32_t tcount = 0;
     for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * kMaxBlockN;
       int last_q = -1;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
         const int n0 = n_tile * p.block_n + c0;               // first GEMM column of this chunk (warp-uniform)
         int sq = 0, co0 = n0;
         if (e.out_mode == ATMVFI_OUT_SHUFFLE2) { sq = n0 / p.cq_pad; co0 = n0 - sq * p.cq_pad; }
@@ -418,12 +424,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
         tc_ld32(trow + c0, r);
         tc_wait_ld();
         if (sq != last_q) {
-          s_orow[lane] = row_ok ? epi_out_row(e, m, sq) : -1;
-          s_m[lane] = m;
+          const int64_t orow = row_ok ? epi_out_row(e, m, sq) : -1;
+          s_row[lane] = make_int2((int)orow, (int)m);
           last_q = sq;
         }
 #pragma unroll
-        for (int c = 0; c < 32; ++c) stage[lane * 33 + c] = __uint_as_float(r[c]);
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(&stage[lane * kEpiPitch + c]) =
+              make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
         __syncwarp();
         const int nvalid = min(32, e.Cout - co0);
         const bool full4 = col + 4 <= nvalid;
@@ -435,60 +443,60 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
             if (e.prelu) sl[k] = __ldg(e.prelu + co0 + col + k);
             if (e.out2) sl2[k] = __ldg(e.prelu2 + co0 + col + k);
           }
-#pragma unroll 2
-        for (int rr = 0; rr < 8; ++rr) {
-          const int row = rr * 4 + rsub;
-          const int64_t orow = s_orow[row];
-          if (orow < 0 || col >= nvalid) continue;
-          float v[4];
+        if (col < nvalid) {
+#pragma unroll 4
+          for (int rr = 0; rr < 8; ++rr) {
+            const int row = rr * 4 + rsub;
+            const int2 ri = s_row[row];
+            if (ri.x < 0) continue;
+            const float4 a4 = *reinterpret_cast<const float4*>(&stage[row * kEpiPitch + col]);
+            float v[4] = {a4.x + bz[0], a4.y + bz[1], a4.z + bz[2], a4.w + bz[3]};
+            if (e.residual) {
+              const float* rs = e.residual + (int64_t)ri.y * e.res_pitch + co0 + col;
+              if (full4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(rs));
+                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+              } else {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = stage[row * 33 + col + k] + bz[k];
-          if (e.residual) {
-            const float* rs = e.residual + s_m[row] * e.res_pitch + co0 + col;
-            if (full4) {
-              float4 t = __ldg(reinterpret_cast<const float4*>(rs));
-              v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (col + k < nvalid) v[k] += __ldg(rs + k);
+                for (int k = 0; k < 4; ++k)
+                  if (col + k < nvalid) v[k] += __ldg(rs + k);
+              }
             }
-          }
-          if (e.prelu) {
+            if (e.prelu) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * sl[k];
-          }
-          const bool rnd = e.round != 0;
-          float w[4];
-          if (e.out2) {
+              for (int k = 0; k < 4; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * sl[k];
+            }
+            float w[4];
+            if (e.out2) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) w[k] = round_tf32_if(v[k] > 0.f ? v[k] : v[k] * sl2[k], rnd);
-          }
+              for (int k = 0; k < 4; ++k) w[k] = round_tf32_if(v[k] > 0.f ? v[k] : v[k] * sl2[k], rnd);
+            }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) v[k] = round_tf32_if(v[k], rnd);
-          float* o1 = e.out + orow * e.out_pitch + co0 + col;
-          if (full4) {
-            *reinterpret_cast<float4*>(o1) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (col + k < nvalid) o1[k] = v[k];
-          }
-          if (e.out2) {
-            float* o2 = e.out2 + orow * e.out2_pitch + co0 + col;
+            for (int k = 0; k < 4; ++k) v[k] = round_tf32_if(v[k], rnd);
+            float* o1 = e.out + (int64_t)ri.x * e.out_pitch + co0 + col;
             if (full4) {
-              *reinterpret_cast<float4*>(o2) = make_float4(w[0], w[1], w[2], w[3]);
+              *reinterpret_cast<float4*>(o1) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                if (col + k < nvalid) o2[k] = w[k];
+                if (col + k < nvalid) o1[k] = v[k];
+            }
+            if (e.out2) {
+              float* o2 = e.out2 + (int64_t)ri.x * e.out2_pitch + co0 + col;
+              if (full4) {
+                *reinterpret_cast<float4*>(o2) = make_float4(w[0], w[1], w[2], w[3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (col + k < nvalid) o2[k] = w[k];
+              }
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);                 // 4 epilogue warps -> accumulator stage free
+      if (lane == 0) mbar_arrive(&tempty[as]);                 // kEpiWarps arrivals -> accumulator stage free
     }
   }
 

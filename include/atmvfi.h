@@ -134,6 +134,16 @@ int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out
 int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch,
                           const float* w9c /* [9][C] */, const float* bias, void* stream);
 
+/* First encoder layer (feat_extracts.0.0, network_base.py:103): Conv2d(3 -> Cout, k3, p1) + PReLU read straight from
+ * the planar frame, written channels-last.  wk: [27][ldw] with row = (ky*3+kx)*3 + c (the FP32 packing of atmvfi_gemm_conv). */
+int atmvfi_conv3x3_first(const float* img, const float* wk, int ldw, const float* bias, const float* prelu, float* out,
+                         int out_pitch, int B, int H, int W, int Cout, void* stream);
+
+/* Five planar [B,3,H,W] images -> channels [0,15) of an NHWC buffer (channel 15 zeroed): the image part of
+ * torch.cat([feat, im0, I_t_0, im1, I_t_1, I_t], 1) at network_base.py:418, in one coalesced pass. */
+int atmvfi_pack5_planar(const float* s0, const float* s1, const float* s2, const float* s3, const float* s4, float* out,
+                        int out_pitch, int B, int H, int W, void* stream);
+
 /* flow_warp.flow_warp (flow_warp.py:50-60) on planar tensors: out[b,c] = bilinear(img[b,c], grid+flow[b]). */
 int atmvfi_flow_warp_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream);
 

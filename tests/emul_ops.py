@@ -120,6 +120,20 @@ class EmulOps:
 
         self._emit(run)
 
+    def conv3x3_first(self, img, w: PackedGemm, out: Map):
+        def run():
+            wt = w.w32[:, : w.Cout].reshape(3, 3, 3, w.Cout).permute(3, 2, 0, 1)
+            y = F.conv2d(img, wt, w.bias, padding=1)
+            y = torch.where(y > 0, y, y * w.prelu.view(1, -1, 1, 1))
+            out.view().copy_(y.permute(0, 2, 3, 1))
+        self._emit(run)
+
+    def pack5_planar(self, imgs, out: Map):
+        def run():
+            out.t[..., :15] = torch.cat([t.permute(0, 2, 3, 1) for t in imgs], -1)
+            out.t[..., 15] = 0
+        self._emit(run)
+
     def layernorm(self, x: Map, out: Map, gamma, beta):
         self._emit(lambda: out.view().copy_(F.layer_norm(x.view(), (x.C,), gamma, beta, 1e-5)))
 

@@ -248,3 +248,23 @@ def test_errors_are_loud(ops):
         cu.layernorm(to_gpu(x), to_gpu(x), torch.ones(30).cuda(), torch.zeros(30).cuda())
     with pytest.raises(_lib.AtmvfiError):
         CudaOps(torch.device("cpu"))
+
+
+@pytest.mark.parametrize("Co", [16, 24])
+def test_conv3x3_first_and_pack5(ops, Co):
+    cu, em = ops
+    g = gen(11)
+    P = _conv_weights(3, Co, 3, g)
+    w = pack.pack_conv(P, "c", prelu="p")
+    img = torch.rand(2, 3, 37, 53, generator=g)
+    out = rand_map(2, 37, 53, Co, gen=g)
+    og = to_gpu(out)
+    em.conv3x3_first(img, w, out)
+    cu.conv3x3_first(img.cuda(), _pg_to_gpu(w), og)
+    assert max_err(og, out) < 1e-5
+    imgs = [torch.rand(2, 3, 37, 53, generator=g) for _ in range(5)]
+    m = Map(torch.full((2, 37, 53, 16), 7.0), 0, 15)
+    mg = to_gpu(m)
+    em.pack5_planar(imgs, m)
+    cu.pack5_planar([t.cuda() for t in imgs], mg)
+    assert torch.equal(mg.t.cpu(), m.t)
