@@ -81,9 +81,9 @@ def tc_layout(split: Sequence[int], ksize: int, cout: int, shuffle: bool) -> dic
     chunks = [-(-c // TC_CHUNK) for c in split]
     ktc = ksize * ksize * sum(chunks) * TC_CHUNK
     cq_pad = round_up(cout, 32)
-    n_need = 4 * cq_pad if shuffle else cq_pad
+    n_need = 4 * cq_pad if shuffle else round_up(cout, 16)
     n_tiles = -(-n_need // TC_MAX_N)
-    block_n = round_up(-(-n_need // n_tiles), 32)
+    block_n = round_up(-(-n_need // n_tiles), 32 if shuffle else 16)
     return dict(chunks=chunks, ktc=ktc, cq_pad=cq_pad, n_tiles=n_tiles, block_n=block_n, n_pad=n_tiles * block_n)
 
 

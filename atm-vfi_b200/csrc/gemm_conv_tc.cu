@@ -62,6 +62,7 @@ struct TcParams {
   CUtensorMap mapB;
   int nsrc;
   int chunks[ATMVFI_MAX_SRC];
+  int last_mmas[ATMVFI_MAX_SRC];               // K=8 MMAs needed by the last (partial) 32-channel chunk of each source
   int ntaps, ksize, stride, dil, pad;
   int TW, TH, tiles_x, tiles_y, B;
   int block_n, n_tiles, cq_pad;
@@ -195,11 +196,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte swizzle: 8-row groups of 1024 B (SBO = 1024), LBO unused, descriptor version 1 (sm_100).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);          // start address, bits [0,14)
   d |= (uint64_t)1 << 16;                             // leading byte offset (ignored for swizzled K-major), bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;              // stride byte offset (between 8-row groups), bits [32,46)
   d |= (uint64_t)1 << 46;                             // descriptor version, bits [46,48)
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B, bits [61,64)
   return d;
@@ -229,7 +230,7 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
   ox0 = tx * p.TW;
 }
 
-template <bool kHalo, int kCS>
+template <int kHalo, int kCS>
 __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B atoms need a 1024-byte aligned base
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
   // K is walked as "A groups" (one activation box in smem) x "steps" (one weight tile, 4 MMAs each):
   //   halo mode : group = (source, chunk, kx), steps ky = 0..2 reuse the box at row offset ky*TW
   //   otherwise : group = (tap, source, chunk), a single step
-  constexpr int steps_per_group = kHalo ? 3 : 1;
+  constexpr int steps_per_group = kHalo == 2 ? 9 : (kHalo == 1 ? 3 : 1);
   const int b_rows = p.block_n / cs;                         // rows of the B tile this CTA fetches
   const int kASlots = p.a_slots, kBSlots = p.b_slots;
   uint8_t* const ringA = smem;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
           for (int s = 0; s < p.nsrc; ++s) {
             const CUtensorMap* mapA = s == 0 ? &p.mapA[0] : (s == 1 ? &p.mapA[1] : (s == 2 ? &p.mapA[2] : &p.mapA[3]));
             for (int c = 0; c < p.chunks[s]; ++c) {
-              constexpr int inner = kHalo ? 3 : 1;
+              constexpr int inner = kHalo == 1 ? 3 : 1;
               for (int kx_i = 0; kx_i < inner; ++kx_i) {
                 int ix, iy;
                 if (kHalo) {
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
                 }
                 __syncwarp();
                 for (int st = 0; st < steps_per_group; ++st) {
-                  const int tap = kHalo ? st * 3 + kx_i : tap_o;
+                  const int tap = kHalo == 2 ? st : (kHalo == 1 ? st * 3 + kx_i : tap_o);
                   const int kb = tap * p.sum_chunks + cbase + c;
                   mbar_wait(&emptyB[bs_], bph_ ^ 1);
                   if (elect_one()) {
@@ -333,8 +334,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
     // ======================================= MMA issuer =========================================
     {
       const uint32_t idesc = make_idesc_tf32(p.block_n);
-      const int groups = (kHalo ? 3 : p.ntaps) * p.sum_chunks;
-      const uint32_t a_step = kHalo ? (uint32_t)(p.TW * 128) >> 4 : 0;      // descriptor units of 16 B per vertical tap
+      const int groups = (kHalo == 2 ? 1 : (kHalo == 1 ? 3 : p.ntaps)) * p.sum_chunks;
+      const uint32_t a_step = kHalo == 1 ? (uint32_t)(p.TW * 128) >> 4 : 0;      // descriptor units of 16 B per vertical tap
+      const uint32_t a_sbo = kHalo == 2 ? (uint32_t)((p.TW + 2) * 128) : 1024u;   // full-halo box: tile rows are TW+2 pixels apart
       uint32_t tcount = 0;
       int as_ = 0, bs_ = 0;
       uint32_t aph_ = 0, bph_ = 0;
@@ -349,8 +351,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
         uint32_t first = 1;
         mbar_wait(&fullA[as_], aph_);
         mbar_wait(&fullB[bs_], bph_);
-        for (int g = 0; g < groups; ++g) {
-          const uint64_t adesc0 = make_smem_desc(smem_u32(ringA + as_ * p.a_slot_bytes));
+        int g = 0;
+        const int outer = kHalo ? 1 : p.ntaps;
+        const int inner = kHalo == 1 ? 3 : 1;
+        for (int tap_o = 0; tap_o < outer; ++tap_o)
+        for (int s = 0; s < p.nsrc; ++s)
+        for (int c = 0; c < p.chunks[s]; ++c) {
+          const int nmma = (c == p.chunks[s] - 1) ? p.last_mmas[s] : 4;     // skip all-zero K slices of a partial chunk
+        for (int kx_i = 0; kx_i < inner; ++kx_i, ++g) {
+          const uint64_t adesc0 = make_smem_desc(smem_u32(ringA + as_ * p.a_slot_bytes), a_sbo);
           int as_n = as_ + 1;
           uint32_t aph_n = aph_;
           if (as_n == kASlots) { as_n = 0; aph_n ^= 1; }
@@ -366,12 +375,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
               if (last_step) okA = mbar_test_wait(&fullA[as_n], aph_n);
             }
             tc_fence_after();
-            const uint64_t adesc = adesc0 + (uint64_t)(st * a_step);
+            const uint64_t adesc = adesc0 + (kHalo == 2 ? (uint64_t)((((st / 3) * (p.TW + 2) + (st % 3)) * 128) >> 4) : (uint64_t)(st * a_step));
             const uint64_t bdesc = make_smem_desc(smem_u32(ringB + bs_ * p.b_slot_bytes));
             if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)   // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
-                tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+              for (int j = 0; j < 4; ++j)   // up to 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
+                if (j < nmma) tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
               if (cs > 1) tc_commit_mc(&emptyB[bs_], mc_mask); else tc_commit(&emptyB[bs_]);
               if (last_step) tc_commit(&emptyA[as_]);      // frees the activation box once its MMAs retire
               if (last_of_tile) tc_commit(&tfull[as]);     // accumulator complete
@@ -383,6 +392,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
             if (last_step && !okA) mbar_wait(&fullA[as_n], aph_n);
           }
           as_ = as_n; aph_ = aph_n;
+        }
         }
       }
     }
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
           *reinterpret_cast<float4*>(&stage[lane * kEpiPitch + c]) =
               make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
         __syncwarp();
-        const int nvalid = min(32, e.Cout - co0);
+        const int nvalid = min(min(32, p.block_n - c0), e.Cout - co0);   // block_n may end inside this 32-column chunk
         const bool full4 = col + 4 <= nvalid;
         float bz[4] = {0.f, 0.f, 0.f, 0.f}, sl[4] = {1.f, 1.f, 1.f, 1.f}, sl2[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
@@ -548,7 +558,7 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   // 3x3 stride-1 layers fetch activation boxes with a vertical halo and reuse them for the 3 vertical taps
   static int halo_ok = -1;
   if (halo_ok < 0) { const char* ev = getenv("ATMVFI_TC_HALO"); halo_ok = ev ? atoi(ev) : 1; }
-  pl->halo = (halo_ok && d->ksize == 3 && d->stride == 1 && d->dil == 1) ? 1 : 0;
+  pl->halo = (halo_ok && d->ksize == 3 && d->stride == 1 && d->dil == 1) ? halo_ok : 0;   // 1: 3 boxes / chunk, 2: one full-halo box
   // pixel tile TW x TH = 128: least padding waste, then squarest.  Element-strided boxes are capped at 256
   // per dimension; halo boxes need TW % 8 == 0 (vertical taps = whole swizzle atoms) and (TH+2)*TW <= 192 rows.
   int best_tw = 0;
@@ -557,7 +567,8 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   for (int i = 0; i < 5; ++i) {
     int tw = cands[i], th = 128 / tw;
     if (tw * d->stride > 256 || th * d->stride > 256) continue;
-    if (pl->halo && (th + 2) * tw * 128 > kMaxABoxBytes) continue;
+    if (pl->halo == 1 && (th + 2) * tw * 128 > kMaxABoxBytes) continue;
+    if (pl->halo == 2 && tw != 8) continue;          // full-halo box: every tile row must be one 8-row swizzle group
     int64_t cost = (int64_t)cdiv(d->Wout, tw) * cdiv(d->Hout, th);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
   }
@@ -574,10 +585,10 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   }
 
   const bool shuffle = d->out_mode == ATMVFI_OUT_SHUFFLE2;
-  pl->cq_pad = round_up_i(d->Cout, 32);
-  const int n_need = shuffle ? 4 * pl->cq_pad : pl->cq_pad;
+  pl->cq_pad = round_up_i(d->Cout, 32);           // ConvTranspose: each of the 4 column blocks starts on a 32-column chunk
+  const int n_need = shuffle ? 4 * pl->cq_pad : round_up_i(d->Cout, 16);
   pl->n_tiles = cdiv(n_need, kMaxBlockN);
-  pl->block_n = round_up_i(cdiv(n_need, pl->n_tiles), 32);
+  pl->block_n = round_up_i(cdiv(n_need, pl->n_tiles), shuffle ? 32 : 16);
   const int n_pad = pl->n_tiles * pl->block_n;
 
   int ktc = 0;
@@ -593,7 +604,8 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     ATMVFI_REQUIRE(((uintptr_t)sr.ptr & 15) == 0 && sr.pitch % 4 == 0, "gemm_conv(tf32): source %d must be 16-byte aligned with pitch %% 4 == 0", s);
     cuuint64_t gdim[4] = {(cuuint64_t)sr.C, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
     cuuint64_t gstr[3] = {(cuuint64_t)sr.pitch * 4, (cuuint64_t)sr.pitch * 4 * d->Win, (cuuint64_t)sr.pitch * 4 * d->Win * d->Hin};
-    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)(pl->TW * d->stride), (cuuint32_t)((pl->halo ? pl->TH + 2 : pl->TH) * d->stride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)((pl->halo == 2 ? pl->TW + 2 : pl->TW) * d->stride),
+                         (cuuint32_t)((pl->halo ? pl->TH + 2 : pl->TH) * d->stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     CUresult r = enc(&pl->mapA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sr.ptr), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -622,18 +634,18 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   const TcPlan* pl = reinterpret_cast<const TcPlan*>(d->tma_host);
   ATMVFI_REQUIRE(pl && pl->magic == kPlanMagic, "gemm_conv(tf32): missing plan (call atmvfi_gemm_conv_plan first)");
   typedef void (*KernelFn)(TcParams);
-  KernelFn kern = nullptr;
-  if (pl->halo) kern = pl->cluster == 2 ? gemm_conv_tc_kernel<true, 2> : (pl->cluster == 4 ? gemm_conv_tc_kernel<true, 4> : gemm_conv_tc_kernel<true, 1>);
-  else kern = pl->cluster == 2 ? gemm_conv_tc_kernel<false, 2> : (pl->cluster == 4 ? gemm_conv_tc_kernel<false, 4> : gemm_conv_tc_kernel<false, 1>);
+  static const KernelFn table[3][3] = {
+      {gemm_conv_tc_kernel<0, 1>, gemm_conv_tc_kernel<0, 2>, gemm_conv_tc_kernel<0, 4>},
+      {gemm_conv_tc_kernel<1, 1>, gemm_conv_tc_kernel<1, 2>, gemm_conv_tc_kernel<1, 4>},
+      {gemm_conv_tc_kernel<2, 1>, gemm_conv_tc_kernel<2, 2>, gemm_conv_tc_kernel<2, 4>}};
+  KernelFn kern = table[pl->halo][pl->cluster == 4 ? 2 : pl->cluster - 1];
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    KernelFn all[6] = {gemm_conv_tc_kernel<true, 1>, gemm_conv_tc_kernel<true, 2>, gemm_conv_tc_kernel<true, 4>,
-                       gemm_conv_tc_kernel<false, 1>, gemm_conv_tc_kernel<false, 2>, gemm_conv_tc_kernel<false, 4>};
-    for (int i = 0; i < 6; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    for (int i = 0; i < 9; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(table[i / 3][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) {
         num_sms = 0;
         atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
@@ -646,12 +658,17 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   memcpy(&p.mapB, &pl->mapB, sizeof(p.mapB));
   p.nsrc = pl->nsrc;
   int ch = 0;
-  for (int s = 0; s < ATMVFI_MAX_SRC; ++s) { p.chunks[s] = pl->chunks[s]; ch += pl->chunks[s]; }
+  for (int s = 0; s < ATMVFI_MAX_SRC; ++s) {
+    p.chunks[s] = pl->chunks[s];
+    ch += pl->chunks[s];
+    const int rem = s < d->nsrc ? d->src[s].C % kChunk : 0;
+    p.last_mmas[s] = rem ? (rem + 7) / 8 : 4;
+  }
   p.ntaps = pl->ntaps; p.ksize = pl->ksize; p.stride = pl->stride; p.dil = pl->dil; p.pad = pl->pad;
   p.TW = pl->TW; p.TH = pl->TH; p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.B = pl->B;
   p.block_n = pl->block_n; p.n_tiles = pl->n_tiles; p.cq_pad = pl->cq_pad;
   p.halo = pl->halo;
-  p.a_bytes = (pl->halo ? (pl->TH + 2) * pl->TW : kBlockM) * 128;
+  p.a_bytes = (pl->halo == 2 ? (pl->TH + 2) * (pl->TW + 2) : (pl->halo ? (pl->TH + 2) * pl->TW : kBlockM)) * 128;
   p.sum_chunks = ch;
   p.a_slots = pl->halo ? 3 : 4;
   p.a_slot_bytes = (p.a_bytes + 1023) / 1024 * 1024;
