@@ -59,6 +59,7 @@ PROTOTYPES = {
     "atmvfi_window_attention": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     "atmvfi_conv3x3_first": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_pack5_planar": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "atmvfi_window_attention_tc": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     "atmvfi_dwconv3x3_gelu": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "atmvfi_flow_warp_nchw": [_P, _P, _P, _I, _I, _I, _I, _P],
     "atmvfi_flow_warp_nhwc": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P],

@@ -24,6 +24,13 @@ class _Block:
     pass
 
 
+def relative_coord_closed_form(ws: int) -> torch.Tensor:
+    """[2,N,N] key-minus-query offsets: what attention.py:150-165 stores in the ``relative_coord`` buffer."""
+    idx = torch.arange(ws * ws)
+    px, py = (idx % ws).float(), (idx // ws).float()
+    return torch.stack([px[None, :] - px[:, None], py[None, :] - py[:, None]], 0)
+
+
 class PackedModel:
     def __init__(self, arch: Arch, P: Params, local_ws: int, global_ws: int, with_global: bool = True):
         self.arch, self.local_ws, self.global_ws = arch, local_ws, global_ws
@@ -47,6 +54,7 @@ class PackedModel:
             if atm:
                 rc = f32(n + ".attn.relative_coord")
                 b.rc = rc.reshape(2, rc.shape[-2], rc.shape[-1]).contiguous()
+                b.rc_closed = bool(torch.equal(b.rc.cpu(), relative_coord_closed_form(int(round(rc.shape[-1] ** 0.5)))))
                 b.mix = (f32(n + ".attn.mlp.0.weight"), f32(n + ".attn.mlp.0.bias"),
                          f32(n + ".attn.mlp.2.weight").reshape(-1).contiguous(), f32(n + ".attn.mlp.2.bias"))
             return b
@@ -98,7 +106,8 @@ def transformer_block(ops, blk, tok: Map, g: WinGeom, motion: Optional[Map] = No
     ao = ops.new_map(1, 1, g.rows, C)
     if blk.atm and motion is not None:
         scratch = torch.empty(g.rows * NUM_HEADS * 2, device=xw.t.device, dtype=torch.float32)
-        ops.window_attention(qkv, ao, g, NUM_HEADS, True, blk.rc, blk.mix, motion, motion_off, scratch)
+        ops.window_attention(qkv, ao, g, NUM_HEADS, True, blk.rc, blk.mix, motion, motion_off, scratch,
+                             rc_closed_form=getattr(blk, "rc_closed", False))
     else:
         ops.window_attention(qkv, ao, g, NUM_HEADS, blk.atm)
     t2 = ops.new_map(tok.B, tok.H, tok.W, C)

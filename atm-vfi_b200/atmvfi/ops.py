@@ -163,7 +163,13 @@ class CudaOps:
     @staticmethod
     def count_launches(records) -> int:
         # one kernel per record, except attention-with-motion which also launches the head-mix kernel
-        return sum(2 if (name == "atmvfi_window_attention" and args[13] is not None) else 1 for name, _, args, _ in records)
+        def n(name, args):
+            if name == "atmvfi_window_attention":
+                return 2 if args[13] is not None else 1
+            if name == "atmvfi_window_attention_tc":
+                return 2 if args[14] is not None else 1
+            return 1
+        return sum(n(name, args) for name, _, args, _ in records)
 
     # -- GEMM-shaped layers -------------------------------------------------------------------
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride: int = 1, dil: int = 1,
@@ -255,14 +261,17 @@ class CudaOps:
 
     def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads: int, cross: bool, rc: Optional[torch.Tensor] = None,
                          mix: Optional[Sequence[torch.Tensor]] = None, motion: Optional[Map] = None, motion_off: int = 0,
-                         scratch: Optional[torch.Tensor] = None):
+                         scratch: Optional[torch.Tensor] = None, rc_closed_form: bool = False):
         assert qkv.C == 3 * out.C and qkv.nrows == g.rows == out.nrows
         gc = g.c()
         m = [None] * 4 if mix is None else [t.data_ptr() for t in mix]
-        self._emit("atmvfi_window_attention",
-                   (qkv.ptr, qkv.pitch, out.ptr, out.pitch, out.C, heads, C.byref(gc), int(cross), _p(rc), m[0], m[1], m[2], m[3],
-                    None if motion is None else motion.ptr, 0 if motion is None else motion.pitch, motion_off, _p(scratch)),
-                   keep=(qkv, out, gc, rc, mix, motion, scratch))
+        tail = (m[0], m[1], m[2], m[3], None if motion is None else motion.ptr, 0 if motion is None else motion.pitch, motion_off, _p(scratch))
+        head = (qkv.ptr, qkv.pitch, out.ptr, out.pitch, out.C, heads, C.byref(gc), int(cross), _p(rc))
+        keep = (qkv, out, gc, rc, mix, motion, scratch)
+        if self.precision == _lib.TF32:
+            self._emit("atmvfi_window_attention_tc", head + (int(rc_closed_form),) + tail, keep=keep)
+        else:
+            self._emit("atmvfi_window_attention", head + tail, keep=keep)
 
     def dwconv_gelu(self, x: Map, out: Map, w9c: torch.Tensor, bias: torch.Tensor):
         assert x.c0 == 0 and out.c0 == 0 and x.pitch == out.pitch and x.C == out.C

@@ -153,10 +153,34 @@ int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch,
 
 }  // namespace
 
+int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, cudaStream_t st);
+
+static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                          const atmvfi_window_geom* g, int cross, const float* relative_coord, const float* mix_w0, const float* mix_b0,
+                          const float* mix_w2, const float* mix_b2, float* motion, int motion_pitch, int motion_off, float* scratch,
+                          void* stream);
+
+extern "C" int atmvfi_window_attention_tc(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                                          const atmvfi_window_geom* g, int cross, const float* relative_coord, int rc_closed_form,
+                                          const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
+                                          float* motion, int motion_pitch, int motion_off, float* scratch, void* stream) {
+  return attention_impl(true, rc_closed_form, qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, relative_coord, mix_w0, mix_b0, mix_w2,
+                        mix_b2, motion, motion_pitch, motion_off, scratch, stream);
+}
+
 extern "C" int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                                        const atmvfi_window_geom* g, int cross, const float* relative_coord,
                                        const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
                                        float* motion, int motion_pitch, int motion_off, float* scratch, void* stream) {
+  return attention_impl(false, 0, qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, relative_coord, mix_w0, mix_b0, mix_w2, mix_b2,
+                        motion, motion_pitch, motion_off, scratch, stream);
+}
+
+static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                          const atmvfi_window_geom* g, int cross, const float* relative_coord, const float* mix_w0, const float* mix_b0,
+                          const float* mix_w2, const float* mix_b2, float* motion, int motion_pitch, int motion_off, float* scratch,
+                          void* stream) {
   ATMVFI_REQUIRE(heads > 0 && C % heads == 0, "window_attention: dim %d should be divided by num_heads %d", C, heads);
   const int hd = C / heads, N = g->ws * g->ws;
   ATMVFI_REQUIRE(N <= 256, "window_attention: window %d too large (max 16)", g->ws);
@@ -169,7 +193,10 @@ extern "C" int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* o
   cudaStream_t st = (cudaStream_t)stream;
   float* raw = want_motion ? scratch : nullptr;
   const float* rc = want_motion ? relative_coord : nullptr;
-  int rcode;
+  int rcode = 3;
+  if (tensor_cores)
+    rcode = atmvfi_window_attention_tc_launch(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, (want_motion && !rc_closed_form) ? rc : nullptr, raw, st);
+  if (rcode == 3)      // shape outside the tcgen05 kernel's envelope (or fp32 requested): CUDA-core kernel
   switch (hd) {
     case 28: rcode = launch_attention<28>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
     case 44: rcode = launch_attention<44>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;

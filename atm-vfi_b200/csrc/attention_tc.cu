@@ -1,0 +1,370 @@
+// Window attention + attention-to-motion on the 5th-generation tensor cores (attention.py:187-213, 370-390).
+//
+// One CTA (128 threads) per work item = (window group, head, 128-row query tile):
+//   * windows of N <= 64 tokens are processed 128/N at a time (a block-diagonal 128 x 128 problem, the
+//     off-diagonal blocks are excluded in the softmax), larger windows (N = 144 for the global branch) one
+//     at a time in query tiles of 128 rows;
+//   * Q, K (K-major) and V^T are staged in shared memory in the SWIZZLE_128B layout, rounded to TF32;
+//   * S = Q K^T   : tcgen05.mma kind::tf32, M = 128, N = keys (multiple of 16), accumulator in TMEM;
+//   * softmax     : thread r owns row r = TMEM lane r: scale, additive -100 masks evaluated from the window
+//                   geometry, max, exp, sum; the motion expectation sum_j p_ij * relative_coord[:, i, j] is
+//                   accumulated in the same pass; P (unnormalised, TF32) overwrites the Q/K staging area;
+//   * O = P V     : second tcgen05.mma chain into other TMEM columns; rows are scaled by 1/l on the way out.
+// The reference materialises [B',8,N,N] attention and a [B',8,2,N,N] product for the motion; here nothing but
+// the per-head outputs and two floats per (token, head) ever reach HBM.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int kRows = 128;
+constexpr int kThreadsA = 256;     // two threads per query row (they split the key chunks); warps w and w+4 share TMEM lanes
+
+struct AttnParams {
+  const float* qkv;
+  int qkv_pitch;
+  float* out;
+  int out_pitch;
+  int C, heads, hd;
+  atmvfi_window_geom g;
+  int cross;
+  const float* rc;            // [2][N][N] or nullptr (closed form: key position - query position)
+  float* motion_raw;          // [rows][heads][2] or nullptr
+  int N, wpi, mtiles, KP, HP, chunksH, chunksK;
+  int total_windows, nW;
+  int tmem_cols;
+  int round;
+  float scale;
+  // shared memory carve-up (bytes)
+  int offK, offV, offLab, offBar;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t swz(int row, int c) {   // byte offset of float column c (0..31) of a 128-byte row
+  return (uint32_t)(row * 128 + ((((c >> 2) ^ (row & 7)) << 4) | ((c & 3) << 2)));
+}
+__device__ __forceinline__ uint64_t sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(s_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32r(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                         // chunksH x [128 x 128 B]; later P: chunksK x [128 x 128 B]
+  uint8_t* sK = smem + p.offK;                // chunksH x [KP x 128 B]
+  uint8_t* sV = smem + p.offV;                // chunksK x [HP x 128 B]   (V transposed: row = channel, column = key)
+  int* sLab = reinterpret_cast<int*>(smem + p.offLab);           // [KP] mask label per key
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.offBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+  const int tid = threadIdx.x & (kRows - 1), part = threadIdx.x >> 7, warp = (threadIdx.x >> 5) & 3;
+  const int N = p.N, hd = p.hd;
+  float* sRed = reinterpret_cast<float*>(smem + p.offBar + 64);      // [4][2][128] partial max / sum / motion x / motion y
+  // work item
+  int item = blockIdx.x;
+  const int mt = item % p.mtiles;
+  item /= p.mtiles;
+  const int h = item % p.heads;
+  const int wg = item / p.heads;
+  const int64_t total_win = p.total_windows;
+  const int64_t win0 = (int64_t)wg * p.wpi;
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(&bars[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+
+  // ---- row / key bookkeeping (one row per thread: no per-element index arithmetic) ----------------------------
+  const int nslH = (hd + 7) >> 3;             // K = 8 slices of the head dimension
+  const int hd_pad = nslH * 8;
+  const bool masked = (p.g.shift != 0) || p.g.Hp != p.g.H || p.g.Wp != p.g.W;
+  const int nwx = p.g.Wp / p.g.ws;
+  const int ws = p.g.ws;
+  // (window-local index, token) of row / key `r`; window < 0: padding row of the tile
+  auto locate = [&](int r, int base_tok, int& wl, int& tok) -> int64_t {
+    if (p.wpi == 1) { wl = 0; tok = base_tok + r; return tok < N ? win0 : -1; }
+    wl = r / N;
+    tok = r - wl * N;
+    return (wl < p.wpi && win0 + wl < total_win) ? win0 + wl : -1;
+  };
+  auto mask_label = [&](int64_t w, int tok) -> int {
+    if (!masked) return 0;
+    const int wi = (int)(w % p.nW);
+    return win_mask_label(p.g, (wi / nwx) * ws + tok / ws, (wi % nwx) * ws + tok % ws);
+  };
+
+  // ---- stage Q (thread = query row), K and V^T (thread = key), TF32-rounded, swizzled -----------------------
+  int wl_i, tok_i;
+  const int64_t win_i = locate(tid, mt * kRows, wl_i, tok_i);
+  const bool row_ok = win_i >= 0;
+  {
+    const float* src = p.qkv + (row_ok ? (win_i * N + tok_i) * p.qkv_pitch + h * hd : 0);
+    for (int c = part * 4; c < hd_pad; c += 8) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok && c < hd) v = __ldg(reinterpret_cast<const float4*>(src + c));
+      *reinterpret_cast<float4*>(sQ + (c >> 5) * (kRows * 128) + swz(tid, c & 31)) = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
+    }
+  }
+  for (int kk = threadIdx.x; kk < p.chunksK * 32; kk += kThreadsA) {
+    int wl, tok;
+    const int64_t w = kk < p.KP ? locate(kk, 0, wl, tok) : -1;
+    const bool ok = w >= 0;
+    const float* src = p.qkv;
+    if (ok) {
+      const int64_t wk = p.cross ? (w + total_win / 2) % total_win : w;       // the other frame's copy of the window (attention.py:318)
+      src = p.qkv + (wk * N + tok) * p.qkv_pitch + p.C + h * hd;
+    }
+    if (kk < p.KP) {
+      // key meta: bits [0,12) mask label, [12,16) window-local index, [16,24) x, [24,32) y; -1 = excluded key
+      sLab[kk] = ok ? (mask_label(w, tok) | (wl << 12) | ((tok % ws) << 16) | ((tok / ws) << 24)) : -1;
+      for (int c = 0; c < hd_pad; c += 4) {
+        float4 kq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && c < hd) kq = __ldg(reinterpret_cast<const float4*>(src + c));
+        *reinterpret_cast<float4*>(sK + (c >> 5) * (p.KP * 128) + swz(kk, c & 31)) = make_float4(tf32r(kq.x), tf32r(kq.y), tf32r(kq.z), tf32r(kq.w));
+      }
+    }
+    // V^T: column kk of every channel row; rows hd..HP and columns KP.. are zero
+    for (int c = 0; c < p.HP; c += 4) {
+      float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok && c < hd) vq = __ldg(reinterpret_cast<const float4*>(src + p.C + c));
+      uint8_t* col = sV + (kk >> 5) * (p.HP * 128);
+      *reinterpret_cast<float*>(col + swz(c, kk & 31)) = tf32r(vq.x);
+      *reinterpret_cast<float*>(col + swz(c + 1, kk & 31)) = tf32r(vq.y);
+      *reinterpret_cast<float*>(col + swz(c + 2, kk & 31)) = tf32r(vq.z);
+      *reinterpret_cast<float*>(col + swz(c + 3, kk & 31)) = tf32r(vq.w);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + p.KP;
+
+  // ---- S = Q K^T ------------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    const uint32_t id = idesc_tf32(p.KP);
+    for (int s = 0; s < nslH; ++s) {
+      const int c = s >> 2, j = s & 3;
+      mma_tf32(tS, sdesc(s_u32(sQ + c * (kRows * 128))) + 2 * j, sdesc(s_u32(sK + c * (p.KP * 128))) + 2 * j, id, s ? 1u : 0u);
+    }
+    commit(&bars[0]);
+  }
+  bar_wait(&bars[0], 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- softmax + motion, row per thread ---------------------------------------------------------------------
+  const int lab_i = row_ok ? (mask_label(win_i, tok_i) | (wl_i << 12)) : 0;
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const float sc2 = p.scale * 1.4426950408889634f;              // logits are kept in the log2 domain: exp(x) = exp2(x*log2e)
+  const float mask2 = -100.0f * 1.4426950408889634f;
+  auto logit2 = [&](float s, int meta) -> float {               // -inf: excluded; else (scaled logit + additive mask) * log2(e)
+    if (meta < 0 || ((meta ^ lab_i) & 0xF000)) return -INFINITY; // padding key, or a key of another window of the group
+    float x = s * sc2;
+    if ((meta ^ lab_i) & 0xFFF) x += mask2;
+    return x;
+  };
+  // the two threads of a row take alternate 16-key chunks; chunks that belong entirely to another window of the group
+  // (N % 16 == 0) are never read: their probabilities are exactly zero
+  // (decided per WARP - tcgen05.ld is .aligned - from the first and last row of the warp; rows are window-ordered)
+  const bool skip_foreign = p.wpi > 1;
+  const int own_lo = __shfl_sync(0xffffffffu, wl_i * N, 0), own_hi = __shfl_sync(0xffffffffu, wl_i * N + N, 31);
+  float mx = -INFINITY;
+  for (int c0 = part * 16; c0 < p.KP; c0 += 32) {
+    if (skip_foreign && (c0 + 16 <= own_lo || c0 >= own_hi)) continue;
+    float s[16];
+    ld16(tS + lane_addr + c0, s);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) mx = fmaxf(mx, logit2(s[e], sLab[c0 + e]));
+  }
+  sRed[part * kRows + tid] = mx;
+  __syncthreads();
+  mx = fmaxf(sRed[tid], sRed[kRows + tid]);
+  // P may overwrite the Q/K area now: the MMA that read it has retired (bars[0]) and S lives in TMEM
+  float l = 0.f, mvx = 0.f, mvy = 0.f;
+  const int xi = tok_i % ws, yi = tok_i / ws;
+  const bool want_motion = p.motion_raw != nullptr;
+  for (int c0 = part * 16; c0 < p.chunksK * 32; c0 += 32) {
+    uint8_t* prow = sQ + (c0 >> 5) * (kRows * 128);
+    if (c0 >= p.KP || (skip_foreign && (c0 + 16 <= own_lo || c0 >= own_hi))) {
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(prow + swz(tid, (c0 & 31) + e)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    float s[16];
+    ld16(tS + lane_addr + c0, s);
+    float pv[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int meta = sLab[c0 + e];
+      const float x = logit2(s[e], meta);
+      const float pe = (row_ok && x > -INFINITY) ? exp2f(x - mx) : 0.f;
+      l += pe;
+      if (want_motion) {
+        float dx, dy;
+        if (p.rc) {
+          const int tj = ((meta >> 24) & 0xFF) * ws + ((meta >> 16) & 0xFF);
+          dx = pe != 0.f ? __ldg(p.rc + (int64_t)tok_i * N + tj) : 0.f;
+          dy = pe != 0.f ? __ldg(p.rc + (int64_t)N * N + (int64_t)tok_i * N + tj) : 0.f;
+        } else {
+          dx = (float)(((meta >> 16) & 0xFF) - xi);
+          dy = (float)(((meta >> 24) & 0xFF) - yi);
+        }
+        mvx = fmaf(pe, dx, mvx);
+        mvy = fmaf(pe, dy, mvy);
+      }
+      pv[e] = tf32r(pe);
+    }
+#pragma unroll
+    for (int e = 0; e < 16; e += 4)
+      *reinterpret_cast<float4*>(prow + swz(tid, (c0 & 31) + e)) = make_float4(pv[e], pv[e + 1], pv[e + 2], pv[e + 3]);
+  }
+  sRed[(2 + part) * kRows + tid] = l;
+  sRed[(4 + part) * kRows + tid] = mvx;
+  sRed[(6 + part) * kRows + tid] = mvy;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- O = P V ------------------------------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    const uint32_t id = idesc_tf32(p.HP);
+    const int nslK = p.KP >> 3;
+    for (int s = 0; s < nslK; ++s) {
+      const int c = s >> 2, j = s & 3;
+      mma_tf32(tO, sdesc(s_u32(sQ + c * (kRows * 128))) + 2 * j, sdesc(s_u32(sV + c * (p.HP * 128))) + 2 * j, id, s ? 1u : 0u);
+    }
+    commit(&bars[1]);
+  }
+  bar_wait(&bars[1], 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  l = sRed[2 * kRows + tid] + sRed[3 * kRows + tid];
+  mvx = sRed[4 * kRows + tid] + sRed[5 * kRows + tid];
+  mvy = sRed[6 * kRows + tid] + sRed[7 * kRows + tid];
+  const float inv = row_ok ? 1.0f / l : 0.f;
+  const int64_t grow = row_ok ? win_i * N + tok_i : 0;
+  for (int c0 = part * 16; c0 < p.HP; c0 += 32) {
+    float o[16];
+    ld16(tO + lane_addr + c0, o);
+    if (row_ok) {
+      float* dst = p.out + grow * p.out_pitch + h * hd + c0;
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        if (c0 + e < hd) {
+          float4 v = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
+          *reinterpret_cast<float4*>(dst + e) = round_tf32_if(v, p.round != 0);
+        }
+      }
+    }
+  }
+  if (row_ok && p.motion_raw && part == 0) {
+    p.motion_raw[(grow * p.heads + h) * 2 + 0] = mvx * inv;
+    p.motion_raw[(grow * p.heads + h) * 2 + 1] = mvy * inv;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+inline int rup(int x, int m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+// Returns 0 on success, 3 if the shape is outside what this kernel handles (caller falls back to the fp32 kernel).
+int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, cudaStream_t st) {
+  AttnParams p;
+  p.qkv = qkv; p.qkv_pitch = qkv_pitch; p.out = out; p.out_pitch = out_pitch; p.C = C; p.heads = heads; p.hd = C / heads;
+  p.g = *g; p.cross = cross; p.rc = rc; p.motion_raw = motion_raw;
+  p.N = g->ws * g->ws;
+  if (p.N > 256 || p.hd % 4 != 0 || p.hd > 96) return 3;
+  p.nW = (g->Hp / g->ws) * (g->Wp / g->ws);
+  p.total_windows = g->B2 * p.nW;
+  if (p.N <= 64) { p.wpi = kRows / p.N; p.mtiles = 1; } else { p.wpi = 1; p.mtiles = (p.N + kRows - 1) / kRows; }
+  p.KP = rup(p.wpi * p.N, 16);
+  p.HP = rup(p.hd, 16);
+  p.chunksH = (rup(p.hd, 8) + 31) / 32;
+  p.chunksK = (p.KP + 31) / 32;
+  int need = p.KP + p.HP, cols = 32;
+  while (cols < need) cols <<= 1;
+  if (cols > 512) return 3;
+  p.tmem_cols = cols;
+  p.round = atmvfi_output_rounding();
+  p.scale = (float)(1.0 / sqrt((double)p.hd));
+  const int bytesQ = p.chunksH * kRows * 128, bytesK = p.chunksH * p.KP * 128, bytesP = p.chunksK * kRows * 128;
+  const int regionQK = bytesQ + bytesK > bytesP ? bytesQ + bytesK : bytesP;
+  p.offK = bytesQ;
+  p.offV = rup(regionQK, 1024);
+  p.offLab = p.offV + p.chunksK * p.HP * 128;
+  p.offBar = rup(p.offLab + p.KP * 4, 16);
+  const int smem = p.offBar + 64 + 8 * kRows * 4;
+  if (smem > 227 * 1024) return 3;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 100 * 1024 ? 227 * 1024 : 100 * 1024);
+    if (e != cudaSuccess) {
+      atmvfi_set_error("window_attention(tf32): cannot reserve shared memory: %s", cudaGetErrorString(e));
+      return 1;
+    }
+    configured = smem > 100 * 1024 ? 227 * 1024 : 100 * 1024;
+  }
+  const int64_t wgroups = (p.total_windows + p.wpi - 1) / p.wpi;
+  const int64_t items = wgroups * heads * p.mtiles;
+  if (items <= 0) return 0;
+  window_attention_tc_kernel<<<(unsigned)items, kThreadsA, smem, st>>>(p);
+  ATMVFI_CHECK_LAUNCH("window_attention(tf32)");
+  return 0;
+}

@@ -94,6 +94,7 @@ class _WindowBlock(ParamTree):
             if self._ATM:
                 rc = f32("attn.relative_coord")
                 b.rc = rc.reshape(2, rc.shape[-2], rc.shape[-1]).contiguous()
+                b.rc_closed = False
                 b.mix = (f32("attn.mlp.0.weight"), f32("attn.mlp.0.bias"), f32("attn.mlp.2.weight").reshape(-1).contiguous(), f32("attn.mlp.2.bias"))
             self._packed, self._sig = b, sig
         return CudaOps(device, _lib.FP32), self._packed

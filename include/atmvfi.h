@@ -130,6 +130,15 @@ int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out
                             const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
                             float* motion, int motion_pitch, int motion_off, float* scratch, void* stream);
 
+/* Same contract on the tensor cores (tcgen05 kind::tf32, accumulators in TMEM; Q, K, V^T staged in shared memory as
+ * TF32).  rc_closed_form != 0 asserts that relative_coord holds the reference's own buffer contents (key position -
+ * query position, attention.py:150-165), which the kernel then evaluates arithmetically instead of loading it.
+ * Shapes outside the kernel's envelope (N > 256 tokens per window, head dim > 96) run on the CUDA-core kernel. */
+int atmvfi_window_attention_tc(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
+                               const atmvfi_window_geom* g, int cross, const float* relative_coord, int rc_closed_form,
+                               const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
+                               float* motion, int motion_pitch, int motion_off, float* scratch, void* stream);
+
 /* Mlp middle: depth-wise 3x3 (pad 1) + bias + exact-erf GELU on NHWC tokens (attention.py:74-85,118-119). */
 int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch,
                           const float* w9c /* [9][C] */, const float* bias, void* stream);

@@ -143,7 +143,7 @@ class EmulOps:
             win.view().copy_(F.layer_norm(rows, (tok.C,), gamma, beta, 1e-5).reshape(win.view().shape))
         self._emit(run)
 
-    def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads, cross, rc=None, mix=None, motion=None, motion_off=0, scratch=None):
+    def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads, cross, rc=None, mix=None, motion=None, motion_off=0, scratch=None, rc_closed_form=False):
         def run():
             C = out.C
             N = g.ws * g.ws

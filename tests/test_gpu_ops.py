@@ -268,3 +268,32 @@ def test_conv3x3_first_and_pack5(ops, Co):
     em.pack5_planar(imgs, m)
     cu.pack5_planar([t.cuda() for t in imgs], mg)
     assert torch.equal(mg.t.cpu(), m.t)
+
+
+@pytest.mark.parametrize("B2,H,W,ws,shift", WIN_CASES + [(2, 14, 21, 7, 3)])
+@pytest.mark.parametrize("hd", [28, 44, 48, 84])
+@pytest.mark.parametrize("closed", [False, True])
+def test_window_attention_tensor_cores(B2, H, W, ws, shift, hd, closed):
+    """tcgen05 attention (TF32 operands) against the fp32 contract emulation."""
+    em = EmulOps()
+    cu = CudaOps(torch.device("cuda:0"), _lib.TF32)
+    g = gen(12)
+    heads, C = 8, 8 * hd
+    geo = WinGeom(B2, H, W, ws, shift)
+    qkv = rand_map(1, 1, geo.rows, 3 * C, gen=g, scale=1.0)
+    N = ws * ws
+    idx = torch.arange(N)
+    px, py = (idx % ws).float(), (idx // ws).float()
+    rc = torch.stack([px[None] - px[:, None], py[None] - py[:, None]], 0).contiguous()
+    mix = (torch.randn(4, 8, generator=g), torch.randn(4, generator=g), torch.randn(4, generator=g), torch.randn(1, generator=g))
+    out, mo = rand_map(1, 1, geo.rows, C, gen=g), rand_map(B2 // 2, H, W, 8, gen=g)
+    og, mg = to_gpu(out), to_gpu(mo)
+    scratch = torch.empty(geo.rows * heads * 2, device="cuda")
+    em.window_attention(qkv, out, geo, heads, True, rc, mix, mo, 4)
+    cu.window_attention(to_gpu(qkv), og, geo, heads, True, rc.cuda(), to_gpu(mix), mg, 4, scratch, rc_closed_form=closed)
+    # logits have std ~ sqrt(hd)*... / sqrt(hd) = 1: TF32 operand rounding moves them by ~1e-3
+    assert max_err(og, out) < 6e-3
+    assert max_err(mg, mo) < 4e-2
+    em.window_attention(qkv, out, geo, heads, False)
+    cu.window_attention(to_gpu(qkv), og, geo, heads, False)
+    assert max_err(og, out) < 6e-3
