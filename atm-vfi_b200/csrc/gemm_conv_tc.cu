@@ -32,7 +32,7 @@ constexpr int kMaxASlots = 4;
 constexpr int kMaxBSlots = 12;
 constexpr int kMaxBlockN = 256;
 constexpr int kDataBytes = 184 * 1024;          // A ring + B ring, carved per layer (see atmvfi_gemm_conv_tc)
-constexpr int kMaxABoxBytes = 24 * 1024;        // up to 192 rows of 128 B (halo box), 128 rows otherwise
+constexpr int kMaxABoxBytes = 24 * 1024;        // up to 192 rows of 128 B (halo box; 320 rows = 40 KB in pair mode), 128 rows otherwise
 constexpr int kBarOff = kDataBytes;
 constexpr int kEpiWarps = 8;                                  // two warps per TMEM lane quarter, alternating column chunks
 constexpr int kEpiPitch = 36;                                 // floats per staged row: 16-byte aligned, conflict-free for 128-bit access
@@ -52,6 +52,7 @@ struct TcPlan {                                 // host-side, produced by atmvfi
   int block_n, n_tiles, cq_pad;
   int Hout, Wout;
   int halo;                                     // 1: 3x3 stride-1 layer, A boxes carry a vertical halo
+  int pair;                                     // 1: two vertically stacked 128-pixel tiles per CTA step (N <= 128)
   int cluster;                                  // CTAs per cluster (B multicast), 1 or 2
   uint32_t magic;
 };
@@ -67,6 +68,7 @@ struct TcParams {
   int TW, TH, tiles_x, tiles_y, B;
   int block_n, n_tiles, cq_pad;
   int halo, a_bytes, sum_chunks, m_tiles;
+  int th_super;                                 // rows of output covered by one CTA tile (TH, or 2*TH in pair mode)
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes;   // smem rings: A at offset 0, B right after
   int total_ctiles;                             // cluster tiles: ceil(m_tiles / cluster) * n_tiles
   EpiParams epi;
@@ -226,11 +228,11 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
   mt /= p.tiles_x;
   int ty = mt % p.tiles_y;
   b = mt / p.tiles_y;                      // may be >= B for a phantom tile
-  oy0 = ty * p.TH;
+  oy0 = ty * p.th_super;
   ox0 = tx * p.TW;
 }
 
-template <int kHalo, int kCS>
+template <int kHalo, int kCS, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B atoms need a 1024-byte aligned base
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
@@ -381,6 +383,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 4; ++j)   // up to 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
                 if (j < nmma) tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+              if (kPair) {                  // second 128-pixel tile of the pair: next TH rows of the same box, same weights
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < nmma) tc_mma_tf32(tmem_d + 128, adesc + (uint64_t)((kBlockM * 128) >> 4) + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+              }
               if (cs > 1) tc_commit_mc(&emptyB[bs_], mc_mask); else tc_commit(&emptyB[bs_]);
               if (last_step) tc_commit(&emptyA[as_]);      // frees the activation box once its MMAs retire
               if (last_of_tile) tc_commit(&tfull[as]);     // accumulator complete
@@ -417,14 +424,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
       const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
       int n_tile, b, oy0, ox0;
       tile_coords(p, ct, cs, rank, n_tile, b, oy0, ox0);
-      const int oy = oy0 + th, ox = ox0 + tw;
-      const bool row_ok = b < p.B && oy < e.Hout && ox < e.Wout;
-      const int64_t m = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * kMaxBlockN;
-      int last_q = -1;
-      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+      const int nchunks = (p.block_n + 31) >> 5;
+      const int nunits = kPair ? 2 * nchunks : nchunks;       // (sub-tile, 32-column chunk) units, split between the two warps of a quarter
+      int last_q = -1, last_t = -1;
+      int64_t m = 0;
+      bool row_ok = false;
+      for (int u = half; u < nunits; u += 2) {
+        const int t = kPair ? u / nchunks : 0;                // sub-tile of the pair (warp-uniform)
+        const int c0 = (kPair ? u - t * nchunks : u) * 32;
+        if (t != last_t) {
+          const int oy = oy0 + t * p.TH + th, ox = ox0 + tw;
+          row_ok = b < p.B && oy < e.Hout && ox < e.Wout;
+          m = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
+          last_t = t;
+          last_q = -1;
+        }
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * kMaxBlockN + t * 128;
         const int n0 = n_tile * p.block_n + c0;               // first GEMM column of this chunk (warp-uniform)
         int sq = 0, co0 = n0;
         if (e.out_mode == ATMVFI_OUT_SHUFFLE2) { sq = n0 / p.cq_pad; co0 = n0 - sq * p.cq_pad; }
@@ -574,7 +591,21 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   }
   ATMVFI_REQUIRE(best_tw > 0, "gemm_conv(tf32): no tile shape for stride %d", d->stride);
   pl->TW = best_tw; pl->TH = 128 / best_tw;
-  pl->tiles_x = cdiv(d->Wout, pl->TW); pl->tiles_y = cdiv(d->Hout, pl->TH);
+  pl->pair = 0;
+  const bool shuffle = d->out_mode == ATMVFI_OUT_SHUFFLE2;
+  pl->cq_pad = round_up_i(d->Cout, 32);           // ConvTranspose: each of the 4 column blocks starts on a 32-column chunk
+  const int n_need = shuffle ? 4 * pl->cq_pad : round_up_i(d->Cout, 16);
+  pl->n_tiles = cdiv(n_need, kMaxBlockN);
+  pl->block_n = round_up_i(cdiv(n_need, pl->n_tiles), shuffle ? 32 : 16);
+  {
+    // thin 3x3 layers (N <= 128): two vertically stacked pixel tiles per CTA step share each weight tile and one
+    // activation box with a common halo -> weight traffic and issue overhead per pixel halve
+    static int pair_ok = -1;
+    if (pair_ok < 0) { const char* ev = getenv("ATMVFI_TC_PAIR"); pair_ok = ev ? atoi(ev) : 1; }
+    pl->pair = (pair_ok && pl->halo == 1 && pl->block_n <= 128 && d->Hout > pl->TH && (2 * pl->TH + 2) * pl->TW * 128 <= 40 * 1024) ? 1 : 0;
+  }
+  pl->tiles_x = cdiv(d->Wout, pl->TW);
+  pl->tiles_y = cdiv(d->Hout, pl->TH * (pl->pair ? 2 : 1));
   {
     // clusters of 2 CTAs along M share each weight tile through TMA multicast
     static int forced = -1;
@@ -584,11 +615,6 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     ATMVFI_REQUIRE(pl->cluster == 1 || pl->cluster == 2 || pl->cluster == 4, "gemm_conv(tf32): cluster size %d unsupported", pl->cluster);
   }
 
-  const bool shuffle = d->out_mode == ATMVFI_OUT_SHUFFLE2;
-  pl->cq_pad = round_up_i(d->Cout, 32);           // ConvTranspose: each of the 4 column blocks starts on a 32-column chunk
-  const int n_need = shuffle ? 4 * pl->cq_pad : round_up_i(d->Cout, 16);
-  pl->n_tiles = cdiv(n_need, kMaxBlockN);
-  pl->block_n = round_up_i(cdiv(n_need, pl->n_tiles), shuffle ? 32 : 16);
   const int n_pad = pl->n_tiles * pl->block_n;
 
   int ktc = 0;
@@ -605,7 +631,7 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     cuuint64_t gdim[4] = {(cuuint64_t)sr.C, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
     cuuint64_t gstr[3] = {(cuuint64_t)sr.pitch * 4, (cuuint64_t)sr.pitch * 4 * d->Win, (cuuint64_t)sr.pitch * 4 * d->Win * d->Hin};
     cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)((pl->halo == 2 ? pl->TW + 2 : pl->TW) * d->stride),
-                         (cuuint32_t)((pl->halo ? pl->TH + 2 : pl->TH) * d->stride), 1};
+                         (cuuint32_t)((pl->halo ? (pl->pair ? 2 : 1) * pl->TH + 2 : pl->TH) * d->stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
     CUresult r = enc(&pl->mapA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sr.ptr), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -634,17 +660,18 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   const TcPlan* pl = reinterpret_cast<const TcPlan*>(d->tma_host);
   ATMVFI_REQUIRE(pl && pl->magic == kPlanMagic, "gemm_conv(tf32): missing plan (call atmvfi_gemm_conv_plan first)");
   typedef void (*KernelFn)(TcParams);
-  static const KernelFn table[3][3] = {
-      {gemm_conv_tc_kernel<0, 1>, gemm_conv_tc_kernel<0, 2>, gemm_conv_tc_kernel<0, 4>},
-      {gemm_conv_tc_kernel<1, 1>, gemm_conv_tc_kernel<1, 2>, gemm_conv_tc_kernel<1, 4>},
-      {gemm_conv_tc_kernel<2, 1>, gemm_conv_tc_kernel<2, 2>, gemm_conv_tc_kernel<2, 4>}};
-  KernelFn kern = table[pl->halo][pl->cluster == 4 ? 2 : pl->cluster - 1];
+  static const KernelFn table[4][3] = {
+      {gemm_conv_tc_kernel<0, 1, false>, gemm_conv_tc_kernel<0, 2, false>, gemm_conv_tc_kernel<0, 4, false>},
+      {gemm_conv_tc_kernel<1, 1, false>, gemm_conv_tc_kernel<1, 2, false>, gemm_conv_tc_kernel<1, 4, false>},
+      {gemm_conv_tc_kernel<2, 1, false>, gemm_conv_tc_kernel<2, 2, false>, gemm_conv_tc_kernel<2, 4, false>},
+      {gemm_conv_tc_kernel<1, 1, true>, gemm_conv_tc_kernel<1, 2, true>, gemm_conv_tc_kernel<1, 4, true>}};
+  KernelFn kern = table[pl->pair ? 3 : pl->halo][pl->cluster == 4 ? 2 : pl->cluster - 1];
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 9; ++i) {
+    for (int i = 0; i < 12; ++i) {
       cudaError_t e = cudaFuncSetAttribute(table[i / 3][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) {
         num_sms = 0;
@@ -668,7 +695,8 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   p.TW = pl->TW; p.TH = pl->TH; p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.B = pl->B;
   p.block_n = pl->block_n; p.n_tiles = pl->n_tiles; p.cq_pad = pl->cq_pad;
   p.halo = pl->halo;
-  p.a_bytes = (pl->halo == 2 ? (pl->TH + 2) * (pl->TW + 2) : (pl->halo ? (pl->TH + 2) * pl->TW : kBlockM)) * 128;
+  p.a_bytes = (pl->halo == 2 ? (pl->TH + 2) * (pl->TW + 2) : (pl->halo ? ((pl->pair ? 2 : 1) * pl->TH + 2) * pl->TW : kBlockM)) * 128;
+  p.th_super = pl->TH * (pl->pair ? 2 : 1);
   p.sum_chunks = ch;
   p.a_slots = pl->halo ? 3 : 4;
   p.a_slot_bytes = (p.a_bytes + 1023) / 1024 * 1024;
