@@ -102,47 +102,46 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restric
                                                           int H, int W, int C, int pitch,
                                                           const float* __restrict__ w9c, const float* __restrict__ bias,
                                                           bool rnd) {
+  // grid: x = (column, channel quad) flattened, y = row strip, z = image -> one 32-bit division per thread
   const int cv = C >> 2;
-  const int strips = (H + kDwRows - 1) / kDwRows;
-  const int64_t total = (int64_t)B * strips * W * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % cv);
-    int64_t t = i / cv;
-    const int x = (int)(t % W);
-    t /= W;
-    const int y0 = (int)(t % strips) * kDwRows;
-    const int b = (int)(t / strips);
-    float4 k[9];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= W * cv) return;
+  const int x = j / cv, c4 = j - x * cv;
+  const int y0 = blockIdx.y * kDwRows;
+  const int b = blockIdx.z;
+  float4 k[9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) k[j] = __ldg(reinterpret_cast<const float4*>(w9c + j * C) + c4);
-    const float4 bz = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool xl = x > 0, xr = x + 1 < W;
-    auto load_row = [&](int yy, float4& l, float4& m, float4& r) {
-      if (yy < 0 || yy >= H) { l = m = r = zero; return; }
-      const float* rowp = in + ((int64_t)(b * H + yy) * W + x) * pitch;
-      m = __ldg(reinterpret_cast<const float4*>(rowp) + c4);
-      l = xl ? __ldg(reinterpret_cast<const float4*>(rowp - pitch) + c4) : zero;
-      r = xr ? __ldg(reinterpret_cast<const float4*>(rowp + pitch) + c4) : zero;
-    };
-    float4 a0, a1, a2, b0, b1, b2, c0, c1, c2;      // rows y-1, y, y+1
-    load_row(y0 - 1, a0, a1, a2);
-    load_row(y0, b0, b1, b2);
+  for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(w9c + t * C) + c4);
+  const float4 bz = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool xl = x > 0, xr = x + 1 < W;
+  const float* base = in + ((size_t)b * H * W + x) * pitch + (c4 << 2);
+  const size_t row_stride = (size_t)W * pitch;
+  auto load_row = [&](int yy, float4& l, float4& m, float4& r) {
+    if (yy < 0 || yy >= H) { l = m = r = zero; return; }
+    const float* rowp = base + yy * row_stride;
+    m = __ldg(reinterpret_cast<const float4*>(rowp));
+    l = xl ? __ldg(reinterpret_cast<const float4*>(rowp - pitch)) : zero;
+    r = xr ? __ldg(reinterpret_cast<const float4*>(rowp + pitch)) : zero;
+  };
+  float4 a0, a1, a2, b0, b1, b2, c0, c1, c2;      // rows y-1, y, y+1
+  load_row(y0 - 1, a0, a1, a2);
+  load_row(y0, b0, b1, b2);
+  float* obase = out + ((size_t)b * H * W + x) * pitch + (c4 << 2);
 #pragma unroll
-    for (int dy = 0; dy < kDwRows; ++dy) {
-      const int y = y0 + dy;
-      if (y >= H) break;
-      load_row(y + 1, c0, c1, c2);
-      // same accumulation order as the per-pixel reference loop: taps row-major starting from the bias
-      float4 acc = bz;
-      acc = fma4(a0, k[0], acc); acc = fma4(a1, k[1], acc); acc = fma4(a2, k[2], acc);
-      acc = fma4(b0, k[3], acc); acc = fma4(b1, k[4], acc); acc = fma4(b2, k[5], acc);
-      acc = fma4(c0, k[6], acc); acc = fma4(c1, k[7], acc); acc = fma4(c2, k[8], acc);
-      float4 o = make_float4(gelu_exact(acc.x), gelu_exact(acc.y), gelu_exact(acc.z), gelu_exact(acc.w));
-      reinterpret_cast<float4*>(out + ((int64_t)(b * H + y) * W + x) * pitch)[c4] = round_tf32_if(o, rnd);
-      a0 = b0; a1 = b1; a2 = b2;
-      b0 = c0; b1 = c1; b2 = c2;
-    }
+  for (int dy = 0; dy < kDwRows; ++dy) {
+    const int y = y0 + dy;
+    if (y >= H) break;
+    load_row(y + 1, c0, c1, c2);
+    // same accumulation order as a per-pixel loop: taps row-major starting from the bias
+    float4 acc = bz;
+    acc = fma4(a0, k[0], acc); acc = fma4(a1, k[1], acc); acc = fma4(a2, k[2], acc);
+    acc = fma4(b0, k[3], acc); acc = fma4(b1, k[4], acc); acc = fma4(b2, k[5], acc);
+    acc = fma4(c0, k[6], acc); acc = fma4(c1, k[7], acc); acc = fma4(c2, k[8], acc);
+    float4 o = make_float4(gelu_exact(acc.x), gelu_exact(acc.y), gelu_exact(acc.z), gelu_exact(acc.w));
+    *reinterpret_cast<float4*>(obase + y * row_stride) = round_tf32_if(o, rnd);
+    a0 = b0; a1 = b1; a2 = b2;
+    b0 = c0; b1 = c1; b2 = c2;
   }
 }
 
@@ -464,9 +463,10 @@ int atmvfi_pack5_planar(const float* s0, const float* s1, const float* s2, const
 int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch, const float* w9c,
                           const float* bias, void* stream) {
   ATMVFI_REQUIRE(C % 4 == 0 && pitch % 4 == 0, "dwconv3x3_gelu: C=%d pitch=%d must be multiples of 4", C, pitch);
-  int64_t n = (int64_t)B * ((H + kDwRows - 1) / kDwRows) * W * (C / 4);
-  if (n <= 0) return 0;
-  dwconv_gelu_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, atmvfi_output_rounding() != 0);
+  if ((int64_t)B * H * W <= 0) return 0;
+  ATMVFI_REQUIRE((int64_t)W * (C / 4) < (1 << 30) && B <= 65535, "dwconv3x3_gelu: shape out of range");
+  dim3 grid((unsigned)((W * (C / 4) + 255) / 256), (unsigned)((H + kDwRows - 1) / kDwRows), (unsigned)B);
+  dwconv_gelu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("dwconv3x3_gelu");
   return 0;
 }

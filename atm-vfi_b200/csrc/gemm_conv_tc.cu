@@ -137,6 +137,46 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// cta_group::2 variants: the two CTAs of a cluster drive one M = 256 MMA.  TMA completions of BOTH CTAs are counted on
+// the LEADER's mbarrier (shared::cluster address with the peer bit cleared), commits are multicast to both CTAs.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_2cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint64_t* bar) {   // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the same barrier in CTA rank 0 of the cluster
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -209,13 +249,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_
 }
 
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n, int m = kBlockM) {
   uint32_t d = 0;
   d |= 1u << 4;                 // D format = F32
   d |= 2u << 7;                 // A format = TF32
   d |= 2u << 10;                // B format = TF32
   d |= (uint32_t)(n >> 3) << 17;
-  d |= (uint32_t)(kBlockM >> 4) << 24;
+  d |= (uint32_t)(m >> 4) << 24;
   return d;
 }
 
@@ -253,15 +293,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kMaxASlots; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], cs); }   // every CTA of the cluster releases a B slot
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps); }
+    for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps * cs); }   // leader's tempty collects both CTAs' epilogues
     mbar_init(&tempty[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 2) {   // whole warp: allocate all 512 TMEM columns (one CTA per SM)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 2) {   // whole warp: allocate all 512 TMEM columns (one CTA per SM); in 2-CTA mode both CTAs of the pair allocate
+    if (cs == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -305,8 +350,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
                 }
                 mbar_wait(&emptyA[as_], aph_ ^ 1);
                 if (elect_one()) {
-                  mbar_expect_tx(&fullA[as_], p.a_bytes);
-                  tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                  if (rank == 0) mbar_expect_tx(&fullA[as_], p.a_bytes * cs);          // leader arms for both CTAs' boxes
+                  if (cs == 2) tma_load_4d_2cta(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                  else tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
                 }
                 __syncwarp();
                 for (int st = 0; st < steps_per_group; ++st) {
@@ -314,10 +360,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
                   const int kb = tap * p.sum_chunks + cbase + c;
                   mbar_wait(&emptyB[bs_], bph_ ^ 1);
                   if (elect_one()) {
-                    mbar_expect_tx(&fullB[bs_], p.block_n * 128);
-                    uint8_t* dst = ringB + bs_ * p.b_slot_bytes + rank * b_rows * 128;
-                    if (cs > 1)
-                      tma_load_2d_mc(dst, &p.mapB, &fullB[bs_], kb * kChunk, n_tile * p.block_n + rank * b_rows, mc_mask);
+                    if (rank == 0) mbar_expect_tx(&fullB[bs_], p.block_n * 128);         // both halves of the weight tile
+                    uint8_t* dst = ringB + bs_ * p.b_slot_bytes;
+                    if (cs == 2)      // this CTA holds columns [rank*N/2, +N/2) of the weight tile
+                      tma_load_2d_2cta(dst, &p.mapB, &fullB[bs_], kb * kChunk, n_tile * p.block_n + rank * b_rows);
                     else
                       tma_load_2d(dst, &p.mapB, &fullB[bs_], kb * kChunk, n_tile * p.block_n);
                   }
@@ -334,8 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ======================================= MMA issuer =========================================
-    {
-      const uint32_t idesc = make_idesc_tf32(p.block_n);
+    if (rank == 0) {   // 2-CTA mode: the leader issues M = 256 MMAs that read both CTAs' shared memory
+      const uint32_t idesc = make_idesc_tf32(p.block_n, cs == 2 ? 256 : kBlockM);
       const int groups = (kHalo == 2 ? 1 : (kHalo == 1 ? 3 : p.ntaps)) * p.sum_chunks;
       const uint32_t a_step = kHalo == 1 ? (uint32_t)(p.TW * 128) >> 4 : 0;      // descriptor units of 16 B per vertical tap
       const uint32_t a_sbo = kHalo == 2 ? (uint32_t)((p.TW + 2) * 128) : 1024u;   // full-halo box: tile rows are TW+2 pixels apart
@@ -382,15 +428,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
             if (elect_one()) {
 #pragma unroll
               for (int j = 0; j < 4; ++j)   // up to 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
-                if (j < nmma) tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+                if (j < nmma) {
+                  if (cs == 2) tc_mma_tf32_2cta(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+                  else tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+                }
               if (kPair) {                  // second 128-pixel tile of the pair: next TH rows of the same box, same weights
+                const uint64_t adesc2 = adesc + (uint64_t)((kBlockM * 128) >> 4);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  if (j < nmma) tc_mma_tf32(tmem_d + 128, adesc + (uint64_t)((kBlockM * 128) >> 4) + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+                  if (j < nmma) {
+                    if (cs == 2) tc_mma_tf32_2cta(tmem_d + 128, adesc2 + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+                    else tc_mma_tf32(tmem_d + 128, adesc2 + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
+                  }
               }
-              if (cs > 1) tc_commit_mc(&emptyB[bs_], mc_mask); else tc_commit(&emptyB[bs_]);
-              if (last_step) tc_commit(&emptyA[as_]);      // frees the activation box once its MMAs retire
-              if (last_of_tile) tc_commit(&tfull[as]);     // accumulator complete
+              if (cs == 2) {
+                tc_commit_2cta(&emptyB[bs_]);
+                if (last_step) tc_commit_2cta(&emptyA[as_]);   // frees the activation boxes of both CTAs once the MMAs retire
+                if (last_of_tile) tc_commit_2cta(&tfull[as]);  // accumulators complete in both CTAs
+              } else {
+                tc_commit(&emptyB[bs_]);
+                if (last_step) tc_commit(&emptyA[as_]);
+                if (last_of_tile) tc_commit(&tfull[as]);
+              }
             }
             __syncwarp();
             first = 0;
@@ -523,7 +582,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);                 // kEpiWarps arrivals -> accumulator stage free
+      if (lane == 0) {                                         // accumulator stage drained (the leader's MMA warp waits for it)
+        if (cs == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]);
+      }
     }
   }
 
@@ -532,7 +593,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
   if (cs > 1) cluster_sync_all();          // no CTA may exit while a peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (cs == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -612,7 +674,7 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     if (forced < 0) { const char* ev = getenv("ATMVFI_TC_CLUSTER"); forced = ev ? atoi(ev) : 0; }
     const int64_t m_tiles = (int64_t)pl->tiles_x * pl->tiles_y * d->B;
     pl->cluster = forced ? forced : (m_tiles >= 2 ? 2 : 1);
-    ATMVFI_REQUIRE(pl->cluster == 1 || pl->cluster == 2 || pl->cluster == 4, "gemm_conv(tf32): cluster size %d unsupported", pl->cluster);
+    ATMVFI_REQUIRE(pl->cluster == 1 || pl->cluster == 2, "gemm_conv(tf32): cluster size %d unsupported", pl->cluster);
   }
 
   const int n_pad = pl->n_tiles * pl->block_n;
@@ -660,19 +722,19 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   const TcPlan* pl = reinterpret_cast<const TcPlan*>(d->tma_host);
   ATMVFI_REQUIRE(pl && pl->magic == kPlanMagic, "gemm_conv(tf32): missing plan (call atmvfi_gemm_conv_plan first)");
   typedef void (*KernelFn)(TcParams);
-  static const KernelFn table[4][3] = {
-      {gemm_conv_tc_kernel<0, 1, false>, gemm_conv_tc_kernel<0, 2, false>, gemm_conv_tc_kernel<0, 4, false>},
-      {gemm_conv_tc_kernel<1, 1, false>, gemm_conv_tc_kernel<1, 2, false>, gemm_conv_tc_kernel<1, 4, false>},
-      {gemm_conv_tc_kernel<2, 1, false>, gemm_conv_tc_kernel<2, 2, false>, gemm_conv_tc_kernel<2, 4, false>},
-      {gemm_conv_tc_kernel<1, 1, true>, gemm_conv_tc_kernel<1, 2, true>, gemm_conv_tc_kernel<1, 4, true>}};
-  KernelFn kern = table[pl->pair ? 3 : pl->halo][pl->cluster == 4 ? 2 : pl->cluster - 1];
+  static const KernelFn table[4][2] = {
+      {gemm_conv_tc_kernel<0, 1, false>, gemm_conv_tc_kernel<0, 2, false>},
+      {gemm_conv_tc_kernel<1, 1, false>, gemm_conv_tc_kernel<1, 2, false>},
+      {gemm_conv_tc_kernel<2, 1, false>, gemm_conv_tc_kernel<2, 2, false>},
+      {gemm_conv_tc_kernel<1, 1, true>, gemm_conv_tc_kernel<1, 2, true>}};
+  KernelFn kern = table[pl->pair ? 3 : pl->halo][pl->cluster - 1];
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 12; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(table[i / 3][i % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    for (int i = 0; i < 8; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(table[i / 2][i % 2], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) {
         num_sms = 0;
         atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
@@ -700,7 +762,7 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   p.sum_chunks = ch;
   p.a_slots = pl->halo ? 3 : 4;
   p.a_slot_bytes = (p.a_bytes + 1023) / 1024 * 1024;
-  p.b_slot_bytes = pl->block_n * 128;
+  p.b_slot_bytes = (pl->block_n / pl->cluster) * 128;        // 2-CTA mode: each CTA holds half of the weight tile
   p.b_slots = (kDataBytes - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
   if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
   p.m_tiles = pl->tiles_x * pl->tiles_y * pl->B;

@@ -59,3 +59,24 @@ if which in ("all", "speed"):
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n; fl = 2.0 * H * W * ci * co * k * k
         print(f"speed {H}x{W} {ci}->{co} k{k}: {ms:.3f} ms  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
+if which == "speed2":
+    import time
+    shapes = [(1, 65280, 384, 1536, 1), (1, 65280, 1536, 384, 1), (1, 65280, 384, 1152, 1), (1, 65280, 384, 384, 1), (544, 960, 197, 197, 3), (1088, 1920, 101, 101, 3)]
+    recs = []
+    for (H, W, ci, co, k) in shapes:
+        P = {"c.weight": torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5, "c.bias": torch.randn(co, generator=g) * 0.1, "p": torch.rand(co, generator=g)}
+        w = pack.pack_conv(P, "c", prelu="p"); wg = PackedGemm(w.name, w.ksize, w.split, w.Cout, False, w.w32.cuda(), w.bias.cuda(), w.prelu.cuda())
+        src = Map(torch.randn(1, H, W, (ci + 3) // 4 * 4, device=dev), 0, ci); out = Map(torch.zeros(1, H, W, (co + 3) // 4 * 4, device=dev), 0, co)
+        tc.recording = rec = []; tc.gemm_conv([src], wg, out); tc.recording = None
+        recs.append((rec, 2.0 * H * W * ci * co * k * k, (H, W, ci, co, k)))
+    t0 = time.time()
+    while time.time() - t0 < 1.5:
+        for rec, _, _ in recs: tc.replay(rec)
+    torch.cuda.synchronize()
+    for rec, fl, shp in recs:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); n = 20
+        for _ in range(n): tc.replay(rec)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        print(f"speed2 {shp}: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s", flush=True)
