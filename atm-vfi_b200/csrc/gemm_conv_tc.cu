@@ -272,7 +272,7 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
   ox0 = tx * p.TW;
 }
 
-template <int kHalo, int kCS, bool kPair>
+template <int kHalo, int kCS, bool kPair, bool kFastEpi>
 __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B atoms need a 1024-byte aligned base
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
         __syncwarp();
         tc_ld32(trow + c0, r);
         tc_wait_ld();
-        if (sq != last_q) {
+        if (!kFastEpi && sq != last_q) {
           const int64_t orow = row_ok ? epi_out_row(e, m, sq) : -1;
           s_row[lane] = make_int2((int)orow, (int)m);
           last_q = sq;
@@ -521,6 +521,35 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
         __syncwarp();
         const int nvalid = min(min(32, p.block_n - c0), e.Cout - co0);   // block_n may end inside this 32-column chunk
         const bool full4 = col + 4 <= nvalid;
+        if (kFastEpi) {
+          // plain layers (pixel-major output, no residual, no second output, Cout % 4 == 0): rows are addressed
+          // arithmetically (TW is a power of two), nothing but the accumulator tile is read from shared memory
+          if (col < nvalid) {
+            float4 bz4 = make_float4(0.f, 0.f, 0.f, 0.f), sl4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (e.bias) bz4 = __ldg(reinterpret_cast<const float4*>(e.bias + co0 + col));
+            const bool act = e.prelu != nullptr;
+            if (act) sl4 = __ldg(reinterpret_cast<const float4*>(e.prelu + co0 + col));
+            const int tw_mask = p.TW - 1, tw_shift = 31 - __clz(p.TW);
+            const int oyb = oy0 + (kPair ? t * p.TH : 0);
+            float* obase = e.out + co0 + col;
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const int row = rr * 4 + rsub, ml = q * 32 + row;
+              const int oy = oyb + (ml >> tw_shift), ox = ox0 + (ml & tw_mask);
+              if (b < p.B && oy < e.Hout && ox < e.Wout) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&stage[row * kEpiPitch + col]);
+                float4 v = make_float4(a4.x + bz4.x, a4.y + bz4.y, a4.z + bz4.z, a4.w + bz4.w);
+                if (act) {
+                  v.x = v.x > 0.f ? v.x : v.x * sl4.x; v.y = v.y > 0.f ? v.y : v.y * sl4.y;
+                  v.z = v.z > 0.f ? v.z : v.z * sl4.z; v.w = v.w > 0.f ? v.w : v.w * sl4.w;
+                }
+                const int64_t mrow = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
+                *reinterpret_cast<float4*>(obase + mrow * e.out_pitch) = round_tf32_if(v, rnd);
+              }
+            }
+          }
+          continue;
+        }
         float bz[4] = {0.f, 0.f, 0.f, 0.f}, sl[4] = {1.f, 1.f, 1.f, 1.f}, sl2[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -722,19 +751,26 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   const TcPlan* pl = reinterpret_cast<const TcPlan*>(d->tma_host);
   ATMVFI_REQUIRE(pl && pl->magic == kPlanMagic, "gemm_conv(tf32): missing plan (call atmvfi_gemm_conv_plan first)");
   typedef void (*KernelFn)(TcParams);
-  static const KernelFn table[4][2] = {
-      {gemm_conv_tc_kernel<0, 1, false>, gemm_conv_tc_kernel<0, 2, false>},
-      {gemm_conv_tc_kernel<1, 1, false>, gemm_conv_tc_kernel<1, 2, false>},
-      {gemm_conv_tc_kernel<2, 1, false>, gemm_conv_tc_kernel<2, 2, false>},
-      {gemm_conv_tc_kernel<1, 1, true>, gemm_conv_tc_kernel<1, 2, true>}};
-  KernelFn kern = table[pl->pair ? 3 : pl->halo][pl->cluster - 1];
+  static const KernelFn table[2][4][2] = {
+      {{gemm_conv_tc_kernel<0, 1, false, false>, gemm_conv_tc_kernel<0, 2, false, false>},
+       {gemm_conv_tc_kernel<1, 1, false, false>, gemm_conv_tc_kernel<1, 2, false, false>},
+       {gemm_conv_tc_kernel<2, 1, false, false>, gemm_conv_tc_kernel<2, 2, false, false>},
+       {gemm_conv_tc_kernel<1, 1, true, false>, gemm_conv_tc_kernel<1, 2, true, false>}},
+      {{gemm_conv_tc_kernel<0, 1, false, true>, gemm_conv_tc_kernel<0, 2, false, true>},
+       {gemm_conv_tc_kernel<1, 1, false, true>, gemm_conv_tc_kernel<1, 2, false, true>},
+       {gemm_conv_tc_kernel<2, 1, false, true>, gemm_conv_tc_kernel<2, 2, false, true>},
+       {gemm_conv_tc_kernel<1, 1, true, true>, gemm_conv_tc_kernel<1, 2, true, true>}}};
+  // fast epilogue: pixel-major output, no residual / second output, whole float4 columns, aligned bias and slopes
+  const int fast = (d->out_mode == ATMVFI_OUT_PIXEL && !d->residual && !d->out2 && d->Cout % 4 == 0 &&
+                    (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0) ? 1 : 0;
+  KernelFn kern = table[fast][pl->pair ? 3 : pl->halo][pl->cluster - 1];
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 8; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(table[i / 2][i % 2], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    for (int i = 0; i < 16; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(table[i / 8][(i / 2) % 4][i % 2], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) {
         num_sms = 0;
         atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
