@@ -44,7 +44,16 @@ class GemmConvDesc(C.Structure):
         ("win", WindowGeom),
         ("precision", C.c_int32),
         ("tma_host", C.c_void_p),
+        ("row_begin", C.c_int32), ("row_end", C.c_int32),
     ]
+
+
+class P2PPiece(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("chunk_bytes", C.c_uint64), ("chunk_stride", C.c_uint64),
+                ("nchunks", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+IPC_HANDLE_BYTES, P2P_MAX_PIECES, P2P_MAX_PEERS = 64, 16, 8
 
 
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -55,20 +64,29 @@ PROTOTYPES = {
     "atmvfi_gemm_conv": [_DP, _P],
     "atmvfi_gemm_conv_plan": [_DP, _P],
     "atmvfi_layernorm": [_P, _I, _P, _I, _L, _I, _P, _P, _F, _P],
-    "atmvfi_window_gather_ln": [_P, _I, _P, _I, _I, _GP, _P, _P, _F, _P],
-    "atmvfi_window_attention": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
-    "atmvfi_conv3x3_first": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "atmvfi_pack5_planar": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "atmvfi_window_attention_tc": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _P],
-    "atmvfi_dwconv3x3_gelu": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
-    "atmvfi_flow_warp_nchw": [_P, _P, _P, _I, _I, _I, _I, _P],
-    "atmvfi_flow_warp_nhwc": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _P],
-    "atmvfi_warp_blend": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
-    "atmvfi_resize_bilinear_ac": [_P, _P, _I, _I, _I, _I, _I, _F, _P],
-    "atmvfi_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
-    "atmvfi_residual_finish": [_P, _I, _P, _P, _P, _I, _I, _I, _P],
+    # ... every grid walker ends with (y0, y1, stream): the row window of include/atmvfi.h
+    "atmvfi_window_gather_ln": [_P, _I, _P, _I, _I, _GP, _P, _P, _F, _I, _I, _P],
+    "atmvfi_window_attention": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P],
+    "atmvfi_conv3x3_first": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_pack5_planar": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_window_attention_tc": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P],
+    "atmvfi_dwconv3x3_gelu": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
+    "atmvfi_flow_warp_nchw": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_flow_warp_nhwc": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_warp_blend": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "atmvfi_resize_bilinear_ac": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _P],
+    "atmvfi_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_residual_finish": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_u8_to_planar": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_planar_to_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    # NVLink row exchange (spatial row-slab mode)
+    "atmvfi_arena_alloc": [C.c_size_t, C.POINTER(C.c_void_p)],
+    "atmvfi_arena_free": [_P],
+    "atmvfi_ipc_export": [_P, C.c_char_p],
+    "atmvfi_ipc_open": [C.c_char_p, C.POINTER(C.c_void_p)],
+    "atmvfi_ipc_close": [_P],
+    "atmvfi_p2p_exchange": [C.POINTER(P2PPiece), _I, C.POINTER(C.c_void_p), _I, C.POINTER(C.c_void_p), _I, _P, _P, _P, _P],
+    "atmvfi_p2p_step_begin": [_P, C.POINTER(C.c_void_p), _I, C.POINTER(C.c_void_p), _I, _P, _P],
 }
 _SPECIAL = {
     "atmvfi_last_error": ([], C.c_char_p),
@@ -98,7 +116,7 @@ def load() -> C.CDLL:
     for name, (argt, rest) in _SPECIAL.items():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = argt, rest
-    if lib.atmvfi_abi_version() != 1:
+    if lib.atmvfi_abi_version() != 2:
         raise AtmvfiError("libatmvfi_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -60,7 +60,8 @@ class PackedModel:
             return b
 
         def head(n, c):
-            return (pack.pack_convp(P, n + ".0", split=[NUM_HEADS, c, c]), pack.pack_convp(P, n + ".1"), pack.pack_conv(P, n + ".2"))
+            # inputs: motion of ATMFormer block 0 and block 1 (4 channels each: frame-0 xy, frame-1 xy), tokens of frame 0, frame 1
+            return (pack.pack_convp(P, n + ".0", split=[4, 4, c, c]), pack.pack_convp(P, n + ".1"), pack.pack_conv(P, n + ".2"))
 
         self.fuse_local = fusion("cross_scale_feature_fusion", a.enc[1], a.enc[2], a.enc[3])
         self.enhance = [block(f"feat_enhance_transformer.{k}", False) for k in range(2)]
@@ -95,18 +96,18 @@ class PackedModel:
 # ------------------------------------------------------------------------------------------------
 # building blocks (recorded through ``ops``)
 # ------------------------------------------------------------------------------------------------
-def transformer_block(ops, blk, tok: Map, g: WinGeom, motion: Optional[Map] = None, motion_off: int = 0) -> Map:
+def transformer_block(ops, blk, tok: Map, g: WinGeom, motion: Optional[Map] = None) -> Map:
     """ATMFormer / RefineBottleneck forward (attention.py:265-334, 433-495) on tokens [B2,H,W,C]."""
     C = tok.C
     hidden = blk.fc1.Cout
-    xw = ops.new_map(1, 1, g.rows, C)
+    xw = ops.new_win_map(g, C)
     ops.window_gather_ln(tok, xw, g, blk.g1, blk.b1)                       # pad + roll + partition + norm1
-    qkv = ops.new_map(1, 1, g.rows, 3 * C)
+    qkv = ops.new_win_map(g, 3 * C)
     ops.gemm_conv([xw], blk.qkv, qkv, act=False)
-    ao = ops.new_map(1, 1, g.rows, C)
+    ao = ops.new_win_map(g, C)
     if blk.atm and motion is not None:
         scratch = torch.empty(g.rows * NUM_HEADS * 2, device=xw.t.device, dtype=torch.float32)
-        ops.window_attention(qkv, ao, g, NUM_HEADS, True, blk.rc, blk.mix, motion, motion_off, scratch,
+        ops.window_attention(qkv, ao, g, NUM_HEADS, True, blk.rc, blk.mix, motion, 0, scratch,
                              rc_closed_form=getattr(blk, "rc_closed", False))
     else:
         ops.window_attention(qkv, ao, g, NUM_HEADS, blk.atm)
@@ -144,12 +145,13 @@ def motion_branch(ops, blocks, head, tok: Map, ws: int) -> Tuple[Map, Map]:
     Returns (tokens after the blocks [2B,H,W,C], head [B,H,W,5])."""
     B2, H, W = tok.B, tok.H, tok.W
     B = B2 // 2
-    motion = ops.new_map(B, H, W, 2 * 4)
+    # one 4-channel motion map per block (the two blocks cover different row sets under row slabs)
+    motion = [ops.new_map(B, H, W, 4), ops.new_map(B, H, W, 4)]
     for k, shift in enumerate((0, ws // 2)):
-        tok = transformer_block(ops, blocks[k], tok, WinGeom(B2, H, W, ws, shift), motion, 4 * k)
+        tok = transformer_block(ops, blocks[k], tok, WinGeom(B2, H, W, ws, shift), motion[k])
     h0, h1, h2 = head
     a = ops.new_map(B, H, W, h0.Cout)
-    ops.gemm_conv([motion, tok.batch(0, B), tok.batch(B, B)], h0, a)
+    ops.gemm_conv([motion[0], motion[1], tok.batch(0, B), tok.batch(B, B)], h0, a)
     b = ops.new_map(B, H, W, h1.Cout)
     ops.gemm_conv([a], h1, b)
     out = ops.new_map(B, H, W, MOTION_OUT)
@@ -180,11 +182,14 @@ class Plan:
     # .............................................................................................
     def _build(self, ops, m: PackedModel, a: Arch, B: int, H: int, W: int, glob: bool):
         P = ops.new_planar
+        if hasattr(ops, "begin_plan"):          # row-slab mode (slab.SlabOps): partition the rows, open the step
+            ops.begin_plan(B, H, W, glob)
         self.im0, self.im1 = P(B, 3, H, W), P(B, 3, H, W)
         pyr0, pyr1 = [self.im0], [self.im1]
-        for l in range(1, 4):
-            pyr0.append(P(B, 3, H >> l, W >> l)); pyr1.append(P(B, 3, H >> l, W >> l))
-            ops.resize(pyr0[l - 1], pyr0[l]); ops.resize(pyr1[l - 1], pyr1[l])
+        with ops.replicated():        # warp sources: every rank keeps the whole (3-channel) pyramid under row slabs
+            for l in range(1, 4):
+                pyr0.append(P(B, 3, H >> l, W >> l)); pyr1.append(P(B, 3, H >> l, W >> l))
+                ops.resize(pyr0[l - 1], pyr0[l]); ops.resize(pyr1[l - 1], pyr1[l])
 
         # encoder on the two frames stacked on the batch axis (network_base.py:342-352, 451)
         levels = []
@@ -215,14 +220,16 @@ class Plan:
             gtok = fusion(ops, m.fuse_global, levels[2], levels[3], z)
             _, ghead = motion_branch(ops, m.global_blocks, m.global_head, gtok, m.global_ws)
             i0, i1 = P(B, 3, h16, w16), P(B, 3, h16, w16)
-            ops.resize(pyr0[3], i0); ops.resize(pyr1[3], i1)
+            with ops.replicated():
+                ops.resize(pyr0[3], i0); ops.resize(pyr1[3], i1)
             a0, a1, it = P(B, 3, h16, w16), P(B, 3, h16, w16), P(B, 3, h16, w16)
             f0, f1 = P(B, 2, h16, w16), P(B, 2, h16, w16)
             ops.warp_blend(i0, i1, ghead, a0, a1, it, f0, f1)
             it_list.insert(0, it); w0_list.insert(0, a0); w1_list.insert(0, a1)
             # flows x2 up to 1/8, warp the fused tokens of each frame (network_base.py:471-478)
             f0u, f1u = P(B, 2, h8, w8), P(B, 2, h8, w8)
-            ops.resize(f0, f0u, 2.0); ops.resize(f1, f1u, 2.0)
+            with ops.replicated():    # the global flows drive the warps of the whole image pyramid below
+                ops.resize(f0, f0u, 2.0); ops.resize(f1, f1u, 2.0)
             fl = ops.new_map(2 * B, h8, w8, 2)
             ops.nchw_to_nhwc(f0u, fl.batch(0, B), zero_fill_to=fl.pitch)
             ops.nchw_to_nhwc(f1u, fl.batch(B, B), zero_fill_to=fl.pitch)
@@ -231,14 +238,15 @@ class Plan:
             tok = tokw
             # warp every pyramid level with the global flow, coarse to fine (network_base.py:480-485)
             f0, f1 = f0u, f1u
-            for l in (3, 2, 1, 0):
-                n0, n1 = P(*pyr0[l].shape), P(*pyr1[l].shape)
-                ops.flow_warp_nchw(pyr0[l], f0, n0); ops.flow_warp_nchw(pyr1[l], f1, n1)
-                pyr0[l], pyr1[l] = n0, n1
-                if l:
-                    g0, g1 = P(B, 2, H >> (l - 1), W >> (l - 1)), P(B, 2, H >> (l - 1), W >> (l - 1))
-                    ops.resize(f0, g0, 2.0); ops.resize(f1, g1, 2.0)
-                    f0, f1 = g0, g1
+            with ops.replicated():    # 3-channel images: recomputing them on every rank is cheaper than gathering them
+                for l in (3, 2, 1, 0):
+                    n0, n1 = P(*pyr0[l].shape), P(*pyr1[l].shape)
+                    ops.flow_warp_nchw(pyr0[l], f0, n0); ops.flow_warp_nchw(pyr1[l], f1, n1)
+                    pyr0[l], pyr1[l] = n0, n1
+                    if l:
+                        g0, g1 = P(B, 2, H >> (l - 1), W >> (l - 1)), P(B, 2, H >> (l - 1), W >> (l - 1))
+                        ops.resize(f0, g0, 2.0); ops.resize(f1, g1, 2.0)
+                        f0, f1 = g0, g1
 
         tok, lhead = motion_branch(ops, m.local_blocks, m.local_head, tok, m.local_ws)
         for k, shift in enumerate((0, ENHANCE_WINDOW // 2)):
@@ -314,6 +322,8 @@ class Plan:
 
         self.outputs = {"I_t": out, "im_t_list": it_list, "im0_warped_list": w0_list, "im1_warped_list": w1_list,
                         "opt_flow_0": flow0, "opt_flow_1": flow1, "I_t_0": a0, "I_t_1": a1, "occ_mask1": occ1, "occ_mask2": occ2}
+        if hasattr(ops, "gather_outputs"):      # row slabs: bring every rank's rows of the public tensors to rank 0
+            ops.gather_outputs(self.outputs)
 
     # .............................................................................................
     def launch(self, stream: Optional[int] = None) -> None:

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -116,6 +116,17 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+Rows = Optional[Tuple[int, int]]      # row window [y0, y1) of every image of the op's output grid; None = all rows
+
+
+def _yy(rows: Rows) -> Tuple[int, int]:
+    if rows is None:
+        return 0, 0
+    y0, y1 = rows
+    assert 0 <= y0 < y1, rows             # an empty window is skipped by the caller, (0, 0) means "all" in the C ABI
+    return int(y0), int(y1)
+
+
 class CudaOps:
     """Launches the sm_100a kernels.  No fallback: construction fails without the library or a CUDA device."""
 
@@ -130,15 +141,30 @@ class CudaOps:
         self.recording: Optional[List] = None
         self._keep: List = []
         self.launches = 0
+        # optional allocator (shape, zero) -> fp32 tensor; the row-slab mode places every buffer in an IPC-shared arena
+        self.allocator: Optional[Callable] = None
 
     # -- memory -------------------------------------------------------------------------------
+    def _alloc(self, shape, zero: bool) -> torch.Tensor:
+        if self.allocator is not None:
+            return self.allocator(tuple(shape), zero)
+        return (torch.zeros if zero else torch.empty)(tuple(shape), device=self.device, dtype=torch.float32)
+
     def new_map(self, B: int, H: int, W: int, C: int, zero: bool = False) -> Map:
         pitch = round_up(C, 4)
-        f = torch.zeros if (zero or pitch != C) else torch.empty
-        return Map(f((B, H, W, pitch), device=self.device, dtype=torch.float32), 0, C)
+        return Map(self._alloc((B, H, W, pitch), zero or pitch != C), 0, C)
+
+    def new_win_map(self, g: "WinGeom", C: int) -> Map:
+        """Window-major token rows [1, 1, B2*Hp*Wp, C] (what window_partition produces, attention.py:8-15)."""
+        return self.new_map(1, 1, g.rows, C)
 
     def new_planar(self, *shape: int) -> torch.Tensor:
-        return torch.empty(shape, device=self.device, dtype=torch.float32)
+        return self._alloc(shape, False)
+
+    def replicated(self):
+        """Context in which ops are computed for ALL rows on every rank (a no-op without row slabs)."""
+        import contextlib
+        return contextlib.nullcontext()
 
     # -- launch plumbing ----------------------------------------------------------------------
     def _emit(self, name: str, args: tuple, keep=()):
@@ -149,6 +175,13 @@ class CudaOps:
             self.lib.atmvfi_set_output_rounding(1 if self.precision == _lib.TF32 else 0)
             _lib.check(fn(*args, torch.cuda.current_stream(self.device).cuda_stream), name)
             self.launches += 1
+
+    def emit_host(self, fn: Callable[[], None]) -> None:
+        """Record (or run) a host-side callable in launch order; used by test transports, never by the product path."""
+        if self.recording is not None:
+            self.recording.append(("host", lambda *a: fn() or 0, (), None))
+        else:
+            fn()
 
     def replay(self, records, stream: Optional[int] = None) -> None:
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
@@ -175,7 +208,7 @@ class CudaOps:
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride: int = 1, dil: int = 1,
                   act: bool = True, residual: Optional[Map] = None, out2: Optional[Map] = None,
                   prelu2: Optional[torch.Tensor] = None, win: Optional[WinGeom] = None,
-                  precision: Optional[int] = None):
+                  precision: Optional[int] = None, rows: Rows = None):
         assert [s.C for s in srcs] == list(w.split), (w.name, [s.C for s in srcs], w.split)
         s0 = srcs[0]
         for s in srcs:
@@ -209,6 +242,8 @@ class CudaOps:
         else:
             d.out_mode = _lib.OUT_PIXEL
             assert out.nrows == s0.B * Hout * Wout, (w.name, out.t.shape, (s0.B, Hout, Wout))
+        d.row_begin, d.row_end = _yy(rows)
+        assert d.row_end <= Hout
         prec = self.precision if precision is None else precision
         if prec == _lib.TF32 and not self._tc_eligible(srcs, w, out, out2):
             prec = _lib.FP32
@@ -235,37 +270,46 @@ class CudaOps:
             return False
         return True
 
-    def conv3x3_first(self, img: torch.Tensor, w: PackedGemm, out: Map):
+    def conv3x3_first(self, img: torch.Tensor, w: PackedGemm, out: Map, rows: Rows = None):
         """feat_extracts.0.0 on a planar frame (3 channels) -> NHWC."""
         b, c, h, wd = img.shape
         assert c == 3 and w.ksize == 3 and list(w.split) == [3] and (out.B, out.H, out.W, out.C) == (b, h, wd, w.Cout) and out.c0 == 0
-        self._emit("atmvfi_conv3x3_first", (img.data_ptr(), w.w32.data_ptr(), w.w32.shape[1], _p(w.bias), _p(w.prelu), out.ptr, out.pitch, b, h, wd, w.Cout),
+        self._emit("atmvfi_conv3x3_first", (img.data_ptr(), w.w32.data_ptr(), w.w32.shape[1], _p(w.bias), _p(w.prelu), out.ptr, out.pitch, b, h, wd, w.Cout) + _yy(rows),
                    keep=(img, w, out))
 
-    def pack5_planar(self, imgs: Sequence[torch.Tensor], out: Map):
+    def pack5_planar(self, imgs: Sequence[torch.Tensor], out: Map, rows: Rows = None):
         b, _, h, wd = imgs[0].shape
         assert len(imgs) == 5 and all(t.shape == (b, 3, h, wd) and t.is_contiguous() for t in imgs) and out.c0 == 0 and out.pitch >= 16
-        self._emit("atmvfi_pack5_planar", tuple(t.data_ptr() for t in imgs) + (out.ptr, out.pitch, b, h, wd), keep=(imgs, out))
+        self._emit("atmvfi_pack5_planar", tuple(t.data_ptr() for t in imgs) + (out.ptr, out.pitch, b, h, wd) + _yy(rows), keep=(imgs, out))
 
     # -- transformer pieces -------------------------------------------------------------------
-    def layernorm(self, x: Map, out: Map, gamma: torch.Tensor, beta: torch.Tensor):
+    def layernorm(self, x: Map, out: Map, gamma: torch.Tensor, beta: torch.Tensor, rows: Rows = None):
         assert x.C == out.C == gamma.numel()
-        self._emit("atmvfi_layernorm", (x.ptr, x.pitch, out.ptr, out.pitch, x.nrows, x.C, gamma.data_ptr(), beta.data_ptr(), 1e-5),
-                   keep=(x, out, gamma, beta))
+        if rows is None:
+            self._emit("atmvfi_layernorm", (x.ptr, x.pitch, out.ptr, out.pitch, x.nrows, x.C, gamma.data_ptr(), beta.data_ptr(), 1e-5),
+                       keep=(x, out, gamma, beta))
+            return
+        # per-token op: a row window is a contiguous run of tokens in every image
+        assert (x.B, x.H, x.W) == (out.B, out.H, out.W)
+        y0, y1 = _yy(rows)
+        for b in range(x.B):
+            first = (b * x.H + y0) * x.W
+            self._emit("atmvfi_layernorm", (x.ptr + 4 * first * x.pitch, x.pitch, out.ptr + 4 * first * out.pitch, out.pitch, (y1 - y0) * x.W, x.C,
+                                            gamma.data_ptr(), beta.data_ptr(), 1e-5), keep=(x, out, gamma, beta))
 
-    def window_gather_ln(self, tok: Map, win: Map, g: WinGeom, gamma: torch.Tensor, beta: torch.Tensor):
+    def window_gather_ln(self, tok: Map, win: Map, g: WinGeom, gamma: torch.Tensor, beta: torch.Tensor, rows: Rows = None):
         assert tok.nrows == g.B2 * g.H * g.W and win.nrows == g.rows and tok.C == win.C
         gc = g.c()
-        self._emit("atmvfi_window_gather_ln", (tok.ptr, tok.pitch, win.ptr, win.pitch, tok.C, C.byref(gc), gamma.data_ptr(), beta.data_ptr(), 1e-5),
+        self._emit("atmvfi_window_gather_ln", (tok.ptr, tok.pitch, win.ptr, win.pitch, tok.C, C.byref(gc), gamma.data_ptr(), beta.data_ptr(), 1e-5) + _yy(rows),
                    keep=(tok, win, gc, gamma, beta))
 
     def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads: int, cross: bool, rc: Optional[torch.Tensor] = None,
                          mix: Optional[Sequence[torch.Tensor]] = None, motion: Optional[Map] = None, motion_off: int = 0,
-                         scratch: Optional[torch.Tensor] = None, rc_closed_form: bool = False):
+                         scratch: Optional[torch.Tensor] = None, rc_closed_form: bool = False, rows: Rows = None):
         assert qkv.C == 3 * out.C and qkv.nrows == g.rows == out.nrows
         gc = g.c()
         m = [None] * 4 if mix is None else [t.data_ptr() for t in mix]
-        tail = (m[0], m[1], m[2], m[3], None if motion is None else motion.ptr, 0 if motion is None else motion.pitch, motion_off, _p(scratch))
+        tail = (m[0], m[1], m[2], m[3], None if motion is None else motion.ptr, 0 if motion is None else motion.pitch, motion_off, _p(scratch)) + _yy(rows)
         head = (qkv.ptr, qkv.pitch, out.ptr, out.pitch, out.C, heads, C.byref(gc), int(cross), _p(rc))
         keep = (qkv, out, gc, rc, mix, motion, scratch)
         if self.precision == _lib.TF32:
@@ -273,42 +317,42 @@ class CudaOps:
         else:
             self._emit("atmvfi_window_attention", head + tail, keep=keep)
 
-    def dwconv_gelu(self, x: Map, out: Map, w9c: torch.Tensor, bias: torch.Tensor):
+    def dwconv_gelu(self, x: Map, out: Map, w9c: torch.Tensor, bias: torch.Tensor, rows: Rows = None):
         assert x.c0 == 0 and out.c0 == 0 and x.pitch == out.pitch and x.C == out.C
-        self._emit("atmvfi_dwconv3x3_gelu", (x.ptr, out.ptr, x.B, x.H, x.W, x.C, x.pitch, w9c.data_ptr(), bias.data_ptr()),
+        self._emit("atmvfi_dwconv3x3_gelu", (x.ptr, out.ptr, x.B, x.H, x.W, x.C, x.pitch, w9c.data_ptr(), bias.data_ptr()) + _yy(rows),
                    keep=(x, out, w9c, bias))
 
     # -- warps, resampling, layout ------------------------------------------------------------
-    def flow_warp_nchw(self, img: torch.Tensor, flow: torch.Tensor, out: torch.Tensor):
+    def flow_warp_nchw(self, img: torch.Tensor, flow: torch.Tensor, out: torch.Tensor, rows: Rows = None):
         b, c, h, w = img.shape
         assert flow.shape == (b, 2, h, w) and img.is_contiguous() and flow.is_contiguous() and out.is_contiguous()
-        self._emit("atmvfi_flow_warp_nchw", (img.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w), keep=(img, flow, out))
+        self._emit("atmvfi_flow_warp_nchw", (img.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w) + _yy(rows), keep=(img, flow, out))
 
-    def flow_warp_nhwc(self, src: Map, head: Map, flow_off: int, out: Map):
+    def flow_warp_nhwc(self, src: Map, head: Map, flow_off: int, out: Map, rows: Rows = None):
         assert (src.B, src.H, src.W) == (head.B, head.H, head.W) == (out.B, out.H, out.W) and src.C == out.C
-        self._emit("atmvfi_flow_warp_nhwc", (src.ptr, src.pitch, head.ptr, head.pitch, flow_off, out.ptr, out.pitch, src.B, src.C, src.H, src.W),
+        self._emit("atmvfi_flow_warp_nhwc", (src.ptr, src.pitch, head.ptr, head.pitch, flow_off, out.ptr, out.pitch, src.B, src.C, src.H, src.W) + _yy(rows),
                    keep=(src, head, out))
 
-    def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None):
+    def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None, rows: Rows = None):
         b, _, h, w = im0.shape
         assert (head.B, head.H, head.W) == (b, h, w) and head.C >= 5
         self._emit("atmvfi_warp_blend", (im0.data_ptr(), im1.data_ptr(), head.ptr, head.pitch, 0, w0.data_ptr(), w1.data_ptr(), it.data_ptr(),
-                                         _p(flow0), _p(flow1), _p(occ1), _p(occ2), b, h, w),
+                                         _p(flow0), _p(flow1), _p(occ1), _p(occ2), b, h, w) + _yy(rows),
                    keep=(im0, im1, head, w0, w1, it, flow0, flow1, occ1, occ2))
 
-    def resize(self, x: torch.Tensor, out: torch.Tensor, scale: float = 1.0):
+    def resize(self, x: torch.Tensor, out: torch.Tensor, scale: float = 1.0, rows: Rows = None):
         assert x.is_contiguous() and out.is_contiguous() and x.shape[:2] == out.shape[:2]
-        self._emit("atmvfi_resize_bilinear_ac", (x.data_ptr(), out.data_ptr(), x.shape[0] * x.shape[1], x.shape[2], x.shape[3], out.shape[2], out.shape[3], float(scale)),
+        self._emit("atmvfi_resize_bilinear_ac", (x.data_ptr(), out.data_ptr(), x.shape[0] * x.shape[1], x.shape[2], x.shape[3], out.shape[2], out.shape[3], float(scale)) + _yy(rows),
                    keep=(x, out))
 
-    def nchw_to_nhwc(self, x: torch.Tensor, out: Map, zero_fill_to: int = 0):
+    def nchw_to_nhwc(self, x: torch.Tensor, out: Map, zero_fill_to: int = 0, rows: Rows = None):
         b, c, h, w = x.shape
         assert (out.B, out.H, out.W) == (b, h, w) and out.C >= c and x.is_contiguous()
-        self._emit("atmvfi_nchw_to_nhwc", (x.data_ptr(), out.t.data_ptr(), out.pitch, out.c0, b, c, h, w, zero_fill_to), keep=(x, out))
+        self._emit("atmvfi_nchw_to_nhwc", (x.data_ptr(), out.t.data_ptr(), out.pitch, out.c0, b, c, h, w, zero_fill_to) + _yy(rows), keep=(x, out))
 
-    def residual_finish(self, res: Map, it, it_sum, it_clamped):
+    def residual_finish(self, res: Map, it, it_sum, it_clamped, rows: Rows = None):
         b, _, h, w = it.shape
-        self._emit("atmvfi_residual_finish", (res.ptr, res.pitch, it.data_ptr(), _p(it_sum), it_clamped.data_ptr(), b, h, w),
+        self._emit("atmvfi_residual_finish", (res.ptr, res.pitch, it.data_ptr(), _p(it_sum), it_clamped.data_ptr(), b, h, w) + _yy(rows),
                    keep=(res, it, it_sum, it_clamped))
 
     def u8_to_planar(self, src_u8: torch.Tensor, out: torch.Tensor, H, W, Hp, Wp, top, left, bgr: bool):

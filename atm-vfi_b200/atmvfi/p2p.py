@@ -1,0 +1,200 @@
+"""NVLink peer-to-peer plumbing of the row-slab mode: an IPC-shared arena per rank and the exchange transport
+that ``slab.SlabOps`` schedules against (C side: csrc/p2p.cu, ABI: include/atmvfi.h "Spatial row-slab mode").
+
+One process per GPU (torchrun).  ``torch.distributed`` is used ONLY to pass the 64-byte CUDA IPC handles around
+and for the host-side barrier after set-up; rows move through peer-mapped stores issued by our own kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import PackedModel, Plan
+from .ops import CudaOps
+from .slab import Push, SlabOps
+
+CTRL_BYTES = 1 << 20            # control block at the start of every arena
+OFF_EPOCH, OFF_ERROR, OFF_READY, OFF_COUNTERS, OFF_FLAGS = 0, 16, 64, 4096, 65536
+MAX_SITES = 8192
+ALIGN = 1024
+
+
+class _DevMem:
+    """Raw device memory exposed to torch through __cuda_array_interface__ (no copy, no ownership)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class P2PArena:
+    """One cudaMalloc'ed block per rank with the same layout everywhere; peers' blocks are mapped through CUDA IPC."""
+
+    def __init__(self, device: torch.device, nbytes: int, group=None):
+        self.lib = _lib.load()
+        self.device, self.group = device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > _lib.P2P_MAX_PEERS:
+            raise _lib.AtmvfiError(f"row slabs support up to {_lib.P2P_MAX_PEERS} ranks, got {self.world}")
+        self.nbytes = (nbytes + ALIGN - 1) // ALIGN * ALIGN
+        with torch.cuda.device(device):
+            p = C.c_void_p()
+            _lib.check(self.lib.atmvfi_arena_alloc(self.nbytes, C.byref(p)), "arena_alloc")
+            self.base = p.value
+            self.bytes_view = torch.as_tensor(_DevMem(self.base, self.nbytes), device=device)
+            assert self.bytes_view.data_ptr() == self.base, "torch copied the arena instead of wrapping it"
+            self.bytes_view.zero_()
+            torch.cuda.synchronize(device)
+            handle = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+            _lib.check(self.lib.atmvfi_ipc_export(self.base, handle), "ipc_export")
+            handles: List[Optional[bytes]] = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.peer_base: List[int] = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.peer_base.append(self.base)
+                    continue
+                q = C.c_void_p()
+                _lib.check(self.lib.atmvfi_ipc_open(C.create_string_buffer(h, _lib.IPC_HANDLE_BYTES), C.byref(q)), f"ipc_open(rank {r})")
+                self.peer_base.append(q.value)
+            dist.barrier(group=group)                  # every arena is zeroed and mapped before anyone pushes
+        self.top = CTRL_BYTES
+        self._closed = False
+
+    def alloc(self, shape, zero: bool) -> torch.Tensor:
+        n = 4
+        for s in shape:
+            n *= int(s)
+        off = self.top
+        self.top = (off + n + ALIGN - 1) // ALIGN * ALIGN
+        if self.top > self.nbytes:
+            raise _lib.AtmvfiError(f"row-slab arena of {self.nbytes >> 20} MiB exhausted (need > {self.top >> 20} MiB); pass a larger arena_bytes")
+        # the arena starts zeroed and is never recycled, so `zero` needs no extra work
+        return self.bytes_view[off : off + n].view(torch.float32).view(*shape)
+
+    def peer(self, rank: int, local_ptr: int) -> int:
+        off = local_ptr - self.base
+        assert 0 <= off < self.nbytes, "pointer is not inside the arena"
+        return self.peer_base[rank] + off
+
+    def ctrl(self, rank: int, offset: int) -> int:
+        return self.peer_base[rank] + offset
+
+    def error_flag(self) -> int:
+        return int(self.bytes_view[OFF_ERROR : OFF_ERROR + 4].view(torch.int32).item())
+
+    def close(self) -> None:
+        if self._closed:
+            return
+        self._closed = True
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for r, p in enumerate(self.peer_base):
+            if r != self.rank:
+                self.lib.atmvfi_ipc_close(p)
+        dist.barrier(group=self.group)
+        self.bytes_view = None
+        self.lib.atmvfi_arena_free(self.base)
+
+
+class P2PTransport:
+    """``slab.SlabOps`` transport: one ``atmvfi_p2p_exchange`` launch per exchange site."""
+
+    def __init__(self, arena: P2PArena):
+        self.arena, self.rank, self.world = arena, arena.rank, arena.world
+        self.slab: Optional[SlabOps] = None
+
+    def attach(self, slab: SlabOps) -> None:
+        self.slab = slab
+
+    def _ptr_array(self, ptrs: List[int]):
+        return (C.c_void_p * max(1, len(ptrs)))(*ptrs)
+
+    def step_begin(self) -> None:
+        a = self.arena
+        others = [r for r in range(self.world) if r != self.rank]
+        sig = self._ptr_array([a.ctrl(r, OFF_READY + 4 * self.rank) for r in others])
+        wait = self._ptr_array([a.ctrl(self.rank, OFF_READY + 4 * r) for r in others])
+        self.slab.backend._emit("atmvfi_p2p_step_begin", (a.ctrl(self.rank, OFF_EPOCH), sig, len(others), wait, len(others), a.ctrl(self.rank, OFF_ERROR)),
+                                keep=(sig, wait))
+
+    def exchange(self, site: int, outgoing: List[Push], incoming: List[Push]) -> None:
+        if not outgoing and not incoming:
+            return
+        if site >= MAX_SITES:
+            raise _lib.AtmvfiError(f"more than {MAX_SITES} exchange sites in one plan")
+        a, me = self.arena, self.rank
+        pieces = []
+        for ps in outgoing:
+            b = ps.buf
+            start = b.t.data_ptr() + ((ps.img0 * b.planes) * b.H + ps.lo) * b.row_bytes
+            pc = _lib.P2PPiece(start, a.peer(ps.dst, start), (ps.hi - ps.lo) * b.row_bytes, b.H * b.row_bytes, ps.nimg * b.planes, 0)
+            pieces.append(pc)
+        dsts = sorted({ps.dst for ps in outgoing})
+        srcs = sorted({ps.src for ps in incoming})
+        sig = self._ptr_array([a.ctrl(d, OFF_FLAGS + 4 * (site * _lib.P2P_MAX_PEERS + me)) for d in dsts])
+        wait = self._ptr_array([a.ctrl(me, OFF_FLAGS + 4 * (site * _lib.P2P_MAX_PEERS + s)) for s in srcs])
+        epoch, counter, err = a.ctrl(me, OFF_EPOCH), a.ctrl(me, OFF_COUNTERS + 4 * site), a.ctrl(me, OFF_ERROR)
+        n = _lib.P2P_MAX_PIECES
+        groups = [pieces[i : i + n] for i in range(0, len(pieces), n)] or [[]]
+        for gi, grp in enumerate(groups):
+            arr = (_lib.P2PPiece * max(1, len(grp)))(*grp)
+            last = gi == len(groups) - 1
+            self.slab.backend._emit("atmvfi_p2p_exchange",
+                                    (arr, len(grp), sig, len(dsts) if last else 0, wait, len(srcs) if last else 0, epoch, counter, err),
+                                    keep=(arr, sig, wait, [ps.buf.t for ps in outgoing]))
+
+
+def default_arena_bytes(arch_name: str, B: int, H: int, W: int) -> int:
+    """Plan buffers measured at 19 GB (Base, 1088x1920) / 78 GB (Base, 2176x4096): ~9.2 KB per pixel; Lite is ~half."""
+    per_px = 10.5e3 if arch_name == "base" else 6.5e3
+    return int(per_px * B * H * W) + (768 << 20)
+
+
+class SlabSession:
+    """One frame pair (or batch) split into row slabs over the ranks of ``group``.  Every rank calls ``run`` with the FULL
+    frames; rank 0 returns the gathered outputs (``gather``: "I_t" only, "all" ten entries, "none")."""
+
+    def __init__(self, net, B: int, H: int, W: int, global_motion: Optional[bool] = None, group=None, gather: str = "I_t",
+                 arena_bytes: Optional[int] = None):
+        from .runtime import PRECISIONS
+        dev = next(net.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.AtmvfiError("row slabs need the model on a CUDA device; there is no CPU fallback")
+        if not dist.is_initialized():
+            raise _lib.AtmvfiError("row slabs need torch.distributed (one process per GPU, launched with torchrun)")
+        glob = bool(net.global_motion if global_motion is None else global_motion)
+        self.device = dev
+        with torch.cuda.device(dev):
+            self.arena = P2PArena(dev, arena_bytes or default_arena_bytes(net.ARCH.name, B, H, W), group)
+            self.ops = CudaOps(dev, PRECISIONS[net.precision])
+            self.ops.allocator = self.arena.alloc
+            self.transport = P2PTransport(self.arena)
+            self.slab = SlabOps(self.ops, self.arena.rank, self.arena.world, self.transport, gather)
+            sd = {k: v.detach() for k, v in net.state_dict().items()}
+            self.model = PackedModel(net.ARCH, sd, net.local_motion_args["window_size"], net.global_motion_args["window_size"], with_global=True)
+            self.plan = Plan(self.slab, self.model, B, H, W, glob)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)
+        self.rank, self.world = self.arena.rank, self.arena.world
+
+    def run(self, im0: torch.Tensor, im1: torch.Tensor, use_graph: bool = True) -> Dict[str, object]:
+        with torch.cuda.device(self.device):
+            return self.plan.run(im0, im1, use_graph=use_graph)
+
+    def run_inplace(self, use_graph: bool = True) -> Dict[str, object]:
+        with torch.cuda.device(self.device):
+            return self.plan.run_inplace(use_graph=use_graph)
+
+    def check(self) -> None:
+        """Raise if a peer wait timed out on the device (a rank died or the ranks ran different step counts)."""
+        torch.cuda.synchronize(self.device)
+        if self.arena.error_flag():
+            raise _lib.AtmvfiError("row-slab exchange timed out waiting for a peer (see csrc/p2p.cu kSpinTimeoutNs)")
+
+    def close(self) -> None:
+        self.plan = None
+        self.arena.close()

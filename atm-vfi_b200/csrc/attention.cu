@@ -14,7 +14,7 @@ template <int HD>
 __global__ void __launch_bounds__(256) window_attention_kernel(const float* __restrict__ qkv, int qkv_pitch,
                                                                float* __restrict__ out, int out_pitch, int C, int heads,
                                                                atmvfi_window_geom g, int cross,
-                                                               const float* __restrict__ rc, float* __restrict__ motion_raw, bool rnd) {
+                                                               const float* __restrict__ rc, float* __restrict__ motion_raw, int wy0, int nwy, bool rnd) {
   extern __shared__ float smem[];
   const int N = g.ws * g.ws;
   float* sk = smem;             // [N][HD]
@@ -22,8 +22,10 @@ __global__ void __launch_bounds__(256) window_attention_kernel(const float* __re
   int* slab = reinterpret_cast<int*>(smem + 2 * N * HD);   // [N] mask labels
 
   const int h = blockIdx.y;
-  const int64_t win = blockIdx.x;
   const int nW = (g.Hp / g.ws) * (g.Wp / g.ws);
+  // blockIdx.x enumerates the windows of the row window [wy0, wy0+nwy) of every image
+  const int per_img = nwy * (g.Wp / g.ws);
+  const int64_t win = (int64_t)(blockIdx.x / per_img) * nW + wy0 * (g.Wp / g.ws) + blockIdx.x % per_img;
   const int64_t total_win = (int64_t)g.B2 * nW;
   // the other frame's copy of this window sits half the window batch away (attention.py:318)
   const int64_t kv_win = cross ? (win + total_win / 2) % total_win : win;
@@ -106,14 +108,17 @@ __global__ void __launch_bounds__(256) window_attention_kernel(const float* __re
 
 // motion[b, y, x, off + frame*2 + xy] = w2 . gelu(w0 . m_heads + b0) + b2     (attention.py:143-146, 209-211)
 __global__ void __launch_bounds__(256) motion_mix_kernel(const float* __restrict__ motion_raw, int heads,
-                                                         atmvfi_window_geom g, int64_t rows,
+                                                         atmvfi_window_geom g, int64_t rows, int wy0, int nwy,
                                                          const float* __restrict__ w0, const float* __restrict__ b0,
                                                          const float* __restrict__ w2, const float* __restrict__ b2,
                                                          float* __restrict__ motion, int motion_pitch, int motion_off) {
   const int hid = heads / 2;
   const int pairs = g.B2 / 2;
+  const int64_t per_img = (int64_t)g.Hp * g.Wp, per_win = (int64_t)nwy * g.ws * g.Wp;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < rows * 2; t += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r = t >> 1;
+    const int64_t rr = t >> 1;
+    const int64_t bi = rr / per_win;
+    const int64_t r = bi * per_img + (int64_t)wy0 * g.ws * g.Wp + (rr - bi * per_win);
     int xy = (int)(t & 1);
     WinPos p = win_decode(g, r);
     if (!p.real) continue;
@@ -132,9 +137,10 @@ __global__ void __launch_bounds__(256) motion_mix_kernel(const float* __restrict
 
 template <int HD>
 int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
-                     const atmvfi_window_geom& g, int cross, const float* rc, float* motion_raw, cudaStream_t st) {
+                     const atmvfi_window_geom& g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, cudaStream_t st) {
   const int N = g.ws * g.ws;
-  const int64_t wins = (int64_t)g.B2 * (g.Hp / g.ws) * (g.Wp / g.ws);
+  const int64_t wins = (int64_t)g.B2 * nwy * (g.Wp / g.ws);
+  if (wins <= 0) return 0;
   size_t smem = (size_t)(2 * N * HD) * sizeof(float) + N * sizeof(int);
   auto kern = window_attention_kernel<HD>;
   if (smem > 48 * 1024) {
@@ -146,7 +152,7 @@ int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch,
   }
   dim3 grid((unsigned)wins, (unsigned)heads);
   int threads = ((N + 31) / 32) * 32;
-  kern<<<grid, threads, smem, st>>>(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, rc, motion_raw, atmvfi_output_rounding() != 0);
+  kern<<<grid, threads, smem, st>>>(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, rc, motion_raw, wy0, nwy, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("window_attention");
   return 0;
 }
@@ -154,39 +160,43 @@ int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch,
 }  // namespace
 
 int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
-                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, cudaStream_t st);
+                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, cudaStream_t st);
 
 static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                           const atmvfi_window_geom* g, int cross, const float* relative_coord, const float* mix_w0, const float* mix_b0,
                           const float* mix_w2, const float* mix_b2, float* motion, int motion_pitch, int motion_off, float* scratch,
-                          void* stream);
+                          int wy0, int wy1, void* stream);
 
 extern "C" int atmvfi_window_attention_tc(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                                           const atmvfi_window_geom* g, int cross, const float* relative_coord, int rc_closed_form,
                                           const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
-                                          float* motion, int motion_pitch, int motion_off, float* scratch, void* stream) {
+                                          float* motion, int motion_pitch, int motion_off, float* scratch, int wy0, int wy1,
+                                          void* stream) {
   return attention_impl(true, rc_closed_form, qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, relative_coord, mix_w0, mix_b0, mix_w2,
-                        mix_b2, motion, motion_pitch, motion_off, scratch, stream);
+                        mix_b2, motion, motion_pitch, motion_off, scratch, wy0, wy1, stream);
 }
 
 extern "C" int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                                        const atmvfi_window_geom* g, int cross, const float* relative_coord,
                                        const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
-                                       float* motion, int motion_pitch, int motion_off, float* scratch, void* stream) {
+                                       float* motion, int motion_pitch, int motion_off, float* scratch, int wy0, int wy1,
+                                       void* stream) {
   return attention_impl(false, 0, qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, relative_coord, mix_w0, mix_b0, mix_w2, mix_b2,
-                        motion, motion_pitch, motion_off, scratch, stream);
+                        motion, motion_pitch, motion_off, scratch, wy0, wy1, stream);
 }
 
 static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                           const atmvfi_window_geom* g, int cross, const float* relative_coord, const float* mix_w0, const float* mix_b0,
                           const float* mix_w2, const float* mix_b2, float* motion, int motion_pitch, int motion_off, float* scratch,
-                          void* stream) {
+                          int wy0, int wy1, void* stream) {
   ATMVFI_REQUIRE(heads > 0 && C % heads == 0, "window_attention: dim %d should be divided by num_heads %d", C, heads);
   const int hd = C / heads, N = g->ws * g->ws;
   ATMVFI_REQUIRE(N <= 256, "window_attention: window %d too large (max 16)", g->ws);
   ATMVFI_REQUIRE(g->Hp % g->ws == 0 && g->Wp % g->ws == 0 && g->shift >= 0 && g->shift < g->ws, "window_attention: bad geometry");
   ATMVFI_REQUIRE(!cross || g->B2 % 2 == 0, "window_attention: cross attention needs an even batch");
   ATMVFI_REQUIRE(qkv_pitch % 4 == 0 && out_pitch % 4 == 0 && hd % 4 == 0, "window_attention: pitches / head dim must be multiples of 4");
+  int nwy;
+  ATMVFI_REQUIRE(row_window(g->Hp / g->ws, wy0, wy1, &wy0, &nwy), "window_attention: bad window-row range [%d,%d)", wy0, wy1);
   const bool want_motion = motion != nullptr;
   ATMVFI_REQUIRE(!want_motion || (relative_coord && scratch && mix_w0 && mix_b0 && mix_w2 && mix_b2 && cross),
                  "window_attention: motion output needs relative_coord, scratch and the head-mix MLP");
@@ -195,26 +205,26 @@ static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qk
   const float* rc = want_motion ? relative_coord : nullptr;
   int rcode = 3;
   if (tensor_cores)
-    rcode = atmvfi_window_attention_tc_launch(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, (want_motion && !rc_closed_form) ? rc : nullptr, raw, st);
+    rcode = atmvfi_window_attention_tc_launch(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, (want_motion && !rc_closed_form) ? rc : nullptr, raw, wy0, nwy, st);
   if (rcode == 3)      // shape outside the tcgen05 kernel's envelope (or fp32 requested): CUDA-core kernel
   switch (hd) {
-    case 28: rcode = launch_attention<28>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
-    case 44: rcode = launch_attention<44>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
-    case 48: rcode = launch_attention<48>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
-    case 84: rcode = launch_attention<84>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
-    case 16: rcode = launch_attention<16>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
-    case 32: rcode = launch_attention<32>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
-    case 64: rcode = launch_attention<64>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, st); break;
+    case 28: rcode = launch_attention<28>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
+    case 44: rcode = launch_attention<44>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
+    case 48: rcode = launch_attention<48>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
+    case 84: rcode = launch_attention<84>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
+    case 16: rcode = launch_attention<16>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
+    case 32: rcode = launch_attention<32>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
+    case 64: rcode = launch_attention<64>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
     default:
       atmvfi_set_error("window_attention: head dim %d not instantiated (have 16,28,32,44,48,64,84)", hd);
       return 2;
   }
   if (rcode) return rcode;
   if (want_motion) {
-    int64_t rows = (int64_t)g->B2 * g->Hp * g->Wp;
+    int64_t rows = (int64_t)g->B2 * nwy * g->ws * g->Wp;
     int blocks = (int)((rows * 2 + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    motion_mix_kernel<<<blocks, 256, 0, st>>>(raw, heads, *g, rows, mix_w0, mix_b0, mix_w2, mix_b2, motion, motion_pitch, motion_off);
+    if (blocks > 0) motion_mix_kernel<<<blocks, 256, 0, st>>>(raw, heads, *g, rows, wy0, nwy, mix_w0, mix_b0, mix_w2, mix_b2, motion, motion_pitch, motion_off);
     ATMVFI_CHECK_LAUNCH("motion_mix");
   }
   return 0;

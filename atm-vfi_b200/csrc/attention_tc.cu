@@ -32,6 +32,7 @@ struct AttnParams {
   float* motion_raw;          // [rows][heads][2] or nullptr
   int N, wpi, mtiles, KP, HP, chunksH, chunksK;
   int total_windows, nW;
+  int wy0, per_img, virt_windows;   // row window: windows [wy0*nwx, +per_img) of every image, virt_windows = B2*per_img
   int tmem_cols;
   int round;
   float scale;
@@ -130,10 +131,12 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   const int ws = p.g.ws;
   // (window-local index, token) of row / key `r`; window < 0: padding row of the tile
   auto locate = [&](int r, int base_tok, int& wl, int& tok) -> int64_t {
-    if (p.wpi == 1) { wl = 0; tok = base_tok + r; return tok < N ? win0 : -1; }
+    // virtual window index v (dense over the row window) -> window id in the full window-major tensor
+    auto actual = [&](int64_t v) -> int64_t { const int vi = (int)v, bi = vi / p.per_img; return (int64_t)bi * p.nW + p.wy0 * nwx + (vi - bi * p.per_img); };
+    if (p.wpi == 1) { wl = 0; tok = base_tok + r; return tok < N ? actual(win0) : -1; }
     wl = r / N;
     tok = r - wl * N;
-    return (wl < p.wpi && win0 + wl < total_win) ? win0 + wl : -1;
+    return (wl < p.wpi && win0 + wl < p.virt_windows) ? actual(win0 + wl) : -1;
   };
   auto mask_label = [&](int64_t w, int tok) -> int {
     if (!masked) return 0;
@@ -325,7 +328,7 @@ inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 
 // Returns 0 on success, 3 if the shape is outside what this kernel handles (caller falls back to the fp32 kernel).
 int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
-                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, cudaStream_t st) {
+                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, cudaStream_t st) {
   AttnParams p;
   p.qkv = qkv; p.qkv_pitch = qkv_pitch; p.out = out; p.out_pitch = out_pitch; p.C = C; p.heads = heads; p.hd = C / heads;
   p.g = *g; p.cross = cross; p.rc = rc; p.motion_raw = motion_raw;
@@ -333,6 +336,7 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   if (p.N > 256 || p.hd % 4 != 0 || p.hd > 96) return 3;
   p.nW = (g->Hp / g->ws) * (g->Wp / g->ws);
   p.total_windows = g->B2 * p.nW;
+  p.wy0 = wy0; p.per_img = nwy * (g->Wp / g->ws); p.virt_windows = g->B2 * p.per_img;
   if (p.N <= 64) { p.wpi = kRows / p.N; p.mtiles = 1; } else { p.wpi = 1; p.mtiles = (p.N + kRows - 1) / kRows; }
   p.KP = rup(p.wpi * p.N, 16);
   p.HP = rup(p.hd, 16);
@@ -361,7 +365,7 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
     }
     configured = smem > 100 * 1024 ? 227 * 1024 : 100 * 1024;
   }
-  const int64_t wgroups = (p.total_windows + p.wpi - 1) / p.wpi;
+  const int64_t wgroups = (p.virt_windows + p.wpi - 1) / p.wpi;
   const int64_t items = wgroups * heads * p.mtiles;
   if (items <= 0) return 0;
   window_attention_tc_kernel<<<(unsigned)items, kThreadsA, smem, st>>>(p);

@@ -29,6 +29,15 @@ int atmvfi_output_rounding();
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Row window [y0, y1) of every image of a [B][H][W] grid (include/atmvfi.h "ROW WINDOWS"); y1 == 0 means all rows.
+// Host: normalise to (y0, ny).  Returns false when the window is malformed.
+static inline bool row_window(int H, int y0, int y1, int* o_y0, int* o_ny) {
+  if (y1 == 0 && y0 == 0) { *o_y0 = 0; *o_ny = H; return true; }
+  if (y0 < 0 || y1 > H || y1 < y0) return false;
+  *o_y0 = y0; *o_ny = y1 - y0;
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Window bookkeeping (attention.py:8-71, 275-331) as index arithmetic.
 // A window-major row r enumerates (image b, window row wy, window col wx, token ty, tx) exactly like
@@ -94,6 +103,16 @@ __device__ __forceinline__ float warp_src_coord(float pix, float flow, int size)
   float gsz = (float)(size - 1);
   float g = __fadd_rn(__fdiv_rn(__fmul_rn(2.f, p), gsz), -1.f);          // 2*x/(w-1) - 1
   return __fmul_rn(__fadd_rn(g, 1.f), __fdiv_rn(gsz, 2.f));              // (g+1) * ((w-1)/2)
+}
+
+// flat index over the row window [B][ny][W] -> image b and offset rem = y*W + x inside the FULL [H][W] plane
+__device__ __forceinline__ void rw_decode(int64_t i, int W, int y0, int ny, int& b, int& y, int& x) {
+  const int64_t per = (int64_t)ny * W;
+  b = (int)(i / per);
+  const int r = (int)(i - (int64_t)b * per);
+  const int yy = r / W;
+  y = y0 + yy;
+  x = r - yy * W;
 }
 
 struct Bilin {

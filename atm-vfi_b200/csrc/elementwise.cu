@@ -70,12 +70,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __restrict__ tok, int tok_pitch,
                                                                float* __restrict__ win, int win_pitch, int C,
-                                                               atmvfi_window_geom g, int64_t rows,
+                                                               atmvfi_window_geom g, int64_t rows, int wy0, int nwy,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, bool rnd) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+  const int64_t per_img = (int64_t)g.Hp * g.Wp, per_win = (int64_t)nwy * g.ws * g.Wp;   // tokens per image: all / in the row window
+  for (int64_t rr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rr < rows; rr += warps) {
+    const int64_t bi = rr / per_win;
+    const int64_t r = bi * per_img + (int64_t)wy0 * g.ws * g.Wp + (rr - bi * per_win);
     WinPos p = win_decode(g, r);
     float* dst = win + r * win_pitch;
     if (p.real) {
@@ -101,13 +104,13 @@ __device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.f + 
 __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
                                                           int H, int W, int C, int pitch,
                                                           const float* __restrict__ w9c, const float* __restrict__ bias,
-                                                          bool rnd) {
+                                                          int wy0, int wy1, bool rnd) {
   // grid: x = (column, channel quad) flattened, y = row strip, z = image -> one 32-bit division per thread
   const int cv = C >> 2;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= W * cv) return;
   const int x = j / cv, c4 = j - x * cv;
-  const int y0 = blockIdx.y * kDwRows;
+  const int y0 = wy0 + blockIdx.y * kDwRows;
   const int b = blockIdx.z;
   float4 k[9];
 #pragma unroll
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restric
 #pragma unroll
   for (int dy = 0; dy < kDwRows; ++dy) {
     const int y = y0 + dy;
-    if (y >= H) break;
+    if (y >= wy1) break;
     load_row(y + 1, c0, c1, c2);
     // same accumulation order as a per-pixel loop: taps row-major starting from the bias
     float4 acc = bz;
@@ -151,17 +154,17 @@ template <int COUT>
 __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wk,
                                                             int ldw, const float* __restrict__ bias,
                                                             const float* __restrict__ prelu, float* __restrict__ out,
-                                                            int out_pitch, int B, int H, int W, bool rnd) {
+                                                            int out_pitch, int B, int H, int W, int wy0, int ny, bool rnd) {
   __shared__ float sw[27 * COUT];
   __shared__ float sb[COUT], sp[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = wk[(i / COUT) * ldw + (i % COUT)];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sb[i] = bias[i]; sp[i] = prelu ? prelu[i] : 1.f; }
   __syncthreads();
-  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(i / hw);
-    const int64_t rem = i - b * hw;
-    const int y = (int)(rem / W), x = (int)(rem % W);
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * ny * W;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int b, y, x;
+    rw_decode(j, W, wy0, ny, b, y, x);
+    const int64_t i = (int64_t)b * hw + (int64_t)y * W + x;
     float v[27];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky)
@@ -199,12 +202,13 @@ __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restr
 __global__ void __launch_bounds__(256) pack5_planar_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
                                                            const float* __restrict__ s2, const float* __restrict__ s3,
                                                            const float* __restrict__ s4, float* __restrict__ out,
-                                                           int out_pitch, int B, int H, int W, bool rnd) {
-  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+                                                           int out_pitch, int B, int H, int W, int wy0, int ny, bool rnd) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * ny * W;
   const float* src[5] = {s0, s1, s2, s3, s4};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(i / hw);
-    const int64_t rem = i - b * hw;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int b, y, x;
+    rw_decode(j, W, wy0, ny, b, y, x);
+    const int64_t rem = (int64_t)y * W + x, i = (int64_t)b * hw + rem;
     float v[16];
 #pragma unroll
     for (int j = 0; j < 5; ++j)
@@ -228,12 +232,12 @@ __device__ __forceinline__ float sample_plane(const float* __restrict__ p, const
 }
 
 __global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __restrict__ img, const float* __restrict__ flow,
-                                                             float* __restrict__ out, int B, int C, int H, int W) {
-  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int b = (int)(i / hw);
-    int64_t rem = i - b * hw;
-    int y = (int)(rem / W), x = (int)(rem % W);
+                                                             float* __restrict__ out, int B, int C, int H, int W, int wy0, int ny) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * ny * W;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int b, y, x;
+    rw_decode(j, W, wy0, ny, b, y, x);
+    const int64_t rem = (int64_t)y * W + x;
     float ix = warp_src_coord((float)x, __ldg(flow + (int64_t)b * 2 * hw + rem), W);
     float iy = warp_src_coord((float)y, __ldg(flow + ((int64_t)b * 2 + 1) * hw + rem), H);
     Bilin s = bilin_setup(ix, iy, W, H);
@@ -245,15 +249,14 @@ __global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __rest
 __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __restrict__ src, int src_pitch,
                                                              const float* __restrict__ head, int head_pitch, int flow_off,
                                                              float* __restrict__ out, int out_pitch, int B, int C, int H,
-                                                             int W, bool rnd) {
+                                                             int W, int wy0, int ny, bool rnd) {
   const int cv = C >> 2;
-  const int64_t total = (int64_t)B * H * W * cv;
+  const int64_t total = (int64_t)B * ny * W * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int c4 = (int)(i % cv);
-    int64_t pix = i / cv;
-    int x = (int)(pix % W);
-    int y = (int)((pix / W) % H);
-    int b = (int)(pix / ((int64_t)W * H));
+    int b, y, x;
+    rw_decode(i / cv, W, wy0, ny, b, y, x);
+    const int64_t pix = ((int64_t)b * H + y) * W + x;
     const float* hp = head + pix * head_pitch + flow_off;
     float ix = warp_src_coord((float)x, __ldg(hp), W);
     float iy = warp_src_coord((float)y, __ldg(hp + 1), H);
@@ -282,12 +285,12 @@ __global__ void __launch_bounds__(256) warp_blend_kernel(const float* __restrict
                                                          float* __restrict__ w0, float* __restrict__ w1,
                                                          float* __restrict__ it, float* __restrict__ flow0,
                                                          float* __restrict__ flow1, float* __restrict__ occ1,
-                                                         float* __restrict__ occ2, int B, int H, int W) {
-  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int b = (int)(i / hw);
-    int64_t rem = i - b * hw;
-    int y = (int)(rem / W), x = (int)(rem % W);
+                                                         float* __restrict__ occ2, int B, int H, int W, int wy0, int ny) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * ny * W;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int b, y, x;
+    rw_decode(j, W, wy0, ny, b, y, x);
+    const int64_t rem = (int64_t)y * W + x, i = (int64_t)b * hw + rem;
     const float* hp = head + i * head_pitch + head_off;
     float f0x = __ldg(hp), f0y = __ldg(hp + 1), f1x = __ldg(hp + 2), f1y = __ldg(hp + 3), lg = __ldg(hp + 4);
     Bilin s0 = bilin_setup(warp_src_coord((float)x, f0x, W), warp_src_coord((float)y, f0y, H), W, H);
@@ -319,12 +322,12 @@ __global__ void __launch_bounds__(256) warp_blend_kernel(const float* __restrict
 // F.interpolate(bilinear, align_corners=True): src = dst * (in-1)/(out-1); ATen's weights w1 = src - floor, w0 = 1 - w1.
 __global__ void __launch_bounds__(256) resize_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int planes,
                                                         int Hin, int Win, int Hout, int Wout, float sh, float sw,
-                                                        float scale) {
-  const int64_t total = (int64_t)planes * Hout * Wout;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int x = (int)(i % Wout);
-    int y = (int)((i / Wout) % Hout);
-    int64_t p = i / ((int64_t)Wout * Hout);
+                                                        float scale, int wy0, int ny) {
+  const int64_t total = (int64_t)planes * ny * Wout;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int pl, y, x;
+    rw_decode(j, Wout, wy0, ny, pl, y, x);
+    const int64_t p = pl, i = ((int64_t)pl * Hout + y) * Wout + x;
     float fy = __fmul_rn(sh, (float)y), fx = __fmul_rn(sw, (float)x);
     int y0 = (int)fy, x0 = (int)fx;
     int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
@@ -342,11 +345,12 @@ __global__ void __launch_bounds__(256) resize_ac_kernel(const float* __restrict_
 
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                            int out_pitch, int chan_off, int B, int C, int H, int W,
-                                                           int zero_to, bool rnd) {
-  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int b = (int)(i / hw);
-    int64_t rem = i - b * hw;
+                                                           int zero_to, int wy0, int ny, bool rnd) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * ny * W;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int b, y, x;
+    rw_decode(j, W, wy0, ny, b, y, x);
+    const int64_t rem = (int64_t)y * W + x, i = (int64_t)b * hw + rem;
     float* o = out + i * out_pitch + chan_off;
     for (int c = 0; c < C; ++c) o[c] = round_tf32_if(__ldg(in + ((int64_t)b * C + c) * hw + rem), rnd);
     for (int c = chan_off + C; c < zero_to; ++c) out[i * out_pitch + c] = 0.f;
@@ -355,11 +359,12 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 
 __global__ void __launch_bounds__(256) residual_finish_kernel(const float* __restrict__ res, int res_pitch,
                                                               const float* __restrict__ it, float* __restrict__ it_sum,
-                                                              float* __restrict__ it_clamped, int B, int H, int W) {
-  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int b = (int)(i / hw);
-    int64_t rem = i - b * hw;
+                                                              float* __restrict__ it_clamped, int B, int H, int W, int wy0, int ny) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * ny * W;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
+    int b, y, x;
+    rw_decode(j, W, wy0, ny, b, y, x);
+    const int64_t rem = (int64_t)y * W + x, i = (int64_t)b * hw + rem;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       int64_t o = ((int64_t)b * 3 + c) * hw + rem;
@@ -420,28 +425,32 @@ int atmvfi_layernorm(const float* in, int in_pitch, float* out, int out_pitch, i
 }
 
 int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win_pitch, int C, const atmvfi_window_geom* g,
-                            const float* gamma, const float* beta, float eps, void* stream) {
+                            const float* gamma, const float* beta, float eps, int wy0, int wy1, void* stream) {
   ATMVFI_REQUIRE(C % 4 == 0 && C <= kLnMaxV * 128 && tok_pitch % 4 == 0 && win_pitch % 4 == 0, "window_gather_ln: C=%d unsupported", C);
   ATMVFI_REQUIRE(g->Hp % g->ws == 0 && g->Wp % g->ws == 0 && g->shift >= 0 && g->shift < g->ws, "window_gather_ln: bad geometry");
-  int64_t rows = (int64_t)g->B2 * g->Hp * g->Wp;
+  int w0, nwy;
+  ATMVFI_REQUIRE(row_window(g->Hp / g->ws, wy0, wy1, &w0, &nwy), "window_gather_ln: bad window-row range [%d,%d)", wy0, wy1);
+  int64_t rows = (int64_t)g->B2 * nwy * g->ws * g->Wp;
   if (rows <= 0) return 0;
-  window_gather_ln_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(tok, tok_pitch, win, win_pitch, C, *g, rows, gamma, beta, eps, atmvfi_output_rounding() != 0);
+  window_gather_ln_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(tok, tok_pitch, win, win_pitch, C, *g, rows, w0, nwy, gamma, beta, eps, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("window_gather_ln");
   return 0;
 }
 
 int atmvfi_conv3x3_first(const float* img, const float* wk, int ldw, const float* bias, const float* prelu, float* out,
-                         int out_pitch, int B, int H, int W, int Cout, void* stream) {
+                         int out_pitch, int B, int H, int W, int Cout, int y0, int y1, void* stream) {
   ATMVFI_REQUIRE(out_pitch % 4 == 0 && ((uintptr_t)out & 15) == 0, "conv3x3_first: output must be 16-byte aligned, pitch %% 4 == 0");
-  int64_t n = (int64_t)B * H * W;
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "conv3x3_first: bad row window [%d,%d)", y0, y1);
+  int64_t n = (int64_t)B * ny * W;
   if (n <= 0) return 0;
   const bool rnd = atmvfi_output_rounding() != 0;
   int grid = grid_for(n, 128);
   cudaStream_t st = (cudaStream_t)stream;
   switch (Cout) {
-    case 16: conv3x3_first_kernel<16><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, rnd); break;
-    case 24: conv3x3_first_kernel<24><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, rnd); break;
-    case 32: conv3x3_first_kernel<32><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, rnd); break;
+    case 16: conv3x3_first_kernel<16><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd); break;
+    case 24: conv3x3_first_kernel<24><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd); break;
+    case 32: conv3x3_first_kernel<32><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd); break;
     default:
       atmvfi_set_error("conv3x3_first: Cout=%d not instantiated (16, 24, 32)", Cout);
       return 2;
@@ -451,80 +460,96 @@ int atmvfi_conv3x3_first(const float* img, const float* wk, int ldw, const float
 }
 
 int atmvfi_pack5_planar(const float* s0, const float* s1, const float* s2, const float* s3, const float* s4, float* out,
-                        int out_pitch, int B, int H, int W, void* stream) {
+                        int out_pitch, int B, int H, int W, int y0, int y1, void* stream) {
   ATMVFI_REQUIRE(out_pitch >= 16 && out_pitch % 4 == 0 && ((uintptr_t)out & 15) == 0, "pack5_planar: output needs pitch >= 16 and 16-byte alignment");
-  int64_t n = (int64_t)B * H * W;
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "pack5_planar: bad row window [%d,%d)", y0, y1);
+  int64_t n = (int64_t)B * ny * W;
   if (n <= 0) return 0;
-  pack5_planar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s0, s1, s2, s3, s4, out, out_pitch, B, H, W, atmvfi_output_rounding() != 0);
+  pack5_planar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s0, s1, s2, s3, s4, out, out_pitch, B, H, W, y0, ny, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("pack5_planar");
   return 0;
 }
 
 int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch, const float* w9c,
-                          const float* bias, void* stream) {
+                          const float* bias, int y0, int y1, void* stream) {
   ATMVFI_REQUIRE(C % 4 == 0 && pitch % 4 == 0, "dwconv3x3_gelu: C=%d pitch=%d must be multiples of 4", C, pitch);
-  if ((int64_t)B * H * W <= 0) return 0;
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "dwconv3x3_gelu: bad row window [%d,%d)", y0, y1);
+  if ((int64_t)B * ny * W <= 0) return 0;
   ATMVFI_REQUIRE((int64_t)W * (C / 4) < (1 << 30) && B <= 65535, "dwconv3x3_gelu: shape out of range");
-  dim3 grid((unsigned)((W * (C / 4) + 255) / 256), (unsigned)((H + kDwRows - 1) / kDwRows), (unsigned)B);
-  dwconv_gelu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, atmvfi_output_rounding() != 0);
+  dim3 grid((unsigned)((W * (C / 4) + 255) / 256), (unsigned)((ny + kDwRows - 1) / kDwRows), (unsigned)B);
+  dwconv_gelu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, y0, y0 + ny, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("dwconv3x3_gelu");
   return 0;
 }
 
-int atmvfi_flow_warp_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream) {
-  int64_t n = (int64_t)B * H * W;
+int atmvfi_flow_warp_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W, int y0, int y1, void* stream) {
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "flow_warp_nchw: bad row window [%d,%d)", y0, y1);
+  int64_t n = (int64_t)B * ny * W;
   if (n <= 0 || C <= 0) return 0;
-  flow_warp_nchw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(img, flow, out, B, C, H, W);
+  flow_warp_nchw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(img, flow, out, B, C, H, W, y0, ny);
   ATMVFI_CHECK_LAUNCH("flow_warp_nchw");
   return 0;
 }
 
 int atmvfi_flow_warp_nhwc(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off, float* out,
-                          int out_pitch, int B, int C, int H, int W, void* stream) {
+                          int out_pitch, int B, int C, int H, int W, int y0, int y1, void* stream) {
   ATMVFI_REQUIRE(C % 4 == 0 && src_pitch % 4 == 0 && out_pitch % 4 == 0, "flow_warp_nhwc: C=%d must be a multiple of 4", C);
-  int64_t n = (int64_t)B * H * W * (C / 4);
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "flow_warp_nhwc: bad row window [%d,%d)", y0, y1);
+  int64_t n = (int64_t)B * ny * W * (C / 4);
   if (n <= 0) return 0;
-  flow_warp_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, atmvfi_output_rounding() != 0);
+  flow_warp_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, ny, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("flow_warp_nhwc");
   return 0;
 }
 
 int atmvfi_warp_blend(const float* im0, const float* im1, const float* head, int head_pitch, int head_off, float* w0,
                       float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2, int B, int H, int W,
-                      void* stream) {
-  int64_t n = (int64_t)B * H * W;
+                      int y0, int y1, void* stream) {
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "warp_blend: bad row window [%d,%d)", y0, y1);
+  int64_t n = (int64_t)B * ny * W;
   if (n <= 0) return 0;
-  warp_blend_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(im0, im1, head, head_pitch, head_off, w0, w1, it, flow0, flow1, occ1, occ2, B, H, W);
+  warp_blend_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(im0, im1, head, head_pitch, head_off, w0, w1, it, flow0, flow1, occ1, occ2, B, H, W, y0, ny);
   ATMVFI_CHECK_LAUNCH("warp_blend");
   return 0;
 }
 
 int atmvfi_resize_bilinear_ac(const float* in, float* out, int planes, int Hin, int Win, int Hout, int Wout, float scale,
-                              void* stream) {
-  int64_t n = (int64_t)planes * Hout * Wout;
+                              int y0, int y1, void* stream) {
+  int ny;
+  ATMVFI_REQUIRE(row_window(Hout, y0, y1, &y0, &ny), "resize_bilinear_ac: bad row window [%d,%d)", y0, y1);
+  int64_t n = (int64_t)planes * ny * Wout;
   if (n <= 0) return 0;
   // ATen area_pixel_compute_scale(align_corners=True): (in-1)/(out-1), 0 when out == 1
   float sh = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f;
   float sw = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
-  resize_ac_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hin, Win, Hout, Wout, sh, sw, scale);
+  resize_ac_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hin, Win, Hout, Wout, sh, sw, scale, y0, ny);
   ATMVFI_CHECK_LAUNCH("resize_bilinear_ac");
   return 0;
 }
 
 int atmvfi_nchw_to_nhwc(const float* in, float* out, int out_pitch, int chan_off, int B, int C, int H, int W,
-                        int zero_fill_to, void* stream) {
-  int64_t n = (int64_t)B * H * W;
+                        int zero_fill_to, int y0, int y1, void* stream) {
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "nchw_to_nhwc: bad row window [%d,%d)", y0, y1);
+  int64_t n = (int64_t)B * ny * W;
   if (n <= 0) return 0;
-  nchw_to_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, out_pitch, chan_off, B, C, H, W, zero_fill_to, atmvfi_output_rounding() != 0);
+  nchw_to_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, out_pitch, chan_off, B, C, H, W, zero_fill_to, y0, ny, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("nchw_to_nhwc");
   return 0;
 }
 
 int atmvfi_residual_finish(const float* res, int res_pitch, const float* it, float* it_sum, float* it_clamped, int B, int H,
-                           int W, void* stream) {
-  int64_t n = (int64_t)B * H * W;
+                           int W, int y0, int y1, void* stream) {
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "residual_finish: bad row window [%d,%d)", y0, y1);
+  int64_t n = (int64_t)B * ny * W;
   if (n <= 0) return 0;
-  residual_finish_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(res, res_pitch, it, it_sum, it_clamped, B, H, W);
+  residual_finish_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(res, res_pitch, it, it_sum, it_clamped, B, H, W, y0, ny);
   ATMVFI_CHECK_LAUNCH("residual_finish");
   return 0;
 }

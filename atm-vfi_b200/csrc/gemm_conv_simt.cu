@@ -18,6 +18,7 @@ struct SimtParams {
   int spitch[ATMVFI_MAX_SRC];
   int Hin, Win, ksize, stride, dil, pad;
   int Hout, Wout;
+  int row0, nrows;          // row window: GEMM rows enumerate [B][nrows][Wout], output row = row0 + local row
   int64_t M;
   int Ntot, K, Ctot;
   const float* weight;
@@ -43,8 +44,8 @@ __global__ void __launch_bounds__(THREADS) gemm_conv_simt_kernel(const SimtParam
     if (m < p.M) {
       int ox = (int)(m % p.Wout);
       int64_t t = m / p.Wout;
-      int oy = (int)(t % p.Hout);
-      int b = (int)(t / p.Hout);
+      int oy = p.row0 + (int)(t % p.nrows);
+      int b = (int)(t / p.nrows);
       a_base[i] = b * p.Hin * p.Win;
       a_iy[i] = oy * p.stride - p.pad;
       a_ix[i] = ox * p.stride - p.pad;
@@ -110,6 +111,11 @@ __global__ void __launch_bounds__(THREADS) gemm_conv_simt_kernel(const SimtParam
   for (int i = 0; i < 8; ++i) {
     int64_t m = m0 + ty * 8 + i;
     if (m >= p.M) continue;
+    {   // window-local GEMM row -> row of the full [B][Hout][Wout] grid
+      const int ox = (int)(m % p.Wout);
+      const int64_t t = m / p.Wout;
+      m = ((t / p.nrows) * p.Hout + p.row0 + t % p.nrows) * p.Wout + ox;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
@@ -137,7 +143,9 @@ int atmvfi_gemm_conv_simt(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   p.Hin = d->Hin; p.Win = d->Win; p.ksize = d->ksize; p.stride = d->stride; p.dil = d->dil;
   p.pad = d->dil * (d->ksize - 1) / 2;
   p.Hout = d->Hout; p.Wout = d->Wout;
-  p.M = (int64_t)d->B * d->Hout * d->Wout;
+  ATMVFI_REQUIRE(row_window(d->Hout, d->row_begin, d->row_end, &p.row0, &p.nrows), "gemm_conv(fp32): bad row window [%d,%d) for Hout=%d",
+                 d->row_begin, d->row_end, d->Hout);
+  p.M = (int64_t)d->B * p.nrows * d->Wout;
   p.Ntot = d->out_mode == ATMVFI_OUT_SHUFFLE2 ? 4 * d->Cout : d->Cout;
   p.K = d->ksize * d->ksize * p.Ctot;
   p.weight = d->weight;

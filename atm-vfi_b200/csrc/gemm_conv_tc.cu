@@ -54,9 +54,10 @@ struct TcPlan {                                 // host-side, produced by atmvfi
   int halo;                                     // 1: 3x3 stride-1 layer, A boxes carry a vertical halo
   int pair;                                     // 1: two vertically stacked 128-pixel tiles per CTA step (N <= 128)
   int cluster;                                  // CTAs per cluster (B multicast), 1 or 2
+  int row0, row1;                               // row window of the GEMM grid: tiles cover output rows [row0, row1)
   uint32_t magic;
 };
-constexpr uint32_t kPlanMagic = 0xA7B20002u;
+constexpr uint32_t kPlanMagic = 0xA7B20003u;
 
 struct TcParams {
   CUtensorMap mapA[ATMVFI_MAX_SRC];
@@ -71,6 +72,7 @@ struct TcParams {
   int th_super;                                 // rows of output covered by one CTA tile (TH, or 2*TH in pair mode)
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes;   // smem rings: A at offset 0, B right after
   int total_ctiles;                             // cluster tiles: ceil(m_tiles / cluster) * n_tiles
+  int row0, row1;                               // output rows [row0, row1) of every image (row window)
   EpiParams epi;
 };
 
@@ -268,7 +270,7 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
   mt /= p.tiles_x;
   int ty = mt % p.tiles_y;
   b = mt / p.tiles_y;                      // may be >= B for a phantom tile
-  oy0 = ty * p.th_super;
+  oy0 = p.row0 + ty * p.th_super;
   ox0 = tx * p.TW;
 }
 
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
         const int c0 = (kPair ? u - t * nchunks : u) * 32;
         if (t != last_t) {
           const int oy = oy0 + t * p.TH + th, ox = ox0 + tw;
-          row_ok = b < p.B && oy < e.Hout && ox < e.Wout;
+          row_ok = b < p.B && oy < p.row1 && ox < e.Wout;
           m = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
           last_t = t;
           last_q = -1;
@@ -536,7 +538,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
             for (int rr = 0; rr < 8; ++rr) {
               const int row = rr * 4 + rsub, ml = q * 32 + row;
               const int oy = oyb + (ml >> tw_shift), ox = ox0 + (ml & tw_mask);
-              if (b < p.B && oy < e.Hout && ox < e.Wout) {
+              if (b < p.B && oy < p.row1 && ox < e.Wout) {
                 const float4 a4 = *reinterpret_cast<const float4*>(&stage[row * kEpiPitch + col]);
                 float4 v = make_float4(a4.x + bz4.x, a4.y + bz4.y, a4.z + bz4.z, a4.w + bz4.w);
                 if (act) {
@@ -661,6 +663,13 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   pl->ksize = d->ksize; pl->ntaps = d->ksize * d->ksize; pl->stride = d->stride; pl->dil = d->dil;
   pl->pad = d->dil * (d->ksize - 1) / 2;
   pl->B = d->B; pl->Hout = d->Hout; pl->Wout = d->Wout;
+  {
+    int ny;
+    ATMVFI_REQUIRE(row_window(d->Hout, d->row_begin, d->row_end, &pl->row0, &ny), "gemm_conv(tf32): bad row window [%d,%d) for Hout=%d",
+                   d->row_begin, d->row_end, d->Hout);
+    pl->row1 = pl->row0 + ny;
+  }
+  const int Hwin = pl->row1 - pl->row0;          // rows this launch produces
   ATMVFI_REQUIRE(d->stride == 1 || d->stride == 2 || d->stride == 4, "gemm_conv(tf32): stride %d unsupported", d->stride);
 
   // 3x3 stride-1 layers fetch activation boxes with a vertical halo and reuse them for the 3 vertical taps
@@ -677,7 +686,7 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     if (tw * d->stride > 256 || th * d->stride > 256) continue;
     if (pl->halo == 1 && (th + 2) * tw * 128 > kMaxABoxBytes) continue;
     if (pl->halo == 2 && tw != 8) continue;          // full-halo box: every tile row must be one 8-row swizzle group
-    int64_t cost = (int64_t)cdiv(d->Wout, tw) * cdiv(d->Hout, th);
+    int64_t cost = (int64_t)cdiv(d->Wout, tw) * cdiv(Hwin, th);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tw = tw; }
   }
   ATMVFI_REQUIRE(best_tw > 0, "gemm_conv(tf32): no tile shape for stride %d", d->stride);
@@ -693,10 +702,10 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     // activation box with a common halo -> weight traffic and issue overhead per pixel halve
     static int pair_ok = -1;
     if (pair_ok < 0) { const char* ev = getenv("ATMVFI_TC_PAIR"); pair_ok = ev ? atoi(ev) : 1; }
-    pl->pair = (pair_ok && pl->halo == 1 && pl->block_n <= 128 && d->Hout > pl->TH && (2 * pl->TH + 2) * pl->TW * 128 <= 40 * 1024) ? 1 : 0;
+    pl->pair = (pair_ok && pl->halo == 1 && pl->block_n <= 128 && Hwin > pl->TH && (2 * pl->TH + 2) * pl->TW * 128 <= 40 * 1024) ? 1 : 0;
   }
   pl->tiles_x = cdiv(d->Wout, pl->TW);
-  pl->tiles_y = cdiv(d->Hout, pl->TH * (pl->pair ? 2 : 1));
+  pl->tiles_y = cdiv(Hwin, pl->TH * (pl->pair ? 2 : 1));
   {
     // clusters of 2 CTAs along M share each weight tile through TMA multicast
     static int forced = -1;
@@ -804,6 +813,7 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   p.m_tiles = pl->tiles_x * pl->tiles_y * pl->B;
   const int cs = pl->cluster;
   p.total_ctiles = ((p.m_tiles + cs - 1) / cs) * pl->n_tiles;
+  p.row0 = pl->row0; p.row1 = pl->row1;
   p.epi = make_epi(d);
   if (p.total_ctiles <= 0) return 0;
   int clusters = num_sms / cs;

@@ -11,6 +11,10 @@
  *   - return 0 on success, non-zero on error; atmvfi_last_error() returns the message (thread-local);
  *   - feature maps are channels-last ("NHWC": [B][H][W][pitch], pitch >= C floats, pitch % 4 == 0),
  *     3-channel images, flows and masks are planar ("NCHW") like the reference's public tensors;
+ *   - ROW WINDOWS (spatial row slabs): every operator that walks a grid takes `y0, y1` and produces only
+ *     rows [y0, y1) of every image of its OUTPUT grid (y1 == 0: all rows).  Inputs are always described by their FULL
+ *     extent: padding, align_corners scales, window geometry and warp coordinates stay global, the kernel simply reads the
+ *     halo rows it needs from the full-size input.  For window-major tensors a "row" is a row of windows.
  *   - fp32 storage everywhere; `precision` selects the multiply datapath of the GEMM-shaped ops:
  *     ATMVFI_FP32 = CUDA-core FFMA, ATMVFI_TF32 = tcgen05.mma kind::tf32 (fp32 accumulate in TMEM).
  *
@@ -19,13 +23,14 @@
 #ifndef ATMVFI_H_
 #define ATMVFI_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define ATMVFI_ABI_VERSION 1
+#define ATMVFI_ABI_VERSION 2
 #define ATMVFI_MAX_SRC 4
 
 enum { ATMVFI_FP32 = 0, ATMVFI_TF32 = 1 };
@@ -85,6 +90,8 @@ typedef struct {
   atmvfi_window_geom win;        /* used by ATMVFI_OUT_WINDOW_REV               */
   int32_t precision;             /* ATMVFI_FP32 / ATMVFI_TF32                   */
   const void* tma_host;          /* TF32: host pointer to the plan made by atmvfi_gemm_conv_plan, else NULL */
+  int32_t row_begin, row_end;    /* row window on the GEMM grid [B][Hout][Wout] (window-major sources: rows of windows,
+                                    i.e. Hout = B2-images x window rows); row_end == 0: all rows */
 } atmvfi_gemm_conv_desc;
 
 const char* atmvfi_last_error(void);
@@ -103,7 +110,7 @@ int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_host);
 
 /* LayerNorm over channels of `rows` tokens (nn.LayerNorm, network_base.py:55,84; attention.py:235,333). */
 int atmvfi_layernorm(const float* in, int in_pitch, float* out, int out_pitch, int64_t rows, int C,
-                     const float* gamma, const float* beta, float eps, void* stream);
+                     const float* gamma, const float* beta, float eps, void* stream);   /* row windows: offset the pointers */
 
 /*
  * pad_if_needed + torch.roll + window_partition + norm1 in one pass (attention.py:273-316):
@@ -112,7 +119,7 @@ int atmvfi_layernorm(const float* in, int in_pitch, float* out, int out_pitch, i
  */
 int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win_pitch, int C,
                             const atmvfi_window_geom* g, const float* gamma, const float* beta, float eps,
-                            void* stream);
+                            int wy0, int wy1 /* window rows [wy0, wy1) of every image; wy1 == 0: all */, void* stream);
 
 /*
  * Window attention with the attention-to-motion reduction (attention.py:187-213, 370-390).
@@ -128,7 +135,8 @@ int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win
 int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                             const atmvfi_window_geom* g, int cross, const float* relative_coord,
                             const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
-                            float* motion, int motion_pitch, int motion_off, float* scratch, void* stream);
+                            float* motion, int motion_pitch, int motion_off, float* scratch,
+                            int wy0, int wy1 /* window rows of every image */, void* stream);
 
 /* Same contract on the tensor cores (tcgen05 kind::tf32, accumulators in TMEM; Q, K, V^T staged in shared memory as
  * TF32).  rc_closed_form != 0 asserts that relative_coord holds the reference's own buffer contents (key position -
@@ -137,28 +145,30 @@ int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out
 int atmvfi_window_attention_tc(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                                const atmvfi_window_geom* g, int cross, const float* relative_coord, int rc_closed_form,
                                const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
-                               float* motion, int motion_pitch, int motion_off, float* scratch, void* stream);
+                               float* motion, int motion_pitch, int motion_off, float* scratch,
+                               int wy0, int wy1, void* stream);
 
 /* Mlp middle: depth-wise 3x3 (pad 1) + bias + exact-erf GELU on NHWC tokens (attention.py:74-85,118-119). */
 int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch,
-                          const float* w9c /* [9][C] */, const float* bias, void* stream);
+                          const float* w9c /* [9][C] */, const float* bias, int y0, int y1, void* stream);
 
 /* First encoder layer (feat_extracts.0.0, network_base.py:103): Conv2d(3 -> Cout, k3, p1) + PReLU read straight from
  * the planar frame, written channels-last.  wk: [27][ldw] with row = (ky*3+kx)*3 + c (the FP32 packing of atmvfi_gemm_conv). */
 int atmvfi_conv3x3_first(const float* img, const float* wk, int ldw, const float* bias, const float* prelu, float* out,
-                         int out_pitch, int B, int H, int W, int Cout, void* stream);
+                         int out_pitch, int B, int H, int W, int Cout, int y0, int y1, void* stream);
 
 /* Five planar [B,3,H,W] images -> channels [0,15) of an NHWC buffer (channel 15 zeroed): the image part of
  * torch.cat([feat, im0, I_t_0, im1, I_t_1, I_t], 1) at network_base.py:418, in one coalesced pass. */
 int atmvfi_pack5_planar(const float* s0, const float* s1, const float* s2, const float* s3, const float* s4, float* out,
-                        int out_pitch, int B, int H, int W, void* stream);
+                        int out_pitch, int B, int H, int W, int y0, int y1, void* stream);
 
 /* flow_warp.flow_warp (flow_warp.py:50-60) on planar tensors: out[b,c] = bilinear(img[b,c], grid+flow[b]). */
-int atmvfi_flow_warp_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+int atmvfi_flow_warp_nchw(const float* img, const float* flow, float* out, int B, int C, int H, int W, int y0, int y1,
+                          void* stream);
 
 /* Same sampling on an NHWC map; the flow is read from channels [flow_off, flow_off+2) of an NHWC head. */
 int atmvfi_flow_warp_nhwc(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off,
-                          float* out, int out_pitch, int B, int C, int H, int W, void* stream);
+                          float* out, int out_pitch, int B, int C, int H, int W, int y0, int y1, void* stream);
 
 /*
  * Fused pair warp + occlusion blend (network_base.py:385-387, 464-466, 496-498, 514-525):
@@ -168,20 +178,20 @@ int atmvfi_flow_warp_nhwc(const float* src, int src_pitch, const float* head, in
  */
 int atmvfi_warp_blend(const float* im0, const float* im1, const float* head, int head_pitch, int head_off,
                       float* w0, float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2,
-                      int B, int H, int W, void* stream);
+                      int B, int H, int W, int y0, int y1, void* stream);
 
 /* F.interpolate(bilinear, align_corners=True) on `planes` planar images; values multiplied by `scale`
  * (network_base.py:11-18 uses x2 with scale 2; :445-446 uses x0.5 with scale 1). */
 int atmvfi_resize_bilinear_ac(const float* in, float* out, int planes, int Hin, int Win, int Hout, int Wout,
-                              float scale, void* stream);
+                              float scale, int y0, int y1, void* stream);
 
 /* planar [B][C][H][W] -> channels [chan_off, chan_off+C) of an NHWC buffer (replaces torch.cat with images). */
 int atmvfi_nchw_to_nhwc(const float* in, float* out, int out_pitch, int chan_off, int B, int C, int H, int W,
-                        int zero_fill_to /* also zero channels [chan_off+C, zero_fill_to) */, void* stream);
+                        int zero_fill_to /* also zero channels [chan_off+C, zero_fill_to) */, int y0, int y1, void* stream);
 
 /* I_t += 2*sigmoid(res)-1 ; clamp (network_base.py:429, 532-533).  res: NHWC 3 channels. */
 int atmvfi_residual_finish(const float* res, int res_pitch, const float* it, float* it_sum, float* it_clamped,
-                           int B, int H, int W, void* stream);
+                           int B, int H, int W, int y0, int y1, void* stream);
 
 /* demo_2x.inference_2frame host arithmetic on the device (demo_2x.py:64-75, 79-85):
  * uint8 HWC (optionally BGR) -> fp32 planar RGB / 255, replicate-padded by (left, top) to Hp x Wp, and back
@@ -190,6 +200,46 @@ int atmvfi_u8_to_planar(const uint8_t* in, float* out, int H, int W, int Hp, int
                         int bgr, void* stream);
 int atmvfi_planar_to_u8(const float* in, uint8_t* out, int H, int W, int Hp, int Wp, int top, int left,
                         int bgr, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Spatial row-slab mode over NVLink (BASELINE.json configs[3]: one 4096x2160 pair on 2/4/8 GPUs).
+ * The reference has no multi-GPU code; this replaces nothing in it.  One process per GPU.  Every rank allocates one
+ * arena with the SAME layout, exports it through CUDA IPC and maps the peers' arenas, so the peer copy of a buffer is
+ * peer_base + (ptr - my_base).  Rows that a consumer needs from a neighbour are PUSHED into the consumer's copy of the
+ * buffer by the producer (16-byte stores through the peer mapping), followed by a system-scope release of a flag in the
+ * consumer's memory.  Flags hold the step number ("epoch", a device-resident counter), so a captured CUDA graph
+ * replays without argument patching.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define ATMVFI_IPC_HANDLE_BYTES 64
+#define ATMVFI_P2P_MAX_PIECES 16
+#define ATMVFI_P2P_MAX_PEERS 8
+
+int atmvfi_arena_alloc(size_t bytes, void** ptr);              /* cudaMalloc (IPC-exportable, unlike a caching allocator block) */
+int atmvfi_arena_free(void* ptr);
+int atmvfi_ipc_export(void* ptr, unsigned char* handle64);     /* cudaIpcGetMemHandle */
+int atmvfi_ipc_open(const unsigned char* handle64, void** peer_ptr);   /* cudaIpcOpenMemHandle, lazy peer access */
+int atmvfi_ipc_close(void* peer_ptr);
+
+/* `nchunks` chunks of `chunk_bytes`, `chunk_stride` bytes apart on both sides (rows [y0,y1) of every image / plane). */
+typedef struct {
+  const void* src;       /* local                               */
+  void* dst;             /* peer-mapped address (or local)      */
+  uint64_t chunk_bytes;  /* multiple of 4 (16-byte vectors when everything is 16-byte aligned) */
+  uint64_t chunk_stride;
+  uint32_t nchunks;
+  uint32_t reserved;
+} atmvfi_p2p_piece;
+
+/* One exchange site: copy every piece, then store *epoch (release, system scope) into each signal flag (peer memory),
+ * then wait until each wait flag (local memory, raised by a peer's call of this function) has reached *epoch.
+ * `counter` is a zero-initialised word private to the site.  A wait that lasts > 4 s sets *error_word and returns. */
+int atmvfi_p2p_exchange(const atmvfi_p2p_piece* pieces, int npieces, uint32_t* const* signal_flags, int nsignal,
+                        const uint32_t* const* wait_flags, int nwait, const uint32_t* epoch, uint32_t* counter,
+                        uint32_t* error_word, void* stream);
+/* Start of a step: ++*epoch, publish it to every peer and wait until every peer has published the same value (they
+ * have finished the previous step, so their halo rows may be overwritten). */
+int atmvfi_p2p_step_begin(uint32_t* epoch, uint32_t* const* signal_flags, int nsignal, const uint32_t* const* wait_flags,
+                          int nwait, uint32_t* error_word, void* stream);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,25 @@ def _warp(img, flow):
     return F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=True)
 
 
+def _put(dst, val, rows, dim=1):
+    """dst <- val on the row window [y0, y1) of axis `dim` (all rows when rows is None)."""
+    val = val.reshape(dst.shape) if val.shape != dst.shape else val
+    if rows is None:
+        dst.copy_(val)
+    else:
+        idx = [slice(None)] * dst.dim()
+        idx[dim] = slice(rows[0], rows[1])
+        dst[tuple(idx)] = val[tuple(idx)]
+
+
+def _win_token_mask(g: WinGeom, rows):
+    """[B2,H,W] bool: tokens that belong to the window rows [k0, k1) (after pad / roll / partition)."""
+    nwy, nwx, N = g.Hp // g.ws, g.Wp // g.ws, g.ws * g.ws
+    ind = torch.zeros(g.B2, nwy, nwx, N, 1)
+    ind[:, rows[0] : rows[1]] = 1
+    return _win_reverse(ind.reshape(g.rows, 1), g)[..., 0] > 0
+
+
 class EmulOps:
     def __init__(self):
         self.recording: Optional[List] = None
@@ -74,14 +93,24 @@ class EmulOps:
     def new_map(self, B, H, W, C, zero=False):
         return Map(torch.full((B, H, W, round_up(C, 4)), float("nan") if round_up(C, 4) == C and not zero else 0.0), 0, C)
 
+    def new_win_map(self, g: WinGeom, C):
+        return self.new_map(1, 1, g.rows, C)
+
     def new_planar(self, *shape):
         return torch.full(shape, float("nan"))
+
+    def replicated(self):
+        import contextlib
+        return contextlib.nullcontext()
 
     def _emit(self, fn):
         if self.recording is not None:
             self.recording.append(fn)
         else:
             fn()
+
+    def emit_host(self, fn):
+        self._emit(fn)
 
     def replay(self, records, stream=None):
         for fn in records:
@@ -93,7 +122,7 @@ class EmulOps:
 
     # ---------------------------------------------------------------------------------------------
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride=1, dil=1, act=True, residual=None,
-                  out2=None, prelu2=None, win: Optional[WinGeom] = None, precision=None):
+                  out2=None, prelu2=None, win: Optional[WinGeom] = None, precision=None, rows=None):
         assert [s.C for s in srcs] == list(w.split)
         k, ci = w.ksize, sum(w.split)
         n_tot = 4 * w.Cout if w.shuffle else w.Cout
@@ -112,38 +141,49 @@ class EmulOps:
                 y = y + residual.view().reshape(y.shape)
             if act and w.prelu is not None:
                 y = torch.where(y > 0, y, y * w.prelu)
+            y2 = torch.where(y > 0, y, y * prelu2) if out2 is not None else None
             if win is not None:
                 y = _win_reverse(y.reshape(win.rows, -1), win)
-            out.view().copy_(y.reshape(out.view().shape))
+                if rows is None:
+                    out.view().copy_(y.reshape(out.view().shape))
+                else:      # rows = window rows of the GEMM grid: only their tokens are produced
+                    m = _win_token_mask(win, rows)
+                    ov = out.view().reshape(y.shape)
+                    ov[m] = y[m]
+                return
+            orow = rows if (rows is None or not w.shuffle) else (2 * rows[0], 2 * rows[1])
+            _put(out.view(), y, orow)
             if out2 is not None:
-                out2.view().copy_(torch.where(y > 0, y, y * prelu2).reshape(out2.view().shape))
+                _put(out2.view(), y2, orow)
 
         self._emit(run)
 
-    def conv3x3_first(self, img, w: PackedGemm, out: Map):
+    def conv3x3_first(self, img, w: PackedGemm, out: Map, rows=None):
         def run():
             wt = w.w32[:, : w.Cout].reshape(3, 3, 3, w.Cout).permute(3, 2, 0, 1)
             y = F.conv2d(img, wt, w.bias, padding=1)
             y = torch.where(y > 0, y, y * w.prelu.view(1, -1, 1, 1))
-            out.view().copy_(y.permute(0, 2, 3, 1))
+            _put(out.view(), y.permute(0, 2, 3, 1), rows)
         self._emit(run)
 
-    def pack5_planar(self, imgs, out: Map):
+    def pack5_planar(self, imgs, out: Map, rows=None):
         def run():
-            out.t[..., :15] = torch.cat([t.permute(0, 2, 3, 1) for t in imgs], -1)
-            out.t[..., 15] = 0
+            v = torch.cat([t.permute(0, 2, 3, 1) for t in imgs] + [torch.zeros_like(imgs[0][:, :1]).permute(0, 2, 3, 1)], -1)
+            _put(out.t[..., :16], v, rows)
         self._emit(run)
 
-    def layernorm(self, x: Map, out: Map, gamma, beta):
-        self._emit(lambda: out.view().copy_(F.layer_norm(x.view(), (x.C,), gamma, beta, 1e-5)))
+    def layernorm(self, x: Map, out: Map, gamma, beta, rows=None):
+        self._emit(lambda: _put(out.view(), F.layer_norm(x.view(), (x.C,), gamma, beta, 1e-5), rows))
 
-    def window_gather_ln(self, tok: Map, win: Map, g: WinGeom, gamma, beta):
+    def window_gather_ln(self, tok: Map, win: Map, g: WinGeom, gamma, beta, rows=None):
         def run():
-            rows = _win_forward(tok.view().reshape(g.B2, g.H, g.W, tok.C), g)
-            win.view().copy_(F.layer_norm(rows, (tok.C,), gamma, beta, 1e-5).reshape(win.view().shape))
+            wr = _win_forward(tok.view().reshape(g.B2, g.H, g.W, tok.C), g)
+            y = F.layer_norm(wr, (tok.C,), gamma, beta, 1e-5)
+            shp = (g.B2, g.Hp // g.ws, g.ws * g.Wp, tok.C)       # window-major rows seen as [image][window row][tokens]
+            _put(win.view().reshape(shp), y.reshape(shp), rows)
         self._emit(run)
 
-    def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads, cross, rc=None, mix=None, motion=None, motion_off=0, scratch=None, rc_closed_form=False):
+    def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads, cross, rc=None, mix=None, motion=None, motion_off=0, scratch=None, rc_closed_form=False, rows=None):
         def run():
             C = out.C
             N = g.ws * g.ws
@@ -161,7 +201,8 @@ class EmulOps:
                 nW = m.shape[0]
                 logits = (logits.reshape(-1, nW, heads, N, N) + m[None, :, None]).reshape(-1, heads, N, N)
             p = logits.softmax(-1)
-            out.view().copy_((p @ sp(v)).transpose(1, 2).reshape(out.view().shape))
+            shp = (g.B2, g.Hp // g.ws, g.ws * g.Wp, C)
+            _put(out.view().reshape(shp), (p @ sp(v)).transpose(1, 2).reshape(shp), rows)
             if motion is not None:
                 mo = (p[:, :, None] * rc[None, None]).sum(-1).permute(0, 2, 3, 1)          # [Bw,2,N,heads]
                 w0, b0, w2, b2 = mix
@@ -169,53 +210,61 @@ class EmulOps:
                 mo = _win_reverse(mo.squeeze(-1).permute(0, 2, 1).reshape(g.rows, 2), g)    # [B2,H,W,2]
                 B = g.B2 // 2
                 mv = motion.view()
-                mv[..., motion_off : motion_off + 2] = mo[:B]
-                mv[..., motion_off + 2 : motion_off + 4] = mo[B:]
+                new = torch.cat([mo[:B], mo[B:]], -1)
+                if rows is None:
+                    mv[..., motion_off : motion_off + 4] = new
+                else:
+                    m = _win_token_mask(g, rows)
+                    for half in range(2):      # frame-0 queries write channels 0-1, frame-1 queries channels 2-3
+                        mh = m[half * B : (half + 1) * B]
+                        sl = mv[..., motion_off + 2 * half : motion_off + 2 * half + 2]
+                        sl[mh] = new[..., 2 * half : 2 * half + 2][mh]
         self._emit(run)
 
-    def dwconv_gelu(self, x: Map, out: Map, w9c, bias):
+    def dwconv_gelu(self, x: Map, out: Map, w9c, bias, rows=None):
         def run():
             c = x.C
             wt = w9c.t().reshape(c, 1, 3, 3)
             y = F.conv2d(x.view().permute(0, 3, 1, 2), wt, bias, padding=1, groups=c)
-            out.view().copy_(F.gelu(y).permute(0, 2, 3, 1))
+            _put(out.view(), F.gelu(y).permute(0, 2, 3, 1), rows)
         self._emit(run)
 
-    def flow_warp_nchw(self, img, flow, out):
-        self._emit(lambda: out.copy_(_warp(img, flow)))
+    def flow_warp_nchw(self, img, flow, out, rows=None):
+        self._emit(lambda: _put(out, _warp(img, flow), rows, 2))
 
-    def flow_warp_nhwc(self, src: Map, head: Map, flow_off, out: Map):
+    def flow_warp_nhwc(self, src: Map, head: Map, flow_off, out: Map, rows=None):
         def run():
             fl = head.view()[..., flow_off : flow_off + 2].permute(0, 3, 1, 2)
-            out.view().copy_(_warp(src.view().permute(0, 3, 1, 2), fl).permute(0, 2, 3, 1))
+            _put(out.view(), _warp(src.view().permute(0, 3, 1, 2), fl).permute(0, 2, 3, 1), rows)
         self._emit(run)
 
-    def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None):
+    def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None, rows=None):
         def run():
             hv = head.view().permute(0, 3, 1, 2)
             a, b = _warp(im0, hv[:, 0:2]), _warp(im1, hv[:, 2:4])
             m = torch.sigmoid(hv[:, 4:5])
-            w0.copy_(a); w1.copy_(b); it.copy_(m * a + (1 - m) * b)
-            if flow0 is not None: flow0.copy_(hv[:, 0:2])
-            if flow1 is not None: flow1.copy_(hv[:, 2:4])
-            if occ1 is not None: occ1.copy_(m)
-            if occ2 is not None: occ2.copy_(1 - m)
+            _put(w0, a, rows, 2); _put(w1, b, rows, 2); _put(it, m * a + (1 - m) * b, rows, 2)
+            if flow0 is not None: _put(flow0, hv[:, 0:2], rows, 2)
+            if flow1 is not None: _put(flow1, hv[:, 2:4], rows, 2)
+            if occ1 is not None: _put(occ1, m, rows, 2)
+            if occ2 is not None: _put(occ2, 1 - m, rows, 2)
         self._emit(run)
 
-    def resize(self, x, out, scale=1.0):
-        self._emit(lambda: out.copy_(F.interpolate(x, size=out.shape[-2:], mode="bilinear", align_corners=True) * scale))
+    def resize(self, x, out, scale=1.0, rows=None):
+        self._emit(lambda: _put(out, F.interpolate(x, size=out.shape[-2:], mode="bilinear", align_corners=True) * scale, rows, 2))
 
-    def nchw_to_nhwc(self, x, out: Map, zero_fill_to=0):
+    def nchw_to_nhwc(self, x, out: Map, zero_fill_to=0, rows=None):
         def run():
             c = x.shape[1]
-            out.t[..., out.c0 : out.c0 + c] = x.permute(0, 2, 3, 1)
+            _put(out.t[..., out.c0 : out.c0 + c], x.permute(0, 2, 3, 1), rows)
             if zero_fill_to > out.c0 + c:
-                out.t[..., out.c0 + c : zero_fill_to] = 0
+                z = out.t[..., out.c0 + c : zero_fill_to]
+                _put(z, torch.zeros_like(z), rows)
         self._emit(run)
 
-    def residual_finish(self, res: Map, it, it_sum, it_clamped):
+    def residual_finish(self, res: Map, it, it_sum, it_clamped, rows=None):
         def run():
             s = it + (2 * torch.sigmoid(res.view()[..., :3].permute(0, 3, 1, 2)) - 1)
-            if it_sum is not None: it_sum.copy_(s)
-            it_clamped.copy_(s.clamp(0, 1))
+            if it_sum is not None: _put(it_sum, s, rows, 2)
+            _put(it_clamped, s.clamp(0, 1), rows, 2)
         self._emit(run)
