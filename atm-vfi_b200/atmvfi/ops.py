@@ -179,7 +179,7 @@ class CudaOps:
     def emit_host(self, fn: Callable[[], None]) -> None:
         """Record (or run) a host-side callable in launch order; used by test transports, never by the product path."""
         if self.recording is not None:
-            self.recording.append(("host", lambda *a: fn() or 0, (), None))
+            self.recording.append(("host", lambda *a: (fn(), 0)[1], (), None))
         else:
             fn()
 

@@ -109,7 +109,7 @@ class _WindowBlock(ParamTree):
             tok = Map(x.detach().float().contiguous())
             g = WinGeom(B2, H, W, self.window_size[0], self.shift_size[0])
             motion = ops.new_map(B2 // 2, H, W, 4) if want_motion else None
-            out = transformer_block(ops, blk, tok, g, motion, 0)
+            out = transformer_block(ops, blk, tok, g, motion)
             feat = out.view().reshape(B2, H * W, C)
             if not want_motion:
                 return feat
