@@ -156,6 +156,8 @@ class SlabOps:
     # ---- plumbing shared with the backend -------------------------------------------------------
     recording = property(lambda s: s.backend.recording, lambda s, v: setattr(s.backend, "recording", v))
     launches = property(lambda s: s.backend.launches)
+    lib = property(lambda s: s.backend.lib)
+    device = property(lambda s: s.backend.device)
     precision = property(lambda s: s.backend.precision, lambda s, v: setattr(s.backend, "precision", v))
 
     def replay(self, records, stream=None):

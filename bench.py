@@ -130,7 +130,8 @@ def measure_kernels(plan, torch):
             if d.precision == 1:
                 cin = sum(d.src[s].C for s in range(d.nsrc))
                 n = d.Cout * (4 if d.out_mode == 1 else 1)
-                tc_flops += 2.0 * d.B * d.Hout * d.Wout * cin * d.ksize * d.ksize * n
+                hrows = (d.row_end - d.row_begin) if d.row_end else d.Hout          # row window of a slab plan
+                tc_flops += 2.0 * d.B * hrows * d.Wout * cin * d.ksize * d.ksize * n
                 tc_ms += ms
                 tc_n += 1
         a = per.setdefault(key, [0, 0.0])
@@ -260,6 +261,98 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_spatial(args):
+    """--spatial: ONE frame pair per step split into row slabs over the N ranks (NVLink P2P halo exchange, atmvfi/slab.py +
+    atmvfi/p2p.py).  Strong scaling: value = pairs/s of the whole job; every rank holds the full input frames, rank 0
+    receives the interpolated frame."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from atmvfi.p2p import SlabSession
+    kind, B, H, W, glob, desc = WORKLOADS[args.workload]
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if not dist.is_initialized():
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29655")
+            os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
+        dist.init_process_group("nccl", device_id=dev)
+    net = build_net(kind, dev, args.precision)
+    net.global_motion = glob
+    Hp, Wp = pad64(H, W)
+    g = torch.Generator().manual_seed(1234)
+    im0 = torch.rand(B, 3, Hp, Wp, generator=g).to(dev)
+    im1 = torch.rand(B, 3, Hp, Wp, generator=g).to(dev)
+    sess = SlabSession(net, B, Hp, Wp, gather="I_t")
+    launches_per_step = sess.plan.num_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sess.plan.im0.copy_(im0); sess.plan.im1.copy_(im1)
+    for _ in range(max(args.warmup, 3)):
+        sess.run_inplace()
+    for _ in range(20):                    # clock ramp; a fixed count keeps the ranks' step numbers equal
+        sess.run_inplace()
+    barrier()
+    sampler.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        sess.run_inplace()
+    e1.record()
+    barrier()
+    sess.check()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = args.steps * B / (ms / 1e3)
+
+    # e2e: uint8 host frames -> every rank uploads both frames (pinned), runs its slab, rank 0 downloads the result
+    a, b = synthetic_u8(1, H, W, 99)[0]
+    for _ in range(3):
+        sess.interpolate_u8(a, b)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = sess.interpolate_u8(a, b)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = {"value": args.steps / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": world * 2 * H * W * 3, "d2h_bytes_per_step": H * W * 3,
+           "api": "atmvfi.p2p.SlabSession.interpolate_u8 (inference_2frame arithmetic; every rank uploads both uint8 frames, rank 0 downloads the frame)"}
+    barrier()
+    per, (tc_flops, tc_ms, tc_n) = measure_kernels(sess.plan, torch)      # all ranks replay in lockstep (exchange sites need the peers)
+    barrier()
+    st = sess.slab.stats
+    if rank == 0:
+        hbm_gbs, bf16_tf, basis = load_peaks()
+        total_ms = sum(v[1] for v in per.values())
+        achieved = tc_flops / tc_n / (tc_ms / tc_n * 1e-3) / 1e12
+        roof = {"kernel": "gemm_conv_tc_kernel (tcgen05 kind::tf32 implicit-GEMM conv/linear), rank 0's row slab", "bound": "tensor",
+                "achieved": round(achieved, 1), "peak": round(bf16_tf / 2, 1), "unit": "TFLOP/s", "frac": round(achieved / (bf16_tf / 2), 3), "traffic": None,
+                "launches_per_step": tc_n, "flops_per_launch": tc_flops / tc_n, "avg_launch_ms": tc_ms / tc_n, "share_of_step": round(tc_ms / total_ms, 3),
+                "peak_basis": f"{basis}; {TF32_PEAK_NOTE}"}
+        kernels = {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])}
+        line = {"metric": "interpolated frames/sec", "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {desc}", "pairs_per_step": B, "padded_shape": [Hp, Wp],
+                           "parallelism": f"ONE pair per step in {world} row slab(s) {sess.slab.bounds}, halo rows pushed over NVLink P2P "
+                                          f"({st['sites']} exchange sites, {st['pushed_bytes'] / 1e6:.1f} MB pushed / {st['received_bytes'] / 1e6:.1f} MB received per step by rank 0)",
+                           "weights": "random-init", "l2": "activations per step exceed the 126 MB L2; no flush needed"},
+                "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "roofline": roof, "kernels_ms_per_step": kernels}
+        print(json.dumps(line))
+    sess.close()
+    dist.destroy_process_group()
+
+
 def cpu_baseline(kind, B, Hp, Wp, glob, steps=1):
     """Times the CPU oracle (oracle/atmvfi_oracle.py, a port of the reference forward) on a bounded sample."""
     import torch
@@ -311,6 +404,7 @@ def main():
     ap.add_argument("--workload", default="base_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--spatial", action="store_true", help="one pair per step split into row slabs over the N GPUs (NVLink P2P halo exchange)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -319,7 +413,7 @@ def main():
             sys.path.insert(0, ROOT)
             import __graft_entry__ as ge
             ge.build()
-        run_ours(args)
+        (run_spatial if args.spatial else run_ours)(args)
 
 
 if __name__ == "__main__":
