@@ -56,6 +56,10 @@ class P2PPiece(C.Structure):
 IPC_HANDLE_BYTES, P2P_MAX_PIECES, P2P_MAX_PEERS = 64, 16, 8
 
 
+class RowOwners(C.Structure):
+    _fields_ = [("nseg", C.c_int32), ("row_lo", C.c_int32 * (P2P_MAX_PEERS * 2 + 1)), ("byte_delta", C.c_int64 * (P2P_MAX_PEERS * 2))]
+
+
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
 _GP, _DP = C.POINTER(WindowGeom), C.POINTER(GemmConvDesc)
 
@@ -73,6 +77,7 @@ PROTOTYPES = {
     "atmvfi_dwconv3x3_gelu": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
     "atmvfi_flow_warp_nchw": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_flow_warp_nhwc": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_flow_warp_nhwc_p2p": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(RowOwners), _P],
     "atmvfi_warp_blend": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_resize_bilinear_ac": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "atmvfi_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -328,10 +328,21 @@ class CudaOps:
         assert flow.shape == (b, 2, h, w) and img.is_contiguous() and flow.is_contiguous() and out.is_contiguous()
         self._emit("atmvfi_flow_warp_nchw", (img.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w) + _yy(rows), keep=(img, flow, out))
 
-    def flow_warp_nhwc(self, src: Map, head: Map, flow_off: int, out: Map, rows: Rows = None):
+    def flow_warp_nhwc(self, src: Map, head: Map, flow_off: int, out: Map, rows: Rows = None, owners=None):
+        """owners: [(row_lo, row_hi, byte_delta)] - source rows held by other GPUs, read in place over NVLink (row slabs)."""
         assert (src.B, src.H, src.W) == (head.B, head.H, head.W) == (out.B, out.H, out.W) and src.C == out.C
-        self._emit("atmvfi_flow_warp_nhwc", (src.ptr, src.pitch, head.ptr, head.pitch, flow_off, out.ptr, out.pitch, src.B, src.C, src.H, src.W) + _yy(rows),
-                   keep=(src, head, out))
+        args = (src.ptr, src.pitch, head.ptr, head.pitch, flow_off, out.ptr, out.pitch, src.B, src.C, src.H, src.W) + _yy(rows)
+        if owners is None:
+            self._emit("atmvfi_flow_warp_nhwc", args, keep=(src, head, out))
+            return
+        ro = _lib.RowOwners()
+        assert 0 < len(owners) <= 2 * _lib.P2P_MAX_PEERS and owners[0][0] == 0 and owners[-1][1] == src.H
+        ro.nseg = len(owners)
+        for i, (lo, hi, delta) in enumerate(owners):
+            assert i == 0 or owners[i - 1][1] == lo
+            ro.row_lo[i], ro.byte_delta[i] = lo, delta
+        ro.row_lo[len(owners)] = src.H
+        self._emit("atmvfi_flow_warp_nhwc_p2p", args + (C.byref(ro),), keep=(src, head, out, ro))
 
     def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None, rows: Rows = None):
         b, _, h, w = im0.shape

@@ -121,6 +121,24 @@ class P2PTransport:
         self.slab.backend._emit("atmvfi_p2p_step_begin", (a.ctrl(self.rank, OFF_EPOCH), sig, len(others), wait, len(others), a.ctrl(self.rank, OFF_ERROR)),
                                 keep=(sig, wait))
 
+    remote_reads = True            # kernels may dereference peer-mapped addresses (flow_warp_nhwc_p2p)
+
+    def byte_delta(self, rank: int) -> int:
+        """Distance from a local arena address to the same buffer in ``rank``'s arena (peer-mapped address space)."""
+        return self.arena.peer_base[rank] - self.arena.base
+
+    def barrier(self, site: int) -> None:
+        """Flag-only site: every rank signals every other rank and waits for all of them."""
+        a, me = self.arena, self.rank
+        others = [r for r in range(self.world) if r != me]
+        if not others:
+            return
+        sig = self._ptr_array([a.ctrl(d, OFF_FLAGS + 4 * (site * _lib.P2P_MAX_PEERS + me)) for d in others])
+        wait = self._ptr_array([a.ctrl(me, OFF_FLAGS + 4 * (site * _lib.P2P_MAX_PEERS + s)) for s in others])
+        arr = (_lib.P2PPiece * 1)()
+        self.slab.backend._emit("atmvfi_p2p_exchange", (arr, 0, sig, len(others), wait, len(others), a.ctrl(me, OFF_EPOCH),
+                                                        a.ctrl(me, OFF_COUNTERS + 4 * site), a.ctrl(me, OFF_ERROR)), keep=(arr, sig, wait))
+
     def exchange(self, site: int, outgoing: List[Push], incoming: List[Push]) -> None:
         if not outgoing and not incoming:
             return

@@ -168,7 +168,8 @@ class SlabOps:
 
     def begin_plan(self, B: int, H: int, W: int, glob: bool) -> None:
         self.H = H
-        self.bounds = slab_bounds(H, 16 if glob else 8, self.world)
+        import os
+        self.bounds = slab_bounds(H, 16 if glob else 8, self.world, int(os.environ.get("ATMVFI_SLAB_ALIGN", "64")))
         self.transport.step_begin()
 
     @contextlib.contextmanager
@@ -451,7 +452,28 @@ class SlabOps:
         self._same_rows([out], [flow], lambda rows: self.backend.flow_warp_nchw(img, flow, out, rows=rows), all_rows_in=[img])
 
     def flow_warp_nhwc(self, src: Map, head: Map, flow_off: int, out: Map):
-        self._same_rows([out], [head], lambda rows: self.backend.flow_warp_nhwc(src, head, flow_off, out, rows=rows), all_rows_in=[src])
+        if not getattr(self.transport, "remote_reads", False) or self._replicated:
+            # transports without peer-mapped memory: gather the whole source in front of the warp
+            self._same_rows([out], [head], lambda rows: self.backend.flow_warp_nhwc(src, head, flow_off, out, rows=rows), all_rows_in=[src])
+            return
+        # NVLink: the source stays where it was produced; the kernel reads each sample from the GPU that owns the row.
+        # One flag-only site makes sure every rank has finished producing its rows.
+        b, i0, ni = self._buf(src)
+        segs = []                                   # (lo, hi, rank) cover of the rows, preferring the local copy
+        todo = [(0, b.H)]
+        for q in [self.rank] + [q for q in range(self.world) if q != self.rank]:
+            have = b.have[q][i0]
+            assert all(b.have[q][i] == have for i in range(i0, i0 + ni)), "images of one view must share their row layout"
+            got = rs_and(todo, have)
+            segs += [(lo, hi, q) for lo, hi in got]
+            todo = rs_sub(todo, got)
+        assert not todo, f"rows {todo} of the warp source exist on no rank"
+        segs.sort()
+        owners = [(lo, hi, self.transport.byte_delta(q)) for lo, hi, q in segs]
+        self.transport.barrier(self.site)
+        self.site += 1
+        self.stats["sites"] += 1
+        self._same_rows([out], [head], lambda rows: self.backend.flow_warp_nhwc(src, head, flow_off, out, rows=rows, owners=owners))
 
     def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None):
         outs = [t for t in (w0, w1, it, flow0, flow1, occ1, occ2) if t is not None]

@@ -1,6 +1,7 @@
 // HBM-bound kernels of the ATM-VFI forward: LayerNorm (plain and fused with the window gather),
 // depth-wise 3x3 + GELU, backward warps (+ occlusion blend), align_corners resize, layout packers.
 // Every kernel is a coalesced streaming pass; grids are sized in multiples of the SM count (148).
+#include <string.h>
 #include "common.cuh"
 
 namespace {
@@ -245,11 +246,27 @@ __global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __rest
   }
 }
 
+// Row-slab mode: source rows [lo[i], lo[i+1]) live in the arena of another GPU, `delta[i]` bytes away from the local copy
+// of the buffer in the peer-mapped address space (0 = local).  The warp reads them in place over NVLink.
+struct RowOwners {
+  int nseg;
+  int lo[ATMVFI_P2P_MAX_PEERS * 2 + 1];
+  long long delta[ATMVFI_P2P_MAX_PEERS * 2];
+};
+__device__ __forceinline__ long long owner_delta(const RowOwners& o, int y) {
+  long long d = 0;
+#pragma unroll 1
+  for (int i = 0; i < o.nseg; ++i)
+    if (y >= o.lo[i] && y < o.lo[i + 1]) d = o.delta[i];
+  return d;
+}
+
 // NHWC gather: a group of (C/4) lanes serves one output pixel, each lane moves one float4 per corner.
+template <bool kPeers>
 __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __restrict__ src, int src_pitch,
                                                              const float* __restrict__ head, int head_pitch, int flow_off,
                                                              float* __restrict__ out, int out_pitch, int B, int C, int H,
-                                                             int W, int wy0, int ny, bool rnd) {
+                                                             int W, int wy0, int ny, bool rnd, const __grid_constant__ RowOwners own) {
   const int cv = C >> 2;
   const int64_t total = (int64_t)B * ny * W * cv;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -262,9 +279,16 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __rest
     float iy = warp_src_coord((float)y, __ldg(hp + 1), H);
     Bilin s = bilin_setup(ix, iy, W, H);
     const float* base = src + (int64_t)b * H * W * src_pitch;
+    long long d0 = 0, d1 = 0;
+    if (kPeers) {
+      if (s.vy0) d0 = owner_delta(own, s.y0);
+      if (s.vy1) d1 = owner_delta(own, s.y0 + 1);
+    }
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     auto corner = [&](int yy, int xx, float w, bool first) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)yy * W + xx) * src_pitch) + c4);
+      const float* rowp = base + ((int64_t)yy * W + xx) * src_pitch;
+      if (kPeers) rowp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(rowp) + (yy == s.y0 ? d0 : d1));
+      float4 v = __ldg(reinterpret_cast<const float4*>(rowp) + c4);
       if (first) {
         o.x = __fmul_rn(v.x, w); o.y = __fmul_rn(v.y, w); o.z = __fmul_rn(v.z, w); o.w = __fmul_rn(v.w, w);
       } else {
@@ -494,16 +518,37 @@ int atmvfi_flow_warp_nchw(const float* img, const float* flow, float* out, int B
   return 0;
 }
 
-int atmvfi_flow_warp_nhwc(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off, float* out,
-                          int out_pitch, int B, int C, int H, int W, int y0, int y1, void* stream) {
+static int flow_warp_nhwc_impl(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off, float* out,
+                               int out_pitch, int B, int C, int H, int W, int y0, int y1, const atmvfi_row_owners* owners, void* stream) {
   ATMVFI_REQUIRE(C % 4 == 0 && src_pitch % 4 == 0 && out_pitch % 4 == 0, "flow_warp_nhwc: C=%d must be a multiple of 4", C);
   int ny;
   ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "flow_warp_nhwc: bad row window [%d,%d)", y0, y1);
   int64_t n = (int64_t)B * ny * W * (C / 4);
   if (n <= 0) return 0;
-  flow_warp_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, ny, atmvfi_output_rounding() != 0);
+  RowOwners own;
+  memset(&own, 0, sizeof(own));
+  const bool rnd = atmvfi_output_rounding() != 0;
+  if (owners && owners->nseg > 0) {
+    ATMVFI_REQUIRE(owners->nseg <= ATMVFI_P2P_MAX_PEERS * 2, "flow_warp_nhwc: %d owner segments (max %d)", owners->nseg, ATMVFI_P2P_MAX_PEERS * 2);
+    own.nseg = owners->nseg;
+    for (int i = 0; i < owners->nseg; ++i) { own.lo[i] = owners->row_lo[i]; own.delta[i] = owners->byte_delta[i]; }
+    own.lo[owners->nseg] = owners->row_lo[owners->nseg];
+    flow_warp_nhwc_kernel<true><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, ny, rnd, own);
+  } else {
+    flow_warp_nhwc_kernel<false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, ny, rnd, own);
+  }
   ATMVFI_CHECK_LAUNCH("flow_warp_nhwc");
   return 0;
+}
+
+int atmvfi_flow_warp_nhwc(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off, float* out,
+                          int out_pitch, int B, int C, int H, int W, int y0, int y1, void* stream) {
+  return flow_warp_nhwc_impl(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, y1, nullptr, stream);
+}
+
+int atmvfi_flow_warp_nhwc_p2p(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off, float* out,
+                              int out_pitch, int B, int C, int H, int W, int y0, int y1, const atmvfi_row_owners* owners, void* stream) {
+  return flow_warp_nhwc_impl(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, y1, owners, stream);
 }
 
 int atmvfi_warp_blend(const float* im0, const float* im1, const float* head, int head_pitch, int head_off, float* w0,

@@ -230,6 +230,20 @@ typedef struct {
   uint32_t reserved;
 } atmvfi_p2p_piece;
 
+/* Which GPU holds which rows of a buffer: rows [row_lo[i], row_lo[i+1]) are read at (local address + byte_delta[i]) in the
+ * peer-mapped address space; byte_delta 0 = the local copy. */
+typedef struct {
+  int32_t nseg;
+  int32_t row_lo[ATMVFI_P2P_MAX_PEERS * 2 + 1];
+  int64_t byte_delta[ATMVFI_P2P_MAX_PEERS * 2];
+} atmvfi_row_owners;
+
+/* atmvfi_flow_warp_nhwc whose SOURCE rows are read in place from the GPUs that own them (backward warps have a
+ * data-dependent reach, so the 1/8-resolution feature maps are not gathered: each sample is one NVLink load). */
+int atmvfi_flow_warp_nhwc_p2p(const float* src, int src_pitch, const float* head, int head_pitch, int flow_off,
+                              float* out, int out_pitch, int B, int C, int H, int W, int y0, int y1,
+                              const atmvfi_row_owners* owners, void* stream);
+
 /* One exchange site: copy every piece, then store *epoch (release, system scope) into each signal flag (peer memory),
  * then wait until each wait flag (local memory, raised by a peer's call of this function) has reached *epoch.
  * `counter` is a zero-initialised word private to the site.  A wait that lasts > 4 s sets *error_word and returns. */
