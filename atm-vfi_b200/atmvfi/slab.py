@@ -169,7 +169,7 @@ class SlabOps:
     def begin_plan(self, B: int, H: int, W: int, glob: bool) -> None:
         self.H = H
         import os
-        self.bounds = slab_bounds(H, 16 if glob else 8, self.world, int(os.environ.get("ATMVFI_SLAB_ALIGN", "64")))
+        self.bounds = slab_bounds(H, 16 if glob else 8, self.world, int(os.environ.get("ATMVFI_SLAB_ALIGN", "16")))
         self.transport.step_begin()
 
     @contextlib.contextmanager

@@ -50,6 +50,12 @@ def inference_2frame(img0, img1, model, isBGR=True):
     return model.interpolate_u8(np.ascontiguousarray(img0), np.ascontiguousarray(img1), isBGR=isBGR, divisor=64)
 
 
+def interpolate_video(frames, model, isBGR=True, include_inputs=True):
+    """The 2x loop of demo_2x.py:129-168 over an iterable of uint8 frames: yields f0, mid, f1, mid, ..., f_last.  Same result
+    per pair as ``inference_2frame``; uploads, downloads and compute of neighbouring pairs overlap (model.interpolate_stream)."""
+    return model.interpolate_stream(frames, isBGR=isBGR, divisor=64, include_inputs=include_inputs)
+
+
 def _build(model_type, ckpt, global_off):
     model = (Network_base if model_type == 'base' else Network_lite)()
     if ckpt:
@@ -72,19 +78,22 @@ def main():
     if args.video:
         cap = cv2.VideoCapture(args.video)
         fps = cap.get(cv2.CAP_PROP_FPS)
-        ok, prev = cap.read()
+        ok, first = cap.read()
         if not ok:
             raise SystemExit(f'cannot read {args.video}')
-        h, w = prev.shape[:2]
+        h, w = first.shape[:2]
         wr = cv2.VideoWriter(args.out_video, cv2.VideoWriter_fourcc(*'mp4v'), 2 * fps, (w, h))
-        while True:
-            ok, cur = cap.read()
-            if not ok:
-                break
-            wr.write(prev)
-            wr.write(inference_2frame(prev, cur, model))
-            prev = cur
-        wr.write(prev)
+
+        def decoded():
+            yield first
+            while True:
+                ok, cur = cap.read()
+                if not ok:
+                    return
+                yield cur
+
+        for frame in interpolate_video(decoded(), model):
+            wr.write(frame)
         wr.release(); cap.release()
     else:
         a, b = cv2.imread(args.frame0), cv2.imread(args.frame1)

