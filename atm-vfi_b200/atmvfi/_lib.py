@@ -81,6 +81,9 @@ PROTOTYPES = {
     "atmvfi_warp_blend": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_resize_bilinear_ac": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _P],
     "atmvfi_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_nhwc_to_nchw": [_P, _I, _P, _I, _I, _I, _I, _P],
+    "atmvfi_l1_mean": [_P, _P, _P, _P, _I, _L, _P],
+    "atmvfi_select_min3": [_P, _P, _P, _P, _P, _P, _P, _I, _L, _P],
     "atmvfi_residual_finish": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_u8_to_planar": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_planar_to_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -98,6 +101,7 @@ _SPECIAL = {
     "atmvfi_abi_version": ([], C.c_int),
     "atmvfi_device_info": ([_I, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     "atmvfi_gemm_conv_plan_bytes": ([], C.c_int),
+    "atmvfi_l1_mean_scratch_floats": ([C.c_int], C.c_int),
     "atmvfi_set_output_rounding": ([C.c_int], None),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))

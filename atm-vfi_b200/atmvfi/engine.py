@@ -162,25 +162,89 @@ def motion_branch(ops, blocks, head, tok: Map, ws: int) -> Tuple[Map, Map]:
 class Plan:
     """Launch list + buffers for one input shape."""
 
-    def __init__(self, ops, model: PackedModel, B: int, H: int, W: int, global_motion: bool):
-        div = 16 if global_motion else 8
+    def __init__(self, ops, model: PackedModel, B: int, H: int, W: int, global_motion: bool, ensemble: bool = False):
+        ensemble = bool(ensemble and global_motion)      # forward_global_ensemble without global motion is forward_normal's local path
+        div = 64 if ensemble else (16 if global_motion else 8)
         if H % div or W % div:
-            raise RuntimeError(f"ATM-VFI forward: input {H}x{W} must be a multiple of {div} (global_motion={global_motion}); "
-                               "pad with InputPadder as the reference does")
+            raise RuntimeError(f"ATM-VFI forward: input {H}x{W} must be a multiple of {div} (global_motion={global_motion}, "
+                               f"ensemble={ensemble}); pad with InputPadder as the reference does")
+        if ensemble and hasattr(ops, "begin_plan"):
+            raise NotImplementedError("the multi-scale global-motion ensemble reduces over whole frames and is not available in row-slab mode")
         if global_motion and not model.with_global:
             raise RuntimeError("global_motion requested but the global-motion weights were not packed")
-        self.ops, self.model, self.key = ops, model, (B, H, W, global_motion)
+        self.ops, self.model, self.key = ops, model, (B, H, W, global_motion, ensemble)
         a = model.arch
         ops.recording = rec = []
         try:
-            self._build(ops, model, a, B, H, W, global_motion)
+            self._build(ops, model, a, B, H, W, global_motion, ensemble)
         finally:
             ops.recording = None
         self.records = rec
         self.graph = None
 
     # .............................................................................................
-    def _build(self, ops, m: PackedModel, a: Arch, B: int, H: int, W: int, glob: bool):
+    @staticmethod
+    def _encode(ops, m: PackedModel, im0: torch.Tensor, im1: torch.Tensor, B: int, H: int, W: int) -> List[Map]:
+        """shared_feat_extraction on the two frames stacked on the batch axis (network_base.py:342-352, 451): 4 levels."""
+        levels, x = [], None
+        for l in range(4):
+            c0, c1 = m.enc[l]
+            h, w = H >> l, W >> l
+            y = ops.new_map(2 * B, h, w, c0.Cout)
+            if l == 0:      # 3 -> C0 straight from the planar frames (no channels-last copy of the inputs)
+                ops.conv3x3_first(im0, c0, y.batch(0, B))
+                ops.conv3x3_first(im1, c0, y.batch(B, B))
+            else:
+                ops.gemm_conv([x], c0, y, stride=2)
+            x = ops.new_map(2 * B, h, w, c1.Cout)
+            ops.gemm_conv([y], c1, x)
+            levels.append(x)
+        return levels
+
+    @staticmethod
+    def _global_head(ops, m: PackedModel, levels: List[Map], B: int, H: int, W: int) -> Map:
+        """estimate_global_motion (network_base.py:391-415): 5-channel head [B, H/16, W/16, 5] of an encoder run on HxW frames."""
+        h16, w16 = H >> 4, W >> 4
+        l0, l1 = m.last
+        y = ops.new_map(2 * B, h16, w16, l0.Cout)
+        ops.gemm_conv([levels[3]], l0, y, stride=2)
+        z = ops.new_map(2 * B, h16, w16, l1.Cout)
+        ops.gemm_conv([y], l1, z)
+        gtok = fusion(ops, m.fuse_global, levels[2], levels[3], z)
+        return motion_branch(ops, m.global_blocks, m.global_head, gtok, m.global_ws)[1]
+
+    def _ensemble_flows(self, ops, m: PackedModel, levels: List[Map], pyr0, pyr1, B: int, H: int, W: int):
+        """multiscale_global_motion_ensemble (network_base.py:564-615): global flows estimated at input scales 1, 1/2, 1/4; per
+        sample the scale whose flows align the full-resolution frames best wins (device-side select, no host round trip)."""
+        P = ops.new_planar
+        h16, w16 = H >> 4, W >> 4
+        losses, cand0, cand1 = [], [], []
+        scratch = P(B, 1, 1, 2048)
+        for s in range(3):
+            hs, ws_ = H >> s, W >> s
+            lev = levels if s == 0 else self._encode(ops, m, pyr0[s], pyr1[s], B, hs, ws_)
+            head = self._global_head(ops, m, lev, B, hs, ws_)
+            f0, f1 = P(B, 2, hs >> 4, ws_ >> 4), P(B, 2, hs >> 4, ws_ >> 4)
+            ops.nhwc_to_nchw(head.chan(0, 2), f0); ops.nhwc_to_nchw(head.chan(2, 2), f1)
+            # global_alignmentness (network_base.py:548-562): warp the FULL-resolution frames with the up-scaled flows
+            u0, u1 = P(B, 2, H, W), P(B, 2, H, W)
+            ops.resize(f0, u0, float(16 << s)); ops.resize(f1, u1, float(16 << s))
+            a0, a1 = P(B, 3, H, W), P(B, 3, H, W)
+            ops.flow_warp_nchw(self.im0, u0, a0); ops.flow_warp_nchw(self.im1, u1, a1)
+            loss = P(B, 1, 1, 1)
+            ops.l1_mean(a0, a1, loss, scratch)
+            losses.append(loss)
+            if s:           # bring the candidate to the 1/16 grid of the original frames (network_base.py:606-611)
+                c0, c1 = P(B, 2, h16, w16), P(B, 2, h16, w16)
+                ops.resize(f0, c0, float(1 << s)); ops.resize(f1, c1, float(1 << s))
+                f0, f1 = c0, c1
+            cand0.append(f0); cand1.append(f1)
+        g0, g1 = P(B, 2, h16, w16), P(B, 2, h16, w16)
+        ops.select3(losses, cand0, g0); ops.select3(losses, cand1, g1)
+        self.ensemble_losses = losses
+        return g0, g1
+
+    def _build(self, ops, m: PackedModel, a: Arch, B: int, H: int, W: int, glob: bool, ensemble: bool = False):
         P = ops.new_planar
         if hasattr(ops, "begin_plan"):          # row-slab mode (slab.SlabOps): partition the rows, open the step
             ops.begin_plan(B, H, W, glob)
@@ -191,41 +255,24 @@ class Plan:
                 pyr0.append(P(B, 3, H >> l, W >> l)); pyr1.append(P(B, 3, H >> l, W >> l))
                 ops.resize(pyr0[l - 1], pyr0[l]); ops.resize(pyr1[l - 1], pyr1[l])
 
-        # encoder on the two frames stacked on the batch axis (network_base.py:342-352, 451)
-        levels = []
-        x = None
-        for l in range(4):
-            c0, c1 = m.enc[l]
-            h, w = H >> l, W >> l
-            y = ops.new_map(2 * B, h, w, c0.Cout)
-            if l == 0:      # 3 -> C0 straight from the planar frames (no channels-last copy of the inputs)
-                ops.conv3x3_first(self.im0, c0, y.batch(0, B))
-                ops.conv3x3_first(self.im1, c0, y.batch(B, B))
-            else:
-                ops.gemm_conv([x], c0, y, stride=2)
-            x = ops.new_map(2 * B, h, w, c1.Cout)
-            ops.gemm_conv([y], c1, x)
-            levels.append(x)
+        levels = self._encode(ops, m, self.im0, self.im1, B, H, W)
         tok = fusion(ops, m.fuse_local, levels[1], levels[2], levels[3])     # [2B, H/8, W/8, C]
         h8, w8 = H >> 3, W >> 3
 
         it_list, w0_list, w1_list = [], [], []
         if glob:
             h16, w16 = H >> 4, W >> 4
-            l0, l1 = m.last
-            y = ops.new_map(2 * B, h16, w16, l0.Cout)
-            ops.gemm_conv([levels[3]], l0, y, stride=2)
-            z = ops.new_map(2 * B, h16, w16, l1.Cout)
-            ops.gemm_conv([y], l1, z)
-            gtok = fusion(ops, m.fuse_global, levels[2], levels[3], z)
-            _, ghead = motion_branch(ops, m.global_blocks, m.global_head, gtok, m.global_ws)
-            i0, i1 = P(B, 3, h16, w16), P(B, 3, h16, w16)
-            with ops.replicated():
-                ops.resize(pyr0[3], i0); ops.resize(pyr1[3], i1)
-            a0, a1, it = P(B, 3, h16, w16), P(B, 3, h16, w16), P(B, 3, h16, w16)
-            f0, f1 = P(B, 2, h16, w16), P(B, 2, h16, w16)
-            ops.warp_blend(i0, i1, ghead, a0, a1, it, f0, f1)
-            it_list.insert(0, it); w0_list.insert(0, a0); w1_list.insert(0, a1)
+            if ensemble:        # forward_global_ensemble (network_base.py:643-649): no 1/16 blend, the lists hold 4 scales
+                f0, f1 = self._ensemble_flows(ops, m, levels, pyr0, pyr1, B, H, W)
+            else:
+                ghead = self._global_head(ops, m, levels, B, H, W)
+                i0, i1 = P(B, 3, h16, w16), P(B, 3, h16, w16)
+                with ops.replicated():
+                    ops.resize(pyr0[3], i0); ops.resize(pyr1[3], i1)
+                a0, a1, it = P(B, 3, h16, w16), P(B, 3, h16, w16), P(B, 3, h16, w16)
+                f0, f1 = P(B, 2, h16, w16), P(B, 2, h16, w16)
+                ops.warp_blend(i0, i1, ghead, a0, a1, it, f0, f1)
+                it_list.insert(0, it); w0_list.insert(0, a0); w1_list.insert(0, a1)
             # flows x2 up to 1/8, warp the fused tokens of each frame (network_base.py:471-478)
             f0u, f1u = P(B, 2, h8, w8), P(B, 2, h8, w8)
             with ops.replicated():    # the global flows drive the warps of the whole image pyramid below

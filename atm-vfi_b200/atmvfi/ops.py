@@ -201,6 +201,8 @@ class CudaOps:
                 return 2 if args[13] is not None else 1
             if name == "atmvfi_window_attention_tc":
                 return 2 if args[14] is not None else 1
+            if name == "atmvfi_l1_mean":
+                return 2
             return 1
         return sum(n(name, args) for name, _, args, _ in records)
 
@@ -360,6 +362,22 @@ class CudaOps:
         b, c, h, w = x.shape
         assert (out.B, out.H, out.W) == (b, h, w) and out.C >= c and x.is_contiguous()
         self._emit("atmvfi_nchw_to_nhwc", (x.data_ptr(), out.t.data_ptr(), out.pitch, out.c0, b, c, h, w, zero_fill_to) + _yy(rows), keep=(x, out))
+
+    def nhwc_to_nchw(self, x: Map, out: torch.Tensor):
+        b, c, h, w = out.shape
+        assert (x.B, x.H, x.W, x.C) == (b, h, w, c) and out.is_contiguous()
+        self._emit("atmvfi_nhwc_to_nchw", (x.ptr, x.pitch, out.data_ptr(), b, c, h, w), keep=(x, out))
+
+    # -- multi-scale global-motion ensemble (network_base.py:548-615) ---------------------------------
+    def l1_mean(self, a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, scratch: torch.Tensor):
+        n = a[0].numel()
+        assert a.shape == b.shape and out.numel() == a.shape[0] and scratch.numel() >= self.lib.atmvfi_l1_mean_scratch_floats(a.shape[0])
+        self._emit("atmvfi_l1_mean", (a.data_ptr(), b.data_ptr(), out.data_ptr(), scratch.data_ptr(), a.shape[0], n), keep=(a, b, out, scratch))
+
+    def select3(self, losses: Sequence[torch.Tensor], cands: Sequence[torch.Tensor], out: torch.Tensor):
+        assert len(losses) == len(cands) == 3 and all(c.shape == out.shape and c.is_contiguous() for c in cands)
+        self._emit("atmvfi_select_min3", tuple(l.data_ptr() for l in losses) + tuple(c.data_ptr() for c in cands) +
+                   (out.data_ptr(), out.shape[0], out[0].numel()), keep=(losses, cands, out))
 
     def residual_finish(self, res: Map, it, it_sum, it_clamped, rows: Rows = None):
         b, _, h, w = it.shape

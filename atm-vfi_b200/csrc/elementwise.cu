@@ -381,6 +381,60 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   }
 }
 
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float* __restrict__ in, int in_pitch, float* __restrict__ out, int B,
+                                                           int C, int H, int W) {
+  const int64_t hw = (int64_t)H * W, total = (int64_t)B * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / hw);
+    const int64_t rem = i - b * hw;
+    for (int c = 0; c < C; ++c) out[((int64_t)b * C + c) * hw + rem] = __ldg(in + i * in_pitch + c);
+  }
+}
+
+// mean |a - b| per sample, deterministic: fixed-shape tree per block -> kL1Blocks partial sums per sample -> one warp adds
+// them in double in a fixed order.
+constexpr int kL1Blocks = 512;
+__global__ void __launch_bounds__(256) l1_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                         float* __restrict__ partial, int64_t n) {
+  __shared__ float red[256];
+  const int s = blockIdx.y;
+  const float* pa = a + (int64_t)s * n;
+  const float* pb = b + (int64_t)s * n;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += fabsf(__ldg(pa + i) - __ldg(pb + i));
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(int64_t)s * kL1Blocks + blockIdx.x] = red[0];
+}
+__global__ void l1_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t n) {
+  const int s = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kL1Blocks; ++i) t += (double)partial[(int64_t)s * kL1Blocks + i];
+    out[s] = (float)(t / (double)n);
+  }
+}
+
+// per sample: the candidate whose loss is the smallest, ties resolved like the reference's if / elif / else chain
+// (network_base.py:596-611)
+__global__ void __launch_bounds__(256) select_min3_kernel(const float* __restrict__ l0, const float* __restrict__ l1,
+                                                          const float* __restrict__ l2, const float* __restrict__ c0,
+                                                          const float* __restrict__ c1, const float* __restrict__ c2,
+                                                          float* __restrict__ out, int B, int64_t n) {
+  const int64_t total = (int64_t)B * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i / n);
+    const float a = __ldg(l0 + s), b = __ldg(l1 + s), c = __ldg(l2 + s);
+    const float m = fminf(a, fminf(b, c));
+    out[i] = a == m ? __ldg(c0 + i) : (b == m ? __ldg(c1 + i) : __ldg(c2 + i));
+  }
+}
+
 __global__ void __launch_bounds__(256) residual_finish_kernel(const float* __restrict__ res, int res_pitch,
                                                               const float* __restrict__ it, float* __restrict__ it_sum,
                                                               float* __restrict__ it_clamped, int B, int H, int W, int wy0, int ny) {
@@ -585,6 +639,33 @@ int atmvfi_nchw_to_nhwc(const float* in, float* out, int out_pitch, int chan_off
   if (n <= 0) return 0;
   nchw_to_nhwc_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, out_pitch, chan_off, B, C, H, W, zero_fill_to, y0, ny, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("nchw_to_nhwc");
+  return 0;
+}
+
+int atmvfi_nhwc_to_nchw(const float* in, int in_pitch, float* out, int B, int C, int H, int W, void* stream) {
+  int64_t n = (int64_t)B * H * W;
+  if (n <= 0 || C <= 0) return 0;
+  nhwc_to_nchw_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, B, C, H, W);
+  ATMVFI_CHECK_LAUNCH("nhwc_to_nchw");
+  return 0;
+}
+
+int atmvfi_l1_mean_scratch_floats(int samples) { return samples * kL1Blocks; }
+
+int atmvfi_l1_mean(const float* a, const float* b, float* out, float* scratch, int samples, int64_t n, void* stream) {
+  ATMVFI_REQUIRE(samples > 0 && samples <= 65535 && n > 0 && scratch != nullptr, "l1_mean: bad arguments");
+  l1_partial_kernel<<<dim3(kL1Blocks, (unsigned)samples), 256, 0, (cudaStream_t)stream>>>(a, b, scratch, n);
+  ATMVFI_CHECK_LAUNCH("l1_mean(partial)");
+  l1_final_kernel<<<samples, 32, 0, (cudaStream_t)stream>>>(scratch, out, n);
+  ATMVFI_CHECK_LAUNCH("l1_mean(final)");
+  return 0;
+}
+
+int atmvfi_select_min3(const float* l0, const float* l1, const float* l2, const float* c0, const float* c1, const float* c2,
+                       float* out, int samples, int64_t n, void* stream) {
+  if ((int64_t)samples * n <= 0) return 0;
+  select_min3_kernel<<<grid_for((int64_t)samples * n, 256), 256, 0, (cudaStream_t)stream>>>(l0, l1, l2, c0, c1, c2, out, samples, n);
+  ATMVFI_CHECK_LAUNCH("select_min3");
   return 0;
 }
 

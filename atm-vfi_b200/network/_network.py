@@ -102,7 +102,7 @@ class NetworkBase(ParamTree):
         if im0.device != im1.device:
             raise RuntimeError("im0 and im1 are on different devices")
 
-    def forward_normal(self, im0, im1):
+    def forward_normal(self, im0, im1, _ensemble=False):
         """im0, im1: [B,3,H,W] float32 in [0,1] on the model's CUDA device -> the reference's 10-entry dict
         (network_base.py:535-545).  Inference only: outputs carry no autograd graph."""
         self._check_inputs(im0, im1)
@@ -110,7 +110,7 @@ class NetworkBase(ParamTree):
         rt.prepare(self, im0.device, self.precision, self.local_motion_args["window_size"], self.global_motion_args["window_size"])
         B, _, H, W = im0.shape
         with torch.cuda.device(im0.device):
-            plan = rt.plan(B, H, W, bool(self.global_motion))
+            plan = rt.plan(B, H, W, bool(self.global_motion), _ensemble)
             out = plan.run(im0, im1, use_graph=self.use_cuda_graph)
             return out if self.zero_copy_outputs else clone_outputs(out)
 
@@ -233,6 +233,7 @@ class NetworkBase(ParamTree):
             main.synchronize()
 
     def forward_global_ensemble(self, im0, im1):
-        raise NotImplementedError(
-            "multi-scale global-motion ensemble (network_base.py:564-712) is not built yet in the B200 engine; "
-            "it is off by default in every reference script (SURVEY.md 8a, row a16)")
+        """forward with the multi-scale global-motion ensemble (network_base.py:564-712): the global flows are estimated at
+        input scales 1, 1/2 and 1/4 and, per sample, the scale that aligns the two frames best is kept (selected on the
+        device).  H and W must be multiples of 64.  ``im_t_list`` and the warped lists hold 4 scales, as in the reference."""
+        return self.forward_normal(im0, im1, _ensemble=True)

@@ -189,6 +189,19 @@ int atmvfi_resize_bilinear_ac(const float* in, float* out, int planes, int Hin, 
 int atmvfi_nchw_to_nhwc(const float* in, float* out, int out_pitch, int chan_off, int B, int C, int H, int W,
                         int zero_fill_to /* also zero channels [chan_off+C, zero_fill_to) */, int y0, int y1, void* stream);
 
+/* channels [0, C) of an NHWC map (pointer already offset to the first channel) -> planar [B][C][H][W]. */
+int atmvfi_nhwc_to_nchw(const float* in, int in_pitch, float* out, int B, int C, int H, int W, void* stream);
+
+/* Multi-scale global-motion ensemble (network_base.py:548-615).
+ * l1_mean: out[s] = mean_i |a[s][i] - b[s][i]| over n elements per sample (nn.L1Loss + torch.mean(dim=[1,2,3]), :560-561);
+ * deterministic two-stage reduction; scratch holds atmvfi_l1_mean_scratch_floats(samples) floats.
+ * select_min3: out[s] = the candidate c_k[s] (n floats per sample) with the smallest loss, first minimum wins like the
+ * reference's if / elif / else chain (:596-611) - evaluated on the device, no host round trip. */
+int atmvfi_l1_mean_scratch_floats(int samples);
+int atmvfi_l1_mean(const float* a, const float* b, float* out, float* scratch, int samples, int64_t n, void* stream);
+int atmvfi_select_min3(const float* l0, const float* l1, const float* l2, const float* c0, const float* c1, const float* c2,
+                       float* out, int samples, int64_t n, void* stream);
+
 /* I_t += 2*sigmoid(res)-1 ; clamp (network_base.py:429, 532-533).  res: NHWC 3 channels. */
 int atmvfi_residual_finish(const float* res, int res_pitch, const float* it, float* it_sum, float* it_clamped,
                            int B, int H, int W, int y0, int y1, void* stream);

@@ -269,13 +269,66 @@ def window_sizes(P: Params) -> Tuple[int, int]:
     return lw, gw
 
 
-def forward(P: Params, im0: Tensor, im1: Tensor, global_motion: bool = True) -> Dict[str, object]:
-    """forward_normal (network_base.py:433-546).  im0, im1: [B,3,H,W] fp32 in [0,1]."""
+def forward(P: Params, im0: Tensor, im1: Tensor, global_motion: bool = True, ensemble: bool = False) -> Dict[str, object]:
+    """forward_normal (network_base.py:433-546) or, with ``ensemble``, forward_global_ensemble (network_base.py:617-712).
+    im0, im1: [B,3,H,W] fp32 in [0,1]."""
     with torch.no_grad():
-        return _forward(P, im0, im1, global_motion)
+        return _forward(P, im0, im1, global_motion, ensemble)
 
 
-def _forward(P: Params, im0: Tensor, im1: Tensor, global_motion: bool) -> Dict[str, object]:
+def _encode(P: Params, x: Tensor):
+    """shared_feat_extraction (network_base.py:342-352): returns (1/8 map, [1/2, 1/4, 1/8 maps])."""
+    levels = []
+    for lvl in range(4):
+        x = _conv_prelu(P, f"feat_extracts.{lvl}.0", x, stride=1 if lvl == 0 else 2)
+        x = _conv_prelu(P, f"feat_extracts.{lvl}.1", x)
+        if lvl:
+            levels.append(x)
+    return x, levels
+
+
+def _global_motion(P: Params, x: Tensor, levels: List[Tensor], gws: int):
+    """estimate_global_motion (network_base.py:391-415): flows and occlusion mask at 1/16 of the encoder's input."""
+    y = _conv_prelu(P, "last_feat_extract.0", x, stride=2)
+    y = _conv_prelu(P, "last_feat_extract.1", y)
+    gtok, gh, gw = cross_scale_fusion(P, "global_feature_fusion", [levels[1], levels[2], y])
+    f0, f1, occ, _, _ = _motion_branch(P, "global_motion_atmformer", "global_motion_mlp", gtok, gh, gw, gws)
+    return f0, f1, occ
+
+
+def upsample_flow(flow: Tensor, factor: int) -> Tensor:
+    """upsample_flow (network_base.py:11-18): one bilinear align_corners resize by ``factor``, values scaled by ``factor``."""
+    return F.interpolate(flow, scale_factor=factor, mode="bilinear", align_corners=True) * factor
+
+
+def multiscale_global_motion_ensemble(P: Params, im0: Tensor, im1: Tensor, gws: int):
+    """network_base.py:564-615: global flows estimated at input scales 1, 1/2, 1/4; per sample the scale whose flows align the
+    two full-resolution frames best (mean L1 of the warped frames, network_base.py:548-562) wins."""
+    B = im0.shape[0]
+    im = torch.cat([im0, im1], 0)
+    cands, losses = [], []
+    for scale in range(3):
+        if scale:
+            im = F.interpolate(im, scale_factor=0.5, mode="bilinear", align_corners=True)
+        x, levels = _encode(P, im)
+        f0, f1, _ = _global_motion(P, x, levels, gws)
+        factor = im0.shape[2] // f0.shape[2]
+        a, b = flow_warp(im0, upsample_flow(f0, factor)), flow_warp(im1, upsample_flow(f1, factor))
+        losses.append((a - b).abs().mean(dim=[1, 2, 3]))
+        cands.append((f0, f1))
+    out0, out1 = torch.zeros_like(cands[0][0]), torch.zeros_like(cands[0][1])
+    for i in range(B):
+        m = min(losses[0][i], losses[1][i], losses[2][i])
+        if losses[0][i] == m:
+            out0[i], out1[i] = cands[0][0][i], cands[0][1][i]
+        elif losses[1][i] == m:
+            out0[i], out1[i] = upsample_flow(cands[1][0][i, None], 2)[0], upsample_flow(cands[1][1][i, None], 2)[0]
+        else:
+            out0[i], out1[i] = upsample_flow(cands[2][0][i, None], 4)[0], upsample_flow(cands[2][1][i, None], 4)[0]
+    return out0, out1, torch.stack(losses, 1)
+
+
+def _forward(P: Params, im0: Tensor, im1: Tensor, global_motion: bool, ensemble: bool = False) -> Dict[str, object]:
     B = im0.shape[0]
     lws, gws = window_sizes(P)
     pyr0, pyr1 = [im0], [im1]
@@ -284,26 +337,20 @@ def _forward(P: Params, im0: Tensor, im1: Tensor, global_motion: bool) -> Dict[s
         pyr1.append(resize_half(pyr1[-1]))
 
     # shared encoder on the two frames stacked on the batch axis (network_base.py:342-352, 451)
-    x = torch.cat([im0, im1], 0)
-    levels = []
-    for lvl in range(4):
-        x = _conv_prelu(P, f"feat_extracts.{lvl}.0", x, stride=1 if lvl == 0 else 2)
-        x = _conv_prelu(P, f"feat_extracts.{lvl}.1", x)
-        if lvl:
-            levels.append(x)
+    x, levels = _encode(P, torch.cat([im0, im1], 0))
     tok, h, w = cross_scale_fusion(P, "cross_scale_feature_fusion", levels)     # [2B, hw, C] at 1/8
     C = tok.shape[-1]
 
     it_list, w0_list, w1_list = [], [], []
     if global_motion:
-        y = _conv_prelu(P, "last_feat_extract.0", x, stride=2)
-        y = _conv_prelu(P, "last_feat_extract.1", y)
-        gtok, gh, gw = cross_scale_fusion(P, "global_feature_fusion", [levels[1], levels[2], y])
-        f0, f1, occ, _, _ = _motion_branch(P, "global_motion_atmformer", "global_motion_mlp", gtok, gh, gw, gws)
-        a, b = flow_warp(resize_half(pyr0[-1]), f0), flow_warp(resize_half(pyr1[-1]), f1)
-        it_list.insert(0, occ * a + (1 - occ) * b)
-        w0_list.insert(0, a)
-        w1_list.insert(0, b)
+        if ensemble:      # network_base.py:643-649: the 1/16 blend is not produced, the lists hold 4 scales
+            f0, f1, _ = multiscale_global_motion_ensemble(P, im0, im1, gws)
+        else:
+            f0, f1, occ = _global_motion(P, x, levels, gws)
+            a, b = flow_warp(resize_half(pyr0[-1]), f0), flow_warp(resize_half(pyr1[-1]), f1)
+            it_list.insert(0, occ * a + (1 - occ) * b)
+            w0_list.insert(0, a)
+            w1_list.insert(0, b)
         f0, f1 = upsample_flow2(f0), upsample_flow2(f1)
         fmap = tok.transpose(1, 2).reshape(2 * B, C, h, w)
         fmap = torch.cat([flow_warp(fmap[:B], f0), flow_warp(fmap[B:], f1)], 0)

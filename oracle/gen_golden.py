@@ -27,25 +27,33 @@ CASES = [
     ("base_default_on_128x192", "base", "default", 1, 128, 192, True, "noise"),
     ("base_stress_on_b2_64x96", "base", "stress", 2, 64, 96, True, "texture"),
     ("lite_stress_off_b2_72x104", "lite", "stress", 2, 72, 104, False, "texture"),
+    # forward_global_ensemble (network_base.py:617-712): ensemble_global_motion=True, H and W multiples of 64
+    ("ensemble_base_default_128x128", "base", "default", 1, 128, 128, True, "noise"),
+    ("ensemble_select_lite_b3_128x192", "lite", "ensemble", 3, 128, 192, True, "shift"),   # a different scale wins per sample
 ]
 
 
 def run_case(name, kind, variant, b, h, w, glob, frames):
     Net = refshim.load_reference_network(kind)
     P = weights.make_weights(kind, variant)
-    net = Net(global_motion=glob).eval()
+    ens = name.startswith("ensemble")
+    net = Net(global_motion=glob, ensemble_global_motion=ens).eval()
     net.load_state_dict(P, strict=True)
     im0, im1 = weights.synthetic_frames(b, h, w, kind=frames)
     with torch.no_grad():
         out = net(im0, im1)
+        if ens:      # also record which scale won, for a meaningful test (the selection must not be degenerate)
+            g0, g1 = net.multiscale_global_motion_ensemble(im0, im1)
     rec = {"I_t": out["I_t"], "opt_flow_0": out["opt_flow_0"], "opt_flow_1": out["opt_flow_1"],
            "occ_mask1": out["occ_mask1"], "I_t_0": out["I_t_0"], "I_t_1": out["I_t_1"]}
     for i, t in enumerate(out["im_t_list"]):
         rec[f"im_t_list_{i}"] = t
     rec["coarse_im0_warped"] = out["im0_warped_list"][-1]
     rec["coarse_im1_warped"] = out["im1_warped_list"][-1]
+    if ens:
+        rec["ensemble_flow_0"], rec["ensemble_flow_1"] = g0, g1
     np.savez_compressed(os.path.join(GOLDEN, f"case_{name}.npz"),
-                        meta=json.dumps(dict(kind=kind, variant=variant, B=b, H=h, W=w, global_motion=glob, frames=frames)),
+                        meta=json.dumps(dict(kind=kind, variant=variant, B=b, H=h, W=w, global_motion=glob, frames=frames, ensemble=ens)),
                         **{k: v.numpy().astype(np.float32) for k, v in rec.items()})
     f0 = out["opt_flow_0"]
     print(f"{name}: I_t mean {out['I_t'].mean():.4f} std {out['I_t'].std():.4f} clamp% "

@@ -142,7 +142,7 @@ _TRANSFORMER_PARTS = ("cross_scale_feature_fusion", "global_feature_fusion", "fe
 
 
 def make_weights(kind: str, variant: str = "default", seed: int = 0, local_ws: int = 8, global_ws: int = 12) -> Dict[str, torch.Tensor]:
-    assert variant in ("default", "stress")
+    assert variant in ("default", "stress", "ensemble")
     S = schema(kind, local_ws, global_ws)
     P: Dict[str, torch.Tensor] = OrderedDict()
     for name, shape in S.items():
@@ -174,8 +174,14 @@ def make_weights(kind: str, variant: str = "default", seed: int = 0, local_ws: i
                 P[name] = (torch.rand(shape, generator=torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)) * 2 - 1) / math.sqrt(fan_in)
         else:                                                 # PReLU slope
             P[name] = torch.full(shape, 0.25)
-    if variant == "stress":
+    if variant in ("stress", "ensemble"):
         _apply_stress(P, kind, seed)
+    if variant == "ensemble":
+        # Scale-selection probe for forward_global_ensemble (network_base.py:564-615): the global head emits a constant flow of
+        # +-0.125 grid pixels (plus a small data term), i.e. +-2 / +-4 / +-8 full-resolution pixels when estimated at input
+        # scale 1, 1/2, 1/4.  With the "shift" frames below (sample i shifted by 4, 8, 16 px) a different scale wins per sample.
+        P["global_motion_mlp.2.weight"] = P["global_motion_mlp.2.weight"] * 0.002
+        P["global_motion_mlp.2.bias"] = torch.tensor([0.125, 0.0, -0.125, 0.0, 0.0])
     return P
 
 
@@ -214,6 +220,12 @@ def synthetic_frames(batch: int, h: int, w: int, seed: int = 1234, kind: str = "
     """Frame pairs in [0,1).  ``noise`` = torch.rand; ``texture`` = a smooth random field and a
     shifted copy, so that flows are meaningful with the stress weights."""
     g = torch.Generator().manual_seed(seed)
+    if kind == "shift":       # sample i: frame 1 = frame 0 moved by 4 * 2^(i % 3) pixels along x (smooth texture)
+        low = torch.rand(batch, 3, h // 16 + 3, (w + 32) // 16 + 3, generator=g)
+        big = torch.nn.functional.interpolate(low, size=(h, w + 32), mode="bicubic", align_corners=True).clamp(0, 1)
+        im0 = big[:, :, :, 0:w].contiguous()
+        im1 = torch.stack([big[i, :, :, 4 * 2 ** (i % 3) : 4 * 2 ** (i % 3) + w] for i in range(batch)]).contiguous()
+        return im0, im1
     if kind == "noise":
         return torch.rand(batch, 3, h, w, generator=g), torch.rand(batch, 3, h, w, generator=g)
     low = torch.rand(batch, 3, h // 8 + 3, w // 8 + 3, generator=g)

@@ -262,6 +262,20 @@ class EmulOps:
                 _put(z, torch.zeros_like(z), rows)
         self._emit(run)
 
+    def nhwc_to_nchw(self, x: Map, out):
+        self._emit(lambda: out.copy_(x.view().permute(0, 3, 1, 2)))
+
+    def l1_mean(self, a, b, out, scratch):
+        self._emit(lambda: out.copy_((a - b).abs().mean(dim=[1, 2, 3]).reshape(out.shape)))
+
+    def select3(self, losses, cands, out):
+        def run():
+            for i in range(out.shape[0]):
+                l = [float(x.reshape(-1)[i]) for x in losses]
+                k = 0 if l[0] == min(l) else (1 if l[1] == min(l) else 2)
+                out[i] = cands[k][i]
+        self._emit(run)
+
     def residual_finish(self, res: Map, it, it_sum, it_clamped, rows=None):
         def run():
             s = it + (2 * torch.sigmoid(res.view()[..., :3].permute(0, 3, 1, 2)) - 1)

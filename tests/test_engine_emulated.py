@@ -42,3 +42,23 @@ def test_bad_shape_raises():
     model = PackedModel(ARCHS["lite"], P, 8, 12)
     with pytest.raises(RuntimeError):
         Plan(EmulOps(), model, 1, 72, 104, True)    # not a multiple of 16 with global motion
+
+
+@pytest.mark.parametrize("kind,variant,B,H,W,frames", [("lite", "ensemble", 3, 128, 192, "shift"), ("base", "default", 1, 128, 128, "noise")])
+def test_ensemble_plan_matches_oracle(kind, variant, B, H, W, frames):
+    """forward_global_ensemble (network_base.py:564-712): 3-scale global motion + per-sample selection."""
+    P = weights.make_weights(kind, variant)
+    im0, im1 = weights.synthetic_frames(B, H, W, kind=frames)
+    ref = oracle.forward(P, im0, im1, True, ensemble=True)
+    model = PackedModel(ARCHS[kind], P, 8, 12, with_global=True)
+    plan = Plan(EmulOps(), model, B, H, W, True, ensemble=True)
+    out = plan.run(im0, im1)
+    if variant == "ensemble":      # a different scale wins for every sample
+        losses = torch.stack([l.reshape(-1) for l in plan.ensemble_losses], 1)
+        assert losses.argmin(1).tolist() == [0, 1, 2]
+    tol = 5e-3 if variant != "default" else 2e-5
+    for key in ("I_t", "opt_flow_0", "opt_flow_1", "occ_mask1"):
+        assert (out[key] - ref[key]).abs().max().item() <= tol, key
+    assert len(out["im_t_list"]) == len(ref["im_t_list"]) == 4
+    with pytest.raises(RuntimeError):
+        Plan(EmulOps(), model, 1, 96, 128, True, ensemble=True)     # 96 is not a multiple of 64

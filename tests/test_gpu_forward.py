@@ -26,6 +26,7 @@ CASES = [p for p in sorted(glob.glob(os.path.join(GOLDEN, "case_*.npz"))) if "co
 #         occlusion logit), so with tf32 it is checked on mean error and final outputs only.
 TOL = {("fp32", "default"): dict(img=1e-4, flow=1e-4, mean=1e-5), ("fp32", "stress"): dict(img=2e-3, flow=1e-4, mean=1e-4),
        ("tf32", "default"): dict(img=8e-3, flow=2e-4, mean=1e-3), ("tf32", "stress"): dict(img=0.1, flow=0.1, mean=5e-3)}
+TOL[("fp32", "ensemble")], TOL[("tf32", "ensemble")] = TOL[("fp32", "stress")], TOL[("tf32", "stress")]     # stress gains + scale selection
 
 
 def _net(kind, P):
@@ -52,6 +53,7 @@ def test_forward_matches_reference_golden(path, precision):
     im0, im1 = weights.synthetic_frames(meta["B"], meta["H"], meta["W"], kind=meta["frames"])
     net = _net(meta["kind"], P)
     net.global_motion = meta["global_motion"]
+    net.ensemble_global_motion = bool(meta.get("ensemble", False))      # forward_global_ensemble (network_base.py:617-712)
     net.precision = precision
     out = net(im0.cuda(), im1.cuda())
     tol = TOL[(precision, meta["variant"])]
@@ -62,9 +64,13 @@ def test_forward_matches_reference_golden(path, precision):
         err = np.abs(out[key].cpu().numpy() - z[key]).max()
         assert err <= tol["flow"], (key, err)
     assert np.abs(out["I_t"].cpu().numpy() - z["I_t"]).mean() <= tol["mean"]
-    n = 5 if meta["global_motion"] else 4
+    n = 5 if meta["global_motion"] and not meta.get("ensemble", False) else 4
     assert len(out["im_t_list"]) == len(out["im0_warped_list"]) == len(out["im1_warped_list"]) == n
-    noisy = precision == "tf32" and meta["variant"] == "stress"     # amplified rounding noise: means only
+    noisy = precision == "tf32" and meta["variant"] != "default"    # amplified rounding noise: means only
+    if meta["variant"] == "ensemble":      # every sample selects a different input scale (device-side select)
+        plan = net._runtime.plan(meta["B"], meta["H"], meta["W"], True, True)
+        losses = torch.stack([l.reshape(-1) for l in plan.ensemble_losses], 1).cpu()
+        assert losses.argmin(1).tolist() == [0, 1, 2], losses
     for i in range(n):
         d = np.abs(out["im_t_list"][i].cpu().numpy() - z[f"im_t_list_{i}"])
         assert (d.mean() <= 2e-2) if noisy else (d.max() <= tol["img"]), (i, d.max(), d.mean())

@@ -297,3 +297,27 @@ def test_window_attention_tensor_cores(B2, H, W, ws, shift, hd, closed):
     em.window_attention(qkv, out, geo, heads, False)
     cu.window_attention(to_gpu(qkv), og, geo, heads, False)
     assert max_err(og, out) < 6e-3
+
+
+def test_ensemble_reduction_and_select():
+    """atmvfi_l1_mean / atmvfi_select_min3 / atmvfi_nhwc_to_nchw against their contracts (network_base.py:548-611)."""
+    import torch
+    from atmvfi import _lib
+    from atmvfi.ops import CudaOps, Map
+    ops = CudaOps(torch.device("cuda:0"), _lib.FP32)
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(3, 3, 70, 90, generator=g).cuda(), torch.rand(3, 3, 70, 90, generator=g).cuda()
+    out = torch.empty(3, 1, 1, 1, device="cuda")
+    scratch = torch.empty(3, 1, 1, 2048, device="cuda")
+    ops.l1_mean(a, b, out, scratch)
+    ref = (a.double() - b.double()).abs().mean(dim=[1, 2, 3])
+    assert (out.reshape(-1).double() - ref).abs().max().item() <= 1e-7
+    l = [torch.tensor([0.1, 0.3, 0.2], device="cuda"), torch.tensor([0.1, 0.2, 0.2], device="cuda"), torch.tensor([0.5, 0.2, 0.1], device="cuda")]
+    c = [torch.full((3, 2, 4, 5), float(k), device="cuda") for k in range(3)]
+    sel = torch.empty(3, 2, 4, 5, device="cuda")
+    ops.select3(l, c, sel)
+    assert sel[:, 0, 0, 0].tolist() == [0.0, 1.0, 2.0]          # ties go to the first minimum (if / elif / else chain)
+    m = Map(torch.rand(2, 6, 7, 8, generator=g).cuda(), 0, 5)
+    pl = torch.empty(2, 2, 6, 7, device="cuda")
+    ops.nhwc_to_nchw(m.chan(2, 2), pl)
+    assert torch.equal(pl, m.t[..., 2:4].permute(0, 3, 1, 2))

@@ -41,7 +41,8 @@ def test_oracle_matches_reference_output(path):
     P = weights.make_weights(meta["kind"], meta["variant"])
     im0, im1 = weights.synthetic_frames(meta["B"], meta["H"], meta["W"], kind=meta["frames"])
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    out = oracle.forward(P, im0, im1, meta["global_motion"])
+    ens = bool(meta.get("ensemble", False))
+    out = oracle.forward(P, im0, im1, meta["global_motion"], ensemble=ens)
     # same ATen kernels, same op order -> agreement to fp32 round-off (thread-count noise floor 8.7e-6,
     # multiplied by the stress gains)
     tol = 2e-5 if meta["variant"] == "default" else 5e-3
@@ -49,7 +50,10 @@ def test_oracle_matches_reference_output(path):
         err = np.abs(out[key].numpy() - z[key]).max()
         assert err <= tol, (key, err)
     n = len([k for k in z.files if k.startswith("im_t_list_")])
-    assert len(out["im_t_list"]) == n == (5 if meta["global_motion"] else 4)
+    assert len(out["im_t_list"]) == n == (5 if meta["global_motion"] and not ens else 4)
+    if ens:      # the 3-scale selection itself (network_base.py:564-615)
+        g0, g1, losses = oracle.multiscale_global_motion_ensemble(P, im0, im1, oracle.window_sizes(P)[1])
+        assert np.abs(g0.numpy() - z["ensemble_flow_0"]).max() <= tol and np.abs(g1.numpy() - z["ensemble_flow_1"]).max() <= tol
     for i in range(n):
         err = np.abs(out["im_t_list"][i].numpy() - z[f"im_t_list_{i}"]).max()
         assert err <= tol, (i, err)
