@@ -92,6 +92,9 @@ __device__ __forceinline__ float tf32r(float v) {
   return __uint_as_float(u);
 }
 
+// kHD > 0: head dimension known at compile time - the Q / K / V staging loops unroll and their global loads are issued
+// back to back (with a run-time bound every 16-byte load waited for the previous one: ~18k of the ~46k cycles of a CTA).
+template <int kHD>
 __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                         // chunksH x [128 x 128 B]; later P: chunksK x [128 x 128 B]
@@ -102,7 +105,8 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
 
   const int tid = threadIdx.x & (kRows - 1), part = threadIdx.x >> 7, warp = (threadIdx.x >> 5) & 3;
-  const int N = p.N, hd = p.hd;
+  const int N = p.N, hd = kHD ? kHD : p.hd;
+  const int HP = kHD ? (kHD + 15) / 16 * 16 : p.HP;
   float* sRed = reinterpret_cast<float*>(smem + p.offBar + 64);      // [4][2][128] partial max / sum / motion x / motion y
   // work item
   int item = blockIdx.x;
@@ -150,6 +154,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   const bool row_ok = win_i >= 0;
   {
     const float* src = p.qkv + (row_ok ? (win_i * N + tok_i) * p.qkv_pitch + h * hd : 0);
+#pragma unroll
     for (int c = part * 4; c < hd_pad; c += 8) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row_ok && c < hd) v = __ldg(reinterpret_cast<const float4*>(src + c));
@@ -168,6 +173,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
     if (kk < p.KP) {
       // key meta: bits [0,12) mask label, [12,16) window-local index, [16,24) x, [24,32) y; -1 = excluded key
       sLab[kk] = ok ? (mask_label(w, tok) | (wl << 12) | ((tok % ws) << 16) | ((tok / ws) << 24)) : -1;
+#pragma unroll
       for (int c = 0; c < hd_pad; c += 4) {
         float4 kq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ok && c < hd) kq = __ldg(reinterpret_cast<const float4*>(src + c));
@@ -175,10 +181,11 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
       }
     }
     // V^T: column kk of every channel row; rows hd..HP and columns KP.. are zero
-    for (int c = 0; c < p.HP; c += 4) {
+#pragma unroll
+    for (int c = 0; c < HP; c += 4) {
       float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
       if (ok && c < hd) vq = __ldg(reinterpret_cast<const float4*>(src + p.C + c));
-      uint8_t* col = sV + (kk >> 5) * (p.HP * 128);
+      uint8_t* col = sV + (kk >> 5) * (HP * 128);
       *reinterpret_cast<float*>(col + swz(c, kk & 31)) = tf32r(vq.x);
       *reinterpret_cast<float*>(col + swz(c + 1, kk & 31)) = tf32r(vq.y);
       *reinterpret_cast<float*>(col + swz(c + 2, kk & 31)) = tf32r(vq.z);
@@ -280,11 +287,11 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
 
   // ---- O = P V ------------------------------------------------------------------------------------------------
   if (threadIdx.x == 0) {
-    const uint32_t id = idesc_tf32(p.HP);
+    const uint32_t id = idesc_tf32(HP);
     const int nslK = p.KP >> 3;
     for (int s = 0; s < nslK; ++s) {
       const int c = s >> 2, j = s & 3;
-      mma_tf32(tO, sdesc(s_u32(sQ + c * (kRows * 128))) + 2 * j, sdesc(s_u32(sV + c * (p.HP * 128))) + 2 * j, id, s ? 1u : 0u);
+      mma_tf32(tO, sdesc(s_u32(sQ + c * (kRows * 128))) + 2 * j, sdesc(s_u32(sV + c * (HP * 128))) + 2 * j, id, s ? 1u : 0u);
     }
     commit(&bars[1]);
   }
@@ -296,7 +303,8 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   mvy = sRed[6 * kRows + tid] + sRed[7 * kRows + tid];
   const float inv = row_ok ? 1.0f / l : 0.f;
   const int64_t grow = row_ok ? win_i * N + tok_i : 0;
-  for (int c0 = part * 16; c0 < p.HP; c0 += 32) {
+#pragma unroll
+  for (int c0 = part * 16; c0 < HP; c0 += 32) {
     float o[16];
     ld16(tO + lane_addr + c0, o);
     if (row_ok) {
@@ -356,19 +364,28 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   p.offBar = rup(p.offLab + p.KP * 4, 16);
   const int smem = p.offBar + 64 + 8 * kRows * 4;
   if (smem > 227 * 1024) return 3;
+  typedef void (*KernFn)(AttnParams);
+  static const KernFn kerns[5] = {window_attention_tc_kernel<0>, window_attention_tc_kernel<48>, window_attention_tc_kernel<84>,
+                                  window_attention_tc_kernel<28>, window_attention_tc_kernel<44>};
+  const int ki = p.hd == 48 ? 1 : (p.hd == 84 ? 2 : (p.hd == 28 ? 3 : (p.hd == 44 ? 4 : 0)));
   static int configured = 0;
   if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem > 100 * 1024 ? 227 * 1024 : 100 * 1024);
-    if (e != cudaSuccess) {
-      atmvfi_set_error("window_attention(tf32): cannot reserve shared memory: %s", cudaGetErrorString(e));
-      return 1;
+    const int want = smem > 100 * 1024 ? 227 * 1024 : 100 * 1024;
+    for (int i = 0; i < 5; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+      if (e != cudaSuccess) {
+        atmvfi_set_error("window_attention(tf32): cannot reserve shared memory: %s", cudaGetErrorString(e));
+        return 1;
+      }
     }
-    configured = smem > 100 * 1024 ? 227 * 1024 : 100 * 1024;
+    configured = want;
+    // (measured: forcing cudaSharedmemCarveoutMaxShared makes this kernel 15 % SLOWER - two CTAs already fit and the
+    // gathers of Q/K/V profit from the L1 that the default split leaves)
   }
   const int64_t wgroups = (p.virt_windows + p.wpi - 1) / p.wpi;
   const int64_t items = wgroups * heads * p.mtiles;
   if (items <= 0) return 0;
-  window_attention_tc_kernel<<<(unsigned)items, kThreadsA, smem, st>>>(p);
+  kerns[ki]<<<(unsigned)items, kThreadsA, smem, st>>>(p);
   ATMVFI_CHECK_LAUNCH("window_attention(tf32)");
   return 0;
 }

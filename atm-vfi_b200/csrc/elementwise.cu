@@ -1,6 +1,7 @@
 // HBM-bound kernels of the ATM-VFI forward: LayerNorm (plain and fused with the window gather),
 // depth-wise 3x3 + GELU, backward warps (+ occlusion blend), align_corners resize, layout packers.
 // Every kernel is a coalesced streaming pass; grids are sized in multiples of the SM count (148).
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -93,59 +94,119 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __re
   }
 }
 
-// depth-wise 3x3, pad 1, + bias + exact GELU.  One thread owns (x, 4 channels) and walks down a strip of kDwRows
-// rows with a 3x3 register window, so every input row is fetched once per strip (3 loads per output instead of 9);
-// consecutive threads cover consecutive channel quads -> 512-byte coalesced segments per warp.
+// depth-wise 3x3, pad 1, + bias + exact GELU.  One thread owns (x, V channels) and walks down a strip of kDwRows rows.
+// Every input row is fetched once per strip and SCATTERED into the accumulators of the three output rows it feeds (taps
+// arrive in row-major order, so the sum is formed exactly like a per-pixel loop starting from the bias).  Only the
+// weights, three accumulators and two input rows (the current one and the prefetched next one) live in registers:
+// A CTA covers kDwCg consecutive channel groups (one warp = one contiguous segment) x kDwX neighbouring columns, so the
+// left / right neighbours a thread needs are the centre loads of its CTA mates and hit in L1: only ~1.25 x 1.25 of the
+// map crosses the L2 (with one thread per (column, group) flattened over the row, every neighbour came from another
+// CTA and the kernel ran at the L2 bandwidth of 3 reads per element).
 constexpr int kDwRows = 8;
-__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
-  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
-}
+constexpr int kDwCg = 32, kDwX = 8;          // 256 threads
 __device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
+// TF32 mode only (the result is rounded to a 10-bit mantissa right after): erf by Abramowitz-Stegun 7.1.26,
+// 1 - (a1 t + ... + a5 t^5) exp(-x^2), t = 1 / (1 + p |x|): branch-free, 2 MUFU + ~14 FP32 instructions instead of the
+// ~45 predicated instructions of erff, which made this kernel issue-bound (333 us per launch at 802 MB, 37 % of the HBM
+// roofline).  |erf error| <= 6e-7, |GELU error| <= 2.6e-7 (measured over [-8.5, 8.5] against float64), i.e. three orders of
+// magnitude below the TF32 rounding step.  The FP32 mode keeps erff.
+__device__ __forceinline__ float gelu_fast(float v) {
+  const float x = v * 0.70710678118654752440f;
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = __expf(-ax * ax);
+  const float r = copysignf(fmaf(-p, e, 1.f), x);
+  return 0.5f * v * (1.f + r);
+}
 
+template <int V>
+struct DwVec {
+  float v[V];
+};
+template <int V>
+__device__ __forceinline__ DwVec<V> dw_load(const float* p) {
+  DwVec<V> r;
+  if (V == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2 % V] = t.z; r.v[3 % V] = t.w;
+  } else {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  }
+  return r;
+}
+
+template <int V, bool kFastErf, int kDepth>
 __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
                                                           int H, int W, int C, int pitch,
                                                           const float* __restrict__ w9c, const float* __restrict__ bias,
                                                           int wy0, int wy1, bool rnd) {
-  // grid: x = (column, channel quad) flattened, y = row strip, z = image -> one 32-bit division per thread
-  const int cv = C >> 2;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= W * cv) return;
-  const int x = j / cv, c4 = j - x * cv;
+  // grid: x = (column block, channel-group block), y = row strip, z = image
+  const int cv = C / V;
+  const int cgb = (cv + kDwCg - 1) / kDwCg;
+  const int xb = blockIdx.x / cgb;
+  const int cg = (blockIdx.x - xb * cgb) * kDwCg + (threadIdx.x & (kDwCg - 1));
+  const int x = xb * kDwX + (threadIdx.x >> 5);
+  if (cg >= cv || x >= W) return;
   const int y0 = wy0 + blockIdx.y * kDwRows;
+  const int y1 = min(y0 + kDwRows, wy1);
   const int b = blockIdx.z;
-  float4 k[9];
+  DwVec<V> k[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) k[t] = __ldg(reinterpret_cast<const float4*>(w9c + t * C) + c4);
-  const float4 bz = __ldg(reinterpret_cast<const float4*>(bias) + c4);
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < 9; ++t) k[t] = dw_load<V>(w9c + t * C + cg * V);
+  const DwVec<V> bz = dw_load<V>(bias + cg * V);
   const bool xl = x > 0, xr = x + 1 < W;
-  const float* base = in + ((size_t)b * H * W + x) * pitch + (c4 << 2);
+  const float* base = in + ((size_t)b * H * W + x) * pitch + cg * V;
   const size_t row_stride = (size_t)W * pitch;
-  auto load_row = [&](int yy, float4& l, float4& m, float4& r) {
+  DwVec<V> zero;
+#pragma unroll
+  for (int e = 0; e < V; ++e) zero.v[e] = 0.f;
+  auto load_row = [&](int yy, DwVec<V>& l, DwVec<V>& m, DwVec<V>& r) {
     if (yy < 0 || yy >= H) { l = m = r = zero; return; }
     const float* rowp = base + yy * row_stride;
-    m = __ldg(reinterpret_cast<const float4*>(rowp));
-    l = xl ? __ldg(reinterpret_cast<const float4*>(rowp - pitch)) : zero;
-    r = xr ? __ldg(reinterpret_cast<const float4*>(rowp + pitch)) : zero;
+    m = dw_load<V>(rowp);
+    l = xl ? dw_load<V>(rowp - pitch) : zero;
+    r = xr ? dw_load<V>(rowp + pitch) : zero;
   };
-  float4 a0, a1, a2, b0, b1, b2, c0, c1, c2;      // rows y-1, y, y+1
-  load_row(y0 - 1, a0, a1, a2);
-  load_row(y0, b0, b1, b2);
-  float* obase = out + ((size_t)b * H * W + x) * pitch + (c4 << 2);
+  float* obase = out + ((size_t)b * H * W + x) * pitch + cg * V;
+  // acc0: output row yy-1 (complete after input row yy), acc1: row yy, acc2: row yy+1
+  DwVec<V> acc0 = bz, acc1 = bz, acc2 = bz;
+  // register ring of input rows: row (y0 - 1 + i) lives in slot i % (kDepth + 1); kDepth rows are in flight ahead of the
+  // one being consumed (the kernel is latency-bound: ncu showed 52 % of the stalls on the first use of the next row)
+  DwVec<V> rl[kDepth + 1], rm[kDepth + 1], rr[kDepth + 1];
 #pragma unroll
-  for (int dy = 0; dy < kDwRows; ++dy) {
-    const int y = y0 + dy;
-    if (y >= wy1) break;
-    load_row(y + 1, c0, c1, c2);
-    // same accumulation order as a per-pixel loop: taps row-major starting from the bias
-    float4 acc = bz;
-    acc = fma4(a0, k[0], acc); acc = fma4(a1, k[1], acc); acc = fma4(a2, k[2], acc);
-    acc = fma4(b0, k[3], acc); acc = fma4(b1, k[4], acc); acc = fma4(b2, k[5], acc);
-    acc = fma4(c0, k[6], acc); acc = fma4(c1, k[7], acc); acc = fma4(c2, k[8], acc);
-    float4 o = make_float4(gelu_exact(acc.x), gelu_exact(acc.y), gelu_exact(acc.z), gelu_exact(acc.w));
-    *reinterpret_cast<float4*>(obase + y * row_stride) = round_tf32_if(o, rnd);
-    a0 = b0; a1 = b1; a2 = b2;
-    b0 = c0; b1 = c1; b2 = c2;
+  for (int i = 0; i < kDepth; ++i) load_row(y0 - 1 + i, rl[i], rm[i], rr[i]);
+#pragma unroll
+  for (int i = 0; i < kDwRows + 2; ++i) {
+    const int yy = y0 - 1 + i;
+    if (yy > y1) break;
+    if (i + kDepth < kDwRows + 2 && yy + kDepth <= y1)
+      load_row(yy + kDepth, rl[(i + kDepth) % (kDepth + 1)], rm[(i + kDepth) % (kDepth + 1)], rr[(i + kDepth) % (kDepth + 1)]);
+    const DwVec<V>& l = rl[i % (kDepth + 1)];
+    const DwVec<V>& m = rm[i % (kDepth + 1)];
+    const DwVec<V>& r = rr[i % (kDepth + 1)];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      // input row yy is the bottom row (taps 6-8) of output yy-1, the middle row (3-5) of yy, the top row (0-2) of yy+1
+      acc0.v[e] = fmaf(l.v[e], k[6].v[e], acc0.v[e]); acc0.v[e] = fmaf(m.v[e], k[7].v[e], acc0.v[e]); acc0.v[e] = fmaf(r.v[e], k[8].v[e], acc0.v[e]);
+      acc1.v[e] = fmaf(l.v[e], k[3].v[e], acc1.v[e]); acc1.v[e] = fmaf(m.v[e], k[4].v[e], acc1.v[e]); acc1.v[e] = fmaf(r.v[e], k[5].v[e], acc1.v[e]);
+      acc2.v[e] = fmaf(l.v[e], k[0].v[e], acc2.v[e]); acc2.v[e] = fmaf(m.v[e], k[1].v[e], acc2.v[e]); acc2.v[e] = fmaf(r.v[e], k[2].v[e], acc2.v[e]);
+    }
+    if (i >= 2) {                                         // output row yy-1 has received its three input rows
+      float o[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) o[e] = round_tf32_if(kFastErf ? gelu_fast(acc0.v[e]) : gelu_exact(acc0.v[e]), rnd);
+      float* op = obase + (size_t)(yy - 1) * row_stride;
+      if (V == 4) *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2 % V], o[3 % V]);
+      else *reinterpret_cast<float2*>(op) = make_float2(o[0], o[1]);
+    }
+    acc0 = acc1; acc1 = acc2; acc2 = bz;
   }
 }
 
@@ -556,8 +617,23 @@ int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int 
   ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "dwconv3x3_gelu: bad row window [%d,%d)", y0, y1);
   if ((int64_t)B * ny * W <= 0) return 0;
   ATMVFI_REQUIRE((int64_t)W * (C / 4) < (1 << 30) && B <= 65535, "dwconv3x3_gelu: shape out of range");
-  dim3 grid((unsigned)((W * (C / 4) + 255) / 256), (unsigned)((ny + kDwRows - 1) / kDwRows), (unsigned)B);
-  dwconv_gelu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, y0, y0 + ny, atmvfi_output_rounding() != 0);
+  static_assert(kDwCg * kDwX == 256, "dwconv CTA shape");
+  static int vsel = 0, dsel = 0;
+  if (!vsel) { const char* ev = getenv("ATMVFI_DW_V"); vsel = ev ? atoi(ev) : 4; }
+  if (!dsel) { const char* ev = getenv("ATMVFI_DW_DEPTH"); dsel = ev ? atoi(ev) : 3; }
+  const bool rnd = atmvfi_output_rounding() != 0;
+#define ATMVFI_DW_LAUNCH(V_, D_)                                                                                                        \
+  do {                                                                                                                                  \
+    dim3 grid((unsigned)(((C / V_ + kDwCg - 1) / kDwCg) * ((W + kDwX - 1) / kDwX)), (unsigned)((ny + kDwRows - 1) / kDwRows), (unsigned)B); \
+    if (rnd) dwconv_gelu_kernel<V_, true, D_><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, y0, y0 + ny, rnd);  \
+    else dwconv_gelu_kernel<V_, false, D_><<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, pitch, w9c, bias, y0, y0 + ny, rnd);     \
+  } while (0)
+  if (vsel == 2) {
+    if (dsel == 1) ATMVFI_DW_LAUNCH(2, 1); else if (dsel == 2) ATMVFI_DW_LAUNCH(2, 2); else if (dsel == 3) ATMVFI_DW_LAUNCH(2, 3); else ATMVFI_DW_LAUNCH(2, 4);
+  } else {
+    if (dsel == 1) ATMVFI_DW_LAUNCH(4, 1); else if (dsel == 2) ATMVFI_DW_LAUNCH(4, 2); else if (dsel == 3) ATMVFI_DW_LAUNCH(4, 3); else ATMVFI_DW_LAUNCH(4, 4);
+  }
+#undef ATMVFI_DW_LAUNCH
   ATMVFI_CHECK_LAUNCH("dwconv3x3_gelu");
   return 0;
 }

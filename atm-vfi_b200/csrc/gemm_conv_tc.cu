@@ -274,8 +274,11 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
   ox0 = tx * p.TW;
 }
 
-template <int kHalo, int kCS, bool kPair, bool kFastEpi>
+// kEpi: 0 = generic epilogue, 1 = plain layers (see "fast epilogue" below), 2 = generic with the residual rows prefetched
+template <int kHalo, int kCS, bool kPair, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr bool kFastEpi = kEpi == 1;
+  constexpr bool kResHoist = kEpi == 2;
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B atoms need a 1024-byte aligned base
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
@@ -561,16 +564,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
             if (e.out2) sl2[k] = __ldg(e.prelu2 + co0 + col + k);
           }
         if (col < nvalid) {
-#pragma unroll 4
-          for (int rr = 0; rr < 8; ++rr) {
+          // residual rows of the 8 output rows this lane serves: issued back to back so that 8 loads are in flight per
+          // lane (the layers with a residual - attention proj, fc2 - are bandwidth-bound in this epilogue)
+          float4 res4[kResHoist ? 8 : 1];
+          const bool res_vec = kResHoist && full4;
+          if (res_vec) {
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const int2 ri = s_row[rr * 4 + rsub];
+              res4[rr] = ri.x < 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
+                                  : __ldg(reinterpret_cast<const float4*>(e.residual + (int64_t)ri.y * e.res_pitch + co0 + col));
+            }
+          }
+          auto emit_row = [&](const int rr) {
             const int row = rr * 4 + rsub;
             const int2 ri = s_row[row];
-            if (ri.x < 0) continue;
+            if (ri.x < 0) return;
             const float4 a4 = *reinterpret_cast<const float4*>(&stage[row * kEpiPitch + col]);
             float v[4] = {a4.x + bz[0], a4.y + bz[1], a4.z + bz[2], a4.w + bz[3]};
             if (e.residual) {
               const float* rs = e.residual + (int64_t)ri.y * e.res_pitch + co0 + col;
-              if (full4) {
+              if (res_vec) {
+                const float4 t = res4[kResHoist ? rr : 0];
+                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+              } else if (full4) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(rs));
                 v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
               } else {
@@ -608,6 +625,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
                   if (col + k < nvalid) o2[k] = w[k];
               }
             }
+          };
+          if (kResHoist) {      // full unroll: res4[rr] must stay in registers
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) emit_row(rr);
+          } else {
+#pragma unroll 4
+            for (int rr = 0; rr < 8; ++rr) emit_row(rr);
           }
         }
       }
@@ -761,25 +785,29 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   ATMVFI_REQUIRE(pl && pl->magic == kPlanMagic, "gemm_conv(tf32): missing plan (call atmvfi_gemm_conv_plan first)");
   typedef void (*KernelFn)(TcParams);
   static const KernelFn table[2][4][2] = {
-      {{gemm_conv_tc_kernel<0, 1, false, false>, gemm_conv_tc_kernel<0, 2, false, false>},
-       {gemm_conv_tc_kernel<1, 1, false, false>, gemm_conv_tc_kernel<1, 2, false, false>},
-       {gemm_conv_tc_kernel<2, 1, false, false>, gemm_conv_tc_kernel<2, 2, false, false>},
-       {gemm_conv_tc_kernel<1, 1, true, false>, gemm_conv_tc_kernel<1, 2, true, false>}},
-      {{gemm_conv_tc_kernel<0, 1, false, true>, gemm_conv_tc_kernel<0, 2, false, true>},
-       {gemm_conv_tc_kernel<1, 1, false, true>, gemm_conv_tc_kernel<1, 2, false, true>},
-       {gemm_conv_tc_kernel<2, 1, false, true>, gemm_conv_tc_kernel<2, 2, false, true>},
-       {gemm_conv_tc_kernel<1, 1, true, true>, gemm_conv_tc_kernel<1, 2, true, true>}}};
+      {{gemm_conv_tc_kernel<0, 1, false, 0>, gemm_conv_tc_kernel<0, 2, false, 0>},
+       {gemm_conv_tc_kernel<1, 1, false, 0>, gemm_conv_tc_kernel<1, 2, false, 0>},
+       {gemm_conv_tc_kernel<2, 1, false, 0>, gemm_conv_tc_kernel<2, 2, false, 0>},
+       {gemm_conv_tc_kernel<1, 1, true, 0>, gemm_conv_tc_kernel<1, 2, true, 0>}},
+      {{gemm_conv_tc_kernel<0, 1, false, 1>, gemm_conv_tc_kernel<0, 2, false, 1>},
+       {gemm_conv_tc_kernel<1, 1, false, 1>, gemm_conv_tc_kernel<1, 2, false, 1>},
+       {gemm_conv_tc_kernel<2, 1, false, 1>, gemm_conv_tc_kernel<2, 2, false, 1>},
+       {gemm_conv_tc_kernel<1, 1, true, 1>, gemm_conv_tc_kernel<1, 2, true, 1>}}};
+  // linear layers with a residual (attention proj, Mlp fc2): generic epilogue with the residual rows prefetched
+  static const KernelFn res_table[2] = {gemm_conv_tc_kernel<0, 1, false, 2>, gemm_conv_tc_kernel<0, 2, false, 2>};
   // fast epilogue: pixel-major output, no residual / second output, whole float4 columns, aligned bias and slopes
   const int fast = (d->out_mode == ATMVFI_OUT_PIXEL && !d->residual && !d->out2 && d->Cout % 4 == 0 &&
                     (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0) ? 1 : 0;
   KernelFn kern = table[fast][pl->pair ? 3 : pl->halo][pl->cluster - 1];
+  if (d->residual && !pl->halo && !pl->pair && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % 4 == 0)
+    kern = res_table[pl->cluster - 1];
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 16; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(table[i / 8][(i / 2) % 4][i % 2], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    for (int i = 0; i < 18; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(i < 16 ? table[i / 8][(i / 2) % 4][i % 2] : res_table[i - 16], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
       if (e != cudaSuccess) {
         num_sms = 0;
         atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
