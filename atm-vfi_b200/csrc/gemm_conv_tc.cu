@@ -32,15 +32,14 @@ constexpr int kMaxASlots = 4;
 constexpr int kMaxBSlots = 12;
 constexpr int kMaxBlockN = 256;
 constexpr int kDataBytes = 184 * 1024;          // A ring + B ring, carved per layer (see atmvfi_gemm_conv_tc)
+constexpr int kDataBytes16 = 150 * 1024;        // ... when 16 epilogue warps need twice the staging area
 constexpr int kMaxABoxBytes = 24 * 1024;        // up to 192 rows of 128 B (halo box; 320 rows = 40 KB in pair mode), 128 rows otherwise
-constexpr int kBarOff = kDataBytes;
-constexpr int kEpiWarps = 8;                                  // two warps per TMEM lane quarter, alternating column chunks
+// Epilogue warps: 8 (two per TMEM lane quarter, alternating column chunks) or, for layers whose K is so short that the
+// accumulator drain + global stores bound the tile time (k2s2 transposed convs, 1x1 and 24/48-channel 3x3 layers), 16.
 constexpr int kEpiPitch = 36;                                 // floats per staged row: 16-byte aligned, conflict-free for 128-bit access
-constexpr int kEpiOff = kBarOff + 512;                        // per epilogue warp: 32 x 36 floats staging + 32 x int2 row info
-constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4 + 32 * 8;
-constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
-constexpr int kSmemBytes = kEpiOff + kEpiBytes;
-constexpr int kThreads = 128 + 32 * kEpiWarps;
+constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4 + 32 * 8;    // per epilogue warp: 32 x 36 floats staging + 32 x int2 row info
+constexpr int smem_bytes(int epi_warps) { return (epi_warps == 16 ? kDataBytes16 : kDataBytes) + 512 + epi_warps * kEpiWarpBytes; }
+constexpr int threads_for(int epi_warps) { return 128 + 32 * epi_warps; }
 
 struct TcPlan {                                 // host-side, produced by atmvfi_gemm_conv_plan
   CUtensorMap mapA[ATMVFI_MAX_SRC];
@@ -71,6 +70,7 @@ struct TcParams {
   int halo, a_bytes, sum_chunks, m_tiles;
   int th_super;                                 // rows of output covered by one CTA tile (TH, or 2*TH in pair mode)
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes;   // smem rings: A at offset 0, B right after
+  int bar_off;                                  // barriers behind the data rings, epilogue staging 512 B further
   int total_ctiles;                             // cluster tiles: ceil(m_tiles / cluster) * n_tiles
   int row0, row1;                               // output rows [row0, row1) of every image (row window)
   EpiParams epi;
@@ -275,13 +275,15 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
 }
 
 // kEpi: 0 = generic epilogue, 1 = plain layers (see "fast epilogue" below), 2 = generic with the residual rows prefetched
-template <int kHalo, int kCS, bool kPair, int kEpi>
-__global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
+template <int kHalo, int kCS, bool kPair, int kEpi, int kEW = 8>
+__global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr bool kFastEpi = kEpi == 1;
   constexpr bool kResHoist = kEpi == 2;
+  constexpr int kEpiWarps = kEW;
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B atoms need a 1024-byte aligned base
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
+  const int kEpiOff = p.bar_off + 512;
   uint64_t* fullA = bars;                                  // [kMaxASlots]
   uint64_t* emptyA = fullA + kMaxASlots;                   // [kMaxASlots]
   uint64_t* fullB = emptyA + kMaxASlots;                   // [kMaxBSlots]
@@ -473,9 +475,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
     // 32-column chunks.  Accumulators pass through a padded per-warp smem tile so that global traffic is
     // row-coalesced: 8 lanes x float4 cover 128 contiguous bytes of one output row; bias / PReLU slopes are
     // fetched once per lane per chunk.
-    const int ew = warp - 4;                                  // 0..7
+    const int ew = warp - 4;                                  // 0..kEW-1
     const int q = warp & 3;                                   // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                                 // which chunk parity this warp takes
+    const int half = ew >> 2;                                 // which of the kEW/4 interleaved chunk sequences this warp takes
+    constexpr int kSeq = kEW / 4;
     float* stage = reinterpret_cast<float*>(smem + kEpiOff + ew * kEpiWarpBytes);
     int2* s_row = reinterpret_cast<int2*>(smem + kEpiOff + ew * kEpiWarpBytes + 32 * kEpiPitch * 4);   // (orow, m) per row
     const int m_local = q * 32 + lane;
@@ -495,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_conv_tc_kernel(const __grid_
       int last_q = -1, last_t = -1;
       int64_t m = 0;
       bool row_ok = false;
-      for (int u = half; u < nunits; u += 2) {
+      for (int u = half; u < nunits; u += kSeq) {
         const int t = kPair ? u / nchunks : 0;                // sub-tile of the pair (warp-uniform)
         const int c0 = (kPair ? u - t * nchunks : u) * 32;
         if (t != last_t) {
@@ -798,19 +801,42 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   // fast epilogue: pixel-major output, no residual / second output, whole float4 columns, aligned bias and slopes
   const int fast = (d->out_mode == ATMVFI_OUT_PIXEL && !d->residual && !d->out2 && d->Cout % 4 == 0 &&
                     (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0) ? 1 : 0;
+  // 16 epilogue warps for layers whose K loop is shorter than the accumulator drain (tile time = epilogue time):
+  // [epilogue kind][0: no halo, 1: pair mode][cluster]
+  static const KernelFn table16[2][2][2] = {
+      {{gemm_conv_tc_kernel<0, 1, false, 0, 16>, gemm_conv_tc_kernel<0, 2, false, 0, 16>},
+       {gemm_conv_tc_kernel<1, 1, true, 0, 16>, gemm_conv_tc_kernel<1, 2, true, 0, 16>}},
+      {{gemm_conv_tc_kernel<0, 1, false, 1, 16>, gemm_conv_tc_kernel<0, 2, false, 1, 16>},
+       {gemm_conv_tc_kernel<1, 1, true, 1, 16>, gemm_conv_tc_kernel<1, 2, true, 1, 16>}}};
   KernelFn kern = table[fast][pl->pair ? 3 : pl->halo][pl->cluster - 1];
-  if (d->residual && !pl->halo && !pl->pair && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % 4 == 0)
+  int epi_warps = 8;
+  if (d->residual && !pl->halo && !pl->pair && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % 4 == 0) {
     kern = res_table[pl->cluster - 1];
+  } else if (pl->pair || !pl->halo) {
+    static int epi16 = -1;                    // ATMVFI_TC_EPI16: 0 never, 1 (default) short-K layers, 2 every eligible layer
+    if (epi16 < 0) { const char* ev = getenv("ATMVFI_TC_EPI16"); epi16 = ev ? atoi(ev) : 1; }
+    int ktc = 0;
+    for (int s2 = 0; s2 < pl->nsrc; ++s2) ktc += pl->chunks[s2] * kChunk;
+    ktc *= pl->ntaps;
+    // measured (Base 1080p): k2s2 transposed convs 539->380, 290->190, 277->209, 148->107 us; 3x3 layers lose (fewer
+    // activation slots), so only 1x1 / transposed layers take this path by default
+    if (epi16 == 2 || (epi16 == 1 && ktc <= 640 && pl->ksize == 1)) {
+      kern = table16[fast][pl->pair ? 1 : 0][pl->cluster - 1];
+      epi_warps = 16;
+    }
+  }
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 18; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(i < 16 ? table[i / 8][(i / 2) % 4][i % 2] : res_table[i - 16], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    for (int i = 0; i < 26; ++i) {
+      KernelFn f = i < 16 ? table[i / 8][(i / 2) % 4][i % 2] : (i < 18 ? res_table[i - 16] : table16[(i - 18) / 4][((i - 18) / 2) % 2][i % 2]);
+      const int bytes = i < 18 ? smem_bytes(8) : smem_bytes(16);
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) {
         num_sms = 0;
-        atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", kSmemBytes, cudaGetErrorString(e));
+        atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", bytes, cudaGetErrorString(e));
         return 1;
       }
     }
@@ -833,11 +859,14 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   p.a_bytes = (pl->halo == 2 ? (pl->TH + 2) * (pl->TW + 2) : (pl->halo ? ((pl->pair ? 2 : 1) * pl->TH + 2) * pl->TW : kBlockM)) * 128;
   p.th_super = pl->TH * (pl->pair ? 2 : 1);
   p.sum_chunks = ch;
-  p.a_slots = pl->halo ? 3 : 4;
+  const int data_bytes = epi_warps == 16 ? kDataBytes16 : kDataBytes;
+  p.bar_off = data_bytes;
+  p.a_slots = pl->halo ? (epi_warps == 16 ? 2 : 3) : 4;     // 16-warp layers have short K loops: two (large, paired) boxes suffice
   p.a_slot_bytes = (p.a_bytes + 1023) / 1024 * 1024;
   p.b_slot_bytes = (pl->block_n / pl->cluster) * 128;        // 2-CTA mode: each CTA holds half of the weight tile
-  p.b_slots = (kDataBytes - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+  p.b_slots = (data_bytes - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
   if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
+  ATMVFI_REQUIRE(p.b_slots >= 2, "gemm_conv(tf32): shared memory rings too small (%d weight slots)", p.b_slots);
   p.m_tiles = pl->tiles_x * pl->tiles_y * pl->B;
   const int cs = pl->cluster;
   p.total_ctiles = ((p.m_tiles + cs - 1) / cs) * pl->n_tiles;
@@ -849,8 +878,8 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(clusters * cs));
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.blockDim = dim3(threads_for(epi_warps));
+  cfg.dynamicSmemBytes = smem_bytes(epi_warps);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
