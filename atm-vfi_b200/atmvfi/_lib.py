@@ -102,6 +102,7 @@ _SPECIAL = {
     "atmvfi_device_info": ([_I, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     "atmvfi_gemm_conv_plan_bytes": ([], C.c_int),
     "atmvfi_l1_mean_scratch_floats": ([C.c_int], C.c_int),
+    "atmvfi_attn_prof_read": ([C.POINTER(C.c_uint64)], C.c_int),
     "atmvfi_set_output_rounding": ([C.c_int], None),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))

@@ -13,6 +13,7 @@
 // The reference materialises [B',8,N,N] attention and a [B',8,2,N,N] product for the motion; here nothing but
 // the per-head outputs and two floats per (token, head) ever reach HBM.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -30,6 +31,7 @@ struct AttnParams {
   int cross;
   const float* rc;            // [2][N][N] or nullptr (closed form: key position - query position)
   float* motion_raw;          // [rows][heads][2] or nullptr
+  unsigned long long* prof;   // debug: 6 phase cycle counters (stage, QK^T, softmax max, softmax exp, PV, output) or nullptr
   int N, wpi, mtiles, KP, HP, chunksH, chunksK;
   int total_windows, nW;
   int wy0, per_img, virt_windows;   // row window: windows [wy0*nwx, +per_img) of every image, virt_windows = B2*per_img
@@ -86,6 +88,15 @@ __device__ __forceinline__ void ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {   // no wait: several loads may be in flight
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float tf32r(float v) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -127,6 +138,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
+  long long t_prev = p.prof ? clock64() : 0;      // phase timers (debug: ATMVFI_ATTN_PROF)
   // ---- row / key bookkeeping (one row per thread: no per-element index arithmetic) ----------------------------
   const int nslH = (hd + 7) >> 3;             // K = 8 slices of the head dimension
   const int hd_pad = nslH * 8;
@@ -148,53 +160,75 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
     return win_mask_label(p.g, (wi / nwx) * ws + tok / ws, (wi % nwx) * ws + tok % ws);
   };
 
-  // ---- stage Q (thread = query row), K and V^T (thread = key), TF32-rounded, swizzled -----------------------
+  // ---- stage Q, K (K-major) and V^T, TF32-rounded, swizzled ---------------------------------------------------------
+  // Row / key bookkeeping goes to shared memory first; the copy loops then walk (row, 16-byte column) pairs with the
+  // column fastest, so a warp reads whole 192-byte (hd = 48) head slices instead of 32 scattered 16-byte pieces
+  // (measured: the thread-per-row version spent 16.5k of the 35k cycles of a CTA here, bound by L1 tag lookups).
   int wl_i, tok_i;
   const int64_t win_i = locate(tid, mt * kRows, wl_i, tok_i);
   const bool row_ok = win_i >= 0;
-  {
-    const float* src = p.qkv + (row_ok ? (win_i * N + tok_i) * p.qkv_pitch + h * hd : 0);
-#pragma unroll
-    for (int c = part * 4; c < hd_pad; c += 8) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row_ok && c < hd) v = __ldg(reinterpret_cast<const float4*>(src + c));
-      *reinterpret_cast<float4*>(sQ + (c >> 5) * (kRows * 128) + swz(tid, c & 31)) = make_float4(tf32r(v.x), tf32r(v.y), tf32r(v.z), tf32r(v.w));
-    }
-  }
-  for (int kk = threadIdx.x; kk < p.chunksK * 32; kk += kThreadsA) {
+  int* sRowSrc = reinterpret_cast<int*>(sRed + 8 * kRows);      // [128] global row of each query row, -1 = padding row
+  int* sKeySrc = sRowSrc + kRows;                               // [KP]  global row of each key (other frame's window if cross)
+  if (part == 0) sRowSrc[tid] = row_ok ? (int)(win_i * N + tok_i) : -1;
+  for (int kk = threadIdx.x; kk < p.KP; kk += kThreadsA) {
     int wl, tok;
-    const int64_t w = kk < p.KP ? locate(kk, 0, wl, tok) : -1;
+    const int64_t w = locate(kk, 0, wl, tok);
     const bool ok = w >= 0;
-    const float* src = p.qkv;
+    int src = -1;
     if (ok) {
       const int64_t wk = p.cross ? (w + total_win / 2) % total_win : w;       // the other frame's copy of the window (attention.py:318)
-      src = p.qkv + (wk * N + tok) * p.qkv_pitch + p.C + h * hd;
+      src = (int)(wk * N + tok);
     }
-    if (kk < p.KP) {
-      // key meta: bits [0,12) mask label, [12,16) window-local index, [16,24) x, [24,32) y; -1 = excluded key
-      sLab[kk] = ok ? (mask_label(w, tok) | (wl << 12) | ((tok % ws) << 16) | ((tok / ws) << 24)) : -1;
-#pragma unroll
-      for (int c = 0; c < hd_pad; c += 4) {
-        float4 kq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok && c < hd) kq = __ldg(reinterpret_cast<const float4*>(src + c));
-        *reinterpret_cast<float4*>(sK + (c >> 5) * (p.KP * 128) + swz(kk, c & 31)) = make_float4(tf32r(kq.x), tf32r(kq.y), tf32r(kq.z), tf32r(kq.w));
-      }
+    sKeySrc[kk] = src;
+    // key meta: bits [0,12) mask label, [12,16) window-local index, [16,24) x, [24,32) y; -1 = excluded key
+    sLab[kk] = ok ? (mask_label(w, tok) | (wl << 12) | ((tok % ws) << 16) | ((tok / ws) << 24)) : -1;
+  }
+  __syncthreads();
+  {
+    // Asynchronous copies (cp.async): every load of the CTA is in flight at once and no registers are tied up.  The
+    // head slices are 192-byte pieces of 4.6 KB rows, so DRAM latency under this access pattern is long (measured:
+    // 4-6 dependent round trips of ~4k cycles each with register staging); here it is paid once.  Operands are NOT
+    // re-rounded: the runtime's producer (the qkv GEMM) already stores TF32 values; a caller that passes unrounded
+    // fp32 gets the tensor core's truncation instead of round-to-nearest.
+    const int F4 = hd >> 2, F4P = hd_pad >> 2;                  // float4 per row: real / padded to the K = 8 slices of the MMA
+    const float* qbase = p.qkv + h * hd;
+    const float* kbase = qbase + p.C;
+    const float* vbase = kbase + p.C;
+    auto cp16 = [](uint32_t dst, const void* src, bool valid) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+    };
+    auto cp4 = [](uint32_t dst, const void* src, bool valid) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+    };
+    const uint32_t aQ = s_u32(sQ), aK = s_u32(sK), aV = s_u32(sV);
+    for (int i = threadIdx.x; i < kRows * F4P; i += kThreadsA) {
+      const int r = i / F4P, c4 = i - r * F4P, c = c4 << 2;
+      const int src = sRowSrc[r];
+      const bool ok = src >= 0 && c4 < F4;
+      cp16(aQ + (c >> 5) * (kRows * 128) + swz(r, c & 31), ok ? qbase + (int64_t)src * p.qkv_pitch + c : p.qkv, ok);
     }
-    // V^T: column kk of every channel row; rows hd..HP and columns KP.. are zero
-#pragma unroll
-    for (int c = 0; c < HP; c += 4) {
-      float4 vq = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok && c < hd) vq = __ldg(reinterpret_cast<const float4*>(src + p.C + c));
-      uint8_t* col = sV + (kk >> 5) * (HP * 128);
-      *reinterpret_cast<float*>(col + swz(c, kk & 31)) = tf32r(vq.x);
-      *reinterpret_cast<float*>(col + swz(c + 1, kk & 31)) = tf32r(vq.y);
-      *reinterpret_cast<float*>(col + swz(c + 2, kk & 31)) = tf32r(vq.z);
-      *reinterpret_cast<float*>(col + swz(c + 3, kk & 31)) = tf32r(vq.w);
+    for (int i = threadIdx.x; i < p.KP * F4P; i += kThreadsA) {
+      const int kk = i / F4P, c4 = i - kk * F4P, c = c4 << 2;
+      const int src = sKeySrc[kk];
+      const bool ok = src >= 0 && c4 < F4;
+      cp16(aK + (c >> 5) * (p.KP * 128) + swz(kk, c & 31), ok ? kbase + (int64_t)src * p.qkv_pitch + c : p.qkv, ok);
     }
+    // V^T (row = channel, column = key): 4-byte copies, lanes along the channels of one key (coalesced reads).  Columns
+    // of excluded keys are zero-filled (P is zero there, but 0 x garbage could be NaN); rows hd.. feed output columns
+    // that are never stored.
+    for (int i = threadIdx.x; i < p.KP * hd; i += kThreadsA) {
+      const int kk = i / hd, c = i - kk * hd;
+      const int src = sKeySrc[kk];
+      const bool ok = src >= 0;
+      cp4(aV + (kk >> 5) * (HP * 128) + swz(c, kk & 31), ok ? vbase + (int64_t)src * p.qkv_pitch + c : p.qkv, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[0], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tO = tmem + p.KP;
@@ -209,6 +243,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
     commit(&bars[0]);
   }
   bar_wait(&bars[0], 0);
+  if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[1], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- softmax + motion, row per thread ---------------------------------------------------------------------
@@ -227,35 +262,67 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   // (decided per WARP - tcgen05.ld is .aligned - from the first and last row of the warp; rows are window-ordered)
   const bool skip_foreign = p.wpi > 1;
   const int own_lo = __shfl_sync(0xffffffffu, wl_i * N, 0), own_hi = __shfl_sync(0xffffffffu, wl_i * N + N, 31);
+  // this thread's chunks: c0 = first + 32 j < lim.  With at most two of them (8x8 windows: 64 keys per row, two threads per
+  // row) S stays in registers between the two passes and both tcgen05.ld are in flight together; larger windows re-read
+  // S from TMEM in the second pass (keeping 5 chunks live cost more in register pressure than the reload).
+  constexpr int kMaxOwn = 2;
+  int first = part * 16, lim = p.KP;
+  if (skip_foreign) {
+    int ci = own_lo >> 4;
+    if ((ci & 1) != part) ++ci;
+    first = ci * 16;
+    lim = min(own_hi, p.KP);
+  }
+  const bool keep = first + 32 * kMaxOwn >= lim;                // warp-uniform
+  uint32_t sraw[kMaxOwn][16];
   float mx = -INFINITY;
-  for (int c0 = part * 16; c0 < p.KP; c0 += 32) {
-    if (skip_foreign && (c0 + 16 <= own_lo || c0 >= own_hi)) continue;
-    float s[16];
-    ld16(tS + lane_addr + c0, s);
+  if (keep) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) mx = fmaxf(mx, logit2(s[e], sLab[c0 + e]));
+    for (int j = 0; j < kMaxOwn; ++j)
+      if (first + 32 * j < lim) ld16_issue(tS + lane_addr + first + 32 * j, sraw[j]);
+    ld_wait();
+#pragma unroll
+    for (int j = 0; j < kMaxOwn; ++j) {
+      const int c0 = first + 32 * j;
+      if (c0 < lim) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float x = logit2(__uint_as_float(sraw[j][e]), sLab[c0 + e]);
+          sraw[j][e] = __float_as_uint(x);
+          mx = fmaxf(mx, x);
+        }
+      }
+    }
+  } else {
+    for (int c0 = first; c0 < lim; c0 += 32) {
+      float sv[16];
+      ld16(tS + lane_addr + c0, sv);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) mx = fmaxf(mx, logit2(sv[e], sLab[c0 + e]));
+    }
   }
   sRed[part * kRows + tid] = mx;
   __syncthreads();
+  if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[2], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
   mx = fmaxf(sRed[tid], sRed[kRows + tid]);
-  // P may overwrite the Q/K area now: the MMA that read it has retired (bars[0]) and S lives in TMEM
+  // P may overwrite the Q/K area now: the MMA that read it has retired (bars[0]) and S lives in TMEM / registers
   float l = 0.f, mvx = 0.f, mvy = 0.f;
   const int xi = tok_i % ws, yi = tok_i / ws;
   const bool want_motion = p.motion_raw != nullptr;
+  // chunks of this thread that are not its own (another window of the group, or beyond KP): P = 0
   for (int c0 = part * 16; c0 < p.chunksK * 32; c0 += 32) {
+    if (c0 >= first && c0 < lim) continue;
     uint8_t* prow = sQ + (c0 >> 5) * (kRows * 128);
-    if (c0 >= p.KP || (skip_foreign && (c0 + 16 <= own_lo || c0 >= own_hi))) {
 #pragma unroll
-      for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(prow + swz(tid, (c0 & 31) + e)) = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
-    }
-    float s[16];
-    ld16(tS + lane_addr + c0, s);
+    for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(prow + swz(tid, (c0 & 31) + e)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  auto emit_chunk = [&](const int c0, const float (&x16)[16]) {      // x16: masked logits (log2 domain) of 16 keys
+    uint8_t* prow = sQ + (c0 >> 5) * (kRows * 128);
     float pv[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const int meta = sLab[c0 + e];
-      const float x = logit2(s[e], meta);
+      const float x = x16[e];
       const float pe = (row_ok && x > -INFINITY) ? exp2f(x - mx) : 0.f;
       l += pe;
       if (want_motion) {
@@ -276,6 +343,26 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
 #pragma unroll
     for (int e = 0; e < 16; e += 4)
       *reinterpret_cast<float4*>(prow + swz(tid, (c0 & 31) + e)) = make_float4(pv[e], pv[e + 1], pv[e + 2], pv[e + 3]);
+  };
+  if (keep) {
+#pragma unroll
+    for (int j = 0; j < kMaxOwn; ++j) {
+      const int c0 = first + 32 * j;
+      if (c0 < lim) {
+        float x16[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x16[e] = __uint_as_float(sraw[j][e]);
+        emit_chunk(c0, x16);
+      }
+    }
+  } else {
+    for (int c0 = first; c0 < lim; c0 += 32) {
+      float sv[16], x16[16];
+      ld16(tS + lane_addr + c0, sv);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) x16[e] = logit2(sv[e], sLab[c0 + e]);
+      emit_chunk(c0, x16);
+    }
   }
   sRed[(2 + part) * kRows + tid] = l;
   sRed[(4 + part) * kRows + tid] = mvx;
@@ -283,6 +370,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[3], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- O = P V ------------------------------------------------------------------------------------------------
@@ -296,6 +384,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
     commit(&bars[1]);
   }
   bar_wait(&bars[1], 0);
+  if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[4], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   l = sRed[2 * kRows + tid] + sRed[3 * kRows + tid];
@@ -324,6 +413,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[5], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
   if (threadIdx.x < 32) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
@@ -332,7 +422,27 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
 
 inline int rup(int x, int m) { return (x + m - 1) / m * m; }
 
+unsigned long long* g_prof = nullptr;
+
 }  // namespace
+
+// Debug aid: ATMVFI_ATTN_PROF=1 makes thread 0 of every CTA accumulate the cycles of the six phases of the kernel into a
+// device buffer (read back with atmvfi_attn_prof_read).
+static unsigned long long* atmvfi_attn_prof_buffer() {
+  static int on = -1;
+  if (on < 0) {
+    const char* ev = getenv("ATMVFI_ATTN_PROF");
+    on = ev && atoi(ev) ? 1 : 0;
+    if (on) { cudaMalloc(&g_prof, 8 * sizeof(unsigned long long)); cudaMemset(g_prof, 0, 8 * sizeof(unsigned long long)); }
+  }
+  return on ? g_prof : nullptr;
+}
+extern "C" int atmvfi_attn_prof_read(unsigned long long* out6) {
+  if (!g_prof) return 1;
+  cudaMemcpy(out6, g_prof, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_prof, 0, 8 * sizeof(unsigned long long));
+  return 0;
+}
 
 // Returns 0 on success, 3 if the shape is outside what this kernel handles (caller falls back to the fp32 kernel).
 int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
@@ -340,6 +450,7 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   AttnParams p;
   p.qkv = qkv; p.qkv_pitch = qkv_pitch; p.out = out; p.out_pitch = out_pitch; p.C = C; p.heads = heads; p.hd = C / heads;
   p.g = *g; p.cross = cross; p.rc = rc; p.motion_raw = motion_raw;
+  p.prof = atmvfi_attn_prof_buffer();
   p.N = g->ws * g->ws;
   if (p.N > 256 || p.hd % 4 != 0 || p.hd > 96) return 3;
   p.nW = (g->Hp / g->ws) * (g->Wp / g->ws);
@@ -362,7 +473,7 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   p.offV = rup(regionQK, 1024);
   p.offLab = p.offV + p.chunksK * p.HP * 128;
   p.offBar = rup(p.offLab + p.KP * 4, 16);
-  const int smem = p.offBar + 64 + 8 * kRows * 4;
+  const int smem = p.offBar + 64 + 8 * kRows * 4 + (kRows + 256) * 4;      // + row / key source tables
   if (smem > 227 * 1024) return 3;
   typedef void (*KernFn)(AttnParams);
   static const KernFn kerns[5] = {window_attention_tc_kernel<0>, window_attention_tc_kernel<48>, window_attention_tc_kernel<84>,

@@ -148,6 +148,11 @@ int atmvfi_window_attention_tc(const float* qkv, int qkv_pitch, float* out, int 
                                float* motion, int motion_pitch, int motion_off, float* scratch,
                                int wy0, int wy1, void* stream);
 
+/* Debug aid: with ATMVFI_ATTN_PROF=1 in the environment, thread 0 of every CTA of the tcgen05 attention kernel accumulates the
+ * clock cycles of its six phases (staging, QK^T, softmax max, softmax exp + P, PV, output); this reads and clears the totals.
+ * Returns non-zero when profiling is off. */
+int atmvfi_attn_prof_read(unsigned long long* out6_host);
+
 /* Mlp middle: depth-wise 3x3 (pad 1) + bias + exact-erf GELU on NHWC tokens (attention.py:74-85,118-119). */
 int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch,
                           const float* w9c /* [9][C] */, const float* bias, int y0, int y1, void* stream);
