@@ -5,6 +5,9 @@
 #include <string.h>
 #include "common.cuh"
 
+int atmvfi_dwconv_tma_launch(const float* in, float* out, int B, int H, int W, int C, int pitch, const float* w9c,
+                             const float* bias, int y0, int ny, bool rnd, cudaStream_t st);
+
 namespace {
 
 constexpr int kSMs = 148;
@@ -618,6 +621,10 @@ int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int 
   if ((int64_t)B * ny * W <= 0) return 0;
   ATMVFI_REQUIRE((int64_t)W * (C / 4) < (1 << 30) && B <= 65535, "dwconv3x3_gelu: shape out of range");
   static_assert(kDwCg * kDwX == 256, "dwconv CTA shape");
+  {   // TMA-fed streaming kernel (dwconv_tma.cu); falls through to the register-ring kernel when it does not apply
+    const int rc = atmvfi_dwconv_tma_launch(in, out, B, H, W, C, pitch, w9c, bias, y0, ny, atmvfi_output_rounding() != 0, (cudaStream_t)stream);
+    if (rc != 3) return rc;
+  }
   static int vsel = 0, dsel = 0;
   if (!vsel) { const char* ev = getenv("ATMVFI_DW_V"); vsel = ev ? atoi(ev) : 4; }
   if (!dsel) { const char* ev = getenv("ATMVFI_DW_DEPTH"); dsel = ev ? atoi(ev) : 3; }

@@ -168,14 +168,21 @@ def test_layernorm_dwconv(ops):
         em.layernorm(x, o, gamma, beta)
         cu.layernorm(to_gpu(x), og, gamma.cuda(), beta.cuda())
         assert max_err(og, o) < 2e-5
-    C = 448
-    x, o = rand_map(2, 9, 13, C, gen=g), rand_map(2, 9, 13, C, gen=g)
-    P = {"d.weight": torch.randn(C, 1, 3, 3, generator=g) * 0.4, "d.bias": torch.randn(C, generator=g)}
-    w9c, b = pack.pack_dw(P, "d")
-    og = to_gpu(o)
-    em.dwconv_gelu(x, o, w9c, b)
-    cu.dwconv_gelu(to_gpu(x), og, w9c.cuda(), b.cuda())
-    assert max_err(og, o) < 2e-5
+    # channel counts that are / are not multiples of the TMA kernel's 64-channel block, widths off the 16-column tile,
+    # heights beyond one 34-row strip
+    for (B, H, W, C) in ((2, 9, 13, 448), (1, 40, 37, 224), (2, 5, 16, 100), (1, 70, 8, 64)):
+        x, o = rand_map(B, H, W, C, gen=g), rand_map(B, H, W, C, gen=g)
+        P = {"d.weight": torch.randn(C, 1, 3, 3, generator=g) * 0.4, "d.bias": torch.randn(C, generator=g)}
+        w9c, b = pack.pack_dw(P, "d")
+        og = to_gpu(o)
+        em.dwconv_gelu(x, o, w9c, b)
+        cu.dwconv_gelu(to_gpu(x), og, w9c.cuda(), b.cuda())
+        assert max_err(og, o) < 2e-5, (B, H, W, C)
+        # row window: only rows [3, H-1) are produced, everything else keeps its previous contents
+        og2 = to_gpu(rand_map(B, H, W, C, gen=g))
+        before = og2.t.clone()
+        cu.dwconv_gelu(to_gpu(x), og2, w9c.cuda(), b.cuda(), rows=(3, H - 1))
+        assert torch.equal(og2.t[:, 3 : H - 1], og.t[:, 3 : H - 1]) and torch.equal(og2.t[:, :3], before[:, :3]) and torch.equal(og2.t[:, H - 1 :], before[:, H - 1 :])
 
 
 @pytest.mark.parametrize("H,W,mag", [(17, 29, 3.0), (68, 120, 40.0), (136, 240, 300.0)])
