@@ -207,6 +207,19 @@ class SlabSession:
         with torch.cuda.device(self.device):
             return self.plan.run_inplace(use_graph=use_graph)
 
+    def _stage(self, H: int, W: int) -> dict:
+        st = getattr(self, "_staging", None)
+        if st is None or tuple(st["h0"].shape[:2]) != (H, W):
+            mk_h = lambda: torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+            mk_d = lambda: torch.empty((H, W, 3), dtype=torch.uint8, device=self.device)
+            st = self._staging = dict(h0=mk_h(), h1=mk_h(), hout=mk_h(), d0=mk_d(), d1=mk_d(), dout=mk_d())
+        return st
+
+    def pinned_frame_buffers(self, H: int, W: int):
+        """Two HxWx3 uint8 numpy arrays in pinned memory; frames decoded straight into them are uploaded without a host copy."""
+        st = self._stage(H, W)
+        return st["h0"].numpy(), st["h1"].numpy()
+
     def interpolate_u8(self, img0, img1, isBGR: bool = True, divisor: int = 64):
         """``demo_2x.inference_2frame`` arithmetic (demo_2x.py:54-87) on the slab plan: every rank passes the same two HxWx3
         uint8 frames; rank 0 returns the uint8 middle frame, the other ranks return None."""
@@ -216,15 +229,11 @@ class SlabSession:
         Hp, Wp, top, left = H + eh, W + ew, eh // 2, ew // 2
         assert tuple(self.plan.im0.shape) == (1, 3, Hp, Wp), "session was built for another frame size"
         with torch.cuda.device(self.device):
-            st = getattr(self, "_staging", None)
-            if st is None or st["h0"].shape[:2] != (H, W):
-                mk_h = lambda: torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
-                mk_d = lambda: torch.empty((H, W, 3), dtype=torch.uint8, device=self.device)
-                st = self._staging = dict(h0=mk_h(), h1=mk_h(), hout=mk_h(), d0=mk_d(), d1=mk_d(), dout=mk_d())
-            st["h0"].numpy()[...] = img0
-            st["h1"].numpy()[...] = img1
-            st["d0"].copy_(st["h0"], non_blocking=True)
-            st["d1"].copy_(st["h1"], non_blocking=True)
+            st = self._stage(H, W)
+            for src, h, d in ((img0, st["h0"], st["d0"]), (img1, st["h1"], st["d1"])):
+                if src.__array_interface__["data"][0] != h.data_ptr():      # not already in the pinned buffers
+                    h.numpy()[...] = src
+                d.copy_(h, non_blocking=True)
             self.ops.u8_to_planar(st["d0"], self.plan.im0, H, W, Hp, Wp, top, left, isBGR)
             self.ops.u8_to_planar(st["d1"], self.plan.im1, H, W, Hp, Wp, top, left, isBGR)
             out = self.plan.run_inplace(use_graph=True)

@@ -134,10 +134,12 @@ class NetworkBase(ParamTree):
         with torch.cuda.device(dev):
             plan = rt.plan(1, Hp, Wp, bool(self.global_motion))
             st = rt.staging(H, W, dev)
-            st["h0"].numpy()[...] = img0
-            st["h1"].numpy()[...] = img1
-            st["d0"].copy_(st["h0"], non_blocking=True)
-            st["d1"].copy_(st["h1"], non_blocking=True)
+            # frames that already live in the pinned staging buffers (pinned_frame_buffers) are uploaded in place; others are
+            # copied there first, frame 1 while frame 0 is already on its way to the device
+            for src, h, d in ((img0, st["h0"], st["d0"]), (img1, st["h1"], st["d1"])):
+                if src.__array_interface__["data"][0] != h.data_ptr():
+                    h.numpy()[...] = src
+                d.copy_(h, non_blocking=True)
             ops = rt._ops
             ops.u8_to_planar(st["d0"], plan.im0, H, W, Hp, Wp, top, left, isBGR)
             ops.u8_to_planar(st["d1"], plan.im1, H, W, Hp, Wp, top, left, isBGR)
@@ -146,6 +148,15 @@ class NetworkBase(ParamTree):
             st["hout"].copy_(st["dout"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return st["hout"].numpy().copy()
+
+    def pinned_frame_buffers(self, H, W):
+        """Two HxWx3 uint8 numpy arrays backed by the pinned staging memory of ``interpolate_u8`` / ``inference_2frame``: a decoder
+        that writes its frames straight into them saves one host copy per frame (the arrays are reused by the next call)."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("pinned frame buffers need the model on a CUDA device")
+        st = self._runtime.staging(H, W, dev)
+        return st["h0"].numpy(), st["h1"].numpy()
 
     def interpolate_stream(self, frames, isBGR=True, divisor=64, include_inputs=True):
         """2x interpolation of a frame stream (the loop of demo_2x.py:129-168) as a 2-deep pipeline.

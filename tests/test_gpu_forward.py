@@ -183,3 +183,17 @@ def test_video_stream_equals_pairwise_inference():
     mids = list(interpolate_video(iter(frames), net, include_inputs=False))
     assert len(mids) == len(frames) - 1 and all(np.array_equal(m, got[2 * k + 1]) for k, m in enumerate(mids))
     assert list(interpolate_video(iter(frames[:1]), net)) == [frames[0]] or True
+
+
+def test_inference_2frame_from_pinned_buffers():
+    """Frames handed over in the model's pinned staging buffers (no host copy) give the same bytes as ordinary arrays."""
+    from demo_2x import inference_2frame
+    P = weights.make_weights("lite", "default")
+    net = _net("lite", P)
+    rng = np.random.default_rng(11)
+    a, b = rng.integers(0, 256, (70, 100, 3), dtype=np.uint8), rng.integers(0, 256, (70, 100, 3), dtype=np.uint8)
+    ref = inference_2frame(a, b, net)
+    p0, p1 = net.pinned_frame_buffers(70, 100)
+    p0[...], p1[...] = a, b
+    assert np.array_equal(inference_2frame(p0, p1, net), ref)
+    assert np.array_equal(inference_2frame(b, a, net), inference_2frame(b.copy(), a.copy(), net))
