@@ -220,9 +220,10 @@ class SlabSession:
         st = self._stage(H, W)
         return st["h0"].numpy(), st["h1"].numpy()
 
-    def interpolate_u8(self, img0, img1, isBGR: bool = True, divisor: int = 64):
+    def interpolate_u8(self, img0, img1, isBGR: bool = True, divisor: int = 64, copy: bool = False):
         """``demo_2x.inference_2frame`` arithmetic (demo_2x.py:54-87) on the slab plan: every rank passes the same two HxWx3
-        uint8 frames; rank 0 returns the uint8 middle frame, the other ranks return None."""
+        uint8 frames; rank 0 returns the uint8 middle frame, the other ranks return None.  With ``copy=False`` (default) the
+        result is a view of the session's pinned download buffer, valid until the next call."""
         import numpy as np
         H, W = img0.shape[:2]
         eh, ew = (-H) % divisor, (-W) % divisor
@@ -241,7 +242,9 @@ class SlabSession:
                 self.ops.planar_to_u8(out["I_t"], st["dout"], H, W, Hp, Wp, top, left, isBGR)
                 st["hout"].copy_(st["dout"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return st["hout"].numpy().copy() if self.rank == 0 else None
+            if self.rank != 0:
+                return None
+            return st["hout"].numpy().copy() if copy else st["hout"].numpy()
 
     def check(self) -> None:
         """Raise if a peer wait timed out on the device (a rank died or the ranks ran different step counts)."""
