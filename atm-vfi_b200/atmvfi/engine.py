@@ -9,6 +9,7 @@ cat / slice / einops.rearrange of the reference is a pointer offset.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -285,15 +286,18 @@ class Plan:
             tok = tokw
             # warp every pyramid level with the global flow, coarse to fine (network_base.py:480-485)
             f0, f1 = f0u, f1u
-            with ops.replicated():    # 3-channel images: recomputing them on every rank is cheaper than gathering them
-                for l in (3, 2, 1, 0):
-                    n0, n1 = P(*pyr0[l].shape), P(*pyr1[l].shape)
-                    ops.flow_warp_nchw(pyr0[l], f0, n0); ops.flow_warp_nchw(pyr1[l], f1, n1)
-                    pyr0[l], pyr1[l] = n0, n1
-                    if l:
-                        g0, g1 = P(B, 2, H >> (l - 1), W >> (l - 1)), P(B, 2, H >> (l - 1), W >> (l - 1))
+            # Row slabs: the un-warped pyramid is whole on every rank, so each rank warps only its own rows; the later
+            # warp_blend launches read the warped levels in place from their owners.  The flows stay replicated down to 1/2
+            # resolution (cheap) so that no up-sampling step needs halo rows from a neighbour.
+            for l in (3, 2, 1, 0):
+                n0, n1 = P(*pyr0[l].shape), P(*pyr1[l].shape)
+                ops.flow_warp_nchw(pyr0[l], f0, n0); ops.flow_warp_nchw(pyr1[l], f1, n1)
+                pyr0[l], pyr1[l] = n0, n1
+                if l:
+                    g0, g1 = P(B, 2, H >> (l - 1), W >> (l - 1)), P(B, 2, H >> (l - 1), W >> (l - 1))
+                    with (ops.replicated() if l > 1 else contextlib.nullcontext()):
                         ops.resize(f0, g0, 2.0); ops.resize(f1, g1, 2.0)
-                        f0, f1 = g0, g1
+                    f0, f1 = g0, g1
 
         tok, lhead = motion_branch(ops, m.local_blocks, m.local_head, tok, m.local_ws)
         for k, shift in enumerate((0, ENHANCE_WINDOW // 2)):

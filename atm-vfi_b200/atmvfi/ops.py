@@ -330,6 +330,18 @@ class CudaOps:
         assert flow.shape == (b, 2, h, w) and img.is_contiguous() and flow.is_contiguous() and out.is_contiguous()
         self._emit("atmvfi_flow_warp_nchw", (img.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w) + _yy(rows), keep=(img, flow, out))
 
+    @staticmethod
+    def _row_owners(owners, H: int):
+        """[(row_lo, row_hi, byte_delta)] covering [0, H) -> the C struct (rows held by other GPUs, read in place over NVLink)."""
+        ro = _lib.RowOwners()
+        assert 0 < len(owners) <= 2 * _lib.P2P_MAX_PEERS and owners[0][0] == 0 and owners[-1][1] == H
+        ro.nseg = len(owners)
+        for i, (lo, hi, delta) in enumerate(owners):
+            assert i == 0 or owners[i - 1][1] == lo
+            ro.row_lo[i], ro.byte_delta[i] = lo, delta
+        ro.row_lo[len(owners)] = H
+        return ro
+
     def flow_warp_nhwc(self, src: Map, head: Map, flow_off: int, out: Map, rows: Rows = None, owners=None):
         """owners: [(row_lo, row_hi, byte_delta)] - source rows held by other GPUs, read in place over NVLink (row slabs)."""
         assert (src.B, src.H, src.W) == (head.B, head.H, head.W) == (out.B, out.H, out.W) and src.C == out.C
@@ -337,21 +349,20 @@ class CudaOps:
         if owners is None:
             self._emit("atmvfi_flow_warp_nhwc", args, keep=(src, head, out))
             return
-        ro = _lib.RowOwners()
-        assert 0 < len(owners) <= 2 * _lib.P2P_MAX_PEERS and owners[0][0] == 0 and owners[-1][1] == src.H
-        ro.nseg = len(owners)
-        for i, (lo, hi, delta) in enumerate(owners):
-            assert i == 0 or owners[i - 1][1] == lo
-            ro.row_lo[i], ro.byte_delta[i] = lo, delta
-        ro.row_lo[len(owners)] = src.H
+        ro = self._row_owners(owners, src.H)
         self._emit("atmvfi_flow_warp_nhwc_p2p", args + (C.byref(ro),), keep=(src, head, out, ro))
 
-    def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None, rows: Rows = None):
+    def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None, rows: Rows = None, owners=None):
         b, _, h, w = im0.shape
         assert (head.B, head.H, head.W) == (b, h, w) and head.C >= 5
-        self._emit("atmvfi_warp_blend", (im0.data_ptr(), im1.data_ptr(), head.ptr, head.pitch, 0, w0.data_ptr(), w1.data_ptr(), it.data_ptr(),
-                                         _p(flow0), _p(flow1), _p(occ1), _p(occ2), b, h, w) + _yy(rows),
-                   keep=(im0, im1, head, w0, w1, it, flow0, flow1, occ1, occ2))
+        args = (im0.data_ptr(), im1.data_ptr(), head.ptr, head.pitch, 0, w0.data_ptr(), w1.data_ptr(), it.data_ptr(),
+                _p(flow0), _p(flow1), _p(occ1), _p(occ2), b, h, w) + _yy(rows)
+        keep = (im0, im1, head, w0, w1, it, flow0, flow1, occ1, occ2)
+        if owners is None:
+            self._emit("atmvfi_warp_blend", args, keep=keep)
+        else:
+            ro = self._row_owners(owners, h)
+            self._emit("atmvfi_warp_blend_p2p", args + (C.byref(ro),), keep=keep + (ro,))
 
     def resize(self, x: torch.Tensor, out: torch.Tensor, scale: float = 1.0, rows: Rows = None):
         assert x.is_contiguous() and out.is_contiguous() and x.shape[:2] == out.shape[:2]

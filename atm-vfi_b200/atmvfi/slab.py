@@ -458,8 +458,17 @@ class SlabOps:
             return
         # NVLink: the source stays where it was produced; the kernel reads each sample from the GPU that owns the row.
         # One flag-only site makes sure every rank has finished producing its rows.
-        b, i0, ni = self._buf(src)
-        segs = []                                   # (lo, hi, rank) cover of the rows, preferring the local copy
+        owners = self._owners(src)
+        self._sync_site()
+        self._same_rows([out], [head], lambda rows: self.backend.flow_warp_nhwc(src, head, flow_off, out, rows=rows, owners=owners))
+
+    def _owners(self, x):
+        """Cover of the rows of ``x`` by (lo, hi, byte distance to the rank that holds them), preferring the local copy; None
+        when every row is local (external inputs, replicated buffers)."""
+        b, i0, ni = self._buf(x)
+        if b.external:
+            return None
+        segs = []
         todo = [(0, b.H)]
         for q in [self.rank] + [q for q in range(self.world) if q != self.rank]:
             have = b.have[q][i0]
@@ -469,14 +478,28 @@ class SlabOps:
             todo = rs_sub(todo, got)
         assert not todo, f"rows {todo} of the warp source exist on no rank"
         segs.sort()
-        owners = [(lo, hi, self.transport.byte_delta(q)) for lo, hi, q in segs]
+        if all(q == self.rank for _, _, q in segs):
+            return None
+        return [(lo, hi, self.transport.byte_delta(q)) for lo, hi, q in segs]
+
+    def _sync_site(self):
+        """Flag-only exchange site: every rank has finished producing what its peers are about to read in place."""
         self.transport.barrier(self.site)
         self.site += 1
         self.stats["sites"] += 1
-        self._same_rows([out], [head], lambda rows: self.backend.flow_warp_nhwc(src, head, flow_off, out, rows=rows, owners=owners))
 
     def warp_blend(self, im0, im1, head: Map, w0, w1, it, flow0=None, flow1=None, occ1=None, occ2=None):
         outs = [t for t in (w0, w1, it, flow0, flow1, occ1, occ2) if t is not None]
+        if getattr(self.transport, "remote_reads", False) and not self._replicated:
+            # the (per-slab) warped pyramids are read in place from their owners; whether a source is local is the same on all ranks
+            o0, o1 = self._owners(im0), self._owners(im1)
+            if o0 is not None or o1 is not None:
+                b0, b1 = self._buf(im0)[0], self._buf(im1)[0]
+                assert o0 is not None and o1 is not None and b0.have == b1.have, "the two warp sources must share their row layout"
+                self._sync_site()
+                self._same_rows(outs, [head], lambda rows: self.backend.warp_blend(im0, im1, head, w0, w1, it, flow0, flow1, occ1, occ2,
+                                                                                   rows=rows, owners=o0))
+                return
         self._same_rows(outs, [head], lambda rows: self.backend.warp_blend(im0, im1, head, w0, w1, it, flow0, flow1, occ1, occ2, rows=rows),
                         all_rows_in=[im0, im1])
 

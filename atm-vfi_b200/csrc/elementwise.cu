@@ -286,13 +286,30 @@ __global__ void __launch_bounds__(256) pack5_planar_kernel(const float* __restri
   }
 }
 
-__device__ __forceinline__ float sample_plane(const float* __restrict__ p, const Bilin& s, int W) {
+// Row-slab mode: source rows [lo[i], lo[i+1]) live in the arena of another GPU, `delta[i]` bytes away from the local copy
+// of the buffer in the peer-mapped address space (0 = local).  The warp reads them in place over NVLink.
+struct RowOwners {
+  int nseg;
+  int lo[ATMVFI_P2P_MAX_PEERS * 2 + 1];
+  long long delta[ATMVFI_P2P_MAX_PEERS * 2];
+};
+__device__ __forceinline__ long long owner_delta(const RowOwners& o, int y) {
+  long long d = 0;
+#pragma unroll 1
+  for (int i = 0; i < o.nseg; ++i)
+    if (y >= o.lo[i] && y < o.lo[i + 1]) d = o.delta[i];
+  return d;
+}
+
+// d0 / d1: byte distance to the GPU that holds source row y0 / y0+1 (row slabs; 0 = local)
+__device__ __forceinline__ float sample_plane(const float* __restrict__ p, const Bilin& s, int W, long long d0 = 0, long long d1 = 0) {
   float o = 0.f;
-  const float* r0 = p + (int64_t)s.y0 * W + s.x0;
+  const float* r0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p + (int64_t)s.y0 * W + s.x0) + d0);
+  const float* r1 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(p + (int64_t)(s.y0 + 1) * W + s.x0) + d1);
   if (s.vy0 && s.vx0) o = __fmul_rn(__ldg(r0), s.wnw);
   if (s.vy0 && s.vx1) o = __fadd_rn(o, __fmul_rn(__ldg(r0 + 1), s.wne));
-  if (s.vy1 && s.vx0) o = __fadd_rn(o, __fmul_rn(__ldg(r0 + W), s.wsw));
-  if (s.vy1 && s.vx1) o = __fadd_rn(o, __fmul_rn(__ldg(r0 + W + 1), s.wse));
+  if (s.vy1 && s.vx0) o = __fadd_rn(o, __fmul_rn(__ldg(r1), s.wsw));
+  if (s.vy1 && s.vx1) o = __fadd_rn(o, __fmul_rn(__ldg(r1 + 1), s.wse));
   return o;
 }
 
@@ -308,21 +325,6 @@ __global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __rest
     Bilin s = bilin_setup(ix, iy, W, H);
     for (int c = 0; c < C; ++c) out[((int64_t)b * C + c) * hw + rem] = sample_plane(img + ((int64_t)b * C + c) * hw, s, W);
   }
-}
-
-// Row-slab mode: source rows [lo[i], lo[i+1]) live in the arena of another GPU, `delta[i]` bytes away from the local copy
-// of the buffer in the peer-mapped address space (0 = local).  The warp reads them in place over NVLink.
-struct RowOwners {
-  int nseg;
-  int lo[ATMVFI_P2P_MAX_PEERS * 2 + 1];
-  long long delta[ATMVFI_P2P_MAX_PEERS * 2];
-};
-__device__ __forceinline__ long long owner_delta(const RowOwners& o, int y) {
-  long long d = 0;
-#pragma unroll 1
-  for (int i = 0; i < o.nseg; ++i)
-    if (y >= o.lo[i] && y < o.lo[i + 1]) d = o.delta[i];
-  return d;
 }
 
 // NHWC gather: a group of (C/4) lanes serves one output pixel, each lane moves one float4 per corner.
@@ -368,12 +370,14 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __rest
   }
 }
 
+template <bool kPeers>
 __global__ void __launch_bounds__(256) warp_blend_kernel(const float* __restrict__ im0, const float* __restrict__ im1,
                                                          const float* __restrict__ head, int head_pitch, int head_off,
                                                          float* __restrict__ w0, float* __restrict__ w1,
                                                          float* __restrict__ it, float* __restrict__ flow0,
                                                          float* __restrict__ flow1, float* __restrict__ occ1,
-                                                         float* __restrict__ occ2, int B, int H, int W, int wy0, int ny) {
+                                                         float* __restrict__ occ2, int B, int H, int W, int wy0, int ny,
+                                                         const __grid_constant__ RowOwners own) {
   const int64_t hw = (int64_t)H * W, total = (int64_t)B * ny * W;
   for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
     int b, y, x;
@@ -385,11 +389,18 @@ __global__ void __launch_bounds__(256) warp_blend_kernel(const float* __restrict
     Bilin s1 = bilin_setup(warp_src_coord((float)x, f1x, W), warp_src_coord((float)y, f1y, H), W, H);
     float m1 = sigmoidf_exact(lg);
     float m2 = __fsub_rn(1.f, m1);
+    long long d00 = 0, d01 = 0, d10 = 0, d11 = 0;       // both sources share the row layout
+    if (kPeers) {
+      if (s0.vy0) d00 = owner_delta(own, s0.y0);
+      if (s0.vy1) d01 = owner_delta(own, s0.y0 + 1);
+      if (s1.vy0) d10 = owner_delta(own, s1.y0);
+      if (s1.vy1) d11 = owner_delta(own, s1.y0 + 1);
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       int64_t o = ((int64_t)b * 3 + c) * hw;
-      float a = sample_plane(im0 + o, s0, W);
-      float bb = sample_plane(im1 + o, s1, W);
+      float a = sample_plane(im0 + o, s0, W, d00, d01);
+      float bb = sample_plane(im1 + o, s1, W, d10, d11);
       w0[o + rem] = a;
       w1[o + rem] = bb;
       it[o + rem] = __fadd_rn(__fmul_rn(m1, a), __fmul_rn(m2, bb));
@@ -688,16 +699,38 @@ int atmvfi_flow_warp_nhwc_p2p(const float* src, int src_pitch, const float* head
   return flow_warp_nhwc_impl(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, y1, owners, stream);
 }
 
-int atmvfi_warp_blend(const float* im0, const float* im1, const float* head, int head_pitch, int head_off, float* w0,
-                      float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2, int B, int H, int W,
-                      int y0, int y1, void* stream) {
+static int warp_blend_impl(const float* im0, const float* im1, const float* head, int head_pitch, int head_off, float* w0,
+                           float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2, int B, int H, int W,
+                           int y0, int y1, const atmvfi_row_owners* owners, void* stream) {
   int ny;
   ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "warp_blend: bad row window [%d,%d)", y0, y1);
   int64_t n = (int64_t)B * ny * W;
   if (n <= 0) return 0;
-  warp_blend_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(im0, im1, head, head_pitch, head_off, w0, w1, it, flow0, flow1, occ1, occ2, B, H, W, y0, ny);
+  RowOwners own;
+  memset(&own, 0, sizeof(own));
+  if (owners && owners->nseg > 0) {
+    ATMVFI_REQUIRE(owners->nseg <= ATMVFI_P2P_MAX_PEERS * 2, "warp_blend: %d owner segments (max %d)", owners->nseg, ATMVFI_P2P_MAX_PEERS * 2);
+    own.nseg = owners->nseg;
+    for (int i = 0; i < owners->nseg; ++i) { own.lo[i] = owners->row_lo[i]; own.delta[i] = owners->byte_delta[i]; }
+    own.lo[owners->nseg] = owners->row_lo[owners->nseg];
+    warp_blend_kernel<true><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(im0, im1, head, head_pitch, head_off, w0, w1, it, flow0, flow1, occ1, occ2, B, H, W, y0, ny, own);
+  } else {
+    warp_blend_kernel<false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(im0, im1, head, head_pitch, head_off, w0, w1, it, flow0, flow1, occ1, occ2, B, H, W, y0, ny, own);
+  }
   ATMVFI_CHECK_LAUNCH("warp_blend");
   return 0;
+}
+
+int atmvfi_warp_blend(const float* im0, const float* im1, const float* head, int head_pitch, int head_off, float* w0,
+                      float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2, int B, int H, int W,
+                      int y0, int y1, void* stream) {
+  return warp_blend_impl(im0, im1, head, head_pitch, head_off, w0, w1, it, flow0, flow1, occ1, occ2, B, H, W, y0, y1, nullptr, stream);
+}
+
+int atmvfi_warp_blend_p2p(const float* im0, const float* im1, const float* head, int head_pitch, int head_off, float* w0,
+                          float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2, int B, int H, int W,
+                          int y0, int y1, const atmvfi_row_owners* owners, void* stream) {
+  return warp_blend_impl(im0, im1, head, head_pitch, head_off, w0, w1, it, flow0, flow1, occ1, occ2, B, H, W, y0, y1, owners, stream);
 }
 
 int atmvfi_resize_bilinear_ac(const float* in, float* out, int planes, int Hin, int Win, int Hout, int Wout, float scale,

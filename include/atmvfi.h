@@ -262,6 +262,11 @@ int atmvfi_flow_warp_nhwc_p2p(const float* src, int src_pitch, const float* head
                               float* out, int out_pitch, int B, int C, int H, int W, int y0, int y1,
                               const atmvfi_row_owners* owners, void* stream);
 
+/* atmvfi_warp_blend whose two SOURCE images (same row layout) are read in place from the GPUs that own their rows. */
+int atmvfi_warp_blend_p2p(const float* im0, const float* im1, const float* head, int head_pitch, int head_off,
+                          float* w0, float* w1, float* it, float* flow0, float* flow1, float* occ1, float* occ2,
+                          int B, int H, int W, int y0, int y1, const atmvfi_row_owners* owners, void* stream);
+
 /* One exchange site: copy every piece, then store *epoch (release, system scope) into each signal flag (peer memory),
  * then wait until each wait flag (local memory, raised by a peer's call of this function) has reached *epoch.
  * `counter` is a zero-initialised word private to the site.  A wait that lasts > 4 s sets *error_word and returns. */
