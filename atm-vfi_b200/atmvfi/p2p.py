@@ -224,7 +224,6 @@ class SlabSession:
         """``demo_2x.inference_2frame`` arithmetic (demo_2x.py:54-87) on the slab plan: every rank passes the same two HxWx3
         uint8 frames; rank 0 returns the uint8 middle frame, the other ranks return None.  With ``copy=False`` (default) the
         result is a view of the session's pinned download buffer, valid until the next call."""
-        import numpy as np
         H, W = img0.shape[:2]
         eh, ew = (-H) % divisor, (-W) % divisor
         Hp, Wp, top, left = H + eh, W + ew, eh // 2, ew // 2

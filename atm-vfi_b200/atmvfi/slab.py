@@ -22,7 +22,6 @@ from __future__ import annotations
 
 import bisect
 import contextlib
-import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
