@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libatmvfi_b200.so")
 
 MAX_SRC = 4
 FP32, TF32 = 0, 1
-OUT_PIXEL, OUT_SHUFFLE2, OUT_WINDOW_REV = 0, 1, 2
+OUT_PIXEL, OUT_SHUFFLE2, OUT_WINDOW_REV, OUT_QKV_HEADS = 0, 1, 2, 3
 
 
 class AtmvfiError(RuntimeError):
@@ -45,6 +45,7 @@ class GemmConvDesc(C.Structure):
         ("precision", C.c_int32),
         ("tma_host", C.c_void_p),
         ("row_begin", C.c_int32), ("row_end", C.c_int32),
+        ("qkv_heads", C.c_int32),
     ]
 
 
@@ -70,10 +71,10 @@ PROTOTYPES = {
     "atmvfi_layernorm": [_P, _I, _P, _I, _L, _I, _P, _P, _F, _P],
     # ... every grid walker ends with (y0, y1, stream): the row window of include/atmvfi.h
     "atmvfi_window_gather_ln": [_P, _I, _P, _I, _I, _GP, _P, _P, _F, _I, _I, _P],
-    "atmvfi_window_attention": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P],
+    "atmvfi_window_attention": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P],
     "atmvfi_conv3x3_first": [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_pack5_planar": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "atmvfi_window_attention_tc": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P],
+    "atmvfi_window_attention_tc": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P],
     "atmvfi_dwconv3x3_gelu": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
     "atmvfi_flow_warp_nchw": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_flow_warp_nhwc": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -104,14 +104,15 @@ def transformer_block(ops, blk, tok: Map, g: WinGeom, motion: Optional[Map] = No
     xw = ops.new_win_map(g, C)
     ops.window_gather_ln(tok, xw, g, blk.g1, blk.b1)                       # pad + roll + partition + norm1
     qkv = ops.new_win_map(g, 3 * C)
-    ops.gemm_conv([xw], blk.qkv, qkv, act=False)
+    hm = bool(getattr(ops, "qkv_head_major", False))
+    ops.gemm_conv([xw], blk.qkv, qkv, act=False, qkv_heads=NUM_HEADS if hm else 0)
     ao = ops.new_win_map(g, C)
     if blk.atm and motion is not None:
         scratch = torch.empty(g.rows * NUM_HEADS * 2, device=xw.t.device, dtype=torch.float32)
         ops.window_attention(qkv, ao, g, NUM_HEADS, True, blk.rc, blk.mix, motion, 0, scratch,
-                             rc_closed_form=getattr(blk, "rc_closed", False))
+                             rc_closed_form=getattr(blk, "rc_closed", False), head_major=hm)
     else:
-        ops.window_attention(qkv, ao, g, NUM_HEADS, blk.atm)
+        ops.window_attention(qkv, ao, g, NUM_HEADS, blk.atm, head_major=hm)
     t2 = ops.new_map(tok.B, tok.H, tok.W, C)
     ops.gemm_conv([ao], blk.proj, t2, act=False, residual=xw, win=g)       # proj + residual on the NORMED tokens, window reverse
     t3 = ops.new_map(tok.B, tok.H, tok.W, C)

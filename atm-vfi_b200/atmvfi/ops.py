@@ -143,6 +143,9 @@ class CudaOps:
         self.launches = 0
         # optional allocator (shape, zero) -> fp32 tensor; the row-slab mode places every buffer in an IPC-shared arena
         self.allocator: Optional[Callable] = None
+        # TF32 mode: the fused q|k|v linear writes the head-major layout that the tcgen05 attention kernel fetches with TMA
+        import os
+        self.qkv_head_major = precision == _lib.TF32 and os.environ.get("ATMVFI_QKV_HEADS", "1") != "0"
 
     # -- memory -------------------------------------------------------------------------------
     def _alloc(self, shape, zero: bool) -> torch.Tensor:
@@ -210,7 +213,7 @@ class CudaOps:
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride: int = 1, dil: int = 1,
                   act: bool = True, residual: Optional[Map] = None, out2: Optional[Map] = None,
                   prelu2: Optional[torch.Tensor] = None, win: Optional[WinGeom] = None,
-                  precision: Optional[int] = None, rows: Rows = None):
+                  precision: Optional[int] = None, rows: Rows = None, qkv_heads: int = 0):
         assert [s.C for s in srcs] == list(w.split), (w.name, [s.C for s in srcs], w.split)
         s0 = srcs[0]
         for s in srcs:
@@ -241,6 +244,11 @@ class CudaOps:
         elif w.shuffle:
             d.out_mode = _lib.OUT_SHUFFLE2
             assert (out.B, out.H, out.W) == (s0.B, 2 * Hout, 2 * Wout), w.name
+        elif qkv_heads:
+            # fused q|k|v linear written head-major (include/atmvfi.h ATMVFI_OUT_QKV_HEADS); `out` is the [rows][3C] buffer reinterpreted
+            d.out_mode, d.qkv_heads = _lib.OUT_QKV_HEADS, qkv_heads
+            assert out.c0 == 0 and out.pitch == w.Cout and w.Cout % (3 * qkv_heads) == 0 and out.nrows == s0.B * Hout * Wout
+            assert residual is None and out2 is None and w.ksize == 1 and stride == 1
         else:
             d.out_mode = _lib.OUT_PIXEL
             assert out.nrows == s0.B * Hout * Wout, (w.name, out.t.shape, (s0.B, Hout, Wout))
@@ -307,11 +315,12 @@ class CudaOps:
 
     def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads: int, cross: bool, rc: Optional[torch.Tensor] = None,
                          mix: Optional[Sequence[torch.Tensor]] = None, motion: Optional[Map] = None, motion_off: int = 0,
-                         scratch: Optional[torch.Tensor] = None, rc_closed_form: bool = False, rows: Rows = None):
+                         scratch: Optional[torch.Tensor] = None, rc_closed_form: bool = False, rows: Rows = None, head_major: bool = False):
         assert qkv.C == 3 * out.C and qkv.nrows == g.rows == out.nrows
+        assert not head_major or (qkv.c0 == 0 and qkv.pitch == qkv.C)
         gc = g.c()
         m = [None] * 4 if mix is None else [t.data_ptr() for t in mix]
-        tail = (m[0], m[1], m[2], m[3], None if motion is None else motion.ptr, 0 if motion is None else motion.pitch, motion_off, _p(scratch)) + _yy(rows)
+        tail = (m[0], m[1], m[2], m[3], None if motion is None else motion.ptr, 0 if motion is None else motion.pitch, motion_off, _p(scratch)) + _yy(rows) + (int(head_major),)
         head = (qkv.ptr, qkv.pitch, out.ptr, out.pitch, out.C, heads, C.byref(gc), int(cross), _p(rc))
         keep = (qkv, out, gc, rc, mix, motion, scratch)
         if self.precision == _lib.TF32:

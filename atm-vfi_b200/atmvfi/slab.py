@@ -158,6 +158,7 @@ class SlabOps:
     lib = property(lambda s: s.backend.lib)
     device = property(lambda s: s.backend.device)
     precision = property(lambda s: s.backend.precision, lambda s, v: setattr(s.backend, "precision", v))
+    qkv_head_major = property(lambda s: bool(getattr(s.backend, "qkv_head_major", False)))
 
     def replay(self, records, stream=None):
         return self.backend.replay(records, stream)
@@ -315,7 +316,7 @@ class SlabOps:
 
     # ---- GEMM-shaped layers -----------------------------------------------------------------------
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride=1, dil=1, act=True, residual=None, out2=None,
-                  prelu2=None, win: Optional[WinGeom] = None, precision=None):
+                  prelu2=None, win: Optional[WinGeom] = None, precision=None, qkv_heads: int = 0):
         ob = self._buf(out)[0]
         sb = self._buf(srcs[0])[0]
         gsrcs = [self._buf(s)[0].grid_map(s) for s in srcs]
@@ -358,7 +359,7 @@ class SlabOps:
         def launch():
             if mine[1] > mine[0]:
                 self.backend.gemm_conv(gsrcs, w, gout, stride=stride, dil=dil, act=act, residual=gres, out2=gout2, prelu2=prelu2,
-                                       win=win, precision=precision, rows=mine)
+                                       win=win, precision=precision, rows=mine, qkv_heads=qkv_heads)
 
         self._run(reads, writes, launch)
 
@@ -411,7 +412,7 @@ class SlabOps:
         self._run(reads, writes, lambda: self.backend.window_gather_ln(tok, win, g, gamma, beta, rows=mine) if mine[1] > mine[0] else None)
 
     def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads, cross, rc=None, mix=None, motion=None, motion_off=0,
-                         scratch=None, rc_closed_form=False):
+                         scratch=None, rc_closed_form=False, head_major=False):
         qb = self._buf(qkv)[0]
 
         def deps(p):
@@ -429,7 +430,7 @@ class SlabOps:
         def launch():
             if mine[1] > mine[0]:
                 self.backend.window_attention(qkv, out, g, heads, cross, rc, mix, motion, motion_off, scratch,
-                                              rc_closed_form=rc_closed_form, rows=mine)
+                                              rc_closed_form=rc_closed_form, rows=mine, head_major=head_major)
 
         self._run(reads, writes, launch)
 

@@ -45,7 +45,10 @@ int atmvfi_gemm_conv(const atmvfi_gemm_conv_desc* d, void* stream) {
   ATMVFI_REQUIRE(d->nsrc >= 1 && d->nsrc <= ATMVFI_MAX_SRC, "gemm_conv: nsrc=%d out of range", d->nsrc);
   ATMVFI_REQUIRE(d->ksize == 1 || d->ksize == 3, "gemm_conv: kernel size %d unsupported (1 or 3)", d->ksize);
   ATMVFI_REQUIRE(d->stride >= 1 && d->dil >= 1, "gemm_conv: bad stride/dilation");
-  ATMVFI_REQUIRE(d->out_mode >= ATMVFI_OUT_PIXEL && d->out_mode <= ATMVFI_OUT_WINDOW_REV, "gemm_conv: bad out_mode %d", d->out_mode);
+  ATMVFI_REQUIRE(d->out_mode >= ATMVFI_OUT_PIXEL && d->out_mode <= ATMVFI_OUT_QKV_HEADS, "gemm_conv: bad out_mode %d", d->out_mode);
+  ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_QKV_HEADS ||
+                     (d->ksize == 1 && d->stride == 1 && !d->residual && !d->out2 && d->qkv_heads > 0 && d->Cout % (12 * d->qkv_heads) == 0),
+                 "gemm_conv: QKV_HEADS needs a 1x1 layer without residual / second output and Cout = 3 * heads * hd with hd %% 4 == 0");
   ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_SHUFFLE2 || (d->ksize == 1 && d->stride == 1), "gemm_conv: SHUFFLE2 needs ksize=1, stride=1");
   ATMVFI_REQUIRE(!d->out2 || d->prelu2, "gemm_conv: out2 needs prelu2 slopes");
   if (d->precision == ATMVFI_FP32) return atmvfi_gemm_conv_simt(d, (cudaStream_t)stream);

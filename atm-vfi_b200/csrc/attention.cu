@@ -14,7 +14,8 @@ template <int HD>
 __global__ void __launch_bounds__(256) window_attention_kernel(const float* __restrict__ qkv, int qkv_pitch,
                                                                float* __restrict__ out, int out_pitch, int C, int heads,
                                                                atmvfi_window_geom g, int cross,
-                                                               const float* __restrict__ rc, float* __restrict__ motion_raw, int wy0, int nwy, bool rnd) {
+                                                               const float* __restrict__ rc, float* __restrict__ motion_raw, int wy0, int nwy, bool rnd,
+                                                               int layout) {
   extern __shared__ float smem[];
   const int N = g.ws * g.ws;
   float* sk = smem;             // [N][HD]
@@ -30,12 +31,24 @@ __global__ void __launch_bounds__(256) window_attention_kernel(const float* __re
   // the other frame's copy of this window sits half the window batch away (attention.py:318)
   const int64_t kv_win = cross ? (win + total_win / 2) % total_win : win;
 
-  const float* kbase = qkv + kv_win * N * qkv_pitch + C + h * HD;
-  const float* vbase = kbase + C;
-  for (int i = threadIdx.x; i < N * (HD / 4); i += blockDim.x) {
-    int r = i / (HD / 4), c4 = i % (HD / 4);
-    reinterpret_cast<float4*>(sk + r * HD)[c4] = __ldg(reinterpret_cast<const float4*>(kbase + (int64_t)r * qkv_pitch) + c4);
-    reinterpret_cast<float4*>(sv + r * HD)[c4] = __ldg(reinterpret_cast<const float4*>(vbase + (int64_t)r * qkv_pitch) + c4);
+  const int64_t R = total_win * N;                 // head-major layout (ATMVFI_OUT_QKV_HEADS): rows of the whole tensor
+  if (layout == 0) {
+    const float* kbase = qkv + kv_win * N * qkv_pitch + C + h * HD;
+    const float* vbase = kbase + C;
+    for (int i = threadIdx.x; i < N * (HD / 4); i += blockDim.x) {
+      int r = i / (HD / 4), c4 = i % (HD / 4);
+      reinterpret_cast<float4*>(sk + r * HD)[c4] = __ldg(reinterpret_cast<const float4*>(kbase + (int64_t)r * qkv_pitch) + c4);
+      reinterpret_cast<float4*>(sv + r * HD)[c4] = __ldg(reinterpret_cast<const float4*>(vbase + (int64_t)r * qkv_pitch) + c4);
+    }
+  } else {
+    const float* kbase = qkv + ((int64_t)(heads + h) * R + kv_win * N) * HD;          // K[h][r][d]
+    for (int i = threadIdx.x; i < N * (HD / 4); i += blockDim.x)
+      reinterpret_cast<float4*>(sk)[i] = __ldg(reinterpret_cast<const float4*>(kbase) + i);
+    const float* vbase = qkv + 2 * (int64_t)C * R + (int64_t)h * HD * R + kv_win * N;   // V^T[h][d][r]
+    for (int i = threadIdx.x; i < N * HD; i += blockDim.x) {
+      const int c = i / N, r = i - c * N;
+      sv[r * HD + c] = __ldg(vbase + (int64_t)c * R + r);
+    }
   }
   const bool masked = (g.shift != 0) || g.Hp != g.H || g.Wp != g.W;
   const int wy = (int)((win % nW) / (g.Wp / g.ws)), wx = (int)((win % nW) % (g.Wp / g.ws));
@@ -48,7 +61,7 @@ __global__ void __launch_bounds__(256) window_attention_kernel(const float* __re
   const int64_t row = win * N + i;
   float q[HD];
   {
-    const float4* qp = reinterpret_cast<const float4*>(qkv + row * qkv_pitch + h * HD);
+    const float4* qp = reinterpret_cast<const float4*>(layout == 0 ? qkv + row * qkv_pitch + h * HD : qkv + ((int64_t)h * R + row) * HD);
 #pragma unroll
     for (int d = 0; d < HD / 4; ++d) {
       float4 t = __ldg(qp + d);
@@ -137,7 +150,7 @@ __global__ void __launch_bounds__(256) motion_mix_kernel(const float* __restrict
 
 template <int HD>
 int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
-                     const atmvfi_window_geom& g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, cudaStream_t st) {
+                     const atmvfi_window_geom& g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, int layout, cudaStream_t st) {
   const int N = g.ws * g.ws;
   const int64_t wins = (int64_t)g.B2 * nwy * (g.Wp / g.ws);
   if (wins <= 0) return 0;
@@ -152,7 +165,7 @@ int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch,
   }
   dim3 grid((unsigned)wins, (unsigned)heads);
   int threads = ((N + 31) / 32) * 32;
-  kern<<<grid, threads, smem, st>>>(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, rc, motion_raw, wy0, nwy, atmvfi_output_rounding() != 0);
+  kern<<<grid, threads, smem, st>>>(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, rc, motion_raw, wy0, nwy, atmvfi_output_rounding() != 0, layout);
   ATMVFI_CHECK_LAUNCH("window_attention");
   return 0;
 }
@@ -160,41 +173,43 @@ int launch_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch,
 }  // namespace
 
 int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
-                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, cudaStream_t st);
+                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, int layout,
+                                      cudaStream_t st);
 
 static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                           const atmvfi_window_geom* g, int cross, const float* relative_coord, const float* mix_w0, const float* mix_b0,
                           const float* mix_w2, const float* mix_b2, float* motion, int motion_pitch, int motion_off, float* scratch,
-                          int wy0, int wy1, void* stream);
+                          int wy0, int wy1, int layout, void* stream);
 
 extern "C" int atmvfi_window_attention_tc(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                                           const atmvfi_window_geom* g, int cross, const float* relative_coord, int rc_closed_form,
                                           const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
                                           float* motion, int motion_pitch, int motion_off, float* scratch, int wy0, int wy1,
-                                          void* stream) {
+                                          int qkv_layout, void* stream) {
   return attention_impl(true, rc_closed_form, qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, relative_coord, mix_w0, mix_b0, mix_w2,
-                        mix_b2, motion, motion_pitch, motion_off, scratch, wy0, wy1, stream);
+                        mix_b2, motion, motion_pitch, motion_off, scratch, wy0, wy1, qkv_layout, stream);
 }
 
 extern "C" int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                                        const atmvfi_window_geom* g, int cross, const float* relative_coord,
                                        const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
                                        float* motion, int motion_pitch, int motion_off, float* scratch, int wy0, int wy1,
-                                       void* stream) {
+                                       int qkv_layout, void* stream) {
   return attention_impl(false, 0, qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, relative_coord, mix_w0, mix_b0, mix_w2, mix_b2,
-                        motion, motion_pitch, motion_off, scratch, wy0, wy1, stream);
+                        motion, motion_pitch, motion_off, scratch, wy0, wy1, qkv_layout, stream);
 }
 
 static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
                           const atmvfi_window_geom* g, int cross, const float* relative_coord, const float* mix_w0, const float* mix_b0,
                           const float* mix_w2, const float* mix_b2, float* motion, int motion_pitch, int motion_off, float* scratch,
-                          int wy0, int wy1, void* stream) {
+                          int wy0, int wy1, int layout, void* stream) {
   ATMVFI_REQUIRE(heads > 0 && C % heads == 0, "window_attention: dim %d should be divided by num_heads %d", C, heads);
   const int hd = C / heads, N = g->ws * g->ws;
   ATMVFI_REQUIRE(N <= 256, "window_attention: window %d too large (max 16)", g->ws);
   ATMVFI_REQUIRE(g->Hp % g->ws == 0 && g->Wp % g->ws == 0 && g->shift >= 0 && g->shift < g->ws, "window_attention: bad geometry");
   ATMVFI_REQUIRE(!cross || g->B2 % 2 == 0, "window_attention: cross attention needs an even batch");
   ATMVFI_REQUIRE(qkv_pitch % 4 == 0 && out_pitch % 4 == 0 && hd % 4 == 0, "window_attention: pitches / head dim must be multiples of 4");
+  ATMVFI_REQUIRE(layout == 0 || layout == 1, "window_attention: unknown qkv layout %d", layout);
   int nwy;
   ATMVFI_REQUIRE(row_window(g->Hp / g->ws, wy0, wy1, &wy0, &nwy), "window_attention: bad window-row range [%d,%d)", wy0, wy1);
   const bool want_motion = motion != nullptr;
@@ -205,16 +220,16 @@ static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qk
   const float* rc = want_motion ? relative_coord : nullptr;
   int rcode = 3;
   if (tensor_cores)
-    rcode = atmvfi_window_attention_tc_launch(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, (want_motion && !rc_closed_form) ? rc : nullptr, raw, wy0, nwy, st);
+    rcode = atmvfi_window_attention_tc_launch(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, (want_motion && !rc_closed_form) ? rc : nullptr, raw, wy0, nwy, layout, st);
   if (rcode == 3)      // shape outside the tcgen05 kernel's envelope (or fp32 requested): CUDA-core kernel
   switch (hd) {
-    case 28: rcode = launch_attention<28>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
-    case 44: rcode = launch_attention<44>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
-    case 48: rcode = launch_attention<48>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
-    case 84: rcode = launch_attention<84>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
-    case 16: rcode = launch_attention<16>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
-    case 32: rcode = launch_attention<32>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
-    case 64: rcode = launch_attention<64>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, st); break;
+    case 28: rcode = launch_attention<28>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, layout, st); break;
+    case 44: rcode = launch_attention<44>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, layout, st); break;
+    case 48: rcode = launch_attention<48>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, layout, st); break;
+    case 84: rcode = launch_attention<84>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, layout, st); break;
+    case 16: rcode = launch_attention<16>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, layout, st); break;
+    case 32: rcode = launch_attention<32>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, layout, st); break;
+    case 64: rcode = launch_attention<64>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, layout, st); break;
     default:
       atmvfi_set_error("window_attention: head dim %d not instantiated (have 16,28,32,44,48,64,84)", hd);
       return 2;

@@ -40,6 +40,10 @@ struct AttnParams {
   float scale;
   // shared memory carve-up (bytes)
   int offK, offV, offLab, offBar;
+  // layout 1 (ATMVFI_OUT_QKV_HEADS): Q[h][r][d], K[h][r][d], V^T[h][d][r] - operands are fetched by TMA straight into the swizzled
+  // UMMA layouts: mapQ / mapK = 3-D {hd, R, 2*heads} (box 32 x rows x 1), mapV = 2-D {R, C} (box 32 keys x HP channels)
+  int layout, qrows;
+  CUtensorMap mapQ, mapK, mapV;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,7 +110,7 @@ __device__ __forceinline__ float tf32r(float v) {
 // kHD > 0: head dimension known at compile time - the Q / K / V staging loops unroll and their global loads are issued
 // back to back (with a run-time bound every 16-byte load waited for the previous one: ~18k of the ~46k cycles of a CTA).
 template <int kHD>
-__global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                         // chunksH x [128 x 128 B]; later P: chunksK x [128 x 128 B]
   uint8_t* sK = smem + p.offK;                // chunksH x [KP x 128 B]
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   int* sLab = reinterpret_cast<int*>(smem + p.offLab);           // [KP] mask label per key
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.offBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* tbar = bars + 4;                  // TMA completion (head-major layout)
 
   const int tid = threadIdx.x & (kRows - 1), part = threadIdx.x >> 7, warp = (threadIdx.x >> 5) & 3;
   const int N = p.N, hd = kHD ? kHD : p.hd;
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(&bars[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(&bars[1])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(tbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < 32) {
@@ -146,9 +152,9 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
   const int nwx = p.g.Wp / p.g.ws;
   const int ws = p.g.ws;
   // (window-local index, token) of row / key `r`; window < 0: padding row of the tile
+  // virtual window index v (dense over the row window) -> window id in the full window-major tensor
+  auto actual = [&](int64_t v) -> int64_t { const int vi = (int)v, bi = vi / p.per_img; return (int64_t)bi * p.nW + p.wy0 * nwx + (vi - bi * p.per_img); };
   auto locate = [&](int r, int base_tok, int& wl, int& tok) -> int64_t {
-    // virtual window index v (dense over the row window) -> window id in the full window-major tensor
-    auto actual = [&](int64_t v) -> int64_t { const int vi = (int)v, bi = vi / p.per_img; return (int64_t)bi * p.nW + p.wy0 * nwx + (vi - bi * p.per_img); };
     if (p.wpi == 1) { wl = 0; tok = base_tok + r; return tok < N ? actual(win0) : -1; }
     wl = r / N;
     tok = r - wl * N;
@@ -184,7 +190,46 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const At
     sLab[kk] = ok ? (mask_label(w, tok) | (wl << 12) | ((tok % ws) << 16) | ((tok / ws) << 24)) : -1;
   }
   __syncthreads();
-  {
+  if (p.layout == 1) {
+    // Head-major operands: one elected thread issues a handful of TMA boxes per window; they land in the swizzled K-major
+    // layouts of the two MMAs (Q, K: rows = tokens; V^T: rows = channels) with no thread touching the data.
+    const int nkc = (N + 31) >> 5;                               // 32-key chunks of V^T per window
+    for (int wl = 0; wl < p.wpi; ++wl) {                         // windows of the group that do not exist: zero their V^T columns
+      if (win0 + wl < p.virt_windows) continue;                  // (P is zero there, but 0 x garbage could be NaN)
+      uint8_t* z = sV + ((wl * N) >> 5) * (HP * 128);
+      for (int i = threadIdx.x * 16; i < nkc * HP * 128; i += kThreadsA * 16) *reinterpret_cast<float4*>(z + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t bytes = 0;
+      for (int wl = 0; wl < p.wpi; ++wl)
+        if (win0 + wl < p.virt_windows) bytes += (uint32_t)(p.chunksH * p.qrows * 128 + p.chunksH * N * 128 + nkc * HP * 128);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(tbar)), "r"(bytes) : "memory");
+      for (int wl = 0; wl < p.wpi; ++wl) {
+        if (win0 + wl >= p.virt_windows) continue;
+        const int64_t w = actual(win0 + wl);
+        const int64_t wk = p.cross ? (w + total_win / 2) % total_win : w;       // the other frame's copy of the window (attention.py:318)
+        const int qrow0 = (int)(w * N) + mt * kRows, krow0 = (int)(wk * N);
+        for (int c = 0; c < p.chunksH; ++c) {
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                           s_u32(sQ + c * (kRows * 128) + wl * N * 128)),
+                       "l"(&p.mapQ), "r"(s_u32(tbar)), "r"(c * 32), "r"(qrow0), "r"(h)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                           s_u32(sK + c * (p.KP * 128) + wl * N * 128)),
+                       "l"(&p.mapK), "r"(s_u32(tbar)), "r"(c * 32), "r"(krow0), "r"(p.heads + h)
+                       : "memory");
+        }
+        for (int kc = 0; kc < nkc; ++kc)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                           s_u32(sV + (((wl * N) >> 5) + kc) * (HP * 128))),
+                       "l"(&p.mapV), "r"(s_u32(tbar)), "r"(krow0 + kc * 32), "r"(h * hd)
+                       : "memory");
+      }
+    }
+    bar_wait(tbar, 0);
+  } else {
     // Asynchronous copies (cp.async): every load of the CTA is in flight at once and no registers are tied up.  The
     // head slices are 192-byte pieces of 4.6 KB rows, so DRAM latency under this access pattern is long (measured:
     // 4-6 dependent round trips of ~4k cycles each with register staging); here it is paid once.  Operands are NOT
@@ -446,7 +491,8 @@ extern "C" int atmvfi_attn_prof_read(unsigned long long* out6) {
 
 // Returns 0 on success, 3 if the shape is outside what this kernel handles (caller falls back to the fp32 kernel).
 int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* out, int out_pitch, int C, int heads,
-                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, cudaStream_t st) {
+                                      const atmvfi_window_geom* g, int cross, const float* rc, float* motion_raw, int wy0, int nwy, int layout,
+                                      cudaStream_t st) {
   AttnParams p;
   p.qkv = qkv; p.qkv_pitch = qkv_pitch; p.out = out; p.out_pitch = out_pitch; p.C = C; p.heads = heads; p.hd = C / heads;
   p.g = *g; p.cross = cross; p.rc = rc; p.motion_raw = motion_raw;
@@ -473,6 +519,37 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   p.offV = rup(regionQK, 1024);
   p.offLab = p.offV + p.chunksK * p.HP * 128;
   p.offBar = rup(p.offLab + p.KP * 4, 16);
+  p.layout = layout;
+  p.qrows = p.wpi > 1 ? p.N : kRows;
+  if (layout == 1) {
+    // V^T chunks of a window must start on a 32-key boundary of the tile; operands must satisfy the TMA alignment rules
+    if ((p.wpi > 1 && p.N % 32 != 0) || ((uintptr_t)qkv & 15) || p.hd % 4) return 3;
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+      void* fp = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+        enc = reinterpret_cast<EncodeTiledFn>(fp);
+    }
+    if (!enc) return 3;
+    const cuuint64_t R = (cuuint64_t)p.total_windows * p.N;
+    cuuint64_t gdim[3] = {(cuuint64_t)p.hd, R, (cuuint64_t)(2 * heads)};
+    cuuint64_t gstr[2] = {(cuuint64_t)p.hd * 4, R * p.hd * 4};
+    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint32_t boxq[3] = {32, (cuuint32_t)p.qrows, 1}, boxk[3] = {32, (cuuint32_t)p.N, 1};
+    CUresult r1 = enc(&p.mapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(qkv), gdim, gstr, boxq, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&p.mapK, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(qkv), gdim, gstr, boxk, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t vdim[2] = {R, (cuuint64_t)C};
+    cuuint64_t vstr[1] = {R * 4};
+    cuuint32_t boxv[2] = {32, (cuuint32_t)p.HP};
+    CUresult r3 = enc(&p.mapV, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(qkv) + 2 * (size_t)C * R, vdim, vstr, boxv, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS) return 3;
+  }
   const int smem = p.offBar + 64 + 8 * kRows * 4 + (kRows + 256) * 4;      // + row / key source tables
   if (smem > 227 * 1024) return 3;
   typedef void (*KernFn)(AttnParams);

@@ -517,6 +517,18 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
         __syncwarp();
         tc_ld32(trow + c0, r);
         tc_wait_ld();
+        if (e.out_mode == ATMVFI_OUT_QKV_HEADS && n0 >= 2 * e.qkv_C) {
+          // V^T[h][d][r]: consecutive GEMM rows are contiguous for a fixed column, and a TMEM lane IS a row - store straight
+          // from the accumulator registers, 32 rows x 4 bytes = one 128-byte line per column (no shared-memory transpose)
+          if (row_ok) {
+            const int nv = min(min(32, p.block_n - c0), e.Cout - n0);
+            float* vb = e.out + 2 * (int64_t)e.qkv_C * e.qkv_R + (int64_t)(n0 - 2 * e.qkv_C) * e.qkv_R + m;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) vb[(int64_t)j * e.qkv_R] = round_tf32_if(__uint_as_float(r[j]) + (e.bias ? __ldg(e.bias + n0 + j) : 0.f), rnd);
+          }
+          continue;
+        }
         if (!kFastEpi && sq != last_q) {
           const int64_t orow = row_ok ? epi_out_row(e, m, sq) : -1;
           s_row[lane] = make_int2((int)orow, (int)m);
@@ -539,7 +551,12 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
             if (act) sl4 = __ldg(reinterpret_cast<const float4*>(e.prelu + co0 + col));
             const int tw_mask = p.TW - 1, tw_shift = 31 - __clz(p.TW);
             const int oyb = oy0 + (kPair ? t * p.TH : 0);
-            float* obase = e.out + co0 + col;
+            // QKV_HEADS (q / k columns; whole-v chunks never get here): row pitch = head dim, column offset = head plane.
+            // In the one chunk that straddles the k | v boundary the v lanes store their 4 columns one by one.
+            const bool qkv = e.out_mode == ATMVFI_OUT_QKV_HEADS;
+            const bool qkv_v = qkv && co0 + col >= 2 * e.qkv_C;
+            float* obase = qkv ? e.out + (qkv_v ? 0 : epi_qkv_offset(e, 0, co0 + col)) : e.out + co0 + col;
+            const int64_t opitch = qkv ? e.qkv_hd : e.out_pitch;
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr) {
               const int row = rr * 4 + rsub, ml = q * 32 + row;
@@ -552,7 +569,14 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
                   v.z = v.z > 0.f ? v.z : v.z * sl4.z; v.w = v.w > 0.f ? v.w : v.w * sl4.w;
                 }
                 const int64_t mrow = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
-                *reinterpret_cast<float4*>(obase + mrow * e.out_pitch) = round_tf32_if(v, rnd);
+                v = round_tf32_if(v, rnd);
+                if (qkv_v) {
+                  const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) e.out[epi_qkv_offset(e, mrow, co0 + col + k)] = vv[k];
+                } else {
+                  *reinterpret_cast<float4*>(obase + mrow * opitch) = v;
+                }
               }
             }
           }
@@ -579,6 +603,9 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
                                   : __ldg(reinterpret_cast<const float4*>(e.residual + (int64_t)ri.y * e.res_pitch + co0 + col));
             }
           }
+          // QKV_HEADS: the 4 columns of a lane go out as one float4 when they belong to q or k (contiguous inside a head)
+          const bool qkv_vec = e.out_mode == ATMVFI_OUT_QKV_HEADS && full4 && (co0 + col) < 2 * e.qkv_C;
+          const int64_t qkv_base = qkv_vec ? epi_qkv_offset(e, 0, co0 + col) : 0;      // + row * hd (index arithmetic once per chunk)
           auto emit_row = [&](const int rr) {
             const int row = rr * 4 + rsub;
             const int2 ri = s_row[row];
@@ -610,6 +637,17 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[k] = round_tf32_if(v[k], rnd);
+            if (e.out_mode == ATMVFI_OUT_QKV_HEADS) {        // head-major q | k | v^T (uniform branch); ri.y = GEMM row
+#pragma unroll
+              if (qkv_vec) {
+                *reinterpret_cast<float4*>(e.out + qkv_base + (int64_t)ri.y * e.qkv_hd) = make_float4(v[0], v[1], v[2], v[3]);
+                return;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (col + k < nvalid) e.out[epi_qkv_offset(e, ri.y, co0 + col + k)] = v[k];
+              return;
+            }
             float* o1 = e.out + (int64_t)ri.x * e.out_pitch + co0 + col;
             if (full4) {
               *reinterpret_cast<float4*>(o1) = make_float4(v[0], v[1], v[2], v[3]);
@@ -799,7 +837,7 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   // linear layers with a residual (attention proj, Mlp fc2): generic epilogue with the residual rows prefetched
   static const KernelFn res_table[2] = {gemm_conv_tc_kernel<0, 1, false, 2>, gemm_conv_tc_kernel<0, 2, false, 2>};
   // fast epilogue: pixel-major output, no residual / second output, whole float4 columns, aligned bias and slopes
-  const int fast = (d->out_mode == ATMVFI_OUT_PIXEL && !d->residual && !d->out2 && d->Cout % 4 == 0 &&
+  const int fast = ((d->out_mode == ATMVFI_OUT_PIXEL || d->out_mode == ATMVFI_OUT_QKV_HEADS) && !d->residual && !d->out2 && d->Cout % 4 == 0 &&
                     (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0) ? 1 : 0;
   // 16 epilogue warps for layers whose K loop is shorter than the accumulator drain (tile time = epilogue time):
   // [epilogue kind][0: no halo, 1: pair mode][cluster]

@@ -39,7 +39,11 @@ enum { ATMVFI_FP32 = 0, ATMVFI_TF32 = 1 };
 enum {
   ATMVFI_OUT_PIXEL = 0,      /* output pixel (b,y,x) -> row of `out` (plain conv / linear)                      */
   ATMVFI_OUT_SHUFFLE2 = 1,   /* ConvTranspose2d(k=2,s=2): column block q=(dy*2+dx) of pixel (y,x) -> (2y+dy,2x+dx) */
-  ATMVFI_OUT_WINDOW_REV = 2  /* rows are window-major tokens; undo partition / roll / centre pad (attention.py:17-25,65-71,323-331) */
+  ATMVFI_OUT_WINDOW_REV = 2, /* rows are window-major tokens; undo partition / roll / centre pad (attention.py:17-25,65-71,323-331) */
+  ATMVFI_OUT_QKV_HEADS = 3   /* fused q|k|v linear (Cout = 3C) written in the HEAD-MAJOR layout the attention kernels can fetch with
+                                TMA: with R = B*Hout*Wout rows, hd = C/heads,
+                                  Q[h][r][d] at ((0*heads + h)*R + r)*hd + d,   K[h][r][d] at ((heads + h)*R + r)*hd + d,
+                                  V^T[h][d][r] at 2*C*R + (h*hd + d)*R + r      (floats from `out`; out_pitch is ignored) */
 };
 
 /* window geometry shared by the transformer kernels (attention.py:28-62, 275-305) */
@@ -92,6 +96,7 @@ typedef struct {
   const void* tma_host;          /* TF32: host pointer to the plan made by atmvfi_gemm_conv_plan, else NULL */
   int32_t row_begin, row_end;    /* row window on the GEMM grid [B][Hout][Wout] (window-major sources: rows of windows,
                                     i.e. Hout = B2-images x window rows); row_end == 0: all rows */
+  int32_t qkv_heads;             /* ATMVFI_OUT_QKV_HEADS: number of attention heads */
 } atmvfi_gemm_conv_desc;
 
 const char* atmvfi_last_error(void);
@@ -136,7 +141,8 @@ int atmvfi_window_attention(const float* qkv, int qkv_pitch, float* out, int out
                             const atmvfi_window_geom* g, int cross, const float* relative_coord,
                             const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
                             float* motion, int motion_pitch, int motion_off, float* scratch,
-                            int wy0, int wy1 /* window rows of every image */, void* stream);
+                            int wy0, int wy1 /* window rows of every image */,
+                            int qkv_layout /* 0: rows [rows][3C] with qkv_pitch; 1: head-major (ATMVFI_OUT_QKV_HEADS) */, void* stream);
 
 /* Same contract on the tensor cores (tcgen05 kind::tf32, accumulators in TMEM; Q, K, V^T staged in shared memory as
  * TF32).  rc_closed_form != 0 asserts that relative_coord holds the reference's own buffer contents (key position -
@@ -146,7 +152,7 @@ int atmvfi_window_attention_tc(const float* qkv, int qkv_pitch, float* out, int 
                                const atmvfi_window_geom* g, int cross, const float* relative_coord, int rc_closed_form,
                                const float* mix_w0, const float* mix_b0, const float* mix_w2, const float* mix_b2,
                                float* motion, int motion_pitch, int motion_off, float* scratch,
-                               int wy0, int wy1, void* stream);
+                               int wy0, int wy1, int qkv_layout, void* stream);
 
 /* Debug aid: with ATMVFI_ATTN_PROF=1 in the environment, thread 0 of every CTA of the tcgen05 attention kernel accumulates the
  * clock cycles of its six phases (staging, QK^T, softmax max, softmax exp + P, PV, output); this reads and clears the totals.

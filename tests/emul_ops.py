@@ -85,10 +85,30 @@ def _win_token_mask(g: WinGeom, rows):
     return _win_reverse(ind.reshape(g.rows, 1), g)[..., 0] > 0
 
 
+def _to_heads(y, heads):
+    """[R, 3C] q|k|v rows -> flat head-major buffer (include/atmvfi.h ATMVFI_OUT_QKV_HEADS)."""
+    R, C3 = y.shape
+    C = C3 // 3
+    hd = C // heads
+    q = y[:, :C].reshape(R, heads, hd).permute(1, 0, 2)
+    k = y[:, C : 2 * C].reshape(R, heads, hd).permute(1, 0, 2)
+    vt = y[:, 2 * C :].t()
+    return torch.cat([q.reshape(-1), k.reshape(-1), vt.reshape(-1)])
+
+
+def _from_heads(flat, R, C, heads):
+    hd = C // heads
+    q = flat[: C * R].reshape(heads, R, hd).permute(1, 0, 2).reshape(R, C)
+    k = flat[C * R : 2 * C * R].reshape(heads, R, hd).permute(1, 0, 2).reshape(R, C)
+    v = flat[2 * C * R :].reshape(C, R).t()
+    return torch.cat([q, k, v], 1)
+
+
 class EmulOps:
-    def __init__(self):
+    def __init__(self, qkv_head_major: bool = False):
         self.recording: Optional[List] = None
         self.launches = 0
+        self.qkv_head_major = qkv_head_major
 
     def new_map(self, B, H, W, C, zero=False):
         return Map(torch.full((B, H, W, round_up(C, 4)), float("nan") if round_up(C, 4) == C and not zero else 0.0), 0, C)
@@ -122,7 +142,7 @@ class EmulOps:
 
     # ---------------------------------------------------------------------------------------------
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride=1, dil=1, act=True, residual=None,
-                  out2=None, prelu2=None, win: Optional[WinGeom] = None, precision=None, rows=None):
+                  out2=None, prelu2=None, win: Optional[WinGeom] = None, precision=None, rows=None, qkv_heads=0):
         assert [s.C for s in srcs] == list(w.split)
         k, ci = w.ksize, sum(w.split)
         n_tot = 4 * w.Cout if w.shuffle else w.Cout
@@ -150,6 +170,18 @@ class EmulOps:
                     m = _win_token_mask(win, rows)
                     ov = out.view().reshape(y.shape)
                     ov[m] = y[m]
+                return
+            if qkv_heads:       # head-major q | k | v^T; with a row window only the rows of that window are produced
+                R = out.view().numel() // w.Cout
+                flat = out.t.reshape(-1)
+                new = _to_heads(y.reshape(R, w.Cout), qkv_heads)
+                if rows is None:
+                    flat.copy_(new)
+                else:
+                    sel = torch.zeros(y.shape[:3], dtype=torch.bool)
+                    sel[:, rows[0] : rows[1]] = True
+                    keep = _to_heads(sel.reshape(R, 1).expand(R, w.Cout).float(), qkv_heads) > 0
+                    flat[keep] = new[keep]
                 return
             orow = rows if (rows is None or not w.shuffle) else (2 * rows[0], 2 * rows[1])
             _put(out.view(), y, orow)
@@ -183,12 +215,15 @@ class EmulOps:
             _put(win.view().reshape(shp), y.reshape(shp), rows)
         self._emit(run)
 
-    def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads, cross, rc=None, mix=None, motion=None, motion_off=0, scratch=None, rc_closed_form=False, rows=None):
+    def window_attention(self, qkv: Map, out: Map, g: WinGeom, heads, cross, rc=None, mix=None, motion=None, motion_off=0, scratch=None, rc_closed_form=False, rows=None,
+                         head_major=False):
         def run():
             C = out.C
             N = g.ws * g.ws
             hd = C // heads
             x = qkv.view().reshape(-1, N, 3 * C)
+            if head_major:
+                x = _from_heads(qkv.t.reshape(-1), g.rows, C, heads).reshape(-1, N, 3 * C)
             q, k, v = x[..., :C], x[..., C : 2 * C], x[..., 2 * C :]
             if cross:
                 half = x.shape[0] // 2

@@ -62,3 +62,14 @@ def test_ensemble_plan_matches_oracle(kind, variant, B, H, W, frames):
     assert len(out["im_t_list"]) == len(ref["im_t_list"]) == 4
     with pytest.raises(RuntimeError):
         Plan(EmulOps(), model, 1, 96, 128, True, ensemble=True)     # 96 is not a multiple of 64
+
+
+def test_head_major_qkv_layout_matches_oracle():
+    """The fused q|k|v linear writing the head-major layout (ATMVFI_OUT_QKV_HEADS) + attention reading it: same forward."""
+    P = weights.make_weights("lite", "stress")
+    im0, im1 = weights.synthetic_frames(1, 128, 192, kind="texture")
+    ref = oracle.forward(P, im0, im1, True)
+    model = PackedModel(ARCHS["lite"], P, 8, 12, with_global=True)
+    out = Plan(EmulOps(qkv_head_major=True), model, 1, 128, 192, True).run(im0, im1)
+    for key in ("I_t", "opt_flow_0", "opt_flow_1", "occ_mask1"):
+        assert (out[key] - ref[key]).abs().max().item() <= 5e-3, key

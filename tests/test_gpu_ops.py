@@ -328,3 +328,47 @@ def test_ensemble_reduction_and_select():
     pl = torch.empty(2, 2, 6, 7, device="cuda")
     ops.nhwc_to_nchw(m.chan(2, 2), pl)
     assert torch.equal(pl, m.t[..., 2:4].permute(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("precision", [_lib.FP32, _lib.TF32], ids=["fp32", "tf32"])
+@pytest.mark.parametrize("R,C,heads", [(2 * 64 * 6, 384, 8), (2 * 144 * 2, 224, 8), (1000, 96, 8)])
+def test_gemm_qkv_head_major(precision, R, C, heads):
+    """Fused q|k|v linear written in the head-major layout (ATMVFI_OUT_QKV_HEADS) against the contract emulation."""
+    em = EmulOps()
+    cu = CudaOps(torch.device("cuda:0"), precision)
+    g = gen(21)
+    P = {"l.weight": torch.randn(3 * C, C, generator=g) * 0.05, "l.bias": torch.randn(3 * C, generator=g)}
+    w = pack.pack_linear(P, ["l"])
+    x = rand_map(1, 1, R, C, gen=g)
+    out = rand_map(1, 1, R, 3 * C, gen=g)
+    og = to_gpu(out)
+    em.gemm_conv([x], w, out, act=False, qkv_heads=heads)
+    cu.gemm_conv([to_gpu(x)], _pg_to_gpu(w), og, act=False, qkv_heads=heads)
+    assert max_err(og, out) < (2e-5 if precision == _lib.FP32 else 5e-3)
+
+
+@pytest.mark.parametrize("B2,H,W,ws,shift,hd", [(2, 16, 24, 8, 0, 48), (2, 17, 23, 8, 4, 28), (2, 20, 30, 12, 6, 84), (4, 24, 12, 12, 0, 44), (2, 16, 16, 8, 4, 48)])
+@pytest.mark.parametrize("precision", [_lib.FP32, _lib.TF32], ids=["simt", "tcgen05"])
+def test_window_attention_head_major(B2, H, W, ws, shift, hd, precision):
+    """Attention kernels reading the head-major q / k / v^T layout (TMA-fed on the tensor-core path)."""
+    from emul_ops import _to_heads
+    em = EmulOps()
+    cu = CudaOps(torch.device("cuda:0"), precision)
+    g = gen(22)
+    heads, C = 8, 8 * hd
+    geo = WinGeom(B2, H, W, ws, shift)
+    qkv = rand_map(1, 1, geo.rows, 3 * C, gen=g, scale=1.0)
+    qkv_h = Map(_to_heads(qkv.t.reshape(geo.rows, 3 * C), heads).reshape(1, 1, geo.rows, 3 * C).contiguous())
+    N = ws * ws
+    idx = torch.arange(N)
+    px, py = (idx % ws).float(), (idx // ws).float()
+    rc = torch.stack([px[None] - px[:, None], py[None] - py[:, None]], 0).contiguous()
+    mix = (torch.randn(4, 8, generator=g), torch.randn(4, generator=g), torch.randn(4, generator=g), torch.randn(1, generator=g))
+    out, mo = rand_map(1, 1, geo.rows, C, gen=g), rand_map(B2 // 2, H, W, 8, gen=g)
+    og, mg = to_gpu(out), to_gpu(mo)
+    scratch = torch.empty(geo.rows * heads * 2, device="cuda")
+    em.window_attention(qkv, out, geo, heads, True, rc, mix, mo, 4)
+    cu.window_attention(to_gpu(qkv_h), og, geo, heads, True, rc.cuda(), to_gpu(mix), mg, 4, scratch, rc_closed_form=True, head_major=True)
+    tol = 2e-4 if precision == _lib.FP32 else 6e-3
+    assert max_err(og, out) < tol
+    assert max_err(mg, mo) < (1e-3 if precision == _lib.FP32 else 5e-2)

@@ -32,17 +32,17 @@ def test_window_rows_cover_grid_once():
         assert sorted(seen) == list(range(g.H))
 
 
-def run_slabs(kind, variant, B, H, W, glob, world):
+def run_slabs(kind, variant, B, H, W, glob, world, head_major=False):
     P = weights.make_weights(kind, variant)
     im0, im1 = weights.synthetic_frames(B, H, W, kind="texture")
     model = PackedModel(ARCHS[kind], P, 8, 12, with_global=glob)
-    ref = Plan(EmulOps(), model, B, H, W, glob).run(im0, im1)
+    ref = Plan(EmulOps(head_major), model, B, H, W, glob).run(im0, im1)
     tw = ThreadWorld(world)
     outs, errs, stats = [None] * world, [], [None] * world
 
     def worker(r):
         try:
-            ops = SlabOps(EmulOps(), r, world, ThreadTransport(tw, r), gather="all")
+            ops = SlabOps(EmulOps(head_major), r, world, ThreadTransport(tw, r), gather="all")
             plan = Plan(ops, model, B, H, W, glob)
             outs[r] = plan.run(im0, im1)
             stats[r] = ops.stats
@@ -77,3 +77,9 @@ def test_slabs_match_single_rank(kind, variant, B, H, W, glob, world):
             assert not torch.isnan(y).any(), key
             assert (x - y).abs().max().item() <= 1e-5, key
     assert all(s["sites"] > 0 for s in stats)
+
+
+def test_slabs_with_head_major_qkv():
+    ref, outs, _ = run_slabs("lite", "stress", 1, 128, 192, True, 4, head_major=True)
+    for key in ("I_t", "opt_flow_0", "occ_mask1"):
+        assert not torch.isnan(outs[0][key]).any() and (ref[key] - outs[0][key]).abs().max().item() <= 1e-5, key
