@@ -426,6 +426,13 @@ class SlabOps:
 
         reads, writes = self._per_rank(deps)
         mine = self.own(qb, self.rank)
+        if head_major:
+            # Q[h][r][d] / K / V^T planes: a row of windows is not one contiguous chunk of this buffer, so it must never be
+            # exchanged - and it is not: the rank that owns a row of windows produced its q | k | v itself
+            for p in range(self.world):
+                for view, need in reads[p]:
+                    b, i0, ni = self._buf(view)
+                    assert all(not rs_sub(need, b.have[p][i]) for i in range(i0, i0 + ni)), "head-major qkv rows would have to be exchanged"
 
         def launch():
             if mine[1] > mine[0]:
