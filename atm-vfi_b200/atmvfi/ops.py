@@ -146,6 +146,7 @@ class CudaOps:
         # TF32 mode: the fused q|k|v linear writes the head-major layout that the tcgen05 attention kernel fetches with TMA
         import os
         self.qkv_head_major = precision == _lib.TF32 and os.environ.get("ATMVFI_QKV_HEADS", "1") != "0"
+        self.qkv_head_major_min_hd = int(os.environ.get("ATMVFI_QKV_HEADS_MIN_HD", "48"))     # see engine.transformer_block
 
     # -- memory -------------------------------------------------------------------------------
     def _alloc(self, shape, zero: bool) -> torch.Tensor:

@@ -159,6 +159,7 @@ class SlabOps:
     device = property(lambda s: s.backend.device)
     precision = property(lambda s: s.backend.precision, lambda s, v: setattr(s.backend, "precision", v))
     qkv_head_major = property(lambda s: bool(getattr(s.backend, "qkv_head_major", False)))
+    qkv_head_major_min_hd = property(lambda s: getattr(s.backend, "qkv_head_major_min_hd", 48))
 
     def replay(self, records, stream=None):
         return self.backend.replay(records, stream)

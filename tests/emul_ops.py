@@ -109,6 +109,7 @@ class EmulOps:
         self.recording: Optional[List] = None
         self.launches = 0
         self.qkv_head_major = qkv_head_major
+        self.qkv_head_major_min_hd = 0          # tests exercise the layout on every model size
 
     def new_map(self, B, H, W, C, zero=False):
         return Map(torch.full((B, H, W, round_up(C, 4)), float("nan") if round_up(C, 4) == C and not zero else 0.0), 0, C)
