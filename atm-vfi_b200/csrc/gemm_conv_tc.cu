@@ -274,10 +274,13 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
   ox0 = tx * p.TW;
 }
 
-// kEpi: 0 = generic epilogue, 1 = plain layers (see "fast epilogue" below), 2 = generic with the residual rows prefetched
+// kEpi: 0 = generic epilogue, 1 = plain layers (see "fast epilogue" below), 2 = generic with the residual rows prefetched,
+// 3 = the fast epilogue writing the head-major q | k | v^T layout (its own instantiation: carrying that code in variant 1 cost
+// every plain layer ~5 %)
 template <int kHalo, int kCS, bool kPair, int kEpi, int kEW = 8>
 __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
-  constexpr bool kFastEpi = kEpi == 1;
+  constexpr bool kFastEpi = kEpi == 1 || kEpi == 3;
+  constexpr bool kQkv = kEpi == 3;
   constexpr bool kResHoist = kEpi == 2;
   constexpr int kEpiWarps = kEW;
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B atoms need a 1024-byte aligned base
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
         __syncwarp();
         tc_ld32(trow + c0, r);
         tc_wait_ld();
-        if (e.out_mode == ATMVFI_OUT_QKV_HEADS && n0 >= 2 * e.qkv_C) {
+        if (kQkv && n0 >= 2 * e.qkv_C) {
           // V^T[h][d][r]: consecutive GEMM rows are contiguous for a fixed column, and a TMEM lane IS a row - store straight
           // from the accumulator registers, 32 rows x 4 bytes = one 128-byte line per column (no shared-memory transpose)
           if (row_ok) {
@@ -553,7 +556,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
             const int oyb = oy0 + (kPair ? t * p.TH : 0);
             // QKV_HEADS (q / k columns; whole-v chunks never get here): row pitch = head dim, column offset = head plane.
             // In the one chunk that straddles the k | v boundary the v lanes store their 4 columns one by one.
-            const bool qkv = e.out_mode == ATMVFI_OUT_QKV_HEADS;
+            constexpr bool qkv = kQkv;
             const bool qkv_v = qkv && co0 + col >= 2 * e.qkv_C;
             float* obase = qkv ? e.out + (qkv_v ? 0 : epi_qkv_offset(e, 0, co0 + col)) : e.out + co0 + col;
             const int64_t opitch = qkv ? e.qkv_hd : e.out_pitch;
@@ -603,9 +606,6 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
                                   : __ldg(reinterpret_cast<const float4*>(e.residual + (int64_t)ri.y * e.res_pitch + co0 + col));
             }
           }
-          // QKV_HEADS: the 4 columns of a lane go out as one float4 when they belong to q or k (contiguous inside a head)
-          const bool qkv_vec = e.out_mode == ATMVFI_OUT_QKV_HEADS && full4 && (co0 + col) < 2 * e.qkv_C;
-          const int64_t qkv_base = qkv_vec ? epi_qkv_offset(e, 0, co0 + col) : 0;      // + row * hd (index arithmetic once per chunk)
           auto emit_row = [&](const int rr) {
             const int row = rr * 4 + rsub;
             const int2 ri = s_row[row];
@@ -637,17 +637,6 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[k] = round_tf32_if(v[k], rnd);
-            if (e.out_mode == ATMVFI_OUT_QKV_HEADS) {        // head-major q | k | v^T (uniform branch); ri.y = GEMM row
-#pragma unroll
-              if (qkv_vec) {
-                *reinterpret_cast<float4*>(e.out + qkv_base + (int64_t)ri.y * e.qkv_hd) = make_float4(v[0], v[1], v[2], v[3]);
-                return;
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (col + k < nvalid) e.out[epi_qkv_offset(e, ri.y, co0 + col + k)] = v[k];
-              return;
-            }
             float* o1 = e.out + (int64_t)ri.x * e.out_pitch + co0 + col;
             if (full4) {
               *reinterpret_cast<float4*>(o1) = make_float4(v[0], v[1], v[2], v[3]);
@@ -837,8 +826,14 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   // linear layers with a residual (attention proj, Mlp fc2): generic epilogue with the residual rows prefetched
   static const KernelFn res_table[2] = {gemm_conv_tc_kernel<0, 1, false, 2>, gemm_conv_tc_kernel<0, 2, false, 2>};
   // fast epilogue: pixel-major output, no residual / second output, whole float4 columns, aligned bias and slopes
-  const int fast = ((d->out_mode == ATMVFI_OUT_PIXEL || d->out_mode == ATMVFI_OUT_QKV_HEADS) && !d->residual && !d->out2 && d->Cout % 4 == 0 &&
-                    (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0) ? 1 : 0;
+  const bool plain = !d->residual && !d->out2 && d->Cout % 4 == 0 && (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0;
+  const int fast = (d->out_mode == ATMVFI_OUT_PIXEL && plain) ? 1 : 0;
+  const bool qkv_fast = d->out_mode == ATMVFI_OUT_QKV_HEADS && plain && !pl->halo && !pl->pair;
+  ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_QKV_HEADS || qkv_fast,
+                 "gemm_conv(tf32): QKV_HEADS needs 16-byte aligned bias and Cout %% 4 == 0 (the generic epilogue does not carry this layout)");
+  // [epilogue warps 8 / 16][cluster]
+  static const KernelFn qkv_table[2][2] = {{gemm_conv_tc_kernel<0, 1, false, 3>, gemm_conv_tc_kernel<0, 2, false, 3>},
+                                           {gemm_conv_tc_kernel<0, 1, false, 3, 16>, gemm_conv_tc_kernel<0, 2, false, 3, 16>}};
   // 16 epilogue warps for layers whose K loop is shorter than the accumulator drain (tile time = epilogue time):
   // [epilogue kind][0: no halo, 1: pair mode][cluster]
   static const KernelFn table16[2][2][2] = {
@@ -862,15 +857,17 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
       kern = table16[fast][pl->pair ? 1 : 0][pl->cluster - 1];
       epi_warps = 16;
     }
+    if (qkv_fast) kern = qkv_table[epi_warps == 16 ? 1 : 0][pl->cluster - 1];
   }
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 26; ++i) {
-      KernelFn f = i < 16 ? table[i / 8][(i / 2) % 4][i % 2] : (i < 18 ? res_table[i - 16] : table16[(i - 18) / 4][((i - 18) / 2) % 2][i % 2]);
-      const int bytes = i < 18 ? smem_bytes(8) : smem_bytes(16);
+    for (int i = 0; i < 30; ++i) {
+      KernelFn f = i < 16 ? table[i / 8][(i / 2) % 4][i % 2]
+                          : (i < 18 ? res_table[i - 16] : (i < 26 ? table16[(i - 18) / 4][((i - 18) / 2) % 2][i % 2] : qkv_table[(i - 26) / 2][i % 2]));
+      const int bytes = (i < 18 || i == 26 || i == 27) ? smem_bytes(8) : smem_bytes(16);
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) {
         num_sms = 0;
