@@ -86,6 +86,7 @@ PROTOTYPES = {
     "atmvfi_nhwc_to_nchw": [_P, _I, _P, _I, _I, _I, _I, _P],
     "atmvfi_l1_mean": [_P, _P, _P, _P, _I, _L, _P],
     "atmvfi_select_min3": [_P, _P, _P, _P, _P, _P, _P, _I, _L, _P],
+    "atmvfi_copy": [_P, _P, C.c_size_t, _P],
     "atmvfi_residual_finish": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_u8_to_planar": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_planar_to_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],

@@ -166,7 +166,7 @@ def motion_branch(ops, blocks, head, tok: Map, ws: int) -> Tuple[Map, Map]:
 class Plan:
     """Launch list + buffers for one input shape."""
 
-    def __init__(self, ops, model: PackedModel, B: int, H: int, W: int, global_motion: bool, ensemble: bool = False):
+    def __init__(self, ops, model: PackedModel, B: int, H: int, W: int, global_motion: bool, ensemble: bool = False, stream: bool = False):
         ensemble = bool(ensemble and global_motion)      # forward_global_ensemble without global motion is forward_normal's local path
         div = 64 if ensemble else (16 if global_motion else 8)
         if H % div or W % div:
@@ -176,11 +176,14 @@ class Plan:
             raise NotImplementedError("the multi-scale global-motion ensemble reduces over whole frames and is not available in row-slab mode")
         if global_motion and not model.with_global:
             raise RuntimeError("global_motion requested but the global-motion weights were not packed")
-        self.ops, self.model, self.key = ops, model, (B, H, W, global_motion, ensemble)
+        if stream and (ensemble or hasattr(ops, "begin_plan")):
+            raise NotImplementedError("the video-stream plan (encoder reuse) is not combined with the ensemble or with row slabs")
+        self.ops, self.model, self.key = ops, model, (B, H, W, global_motion, ensemble, stream)
+        self.stream, self.encode_records, self.encode_graph = stream, None, None
         a = model.arch
         ops.recording = rec = []
         try:
-            self._build(ops, model, a, B, H, W, global_motion, ensemble)
+            self._build(ops, model, a, B, H, W, global_motion, ensemble, stream)
         finally:
             ops.recording = None
         self.records = rec
@@ -188,20 +191,24 @@ class Plan:
 
     # .............................................................................................
     @staticmethod
-    def _encode(ops, m: PackedModel, im0: torch.Tensor, im1: torch.Tensor, B: int, H: int, W: int) -> List[Map]:
-        """shared_feat_extraction on the two frames stacked on the batch axis (network_base.py:342-352, 451): 4 levels."""
+    def _encode(ops, m: PackedModel, im0: Optional[torch.Tensor], im1: torch.Tensor, B: int, H: int, W: int) -> List[Map]:
+        """shared_feat_extraction on the two frames stacked on the batch axis (network_base.py:342-352, 451): 4 levels.
+        ``im0 is None``: only the frame-1 half of every level is computed (video-stream plan; the frame-0 half is filled by
+        copying the previous pair's frame-1 features)."""
         levels, x = [], None
+        sel = (lambda t: t) if im0 is not None else (lambda t: t.batch(B, B))
         for l in range(4):
             c0, c1 = m.enc[l]
             h, w = H >> l, W >> l
             y = ops.new_map(2 * B, h, w, c0.Cout)
             if l == 0:      # 3 -> C0 straight from the planar frames (no channels-last copy of the inputs)
-                ops.conv3x3_first(im0, c0, y.batch(0, B))
+                if im0 is not None:
+                    ops.conv3x3_first(im0, c0, y.batch(0, B))
                 ops.conv3x3_first(im1, c0, y.batch(B, B))
             else:
-                ops.gemm_conv([x], c0, y, stride=2)
+                ops.gemm_conv([sel(x)], c0, sel(y), stride=2)
             x = ops.new_map(2 * B, h, w, c1.Cout)
-            ops.gemm_conv([y], c1, x)
+            ops.gemm_conv([sel(y)], c1, sel(x))
             levels.append(x)
         return levels
 
@@ -248,7 +255,7 @@ class Plan:
         self.ensemble_losses = losses
         return g0, g1
 
-    def _build(self, ops, m: PackedModel, a: Arch, B: int, H: int, W: int, glob: bool, ensemble: bool = False):
+    def _build(self, ops, m: PackedModel, a: Arch, B: int, H: int, W: int, glob: bool, ensemble: bool = False, stream: bool = False):
         P = ops.new_planar
         if hasattr(ops, "begin_plan"):          # row-slab mode (slab.SlabOps): partition the rows, open the step
             ops.begin_plan(B, H, W, glob)
@@ -259,7 +266,20 @@ class Plan:
                 pyr0.append(P(B, 3, H >> l, W >> l)); pyr1.append(P(B, 3, H >> l, W >> l))
                 ops.resize(pyr0[l - 1], pyr0[l]); ops.resize(pyr1[l - 1], pyr1[l])
 
-        levels = self._encode(ops, m, self.im0, self.im1, B, H, W)
+        if stream:
+            # Video-stream plan: frame k+1 is frame 1 of pair k and frame 0 of pair k+1, so its encoder features are computed once.
+            # A step = copy the frame-1 half of levels 1-3 to the frame-0 half (175 MB at 1080p) + encode the new frame 1;
+            # `encode_records` alone primes the features of the very first frame (Plan.encode_only).
+            rec = ops.recording
+            ops.recording = enc = []
+            levels = self._encode(ops, m, None, self.im1, B, H, W)
+            ops.recording = rec
+            for l in (1, 2, 3):
+                ops.copy_map(levels[l].batch(B, B), levels[l].batch(0, B))
+            rec.extend(enc)
+            self.encode_records = enc
+        else:
+            levels = self._encode(ops, m, self.im0, self.im1, B, H, W)
         tok = fusion(ops, m.fuse_local, levels[1], levels[2], levels[3])     # [2B, H/8, W/8, C]
         h8, w8 = H >> 3, W >> 3
 
@@ -387,6 +407,22 @@ class Plan:
     def num_launches(self) -> int:
         return self.ops.count_launches(self.records)
 
+    def encode_only(self, use_graph: bool = False) -> None:
+        """Video-stream plan: compute the encoder features of the frame currently in ``self.im1`` (priming the first frame)."""
+        assert self.stream, "encode_only belongs to the video-stream plan"
+        if not use_graph:
+            self.ops.replay(self.encode_records)
+            return
+        if self.encode_graph is None:
+            self.ops.replay(self.encode_records)               # this call's execution; the graph serves later calls
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.ops.replay(self.encode_records)
+            self.encode_graph = g
+            return
+        self.encode_graph.replay()
+
     def run(self, im0: torch.Tensor, im1: torch.Tensor, use_graph: bool = False) -> Dict[str, object]:
         self.im0.copy_(im0); self.im1.copy_(im1)
         return self.run_inplace(use_graph)
@@ -395,12 +431,16 @@ class Plan:
         """Run on whatever ``self.im0`` / ``self.im1`` currently hold (filled by the caller on this stream)."""
         if use_graph:
             if self.graph is None:
-                self.launch()                                    # warm-up outside capture (lazy module load, attributes)
+                # The first call runs eagerly (lazy module load, attributes) and IS this call's execution; the graph is only
+                # captured for the calls that follow.  (Replaying right after the eager run would execute the step twice,
+                # which the video-stream step is not idempotent under: its feature copy reads what its encoder overwrites.)
+                self.launch()
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self.launch()
                 self.graph = g
+                return self.outputs
             self.graph.replay()
         else:
             self.launch()

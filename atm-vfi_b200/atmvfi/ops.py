@@ -400,6 +400,11 @@ class CudaOps:
         self._emit("atmvfi_select_min3", tuple(l.data_ptr() for l in losses) + tuple(c.data_ptr() for c in cands) +
                    (out.data_ptr(), out.shape[0], out[0].numel()), keep=(losses, cands, out))
 
+    def copy_map(self, src: Map, dst: Map):
+        """dst <- src for two whole (contiguous) maps of equal shape."""
+        assert src.t.shape == dst.t.shape and src.t.is_contiguous() and dst.t.is_contiguous() and src.c0 == dst.c0 == 0
+        self._emit("atmvfi_copy", (dst.t.data_ptr(), src.t.data_ptr(), src.t.numel() * 4), keep=(src, dst))
+
     def residual_finish(self, res: Map, it, it_sum, it_clamped, rows: Rows = None):
         b, _, h, w = it.shape
         self._emit("atmvfi_residual_finish", (res.ptr, res.pitch, it.data_ptr(), _p(it_sum), it_clamped.data_ptr(), b, h, w) + _yy(rows),

@@ -43,13 +43,13 @@ class Runtime:
         self._plans.clear()
         self._sig = sig
 
-    def plan(self, B: int, H: int, W: int, global_motion: bool, ensemble: bool = False) -> Plan:
-        key = (B, H, W, bool(global_motion), bool(ensemble and global_motion))
+    def plan(self, B: int, H: int, W: int, global_motion: bool, ensemble: bool = False, stream: bool = False) -> Plan:
+        key = (B, H, W, bool(global_motion), bool(ensemble and global_motion), bool(stream))
         p = self._plans.get(key)
         if p is None:
             if len(self._plans) >= 4:            # plans own all activation buffers; keep the cache small
                 self._plans.pop(next(iter(self._plans)))
-            p = self._plans[key] = Plan(self._ops, self._model, B, H, W, bool(global_motion), bool(ensemble))
+            p = self._plans[key] = Plan(self._ops, self._model, B, H, W, bool(global_motion), bool(ensemble), bool(stream))
         return p
 
     def staging(self, H: int, W: int, device: torch.device) -> dict:

@@ -40,6 +40,16 @@ int atmvfi_device_info(int device, char* name, int* cc_major, int* cc_minor) {
   return prop.multiProcessorCount;
 }
 
+int atmvfi_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return 0;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    atmvfi_set_error("copy: %s", cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
 int atmvfi_gemm_conv(const atmvfi_gemm_conv_desc* d, void* stream) {
   ATMVFI_REQUIRE(d != nullptr, "gemm_conv: null descriptor");
   ATMVFI_REQUIRE(d->nsrc >= 1 && d->nsrc <= ATMVFI_MAX_SRC, "gemm_conv: nsrc=%d out of range", d->nsrc);

@@ -54,6 +54,8 @@ class NetworkBase(ParamTree):
         self.precision = os.environ.get("ATMVFI_PRECISION", "tf32")   # "tf32": tcgen05 kind::tf32; "fp32": CUDA-core FFMA
         self.use_cuda_graph = os.environ.get("ATMVFI_CUDA_GRAPH", "1") != "0"
         self.zero_copy_outputs = False
+        # interpolate_stream: encode every interior frame once (it is frame 1 of one pair and frame 0 of the next)
+        self.stream_encoder_reuse = os.environ.get("ATMVFI_STREAM_REUSE", "1") != "0"
         self._runtime = Runtime(a)
 
     # ---- reference API: window sizes (network_base.py:262-270) -------------------------------------
@@ -183,7 +185,8 @@ class NetworkBase(ParamTree):
         rt = self._runtime
         rt.prepare(self, dev, self.precision, self.local_motion_args["window_size"], self.global_motion_args["window_size"])
         with torch.cuda.device(dev):
-            plan = rt.plan(1, Hp, Wp, bool(self.global_motion))
+            reuse = bool(self.stream_encoder_reuse)
+            plan = rt.plan(1, Hp, Wp, bool(self.global_motion), False, stream=reuse)
             ops = rt._ops
             main = torch.cuda.current_stream()
             side = torch.cuda.Stream()
@@ -203,6 +206,8 @@ class NetworkBase(ParamTree):
             upload(0, first)
             main.wait_event(slots[0]["up"])
             ops.u8_to_planar(slots[0]["d_in"], plan.im1, H, W, Hp, Wp, top, left, isBGR)      # becomes im0 of the first pair
+            if reuse:
+                plan.encode_only(use_graph=self.use_cuda_graph)      # features of the first frame; later frames are encoded by the pair step
             slots[0]["done"].record(main)
             prev_frame, pending, k = first, None, 0
             for nxt in it:

@@ -213,6 +213,11 @@ int atmvfi_l1_mean(const float* a, const float* b, float* out, float* scratch, i
 int atmvfi_select_min3(const float* l0, const float* l1, const float* l2, const float* c0, const float* c1, const float* c2,
                        float* out, int samples, int64_t n, void* stream);
 
+/* Stream-ordered device-to-device copy (cudaMemcpyAsync); used by the video-stream plan to move a frame's encoder features
+ * from the "frame 1" half of the batch axis to the "frame 0" half instead of recomputing them (demo_2x.py:129-168 encodes every
+ * interior frame twice). */
+int atmvfi_copy(void* dst, const void* src, size_t bytes, void* stream);
+
 /* I_t += 2*sigmoid(res)-1 ; clamp (network_base.py:429, 532-533).  res: NHWC 3 channels. */
 int atmvfi_residual_finish(const float* res, int res_pitch, const float* it, float* it_sum, float* it_clamped,
                            int B, int H, int W, int y0, int y1, void* stream);

@@ -312,6 +312,9 @@ class EmulOps:
                 out[i] = cands[k][i]
         self._emit(run)
 
+    def copy_map(self, src: Map, dst: Map):
+        self._emit(lambda: dst.t.copy_(src.t))
+
     def residual_finish(self, res: Map, it, it_sum, it_clamped, rows=None):
         def run():
             s = it + (2 * torch.sigmoid(res.view()[..., :3].permute(0, 3, 1, 2)) - 1)

@@ -73,3 +73,25 @@ def test_head_major_qkv_layout_matches_oracle():
     out = Plan(EmulOps(qkv_head_major=True), model, 1, 128, 192, True).run(im0, im1)
     for key in ("I_t", "opt_flow_0", "opt_flow_1", "occ_mask1"):
         assert (out[key] - ref[key]).abs().max().item() <= 5e-3, key
+
+
+def test_stream_plan_reuses_encoder_features():
+    """Video-stream plan: the encoder features of frame k+1 are computed once (as frame 1 of pair k) and copied to the frame-0 half
+    for pair k+1; every pair must equal the ordinary two-frame forward."""
+    P = weights.make_weights("lite", "stress")
+    model = PackedModel(ARCHS["lite"], P, 8, 12, with_global=True)
+    frames = [weights.synthetic_frames(1, 64, 96, seed=s, kind="texture")[0] for s in (1, 2, 3, 4)]
+    normal = Plan(EmulOps(), model, 1, 64, 96, True)
+    stream = Plan(EmulOps(), model, 1, 64, 96, True, stream=True)
+    assert len(stream.records) < len(normal.records) + 4 and stream.encode_records
+    stream.im1.copy_(frames[0])
+    stream.encode_only()
+    for k in range(len(frames) - 1):
+        ref = {kk: (v.clone() if torch.is_tensor(v) else v) for kk, v in normal.run(frames[k], frames[k + 1]).items()}
+        stream.im0.copy_(stream.im1)
+        stream.im1.copy_(frames[k + 1])
+        out = stream.run_inplace()
+        for key in ("I_t", "opt_flow_0", "opt_flow_1", "occ_mask1"):
+            assert (out[key] - ref[key]).abs().max().item() <= 1e-4, (k, key)     # stress gains x batch-1 vs batch-2 conv summation order on CPU
+    with pytest.raises(NotImplementedError):
+        Plan(EmulOps(), model, 1, 64, 64, True, ensemble=True, stream=True)
