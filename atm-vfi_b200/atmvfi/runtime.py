@@ -49,7 +49,16 @@ class Runtime:
         if p is None:
             if len(self._plans) >= 4:            # plans own all activation buffers; keep the cache small
                 self._plans.pop(next(iter(self._plans)))
-            p = self._plans[key] = Plan(self._ops, self._model, B, H, W, bool(global_motion), bool(ensemble), bool(stream))
+            try:
+                p = Plan(self._ops, self._model, B, H, W, bool(global_motion), bool(ensemble), bool(stream))
+            except torch.cuda.OutOfMemoryError:
+                # plans own all their activation buffers (78 GB for Base at 4K): make room by dropping the cached ones, once
+                if not self._plans:
+                    raise
+                self._plans.clear()
+                torch.cuda.empty_cache()
+                p = Plan(self._ops, self._model, B, H, W, bool(global_motion), bool(ensemble), bool(stream))
+            self._plans[key] = p
         return p
 
     def staging(self, H: int, W: int, device: torch.device) -> dict:
