@@ -63,6 +63,7 @@ CASES = [
     ("lite", "stress", 1, 128, 192, True, 4),     # 32-row slabs: every local window straddles
     ("base", "stress", 2, 64, 96, True, 2),       # B = 2
     ("lite", "default", 1, 192, 64, False, 3),    # global off, uneven split
+    ("lite", "stress", 1, 256, 64, True, 8),      # 8 ranks x 32 rows: most ranks own no row of 12x12 windows at all, every 8x8 window straddles
 ]
 
 
