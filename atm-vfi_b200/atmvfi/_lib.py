@@ -98,6 +98,7 @@ PROTOTYPES = {
     "atmvfi_ipc_close": [_P],
     "atmvfi_p2p_exchange": [C.POINTER(P2PPiece), _I, C.POINTER(C.c_void_p), _I, C.POINTER(C.c_void_p), _I, _P, _P, _P, _P],
     "atmvfi_p2p_step_begin": [_P, C.POINTER(C.c_void_p), _I, C.POINTER(C.c_void_p), _I, _P, _P],
+    "atmvfi_p2p_set_timeout_ms": [_I],
 }
 _SPECIAL = {
     "atmvfi_last_error": ([], C.c_char_p),

@@ -180,6 +180,7 @@ class Plan:
             raise NotImplementedError("the video-stream plan (encoder reuse) is not combined with the ensemble or with row slabs")
         self.ops, self.model, self.key = ops, model, (B, H, W, global_motion, ensemble, stream)
         self.stream, self.encode_records, self.encode_graph = stream, None, None
+        self.in_use = False                     # video-stream plans are owned by one interpolate_stream generator at a time (runtime.acquire_stream_plan)
         a = model.arch
         ops.recording = rec = []
         try:

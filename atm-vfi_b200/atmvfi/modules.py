@@ -53,11 +53,38 @@ def _init_tensor(shape: Tuple[int, ...], kind: str, owner_shape=None) -> torch.T
     return t
 
 
+# Bumped whenever a tensor OBJECT of any ParamTree may have been replaced (attribute assignment, .to() / .cuda() / .half(),
+# load_state_dict).  runtime.Runtime caches the list of a network's 236 tensors and re-walks the module tree only when this moves;
+# in-place value changes are caught per call through (data_ptr, _version).
+STRUCT_EPOCH = [0]
+
+
 class ParamTree(nn.Module):
     """A module whose children / parameters are created from dotted names."""
 
     def __init__(self):
         super().__init__()
+
+    def __setattr__(self, name, value):
+        if isinstance(value, torch.Tensor):
+            STRUCT_EPOCH[0] += 1
+        super().__setattr__(name, value)
+
+    def register_parameter(self, name, param):
+        STRUCT_EPOCH[0] += 1
+        super().register_parameter(name, param)
+
+    def register_buffer(self, name, tensor, persistent=True):
+        STRUCT_EPOCH[0] += 1
+        super().register_buffer(name, tensor, persistent)
+
+    def _apply(self, fn, recurse=True):
+        STRUCT_EPOCH[0] += 1
+        return super()._apply(fn, recurse)
+
+    def load_state_dict(self, *a, **k):
+        STRUCT_EPOCH[0] += 1
+        return super().load_state_dict(*a, **k)
 
     def _descend(self, path: Iterable[str]) -> "ParamTree":
         node = self

@@ -141,6 +141,7 @@ class CudaOps:
         self.recording: Optional[List] = None
         self._keep: List = []
         self.launches = 0
+        self.round_outputs: Optional[bool] = None
         # optional allocator (shape, zero) -> fp32 tensor; the row-slab mode places every buffer in an IPC-shared arena
         self.allocator: Optional[Callable] = None
         # TF32 mode: the fused q|k|v linear writes the head-major layout that the tcgen05 attention kernel fetches with TMA
@@ -171,12 +172,18 @@ class CudaOps:
         return contextlib.nullcontext()
 
     # -- launch plumbing ----------------------------------------------------------------------
+    def set_rounding(self) -> None:
+        """tcgen05 kind::tf32 truncates its operands: in that mode producers round feature maps to the nearest TF32 value.
+        ``round_outputs`` (None = by precision) lets the per-operator tests look at the un-rounded accumulators."""
+        on = self.precision == _lib.TF32 if self.round_outputs is None else bool(self.round_outputs)
+        self.lib.atmvfi_set_output_rounding(1 if on else 0)
+
     def _emit(self, name: str, args: tuple, keep=()):
         fn = getattr(self.lib, name)
         if self.recording is not None:
             self.recording.append((name, fn, args, keep))
         else:
-            self.lib.atmvfi_set_output_rounding(1 if self.precision == _lib.TF32 else 0)
+            self.set_rounding()
             _lib.check(fn(*args, torch.cuda.current_stream(self.device).cuda_stream), name)
             self.launches += 1
 
@@ -189,8 +196,7 @@ class CudaOps:
 
     def replay(self, records, stream: Optional[int] = None) -> None:
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
-        # tcgen05 kind::tf32 truncates its operands: producers round feature maps to TF32 in that mode
-        self.lib.atmvfi_set_output_rounding(1 if self.precision == _lib.TF32 else 0)
+        self.set_rounding()
         for name, fn, args, _ in records:
             rc = fn(*args, st)
             if rc:

@@ -86,6 +86,14 @@ class P2PArena:
     def error_flag(self) -> int:
         return int(self.bytes_view[OFF_ERROR : OFF_ERROR + 4].view(torch.int32).item())
 
+    def reset_control(self) -> None:
+        """Zero the control block (epoch, ready flags, site counters and flags, error word).  Collective: every rank calls it."""
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)                 # nobody is still spinning on / pushing into a control block
+        self.bytes_view[:CTRL_BYTES].zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+
     def close(self) -> None:
         if self._closed:
             return
@@ -177,8 +185,11 @@ class SlabSession:
     frames; rank 0 returns the gathered outputs (``gather``: "I_t" only, "all" ten entries, "none")."""
 
     def __init__(self, net, B: int, H: int, W: int, global_motion: Optional[bool] = None, group=None, gather: str = "I_t",
-                 arena_bytes: Optional[int] = None):
+                 arena_bytes: Optional[int] = None, timeout_ms: Optional[int] = None):
         from .runtime import PRECISIONS
+        self._failed = False
+        if timeout_ms is not None:          # peer-wait time-out of the exchange kernels (default 4 s / ATMVFI_P2P_TIMEOUT_MS)
+            _lib.check(_lib.load().atmvfi_p2p_set_timeout_ms(int(timeout_ms)), "p2p_set_timeout_ms")
         dev = next(net.parameters()).device
         if dev.type != "cuda":
             raise _lib.AtmvfiError("row slabs need the model on a CUDA device; there is no CPU fallback")
@@ -199,13 +210,27 @@ class SlabSession:
             dist.barrier(group=group)
         self.rank, self.world = self.arena.rank, self.arena.world
 
-    def run(self, im0: torch.Tensor, im1: torch.Tensor, use_graph: bool = True) -> Dict[str, object]:
-        with torch.cuda.device(self.device):
-            return self.plan.run(im0, im1, use_graph=use_graph)
+    def _usable(self) -> None:
+        if self._failed:
+            raise _lib.AtmvfiError("this row-slab session saw a peer time-out; call resync() on every rank (or rebuild the session)")
 
-    def run_inplace(self, use_graph: bool = True) -> Dict[str, object]:
+    def run(self, im0: torch.Tensor, im1: torch.Tensor, use_graph: bool = True, check: bool = True) -> Dict[str, object]:
+        """``check=True`` (default) waits for the step and raises if a peer wait timed out - a poisoned step returns garbage rows.
+        Pipelined callers pass ``check=False`` and call ``check()`` themselves before they trust the frames."""
+        self._usable()
         with torch.cuda.device(self.device):
-            return self.plan.run_inplace(use_graph=use_graph)
+            out = self.plan.run(im0, im1, use_graph=use_graph)
+        if check:
+            self.check()
+        return out
+
+    def run_inplace(self, use_graph: bool = True, check: bool = True) -> Dict[str, object]:
+        self._usable()
+        with torch.cuda.device(self.device):
+            out = self.plan.run_inplace(use_graph=use_graph)
+        if check:
+            self.check()
+        return out
 
     def _stage(self, H: int, W: int) -> dict:
         st = getattr(self, "_staging", None)
@@ -228,6 +253,7 @@ class SlabSession:
         eh, ew = (-H) % divisor, (-W) % divisor
         Hp, Wp, top, left = H + eh, W + ew, eh // 2, ew // 2
         assert tuple(self.plan.im0.shape) == (1, 3, Hp, Wp), "session was built for another frame size"
+        self._usable()
         with torch.cuda.device(self.device):
             st = self._stage(H, W)
             for src, h, d in ((img0, st["h0"], st["d0"]), (img1, st["h1"], st["d1"])):
@@ -241,15 +267,25 @@ class SlabSession:
                 self.ops.planar_to_u8(out["I_t"], st["dout"], H, W, Hp, Wp, top, left, isBGR)
                 st["hout"].copy_(st["dout"], non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            self.check()                     # the stream is idle: reading the 4-byte error word costs one tiny D2H copy
             if self.rank != 0:
                 return None
             return st["hout"].numpy().copy() if copy else st["hout"].numpy()
 
     def check(self) -> None:
-        """Raise if a peer wait timed out on the device (a rank died or the ranks ran different step counts)."""
+        """Raise if a peer wait timed out on the device (a rank died, stalled longer than the time-out, or the ranks ran
+        different step counts).  The step that timed out and every later one pushed nothing, so their frames are garbage; the
+        session refuses further work until ``resync()``."""
         torch.cuda.synchronize(self.device)
         if self.arena.error_flag():
-            raise _lib.AtmvfiError("row-slab exchange timed out waiting for a peer (see csrc/p2p.cu kSpinTimeoutNs)")
+            self._failed = True
+            raise _lib.AtmvfiError("row-slab exchange timed out waiting for a peer (time-out: atmvfi_p2p_set_timeout_ms / "
+                                   "ATMVFI_P2P_TIMEOUT_MS); the frames of this step are invalid")
+
+    def resync(self) -> None:
+        """Collective recovery after a time-out: all ranks reset their control blocks (epochs, flags, error word) together."""
+        self.arena.reset_control()
+        self._failed = False
 
     def close(self) -> None:
         self.plan = None

@@ -164,6 +164,9 @@ class SlabOps:
     def replay(self, records, stream=None):
         return self.backend.replay(records, stream)
 
+    def set_rounding(self):
+        return self.backend.set_rounding()
+
     def count_launches(self, records):
         return self.backend.count_launches(records)
 

@@ -556,7 +556,11 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   static const KernFn kerns[5] = {window_attention_tc_kernel<0>, window_attention_tc_kernel<48>, window_attention_tc_kernel<84>,
                                   window_attention_tc_kernel<28>, window_attention_tc_kernel<44>};
   const int ki = p.hd == 48 ? 1 : (p.hd == 84 ? 2 : (p.hd == 28 ? 3 : (p.hd == 44 ? 4 : 0)));
-  static int configured = 0;
+  static int configured_of_device[ATMVFI_MAX_DEVICES] = {0};      // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= ATMVFI_MAX_DEVICES) return 3;
+  int& configured = configured_of_device[dev];
   if (configured < smem) {
     const int want = smem > 100 * 1024 ? 227 * 1024 : 100 * 1024;
     for (int i = 0; i < 5; ++i) {

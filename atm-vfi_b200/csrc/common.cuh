@@ -27,6 +27,8 @@ int atmvfi_output_rounding();
     }                                                                                    \
   } while (0)
 
+constexpr int ATMVFI_MAX_DEVICES = 64;      // per-device launch configuration caches are indexed by the CUDA device ordinal
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // Row window [y0, y1) of every image of a [B][H][W] grid (include/atmvfi.h "ROW WINDOWS"); y1 == 0 means all rows.

@@ -859,23 +859,28 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
     }
     if (qkv_fast) kern = qkv_table[epi_warps == 16 ? 1 : 0][pl->cluster - 1];
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  // SM count and the opt-in to > 48 KB of dynamic shared memory are PER DEVICE: a process that runs models on several GPUs
+  // (model.to another device, two models) configures each device the first time it launches there.
+  static int sms_of_device[ATMVFI_MAX_DEVICES] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  ATMVFI_REQUIRE(dev >= 0 && dev < ATMVFI_MAX_DEVICES, "gemm_conv(tf32): device ordinal %d out of range", dev);
+  if (!sms_of_device[dev]) {
+    int n_sm = 0;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     for (int i = 0; i < 30; ++i) {
       KernelFn f = i < 16 ? table[i / 8][(i / 2) % 4][i % 2]
                           : (i < 18 ? res_table[i - 16] : (i < 26 ? table16[(i - 18) / 4][((i - 18) / 2) % 2][i % 2] : qkv_table[(i - 26) / 2][i % 2]));
       const int bytes = (i < 18 || i == 26 || i == 27) ? smem_bytes(8) : smem_bytes(16);
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) {
-        num_sms = 0;
         atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", bytes, cudaGetErrorString(e));
         return 1;
       }
     }
+    sms_of_device[dev] = n_sm;
   }
+  const int num_sms = sms_of_device[dev];
   TcParams p;
   memcpy(p.mapA, pl->mapA, sizeof(p.mapA));
   memcpy(&p.mapB, &pl->mapB, sizeof(p.mapB));

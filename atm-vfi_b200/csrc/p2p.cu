@@ -8,12 +8,26 @@
 // three (push my pieces, signal my destinations, wait for my sources), so a site costs one launch and the
 // whole forward stays a single CUDA graph per rank.  Flags carry a monotonically increasing step number
 // ("epoch") kept in device memory, so graph replays need no host-side argument patching.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
 namespace {
 
-constexpr unsigned long long kSpinTimeoutNs = 4000000000ull;   // 4 s: a dead peer must not hang the GPU
+// A dead or badly skewed peer must not hang the GPU: every flag wait gives up after this long (default 4 s, set by
+// atmvfi_p2p_set_timeout_ms / ATMVFI_P2P_TIMEOUT_MS; baked into a launch - and into a captured CUDA graph - when it is issued).
+// A time-out sets the rank's sticky error word; from then on every exchange / step-begin kernel of that rank returns at once
+// WITHOUT pushing rows or raising flags (a poisoned step must not write into peers that are still consuming the previous one),
+// so its peers time out on their next wait and the failure spreads in bounded time instead of corrupting frames silently.
+unsigned long long g_spin_timeout_ns = 0;
+unsigned long long spin_timeout_ns() {
+  if (!g_spin_timeout_ns) {
+    const char* ev = getenv("ATMVFI_P2P_TIMEOUT_MS");
+    const long ms = ev ? atol(ev) : 0;
+    g_spin_timeout_ns = (unsigned long long)(ms > 0 ? ms : 4000) * 1000000ull;
+  }
+  return g_spin_timeout_ns;
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -29,16 +43,18 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // spin until *flag has reached `epoch` (wrap-safe); on time-out record the failure and give up
-__device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t epoch, uint32_t* error_word) {
+__device__ __forceinline__ bool spin_until(const uint32_t* flag, uint32_t epoch, uint32_t* error_word, unsigned long long timeout_ns) {
   const unsigned long long t0 = globaltimer_ns();
   while ((int32_t)(ld_acquire_sys(flag) - epoch) < 0) {
-    if (globaltimer_ns() - t0 > kSpinTimeoutNs) {
+    if (globaltimer_ns() - t0 > timeout_ns) {
       atomicExch(error_word, 1u);
-      return;
+      return false;
     }
     __nanosleep(64);
   }
+  return true;
 }
+__device__ __forceinline__ bool poisoned(const uint32_t* error_word) { return *reinterpret_cast<const volatile uint32_t*>(error_word) != 0; }
 
 struct ExchangeParams {
   atmvfi_p2p_piece piece[ATMVFI_P2P_MAX_PIECES];
@@ -50,10 +66,12 @@ struct ExchangeParams {
   const uint32_t* epoch;                         // local step counter
   uint32_t* counter;                             // local CTA-completion counter of this site (returns to 0)
   uint32_t* error_word;
+  unsigned long long timeout_ns;
 };
 
 // grid-strided 16-byte copies; the last CTA to finish signals the destinations, then waits for the sources
 __global__ void __launch_bounds__(256) p2p_exchange_kernel(const __grid_constant__ ExchangeParams p) {
+  if (poisoned(p.error_word)) return;            // set by an earlier kernel of this stream only: uniform over the grid
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int i = 0; i < p.npieces; ++i) {
     const atmvfi_p2p_piece& pc = p.piece[i];
@@ -85,7 +103,8 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const __grid_constant
       const uint32_t e = *p.epoch;
       for (int i = 0; i < p.nsignal; ++i) st_release_sys(p.signal[i], e);
       *p.counter = 0;
-      for (int i = 0; i < p.nwait; ++i) spin_until(p.wait[i], e, p.error_word);
+      for (int i = 0; i < p.nwait; ++i)
+        if (!spin_until(p.wait[i], e, p.error_word, p.timeout_ns)) break;
     }
   }
 }
@@ -94,11 +113,13 @@ __global__ void __launch_bounds__(256) p2p_exchange_kernel(const __grid_constant
 // has finished the previous one: its halo rows may be overwritten).
 __global__ void p2p_step_begin_kernel(uint32_t* epoch, ExchangeParams p) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (poisoned(p.error_word)) return;
     const uint32_t e = *epoch + 1;
     *epoch = e;
     __threadfence_system();
     for (int i = 0; i < p.nsignal; ++i) st_release_sys(p.signal[i], e);
-    for (int i = 0; i < p.nwait; ++i) spin_until(p.wait[i], e, p.error_word);
+    for (int i = 0; i < p.nwait; ++i)
+      if (!spin_until(p.wait[i], e, p.error_word, p.timeout_ns)) break;
   }
 }
 
@@ -157,6 +178,12 @@ int atmvfi_ipc_close(void* peer_ptr) {
   return 0;
 }
 
+int atmvfi_p2p_set_timeout_ms(int ms) {
+  ATMVFI_REQUIRE(ms > 0, "p2p_set_timeout_ms: %d is not a positive number of milliseconds", ms);
+  g_spin_timeout_ns = (unsigned long long)ms * 1000000ull;
+  return 0;
+}
+
 int atmvfi_p2p_exchange(const atmvfi_p2p_piece* pieces, int npieces, uint32_t* const* signal_flags, int nsignal,
                         const uint32_t* const* wait_flags, int nwait, const uint32_t* epoch, uint32_t* counter,
                         uint32_t* error_word, void* stream) {
@@ -177,6 +204,7 @@ int atmvfi_p2p_exchange(const atmvfi_p2p_piece* pieces, int npieces, uint32_t* c
   for (int i = 0; i < nsignal; ++i) p.signal[i] = signal_flags[i];
   for (int i = 0; i < nwait; ++i) p.wait[i] = wait_flags[i];
   p.nsignal = nsignal; p.nwait = nwait; p.epoch = epoch; p.counter = counter; p.error_word = error_word;
+  p.timeout_ns = spin_timeout_ns();
   // enough CTAs to keep the NVLink ports busy for large pushes, one CTA for flag-only sites
   int64_t ctas = (bytes + 65535) / 65536;
   if (ctas < 1) ctas = 1;
@@ -194,6 +222,7 @@ int atmvfi_p2p_step_begin(uint32_t* epoch, uint32_t* const* signal_flags, int ns
   for (int i = 0; i < nsignal; ++i) p.signal[i] = signal_flags[i];
   for (int i = 0; i < nwait; ++i) p.wait[i] = wait_flags[i];
   p.nsignal = nsignal; p.nwait = nwait; p.error_word = error_word;
+  p.timeout_ns = spin_timeout_ns();
   p2p_step_begin_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(epoch, p);
   ATMVFI_CHECK_LAUNCH("p2p_step_begin");
   return 0;

@@ -186,67 +186,89 @@ class NetworkBase(ParamTree):
         rt.prepare(self, dev, self.precision, self.local_motion_args["window_size"], self.global_motion_args["window_size"])
         with torch.cuda.device(dev):
             reuse = bool(self.stream_encoder_reuse)
-            plan = rt.plan(1, Hp, Wp, bool(self.global_motion), False, stream=reuse)
-            ops = rt._ops
-            main = torch.cuda.current_stream()
-            side = torch.cuda.Stream()
-            mk_h = lambda: torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
-            mk_d = lambda: torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
-            slots = [dict(h_in=mk_h(), d_in=mk_d(), h_out=mk_h(), d_out=mk_d(), up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event())
-                     for _ in range(2)]
+            # The generator keeps frame state across yields (the previous frame, and with encoder reuse its features inside the
+            # plan's buffers).  With reuse it therefore OWNS a stream plan until it finishes; without reuse it shares the ordinary
+            # plan of this shape with forward() / inference_2frame and keeps the previous planar frame in a private buffer, so a
+            # consumer that interpolates other pairs of the same shape between two yields cannot disturb the stream.
+            plan = rt.acquire_stream_plan(1, Hp, Wp, bool(self.global_motion)) if reuse else rt.plan(1, Hp, Wp, bool(self.global_motion))
+            try:
+                yield from self._stream_loop(plan, reuse, it, first, H, W, Hp, Wp, top, left, isBGR, include_inputs, dev)
+            finally:
+                if reuse:
+                    rt.release_stream_plan(plan)
 
-            def upload(slot, frame):                 # host -> pinned -> device, on the copy stream
-                s = slots[slot]
-                s["up"].synchronize()                # the previous upload from this pinned buffer has finished
-                s["h_in"].numpy()[...] = frame
-                with torch.cuda.stream(side):
-                    s["d_in"].copy_(s["h_in"], non_blocking=True)
-                    s["up"].record(side)
+    def _stream_loop(self, plan, reuse, it, first, H, W, Hp, Wp, top, left, isBGR, include_inputs, dev):
+        import numpy as np
+        rt = self._runtime
+        ops = rt._ops
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        mk_h = lambda: torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+        mk_d = lambda: torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+        slots = [dict(h_in=mk_h(), d_in=mk_d(), h_out=mk_h(), d_out=mk_d(), up=torch.cuda.Event(), done=torch.cuda.Event(), down=torch.cuda.Event())
+                 for _ in range(2)]
+        prev_planar = torch.empty_like(plan.im1)     # frame k as fp32 planar: im0 of pair (k, k+1)
 
-            upload(0, first)
-            main.wait_event(slots[0]["up"])
-            ops.u8_to_planar(slots[0]["d_in"], plan.im1, H, W, Hp, Wp, top, left, isBGR)      # becomes im0 of the first pair
-            if reuse:
-                plan.encode_only(use_graph=self.use_cuda_graph)      # features of the first frame; later frames are encoded by the pair step
-            slots[0]["done"].record(main)
-            prev_frame, pending, k = first, None, 0
-            for nxt in it:
-                nxt = np.ascontiguousarray(nxt)
-                if nxt.shape != first.shape or nxt.dtype != np.uint8:
-                    raise RuntimeError(f"frame {k + 1} has shape {nxt.shape}, expected {first.shape}")
-                slot = (k + 1) & 1
-                side.wait_event(slots[slot]["done"])     # the pair that used this slot's device buffers has been computed
-                upload(slot, nxt)
-                s = slots[slot]
-                main.wait_event(s["up"])
-                plan.im0.copy_(plan.im1)                 # frame k was im1 of the previous pair
-                ops.u8_to_planar(s["d_in"], plan.im1, H, W, Hp, Wp, top, left, isBGR)
-                main.wait_event(s["down"])               # this slot's previous result has left d_out
-                out = plan.run_inplace(use_graph=self.use_cuda_graph)
-                ops.planar_to_u8(out["I_t"], s["d_out"], H, W, Hp, Wp, top, left, isBGR)
-                s["done"].record(main)
-                with torch.cuda.stream(side):
-                    side.wait_event(s["done"])
-                    s["h_out"].copy_(s["d_out"], non_blocking=True)
-                    s["down"].record(side)
-                if pending is not None:                  # hand out the previous pair while this one runs
-                    ps, pf = pending
-                    ps["down"].synchronize()
-                    if include_inputs:
-                        yield pf
-                    yield ps["h_out"].numpy().copy()
-                pending = (s, prev_frame)
-                prev_frame = nxt
-                k += 1
-            if pending is not None:
+        def upload(slot, frame):                 # host -> pinned -> device, on the copy stream
+            s = slots[slot]
+            s["up"].synchronize()                # the previous upload from this pinned buffer has finished
+            s["h_in"].numpy()[...] = frame
+            with torch.cuda.stream(side):
+                s["d_in"].copy_(s["h_in"], non_blocking=True)
+                s["up"].record(side)
+
+        upload(0, first)
+        main.wait_event(slots[0]["up"])
+        ops.u8_to_planar(slots[0]["d_in"], plan.im1, H, W, Hp, Wp, top, left, isBGR)      # becomes im0 of the first pair
+        prev_planar.copy_(plan.im1)
+        if reuse:
+            plan.encode_only(use_graph=self.use_cuda_graph)      # features of the first frame; later frames are encoded by the pair step
+        slots[0]["done"].record(main)
+        prev_frame, pending, k = first, None, 0
+        for nxt in it:
+            nxt = np.ascontiguousarray(nxt)
+            if nxt.shape != first.shape or nxt.dtype != np.uint8:
+                raise RuntimeError(f"frame {k + 1} has shape {nxt.shape}, expected {first.shape}")
+            if plan is not rt._plans.get(plan.key) and not reuse:
+                plan = rt.plan(1, Hp, Wp, bool(self.global_motion))      # the shared plan was evicted / re-packed between two yields
+            slot = (k + 1) & 1
+            side.wait_event(slots[slot]["done"])     # the pair that used this slot's device buffers has been computed
+            upload(slot, nxt)
+            s = slots[slot]
+            main.wait_event(s["up"])
+            plan.im0.copy_(prev_planar)              # frame k was im1 of the previous pair
+            ops.u8_to_planar(s["d_in"], plan.im1, H, W, Hp, Wp, top, left, isBGR)
+            prev_planar.copy_(plan.im1)
+            main.wait_event(s["down"])               # this slot's previous result has left d_out
+            out = plan.run_inplace(use_graph=self.use_cuda_graph)
+            ops.planar_to_u8(out["I_t"], s["d_out"], H, W, Hp, Wp, top, left, isBGR)
+            s["done"].record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(s["done"])
+                s["h_out"].copy_(s["d_out"], non_blocking=True)
+                s["down"].record(side)
+            if pending is not None:                  # hand out the previous pair while this one runs
                 ps, pf = pending
                 ps["down"].synchronize()
                 if include_inputs:
                     yield pf
                 yield ps["h_out"].numpy().copy()
+            pending = (s, prev_frame)
+            prev_frame = nxt
+            k += 1
+        if pending is not None:
+            ps, pf = pending
+            ps["down"].synchronize()
             if include_inputs:
-                yield prev_frame
-            main.synchronize()
+                yield pf
+            yield ps["h_out"].numpy().copy()
+        if include_inputs:
+            yield prev_frame
+        main.synchronize()
+
+    def invalidate(self):
+        """Drop the packed weights / plans / CUDA graphs (needed only after ``p.data`` edits that bypass autograd's version counter)."""
+        self._runtime.invalidate()
 
     def forward_global_ensemble(self, im0, im1):
         """forward with the multi-scale global-motion ensemble (network_base.py:564-712): the global flows are estimated at

@@ -280,7 +280,9 @@ int atmvfi_warp_blend_p2p(const float* im0, const float* im1, const float* head,
 
 /* One exchange site: copy every piece, then store *epoch (release, system scope) into each signal flag (peer memory),
  * then wait until each wait flag (local memory, raised by a peer's call of this function) has reached *epoch.
- * `counter` is a zero-initialised word private to the site.  A wait that lasts > 4 s sets *error_word and returns. */
+ * `counter` is a zero-initialised word private to the site.  A wait that lasts longer than the time-out (below) sets the
+ * sticky *error_word and returns; while *error_word is non-zero every exchange / step-begin launch of this rank returns
+ * at once without pushing or signalling (the step is poisoned; the host must look at the word - SlabSession.check). */
 int atmvfi_p2p_exchange(const atmvfi_p2p_piece* pieces, int npieces, uint32_t* const* signal_flags, int nsignal,
                         const uint32_t* const* wait_flags, int nwait, const uint32_t* epoch, uint32_t* counter,
                         uint32_t* error_word, void* stream);
@@ -288,6 +290,10 @@ int atmvfi_p2p_exchange(const atmvfi_p2p_piece* pieces, int npieces, uint32_t* c
  * have finished the previous step, so their halo rows may be overwritten). */
 int atmvfi_p2p_step_begin(uint32_t* epoch, uint32_t* const* signal_flags, int nsignal, const uint32_t* const* wait_flags,
                           int nwait, uint32_t* error_word, void* stream);
+
+/* Time-out of every flag wait, in milliseconds (default 4000, or ATMVFI_P2P_TIMEOUT_MS); applies to launches issued - and
+ * CUDA graphs captured - after the call. */
+int atmvfi_p2p_set_timeout_ms(int ms);
 
 #ifdef __cplusplus
 }

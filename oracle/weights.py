@@ -174,8 +174,10 @@ def make_weights(kind: str, variant: str = "default", seed: int = 0, local_ws: i
                 P[name] = (torch.rand(shape, generator=torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)) * 2 - 1) / math.sqrt(fan_in)
         else:                                                 # PReLU slope
             P[name] = torch.full(shape, 0.25)
-    if variant in ("stress", "ensemble"):
+    if variant in ("stress", "ensemble", "varflow"):
         _apply_stress(P, kind, seed)
+    if variant == "varflow":
+        _apply_varflow(P, kind)
     if variant == "ensemble":
         # Scale-selection probe for forward_global_ensemble (network_base.py:564-615): the global head emits a constant flow of
         # +-0.125 grid pixels (plus a small data term), i.e. +-2 / +-4 / +-8 full-resolution pixels when estimated at input
@@ -214,6 +216,35 @@ def _apply_stress(P: Dict[str, torch.Tensor], kind: str, seed: int) -> None:
     for n in ("upsample_pyramid.0.0.0.weight", "upsample_pyramid.1.1.0.weight", "upsample_pyramid.2.1.0.weight"):
         P[n][-5:] *= inv                                       # ConvTranspose layout [Cin, Cout, 2, 2]
     P["proj.0.weight"][:, d["d3"] : d["d3"] + 5] *= inv.view(1, 5, 1, 1)
+
+
+def _apply_varflow(P: Dict[str, torch.Tensor], kind: str) -> None:
+    """On top of the stress set: the flow channels of the four motion producers get their WEIGHT rows scaled by a further
+    x10 / x10 / x15 / x20 (biases untouched, consumers compensated), so the flows are driven by the features instead of by the
+    biases.  Measured with the oracle (Base, 256x448 texture frames): final flows with a spatial std of 2-3.5 px and a range of
+    45 px per component, means of -49 / +10 px (warps cross the frame border over a 50-pixel margin); the plain stress set gives
+    flows that are constant to 0.15 px.  Rounding noise is amplified by the same gains: structural checks only."""
+    d = dims(kind)
+    pairs = (("local_motion_mlp.2", 10.0, "upsample_pyramid.0.0.0.weight"), ("upsample_pyramid.0.2", 10.0, "upsample_pyramid.1.1.0.weight"),
+             ("upsample_pyramid.1.3", 15.0, "upsample_pyramid.2.1.0.weight"), ("upsample_pyramid.2.3", 20.0, "proj.0.weight"))
+    for prod, r, cons in pairs:
+        P[prod + ".weight"][-5:-1] *= r
+        if cons == "proj.0.weight":
+            P[cons][:, d["d3"] : d["d3"] + 4] /= r
+        else:
+            P[cons][-5:-1] /= r
+
+
+def synthetic_triplet(batch: int, h: int, w: int, seed: int = 1234):
+    """(frame 0, ground-truth middle frame, frame 1) of a smooth texture with fine detail that moves by (-2 rows, +3 columns) per
+    half step: a clip with a KNOWN middle frame, for PSNR-versus-ground-truth comparisons."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(batch, 3, h // 8 + 3, w // 8 + 3, generator=g)
+    big = torch.nn.functional.interpolate(low, size=(h + 16, w + 16), mode="bicubic", align_corners=True).clamp(0, 1)
+    fine = 0.15 * (torch.rand(batch, 3, h + 16, w + 16, generator=g) - 0.5)
+    big = (big + fine).clamp(0, 1)
+    crop = lambda dy, dx: big[:, :, dy : dy + h, dx : dx + w].contiguous()
+    return crop(8, 4), crop(6, 7), crop(4, 10)
 
 
 def synthetic_frames(batch: int, h: int, w: int, seed: int = 1234, kind: str = "noise"):

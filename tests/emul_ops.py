@@ -104,12 +104,26 @@ def _from_heads(flat, R, C, heads):
     return torch.cat([q, k, v], 1)
 
 
+def round_tf32(t):
+    """fp32 -> nearest TF32 (ties away from zero): what the producers' cvt.rna.tf32.f32 and pack.pack_tc do."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def trunc_tf32(t):
+    """fp32 -> TF32 by dropping the low 13 mantissa bits: what tcgen05 kind::tf32 does to its operands."""
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
 class EmulOps:
-    def __init__(self, qkv_head_major: bool = False):
+    def __init__(self, qkv_head_major: bool = False, tf32: bool = False, round_outputs: bool = False):
+        """``tf32``: GEMM-shaped layers with >= 16 input channels see their activations truncated and their weights rounded to
+        TF32 (products accumulated exactly), like the tcgen05 path; ``round_outputs``: stored feature maps are rounded to TF32."""
         self.recording: Optional[List] = None
         self.launches = 0
         self.qkv_head_major = qkv_head_major
         self.qkv_head_major_min_hd = 0          # tests exercise the layout on every model size
+        self.tf32, self.round_outputs = tf32, round_outputs
 
     def new_map(self, B, H, W, C, zero=False):
         return Map(torch.full((B, H, W, round_up(C, 4)), float("nan") if round_up(C, 4) == C and not zero else 0.0), 0, C)
@@ -150,8 +164,13 @@ class EmulOps:
         wk = w.w32[:, :n_tot]
         assert wk.shape[0] == k * k * ci
 
+        tc = self.tf32 and ci >= 16
+        rnd = (lambda t: round_tf32(t)) if (self.round_outputs and self.tf32) else (lambda t: t)
+
         def run():
             x = torch.cat([s.view() for s in srcs], -1)                       # [B,H,W,Ci]
+            if tc:          # operands as the tensor core sees them; fp64 accumulation stands in for "exact"
+                return run_tc(trunc_tf32(x).double(), round_tf32(wk).double())
             if w.shuffle:
                 wt = wk.reshape(ci, 2, 2, w.Cout).permute(0, 3, 1, 2)          # [Ci,Co,2,2]
                 y = F.conv_transpose2d(x.permute(0, 3, 1, 2), wt, w.bias, stride=2).permute(0, 2, 3, 1)
@@ -188,6 +207,33 @@ class EmulOps:
             _put(out.view(), y, orow)
             if out2 is not None:
                 _put(out2.view(), y2, orow)
+
+        def run_tc(x, wk):
+            """Same contract on TF32 operands: conv in fp64, epilogue (bias, residual, PReLU) in the kernel's order, optional
+            TF32 rounding of what is stored.  Plain / transposed / window-reverse / dual-output / head-major layouts."""
+            assert rows is None
+            bias = None if w.bias is None else w.bias.double()
+            if w.shuffle:
+                wt = wk.reshape(ci, 2, 2, w.Cout).permute(0, 3, 1, 2)
+                y = F.conv_transpose2d(x.permute(0, 3, 1, 2), wt, bias, stride=2).permute(0, 2, 3, 1)
+            else:
+                wt = wk.reshape(k, k, ci, w.Cout).permute(3, 2, 0, 1)
+                y = F.conv2d(x.permute(0, 3, 1, 2), wt, bias, stride=stride, padding=dil * (k - 1) // 2, dilation=dil).permute(0, 2, 3, 1)
+            if residual is not None:
+                y = y + residual.view().reshape(y.shape).double()
+            if act and w.prelu is not None:
+                y = torch.where(y > 0, y, y * w.prelu.double())
+            y2 = rnd(torch.where(y > 0, y, y * prelu2.double()).float()) if out2 is not None else None
+            y = rnd(y.float())
+            if win is not None:
+                out.view().copy_(_win_reverse(y.reshape(win.rows, -1), win).reshape(out.view().shape))
+                return
+            if qkv_heads:
+                out.t.reshape(-1).copy_(_to_heads(y.reshape(-1, w.Cout), qkv_heads))
+                return
+            _put(out.view(), y, None)
+            if out2 is not None:
+                _put(out2.view(), y2, None)
 
         self._emit(run)
 
