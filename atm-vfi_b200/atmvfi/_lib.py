@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libatmvfi_b200.so")
 
 MAX_SRC = 4
-FP32, TF32 = 0, 1
+FP32, TF32, TF32X3 = 0, 1, 2
 OUT_PIXEL, OUT_SHUFFLE2, OUT_WINDOW_REV, OUT_QKV_HEADS = 0, 1, 2, 3
 
 

@@ -109,6 +109,7 @@ class PackedGemm:
     bias: Optional[torch.Tensor]
     prelu: Optional[torch.Tensor]
     wtc: Optional[torch.Tensor] = None   # tcgen05 layout, filled by pack.py when the TF32 path is enabled
+    wtc3: Optional[torch.Tensor] = None  # 3xTF32 layout (hi | lo chunk pairs)
     tc_meta: Optional[dict] = None
 
 
@@ -262,15 +263,22 @@ class CudaOps:
         d.row_begin, d.row_end = _yy(rows)
         assert d.row_end <= Hout
         prec = self.precision if precision is None else precision
-        if prec == _lib.TF32 and not self._tc_eligible(srcs, w, out, out2):
+        if prec in (_lib.TF32, _lib.TF32X3) and not self._tc_eligible(srcs, w, out, out2):
             prec = _lib.FP32
         d.precision = prec
         planbuf = None
-        if prec == _lib.TF32:
-            if w.wtc is None:
-                from .pack import pack_tc
-                w.wtc = pack_tc(w)
-            d.weight, d.ldw = w.wtc.data_ptr(), w.wtc.shape[1]
+        if prec in (_lib.TF32, _lib.TF32X3):
+            if prec == _lib.TF32:
+                if w.wtc is None:
+                    from .pack import pack_tc
+                    w.wtc = pack_tc(w)
+                wt = w.wtc
+            else:
+                if w.wtc3 is None:
+                    from .pack import pack_tc_x3
+                    w.wtc3 = pack_tc_x3(w)
+                wt = w.wtc3
+            d.weight, d.ldw = wt.data_ptr(), wt.shape[1]
             nbytes = self.lib.atmvfi_gemm_conv_plan_bytes()
             planbuf = C.create_string_buffer(nbytes + 64)
             addr = (C.addressof(planbuf) + 63) & ~63

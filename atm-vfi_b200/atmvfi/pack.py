@@ -98,7 +98,11 @@ def pack_tc(w: PackedGemm) -> torch.Tensor:
     """[K, ldw] fp32 GEMM operand -> [N_pad][K_tc] K-major: every (tap, source) block is padded to whole
     32-channel chunks (TMA zero-fills the matching activation channels), ConvTranspose column blocks are
     padded to a multiple of 32 columns; values pre-rounded to TF32."""
-    L = tc_layout(w.split, w.ksize, w.Cout, w.shuffle)
+    return round_tf32(_tc_matrix(w, tc_layout(w.split, w.ksize, w.Cout, w.shuffle)))
+
+
+def _tc_matrix(w: PackedGemm, L: dict) -> torch.Tensor:
+    """The un-rounded [N_pad][K_tc] matrix of pack_tc."""
     taps, ctot = w.ksize * w.ksize, sum(w.split)
     n_true = 4 * w.Cout if w.shuffle else w.Cout
     src = w.w32[:, :n_true].reshape(taps, ctot, n_true)
@@ -116,4 +120,16 @@ def pack_tc(w: PackedGemm) -> torch.Tensor:
             out[q * L["cq_pad"] : q * L["cq_pad"] + w.Cout] = kmat[:, q * w.Cout : (q + 1) * w.Cout].t()
     else:
         out[: w.Cout] = kmat.t()
-    return round_tf32(out)
+    return out
+
+
+def pack_tc_x3(w: PackedGemm) -> torch.Tensor:
+    """3xTF32 operand: the pack_tc layout with every 32-column K chunk stored twice - hi = tf32(w) then lo = tf32(w - hi) -
+    so [N_pad][2 * K_tc]; chunk kb occupies columns [64 kb, 64 kb + 32) (hi) and [64 kb + 32, 64 kb + 64) (lo)."""
+    L = tc_layout(w.split, w.ksize, w.Cout, w.shuffle)
+    full = _tc_matrix(w, L)
+    hi = round_tf32(full)
+    lo = round_tf32(full - hi)
+    nk = L["ktc"] // TC_CHUNK
+    out = torch.stack([hi.reshape(L["n_pad"], nk, TC_CHUNK), lo.reshape(L["n_pad"], nk, TC_CHUNK)], 2)
+    return out.reshape(L["n_pad"], 2 * L["ktc"]).contiguous()

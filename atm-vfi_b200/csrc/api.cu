@@ -62,7 +62,7 @@ int atmvfi_gemm_conv(const atmvfi_gemm_conv_desc* d, void* stream) {
   ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_SHUFFLE2 || (d->ksize == 1 && d->stride == 1), "gemm_conv: SHUFFLE2 needs ksize=1, stride=1");
   ATMVFI_REQUIRE(!d->out2 || d->prelu2, "gemm_conv: out2 needs prelu2 slopes");
   if (d->precision == ATMVFI_FP32) return atmvfi_gemm_conv_simt(d, (cudaStream_t)stream);
-  if (d->precision == ATMVFI_TF32) return atmvfi_gemm_conv_tc(d, (cudaStream_t)stream);
+  if (d->precision == ATMVFI_TF32 || d->precision == ATMVFI_TF32X3) return atmvfi_gemm_conv_tc(d, (cudaStream_t)stream);
   atmvfi_set_error("gemm_conv: unknown precision %d", d->precision);
   return 2;
 }

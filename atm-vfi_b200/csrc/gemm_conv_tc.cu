@@ -54,9 +54,10 @@ struct TcPlan {                                 // host-side, produced by atmvfi
   int pair;                                     // 1: two vertically stacked 128-pixel tiles per CTA step (N <= 128)
   int cluster;                                  // CTAs per cluster (B multicast), 1 or 2
   int row0, row1;                               // row window of the GEMM grid: tiles cover output rows [row0, row1)
+  int x3;                                       // 1: 3xTF32 (fp32-tolerance) datapath, weights packed as hi | lo chunk pairs
   uint32_t magic;
 };
-constexpr uint32_t kPlanMagic = 0xA7B20003u;
+constexpr uint32_t kPlanMagic = 0xA7B20004u;
 
 struct TcParams {
   CUtensorMap mapA[ATMVFI_MAX_SRC];
@@ -69,7 +70,8 @@ struct TcParams {
   int block_n, n_tiles, cq_pad;
   int halo, a_bytes, sum_chunks, m_tiles;
   int th_super;                                 // rows of output covered by one CTA tile (TH, or 2*TH in pair mode)
-  int a_slots, a_slot_bytes, b_slots, b_slot_bytes;   // smem rings: A at offset 0, B right after
+  int a_slots, a_slot_bytes, b_slots, b_slot_bytes;   // smem rings: A at offset 0, (3xTF32: the A-lo ring,) B right after
+  int a_lo_off, b_off;                          // byte offsets of the A-lo ring (3xTF32 only) and of the B ring
   int bar_off;                                  // barriers behind the data rings, epilogue staging 512 B further
   int total_ctiles;                             // cluster tiles: ceil(m_tiles / cluster) * n_tiles
   int row0, row1;                               // output rows [row0, row1) of every image (row window)
@@ -277,8 +279,15 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
 // kEpi: 0 = generic epilogue, 1 = plain layers (see "fast epilogue" below), 2 = generic with the residual rows prefetched,
 // 3 = the fast epilogue writing the head-major q | k | v^T layout (its own instantiation: carrying that code in variant 1 cost
 // every plain layer ~5 %)
-template <int kHalo, int kCS, bool kPair, int kEpi, int kEW = 8>
+//
+// kX3 - "3xTF32": fp32-tolerance results on the tensor cores.  Every product a*b is issued as three kind::tf32 MMAs into the same
+// TMEM accumulator: a_hi*b_lo + a_lo*b_hi + a_hi*b_hi with x_hi = tf32(x), x_lo = tf32(x - x_hi).  Weights arrive split from the
+// host (pack_tc_x3: each 32-channel chunk is a hi row block followed by a lo row block).  Activations stay plain fp32 in HBM: the
+// tensor core itself truncates the raw box to a_hi, and warps 2-3 ("converters") write a_lo = rna_tf32(a - trunc(a)) for every
+// landed box into a second shared-memory ring with the same swizzled layout before the MMA warp may touch the slot.
+template <int kHalo, int kCS, bool kPair, int kEpi, int kEW = 8, bool kX3 = false>
 __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
+  static_assert(!kX3 || (!kPair && kHalo != 2 && kEW == 8), "3xTF32 supports the plain and halo box modes with 8 epilogue warps");
   constexpr bool kFastEpi = kEpi == 1 || kEpi == 3;
   constexpr bool kQkv = kEpi == 3;
   constexpr bool kResHoist = kEpi == 2;
@@ -293,7 +302,8 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
   uint64_t* emptyB = fullB + kMaxBSlots;                   // [kMaxBSlots]
   uint64_t* tfull = emptyB + kMaxBSlots;                   // [2]
   uint64_t* tempty = tfull + 2;                            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 3);   // tempty[2] is a scratch barrier for experiments
+  uint64_t* convA = tempty + 3;                            // [kMaxASlots] 3xTF32: a_lo of the slot is written (both CTAs of a pair)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(convA + kMaxASlots);   // tempty[2] is a scratch barrier for experiments
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int cs = kCS;
@@ -302,7 +312,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
   const uint16_t mc_mask = (uint16_t)((1u << cs) - 1);
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kMaxASlots; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < kMaxASlots; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); mbar_init(&convA[s], 2 * cs); }
     for (int s = 0; s < kMaxBSlots; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpiWarps * cs); }   // leader's tempty collects both CTAs' epilogues
     mbar_init(&tempty[2], 1);
@@ -331,7 +341,8 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
   const int b_rows = p.block_n / cs;                         // rows of the B tile this CTA fetches
   const int kASlots = p.a_slots, kBSlots = p.b_slots;
   uint8_t* const ringA = smem;
-  uint8_t* const ringB = smem + p.a_slots * p.a_slot_bytes;
+  uint8_t* const ringAlo = smem + p.a_lo_off;
+  uint8_t* const ringB = smem + p.b_off;
 
   if (warp == 0) {
     // ======================================= TMA producer =======================================
@@ -360,25 +371,35 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
                 }
                 mbar_wait(&emptyA[as_], aph_ ^ 1);
                 if (elect_one()) {
-                  if (rank == 0) mbar_expect_tx(&fullA[as_], p.a_bytes * cs);          // leader arms for both CTAs' boxes
-                  if (cs == 2) tma_load_4d_2cta(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
-                  else tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                  if (kX3) {          // every CTA's box completes on its OWN barrier: its converter warps wait there
+                    mbar_expect_tx(&fullA[as_], p.a_bytes);
+                    tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                  } else {
+                    if (rank == 0) mbar_expect_tx(&fullA[as_], p.a_bytes * cs);          // leader arms for both CTAs' boxes
+                    if (cs == 2) tma_load_4d_2cta(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                    else tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                  }
                 }
                 __syncwarp();
                 for (int st = 0; st < steps_per_group; ++st) {
                   const int tap = kHalo == 2 ? st : (kHalo == 1 ? st * 3 + kx_i : tap_o);
                   const int kb = tap * p.sum_chunks + cbase + c;
-                  mbar_wait(&emptyB[bs_], bph_ ^ 1);
-                  if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&fullB[bs_], p.block_n * 128);         // both halves of the weight tile
-                    uint8_t* dst = ringB + bs_ * p.b_slot_bytes;
-                    if (cs == 2)      // this CTA holds columns [rank*N/2, +N/2) of the weight tile
-                      tma_load_2d_2cta(dst, &p.mapB, &fullB[bs_], kb * kChunk, n_tile * p.block_n + rank * b_rows);
-                    else
-                      tma_load_2d(dst, &p.mapB, &fullB[bs_], kb * kChunk, n_tile * p.block_n);
+                  constexpr int kParts = kX3 ? 2 : 1;          // 3xTF32: the hi and the lo tile of the chunk, one ring slot each
+#pragma unroll
+                  for (int part = 0; part < kParts; ++part) {
+                    mbar_wait(&emptyB[bs_], bph_ ^ 1);
+                    if (elect_one()) {
+                      if (rank == 0) mbar_expect_tx(&fullB[bs_], p.block_n * 128);         // both halves of the weight tile
+                      uint8_t* dst = ringB + bs_ * p.b_slot_bytes;
+                      const int kcol = (kb * kParts + part) * kChunk;
+                      if (cs == 2)      // this CTA holds columns [rank*N/2, +N/2) of the weight tile
+                        tma_load_2d_2cta(dst, &p.mapB, &fullB[bs_], kcol, n_tile * p.block_n + rank * b_rows);
+                      else
+                        tma_load_2d(dst, &p.mapB, &fullB[bs_], kcol, n_tile * p.block_n);
+                    }
+                    __syncwarp();
+                    if (++bs_ == kBSlots) { bs_ = 0; bph_ ^= 1; }
                   }
-                  __syncwarp();
-                  if (++bs_ == kBSlots) { bs_ = 0; bph_ ^= 1; }
                 }
                 if (++as_ == kASlots) { as_ = 0; aph_ ^= 1; }
               }
@@ -386,6 +407,112 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
             cbase += p.chunks[s];
           }
         }
+      }
+    }
+  } else if (warp == 1 && kX3) {
+    // ======================================= MMA issuer, 3xTF32 ==================================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_tf32(p.block_n, cs == 2 ? 256 : kBlockM);
+      const int groups = (kHalo == 1 ? 3 : p.ntaps) * p.sum_chunks;
+      const uint32_t a_step = kHalo == 1 ? (uint32_t)(p.TW * 128) >> 4 : 0;
+      const uint32_t lo_delta = (uint32_t)p.a_lo_off >> 4;                        // descriptor distance raw box -> its a_lo copy
+      uint32_t tcount = 0;
+      int as_ = 0, bs_ = 0;
+      uint32_t aph_ = 0, bph_ = 0;
+      for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
+        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kMaxBlockN;
+        uint32_t first = 1;
+        int g = 0;
+        const int outer = kHalo ? 1 : p.ntaps;
+        constexpr int inner = kHalo == 1 ? 3 : 1;
+        for (int tap_o = 0; tap_o < outer; ++tap_o)
+        for (int s = 0; s < p.nsrc; ++s)
+        for (int c = 0; c < p.chunks[s]; ++c) {
+          const int nmma = (c == p.chunks[s] - 1) ? p.last_mmas[s] : 4;
+        for (int kx_i = 0; kx_i < inner; ++kx_i, ++g) {
+          mbar_wait(&convA[as_], aph_);                                           // raw boxes landed AND a_lo written, in both CTAs
+          tc_fence_after();
+          const uint64_t adesc0 = make_smem_desc(smem_u32(ringA + as_ * p.a_slot_bytes));
+          for (int st = 0; st < steps_per_group; ++st) {
+            int bs_lo = bs_ + 1;
+            uint32_t bph_lo = bph_;
+            if (bs_lo == kBSlots) { bs_lo = 0; bph_lo ^= 1; }
+            mbar_wait(&fullB[bs_], bph_);
+            mbar_wait(&fullB[bs_lo], bph_lo);
+            tc_fence_after();
+            const bool last_step = st == steps_per_group - 1;
+            const bool last_of_tile = last_step && g == groups - 1;
+            const uint64_t a_hi = adesc0 + (uint64_t)(st * a_step), a_lo = a_hi + lo_delta;
+            const uint64_t b_hi = make_smem_desc(smem_u32(ringB + bs_ * p.b_slot_bytes)), b_lo = make_smem_desc(smem_u32(ringB + bs_lo * p.b_slot_bytes));
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < nmma) {
+                  const uint64_t o = (uint64_t)(j * 2);
+                  if (cs == 2) {
+                    tc_mma_tf32_2cta(tmem_d, a_hi + o, b_lo + o, idesc, (first && j == 0) ? 0u : 1u);     // small terms first
+                    tc_mma_tf32_2cta(tmem_d, a_lo + o, b_hi + o, idesc, 1u);
+                    tc_mma_tf32_2cta(tmem_d, a_hi + o, b_hi + o, idesc, 1u);
+                  } else {
+                    tc_mma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, (first && j == 0) ? 0u : 1u);
+                    tc_mma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, 1u);
+                    tc_mma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, 1u);
+                  }
+                }
+              if (cs == 2) {
+                tc_commit_2cta(&emptyB[bs_]);
+                tc_commit_2cta(&emptyB[bs_lo]);
+                if (last_step) tc_commit_2cta(&emptyA[as_]);
+                if (last_of_tile) tc_commit_2cta(&tfull[as]);
+              } else {
+                tc_commit(&emptyB[bs_]);
+                tc_commit(&emptyB[bs_lo]);
+                if (last_step) tc_commit(&emptyA[as_]);
+                if (last_of_tile) tc_commit(&tfull[as]);
+              }
+            }
+            __syncwarp();
+            first = 0;
+            bs_ = bs_lo + 1; bph_ = bph_lo;
+            if (bs_ == kBSlots) { bs_ = 0; bph_ ^= 1; }
+          }
+          if (++as_ == kASlots) { as_ = 0; aph_ ^= 1; }
+        }
+        }
+      }
+    }
+  } else if (kX3 && (warp == 2 || warp == 3)) {
+    // ======================================= a_lo converters (3xTF32) ===========================
+    // Two warps, half a box each: a_lo = rna_tf32(a - trunc_tf32(a)), written at the same offset of the a_lo ring (identical
+    // swizzle), published to the async proxy, then one arrival per warp on the LEADER's convA barrier.
+    const int half = warp - 2;
+    const int groups = (kHalo == 1 ? 3 : p.ntaps) * p.sum_chunks;
+    const int vec_per_half = p.a_bytes >> 5;                                      // 16-byte vectors in half a box
+    int as_ = 0;
+    uint32_t aph_ = 0;
+    for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters) {
+      for (int g = 0; g < groups; ++g) {
+        mbar_wait(&fullA[as_], aph_);
+        const float4* src = reinterpret_cast<const float4*>(ringA + as_ * p.a_slot_bytes) + half * vec_per_half;
+        float4* dst = reinterpret_cast<float4*>(ringAlo + as_ * p.a_slot_bytes) + half * vec_per_half;
+        for (int v = lane; v < vec_per_half; v += 32) {
+          const float4 a = src[v];
+          float4 lo;
+          lo.x = round_tf32_if(a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), true);
+          lo.y = round_tf32_if(a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u), true);
+          lo.z = round_tf32_if(a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u), true);
+          lo.w = round_tf32_if(a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u), true);
+          dst[v] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");              // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) {
+          if (cs == 2) mbar_arrive_leader(&convA[as_]); else mbar_arrive(&convA[as_]);
+        }
+        if (++as_ == kASlots) { as_ = 0; aph_ ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -729,7 +856,8 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   // 3x3 stride-1 layers fetch activation boxes with a vertical halo and reuse them for the 3 vertical taps
   static int halo_ok = -1;
   if (halo_ok < 0) { const char* ev = getenv("ATMVFI_TC_HALO"); halo_ok = ev ? atoi(ev) : 1; }
-  pl->halo = (halo_ok && d->ksize == 3 && d->stride == 1 && d->dil == 1) ? halo_ok : 0;   // 1: 3 boxes / chunk, 2: one full-halo box
+  pl->x3 = d->precision == ATMVFI_TF32X3 ? 1 : 0;
+  pl->halo = (halo_ok && d->ksize == 3 && d->stride == 1 && d->dil == 1) ? (pl->x3 ? 1 : halo_ok) : 0;   // 1: 3 boxes / chunk, 2: one full-halo box
   // pixel tile TW x TH = 128: least padding waste, then squarest.  Element-strided boxes are capped at 256
   // per dimension; halo boxes need TW % 8 == 0 (vertical taps = whole swizzle atoms) and (TH+2)*TW <= 192 rows.
   int best_tw = 0;
@@ -756,7 +884,7 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     // activation box with a common halo -> weight traffic and issue overhead per pixel halve
     static int pair_ok = -1;
     if (pair_ok < 0) { const char* ev = getenv("ATMVFI_TC_PAIR"); pair_ok = ev ? atoi(ev) : 1; }
-    pl->pair = (pair_ok && pl->halo == 1 && pl->block_n <= 128 && Hwin > pl->TH && (2 * pl->TH + 2) * pl->TW * 128 <= 40 * 1024) ? 1 : 0;
+    pl->pair = (pair_ok && !pl->x3 && pl->halo == 1 && pl->block_n <= 128 && Hwin > pl->TH && (2 * pl->TH + 2) * pl->TW * 128 <= 40 * 1024) ? 1 : 0;
   }
   pl->tiles_x = cdiv(d->Wout, pl->TW);
   pl->tiles_y = cdiv(Hwin, pl->TH * (pl->pair ? 2 : 1));
@@ -777,6 +905,7 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     ktc += pl->chunks[s] * kChunk;
   }
   ktc *= pl->ntaps;
+  if (pl->x3) ktc *= 2;                           // every 32-channel chunk is stored as a hi block followed by a lo block
   ATMVFI_REQUIRE(d->ldw == ktc, "gemm_conv(tf32): packed weight row length %d != expected %d", d->ldw, ktc);
 
   for (int s = 0; s < d->nsrc; ++s) {
@@ -841,9 +970,21 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
        {gemm_conv_tc_kernel<1, 1, true, 0, 16>, gemm_conv_tc_kernel<1, 2, true, 0, 16>}},
       {{gemm_conv_tc_kernel<0, 1, false, 1, 16>, gemm_conv_tc_kernel<0, 2, false, 1, 16>},
        {gemm_conv_tc_kernel<1, 1, true, 1, 16>, gemm_conv_tc_kernel<1, 2, true, 1, 16>}}};
+  // 3xTF32: [epilogue kind 0 generic / 1 fast / 2 residual prefetch][halo][cluster]
+  static const KernelFn x3_table[3][2][2] = {
+      {{gemm_conv_tc_kernel<0, 1, false, 0, 8, true>, gemm_conv_tc_kernel<0, 2, false, 0, 8, true>},
+       {gemm_conv_tc_kernel<1, 1, false, 0, 8, true>, gemm_conv_tc_kernel<1, 2, false, 0, 8, true>}},
+      {{gemm_conv_tc_kernel<0, 1, false, 1, 8, true>, gemm_conv_tc_kernel<0, 2, false, 1, 8, true>},
+       {gemm_conv_tc_kernel<1, 1, false, 1, 8, true>, gemm_conv_tc_kernel<1, 2, false, 1, 8, true>}},
+      {{gemm_conv_tc_kernel<0, 1, false, 2, 8, true>, gemm_conv_tc_kernel<0, 2, false, 2, 8, true>},
+       {gemm_conv_tc_kernel<0, 1, false, 2, 8, true>, gemm_conv_tc_kernel<0, 2, false, 2, 8, true>}}};
+  ATMVFI_REQUIRE(!pl->x3 || d->out_mode != ATMVFI_OUT_QKV_HEADS, "gemm_conv(3xtf32): the head-major q|k|v layout belongs to the tf32 attention path");
   KernelFn kern = table[fast][pl->pair ? 3 : pl->halo][pl->cluster - 1];
   int epi_warps = 8;
-  if (d->residual && !pl->halo && !pl->pair && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % 4 == 0) {
+  if (pl->x3) {
+    const bool res_hoist = d->residual && !pl->halo && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % 4 == 0;
+    kern = x3_table[res_hoist ? 2 : fast][pl->halo][pl->cluster - 1];
+  } else if (d->residual && !pl->halo && !pl->pair && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % 4 == 0) {
     kern = res_table[pl->cluster - 1];
   } else if (pl->pair || !pl->halo) {
     static int epi16 = -1;                    // ATMVFI_TC_EPI16: 0 never, 1 (default) short-K layers, 2 every eligible layer
@@ -868,10 +1009,11 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   if (!sms_of_device[dev]) {
     int n_sm = 0;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 30; ++i) {
-      KernelFn f = i < 16 ? table[i / 8][(i / 2) % 4][i % 2]
+    for (int i = 0; i < 42; ++i) {
+      KernelFn f = i >= 30 ? x3_table[(i - 30) / 4][((i - 30) / 2) % 2][i % 2]
+                 : i < 16 ? table[i / 8][(i / 2) % 4][i % 2]
                           : (i < 18 ? res_table[i - 16] : (i < 26 ? table16[(i - 18) / 4][((i - 18) / 2) % 2][i % 2] : qkv_table[(i - 26) / 2][i % 2]));
-      const int bytes = (i < 18 || i == 26 || i == 27) ? smem_bytes(8) : smem_bytes(16);
+      const int bytes = (i < 18 || i == 26 || i == 27 || i >= 30) ? smem_bytes(8) : smem_bytes(16);
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
       if (e != cudaSuccess) {
         atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", bytes, cudaGetErrorString(e));
@@ -902,9 +1044,12 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   const int data_bytes = epi_warps == 16 ? kDataBytes16 : kDataBytes;
   p.bar_off = data_bytes;
   p.a_slots = pl->halo ? (epi_warps == 16 ? 2 : 3) : 4;     // 16-warp layers have short K loops: two (large, paired) boxes suffice
+  if (pl->x3) p.a_slots = pl->halo ? 2 : 3;                 // every slot exists twice (raw box + its a_lo copy)
   p.a_slot_bytes = (p.a_bytes + 1023) / 1024 * 1024;
+  p.a_lo_off = p.a_slots * p.a_slot_bytes;
+  p.b_off = (pl->x3 ? 2 : 1) * p.a_slots * p.a_slot_bytes;
   p.b_slot_bytes = (pl->block_n / pl->cluster) * 128;        // 2-CTA mode: each CTA holds half of the weight tile
-  p.b_slots = (data_bytes - p.a_slots * p.a_slot_bytes) / p.b_slot_bytes;
+  p.b_slots = (data_bytes - p.b_off) / p.b_slot_bytes;
   if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
   ATMVFI_REQUIRE(p.b_slots >= 2, "gemm_conv(tf32): shared memory rings too small (%d weight slots)", p.b_slots);
   p.m_tiles = pl->tiles_x * pl->tiles_y * pl->B;

@@ -16,7 +16,10 @@
  *     extent: padding, align_corners scales, window geometry and warp coordinates stay global, the kernel simply reads the
  *     halo rows it needs from the full-size input.  For window-major tensors a "row" is a row of windows.
  *   - fp32 storage everywhere; `precision` selects the multiply datapath of the GEMM-shaped ops:
- *     ATMVFI_FP32 = CUDA-core FFMA, ATMVFI_TF32 = tcgen05.mma kind::tf32 (fp32 accumulate in TMEM).
+ *     ATMVFI_FP32 = CUDA-core FFMA, ATMVFI_TF32 = tcgen05.mma kind::tf32 (fp32 accumulate in TMEM),
+ *     ATMVFI_TF32X3 = "3xTF32": fp32-tolerance products on the same tensor cores, each a*b issued as
+ *     a_hi*b_lo + a_lo*b_hi + a_hi*b_hi (x_hi = tf32(x), x_lo = tf32(x - x_hi)); weights packed as hi|lo chunk pairs
+ *     (pack.pack_tc_x3), activations split on the fly in shared memory; feature maps are stored un-rounded.
  *
  * There is no CPU fallback behind any of these symbols.
  */
@@ -33,7 +36,7 @@ extern "C" {
 #define ATMVFI_ABI_VERSION 2
 #define ATMVFI_MAX_SRC 4
 
-enum { ATMVFI_FP32 = 0, ATMVFI_TF32 = 1 };
+enum { ATMVFI_FP32 = 0, ATMVFI_TF32 = 1, ATMVFI_TF32X3 = 2 };
 
 /* output row mapping of atmvfi_gemm_conv */
 enum {
@@ -92,8 +95,8 @@ typedef struct {
   int32_t out2_pitch;
   int32_t out_mode;              /* ATMVFI_OUT_*                                */
   atmvfi_window_geom win;        /* used by ATMVFI_OUT_WINDOW_REV               */
-  int32_t precision;             /* ATMVFI_FP32 / ATMVFI_TF32                   */
-  const void* tma_host;          /* TF32: host pointer to the plan made by atmvfi_gemm_conv_plan, else NULL */
+  int32_t precision;             /* ATMVFI_FP32 / ATMVFI_TF32 / ATMVFI_TF32X3   */
+  const void* tma_host;          /* TF32 / TF32X3: host pointer to the plan made by atmvfi_gemm_conv_plan, else NULL */
   int32_t row_begin, row_end;    /* row window on the GEMM grid [B][Hout][Wout] (window-major sources: rows of windows,
                                     i.e. Hout = B2-images x window rows); row_end == 0: all rows */
   int32_t qkv_heads;             /* ATMVFI_OUT_QKV_HEADS: number of attention heads */
@@ -103,7 +106,7 @@ const char* atmvfi_last_error(void);
 int atmvfi_abi_version(void);
 /* Thread-local mode for subsequent launches from this thread: when on, kernels that produce channels-last feature
  * maps round their outputs to the nearest TF32 value (the tcgen05 tf32 datapath truncates operands otherwise).
- * The host runtime turns it on for precision ATMVFI_TF32 and off for ATMVFI_FP32. */
+ * The host runtime turns it on for precision ATMVFI_TF32 and off for ATMVFI_FP32 / ATMVFI_TF32X3. */
 void atmvfi_set_output_rounding(int on);
 /* Fills name[] (<=255 chars) with the device name and returns the SM count, or -1 without a usable sm_100 device. */
 int atmvfi_device_info(int device, char* name, int* cc_major, int* cc_minor);

@@ -142,7 +142,7 @@ _TRANSFORMER_PARTS = ("cross_scale_feature_fusion", "global_feature_fusion", "fe
 
 
 def make_weights(kind: str, variant: str = "default", seed: int = 0, local_ws: int = 8, global_ws: int = 12) -> Dict[str, torch.Tensor]:
-    assert variant in ("default", "stress", "ensemble")
+    assert variant in ("default", "stress", "ensemble", "varflow")
     S = schema(kind, local_ws, global_ws)
     P: Dict[str, torch.Tensor] = OrderedDict()
     for name, shape in S.items():

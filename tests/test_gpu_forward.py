@@ -28,6 +28,10 @@ TOL = {("fp32", "default"): dict(img=1e-4, flow=1e-4, mean=1e-5), ("fp32", "stre
        ("tf32", "default"): dict(img=8e-3, flow=2e-4, mean=1e-3), ("tf32", "stress"): dict(img=0.1, flow=0.1, mean=5e-3)}
 # "ensemble" weights = stress gains (x100 on the motion heads) on 8/16-pixel shifts; measured fp32 max-abs 2.1e-3 on I_t_1
 TOL[("fp32", "ensemble")], TOL[("tf32", "ensemble")] = dict(img=5e-3, flow=1e-4, mean=1e-4), TOL[("tf32", "stress")]
+#   fp32x3: 3xTF32 on the tensor cores (hi/lo operand split, three kind::tf32 MMAs per product, fp32 storage): held to the
+#           SAME bounds as the CUDA-core fp32 datapath.
+for _v in ("default", "stress", "ensemble"):
+    TOL[("fp32x3", _v)] = TOL[("fp32", _v)]
 
 
 def _net(kind, P):
@@ -45,7 +49,7 @@ def psnr(a, b):
     return 99.0 if mse == 0 else -10 * np.log10(mse)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("path", CASES, ids=[os.path.basename(p)[5:-4] for p in CASES])
 def test_forward_matches_reference_golden(path, precision):
     z = np.load(path)
@@ -78,10 +82,10 @@ def test_forward_matches_reference_golden(path, precision):
     d = np.abs(out["im0_warped_list"][-1].cpu().numpy() - z["coarse_im0_warped"])
     assert (d.mean() <= 2e-2) if noisy else (d.max() <= tol["img"])
     if meta["variant"] == "default":
-        assert psnr(out["I_t"].cpu(), torch.from_numpy(z["I_t"])) >= (90 if precision == "fp32" else 60)
+        assert psnr(out["I_t"].cpu(), torch.from_numpy(z["I_t"])) >= (60 if precision == "tf32" else 90)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_forward_vs_oracle_larger_shape(precision, use_graph):
     """256x448 (the Vimeo shape: global grid 16x28 -> padded 24x36, both masks live), B=2, Lite."""
@@ -95,7 +99,7 @@ def test_forward_vs_oracle_larger_shape(precision, use_graph):
     tol = TOL[(precision, "default")]
     assert (out["I_t"].cpu() - ref["I_t"]).abs().max().item() <= tol["img"]
     assert (out["opt_flow_0"].cpu() - ref["opt_flow_0"]).abs().max().item() <= tol["flow"]
-    assert psnr(out["I_t"].cpu(), ref["I_t"]) >= (90 if precision == "fp32" else 60)
+    assert psnr(out["I_t"].cpu(), ref["I_t"]) >= (60 if precision == "tf32" else 90)
     # outputs are fresh tensors: a second forward must not overwrite them
     keep = out["I_t"].clone()
     net(im1.cuda(), im0.cuda())
@@ -234,16 +238,17 @@ def test_weight_updates_are_picked_up():
     im0, im1 = [t.cuda() for t in weights.synthetic_frames(1, 64, 96)]
     net.global_motion = False
     a = net(im0, im1)["I_t"]
+    w = net.refine_head._modules["1"]._modules["0"].weight                  # conv weights are re-laid-out at pack time (a copy)
     with torch.no_grad():
-        net.refine_head._modules["1"]._modules["0"].bias.add_(0.05)          # bumps _version
+        w.mul_(1.5)                                                          # bumps _version
     b = net(im0, im1)["I_t"]
     assert (a - b).abs().max().item() > 1e-3
-    net.refine_head._modules["1"]._modules["0"].bias.data.sub_(0.05)         # bypasses the version counter
+    w.data.div_(1.5)                                                         # bypasses the version counter
     c = net(im0, im1)["I_t"]
     assert torch.equal(b, c)                                                 # stale by design ...
     net.invalidate()
     d = net(im0, im1)["I_t"]
-    assert (a - d).abs().max().item() < 1e-6                                 # ... until invalidate()
+    assert (a - d).abs().max().item() < 1e-5                                 # ... until invalidate()
     net2 = _net("lite", weights.make_weights("lite", "stress"))              # load_state_dict into a fresh net: new tensors are seen
     net.load_state_dict(net2.state_dict())
     assert torch.equal(net(im0, im1)["I_t"], net2.to("cuda:0")(im0, im1)["I_t"]) or True
