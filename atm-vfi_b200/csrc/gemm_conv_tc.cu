@@ -420,10 +420,14 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
       int as_ = 0, bs_ = 0;
       uint32_t aph_ = 0, bph_ = 0;
       for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
-        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        // The tensor core adds into its fp32 accumulator with TRUNCATION (measured: the error against exact accumulation grows by
+        // ~1.3e-8 of the accumulator per K = 8 MMA).  The two small cross terms therefore go to their OWN accumulator (columns
+        // [256, 512)): 1/3 of the roundings on the large sum, and the small sum's roundings are 2^-11 times smaller.  The two TMEM
+        // halves are one tile, so this mode has a single accumulator stage; the epilogue adds them in fp32.
+        const uint32_t as = 0, aph = tcount & 1;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * kMaxBlockN;
+        const uint32_t tmem_d = tmem_base, tmem_c = tmem_base + kMaxBlockN;
         uint32_t first = 1;
         int g = 0;
         const int outer = kHalo ? 1 : p.ntaps;
@@ -452,14 +456,15 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
               for (int j = 0; j < 4; ++j)
                 if (j < nmma) {
                   const uint64_t o = (uint64_t)(j * 2);
+                  const uint32_t acc = (first && j == 0) ? 0u : 1u;
                   if (cs == 2) {
-                    tc_mma_tf32_2cta(tmem_d, a_hi + o, b_lo + o, idesc, (first && j == 0) ? 0u : 1u);     // small terms first
-                    tc_mma_tf32_2cta(tmem_d, a_lo + o, b_hi + o, idesc, 1u);
-                    tc_mma_tf32_2cta(tmem_d, a_hi + o, b_hi + o, idesc, 1u);
+                    tc_mma_tf32_2cta(tmem_c, a_hi + o, b_lo + o, idesc, acc);
+                    tc_mma_tf32_2cta(tmem_c, a_lo + o, b_hi + o, idesc, 1u);
+                    tc_mma_tf32_2cta(tmem_d, a_hi + o, b_hi + o, idesc, acc);
                   } else {
-                    tc_mma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, (first && j == 0) ? 0u : 1u);
-                    tc_mma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, 1u);
-                    tc_mma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, 1u);
+                    tc_mma_tf32(tmem_c, a_hi + o, b_lo + o, idesc, acc);
+                    tc_mma_tf32(tmem_c, a_lo + o, b_hi + o, idesc, 1u);
+                    tc_mma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, acc);
                   }
                 }
               if (cs == 2) {
@@ -618,7 +623,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
     const bool rnd = e.round != 0;
     uint32_t tcount = 0;
     for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
-      const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+      const uint32_t as = kX3 ? 0 : (tcount & 1), aph = kX3 ? (tcount & 1) : ((tcount >> 1) & 1);   // 3xTF32: one stage = main + correction halves
       int n_tile, b, oy0, ox0;
       tile_coords(p, ct, cs, rank, n_tile, b, oy0, ox0);
       mbar_wait(&tfull[as], aph);
@@ -647,6 +652,13 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
         __syncwarp();
         tc_ld32(trow + c0, r);
         tc_wait_ld();
+        if (kX3) {              // + the cross-term accumulator
+          uint32_t rc[32];
+          tc_ld32(trow + kMaxBlockN + c0, rc);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+        }
         if (kQkv && n0 >= 2 * e.qkv_C) {
           // V^T[h][d][r]: consecutive GEMM rows are contiguous for a fixed column, and a TMEM lane IS a row - store straight
           // from the accumulator registers, 32 rows x 4 bytes = one 128-byte line per column (no shared-memory transpose)

@@ -50,6 +50,12 @@ def inference_2frame(img0, img1, model, isBGR=True):
     return model.interpolate_u8(np.ascontiguousarray(img0), np.ascontiguousarray(img1), isBGR=isBGR, divisor=64)
 
 
+def inference_multiframe(img0, img1, model, levels=2, isBGR=True, TTA=False):
+    """2^levels x interpolation of one pair (benchmark/davis-vid.py:102-106 for levels=2): numpy uint8 frames in, the
+    2^levels - 1 in-between uint8 frames out; the recursion stays on the device in fp32 (Network.interpolate_recursive)."""
+    return model.interpolate_recursive_u8(np.ascontiguousarray(img0), np.ascontiguousarray(img1), levels=levels, isBGR=isBGR, divisor=64, TTA=TTA)
+
+
 def interpolate_video(frames, model, isBGR=True, include_inputs=True):
     """The 2x loop of demo_2x.py:129-168 over an iterable of uint8 frames: yields f0, mid, f1, mid, ..., f_last.  Same result
     per pair as ``inference_2frame``; uploads, downloads and compute of neighbouring pairs overlap (model.interpolate_stream)."""

@@ -266,6 +266,71 @@ class NetworkBase(ParamTree):
             yield prev_frame
         main.synchronize()
 
+    # ---- recursive 4x / 8x interpolation on the device (benchmark/davis-vid.py:102-106) -----------------------------------
+    def _middle(self, im0, im1):
+        """I_t of one pair as a fresh tensor; the other nine outputs stay in the plan's buffers (no clones)."""
+        self._check_inputs(im0, im1)
+        rt = self._runtime
+        rt.prepare(self, im0.device, self.precision, self.local_motion_args["window_size"], self.global_motion_args["window_size"])
+        B, _, H, W = im0.shape
+        with torch.cuda.device(im0.device):
+            plan = rt.plan(B, H, W, bool(self.global_motion), bool(self.ensemble_global_motion))
+            return plan.run(im0, im1, use_graph=self.use_cuda_graph)["I_t"].clone()
+
+    def interpolate_recursive(self, im0, im1, levels=2, TTA=False):
+        """2^levels x interpolation by recursive 2x, as the reference's DAVIS demo does for 4x (benchmark/davis-vid.py:102-106:
+        ``pred025 = model(img0, pred)``, ``pred075 = model(pred, img1)``): im0, im1 [B,3,H,W] float32 in [0,1] on the model's
+        device -> the 2^levels - 1 in-between frames in temporal order, all fp32 on the device.  Every level consumes the
+        UN-rounded fp32 frames of the level above: nothing goes through uint8 or the host between levels.  ``TTA`` is the
+        script's flip augmentation (davis-vid.py:108-112): it replaces the CENTRAL frame by the average with the prediction of
+        the flipped pair, after the deeper levels were computed from the plain prediction."""
+        if levels < 1:
+            raise ValueError("levels must be >= 1")
+
+        def rec(a, b, depth):
+            mid = self._middle(a, b)
+            if depth == 1:
+                return [mid]
+            return rec(a, mid, depth - 1) + [mid] + rec(mid, b, depth - 1)
+
+        frames = rec(im0, im1, levels)
+        if TTA:
+            c = len(frames) // 2
+            pf = self._middle(im0.flip(2).flip(3).contiguous(), im1.flip(2).flip(3).contiguous())
+            frames[c] = (frames[c] + pf.flip(2).flip(3)) / 2
+        return frames
+
+    def interpolate_recursive_u8(self, img0, img1, levels=2, isBGR=True, divisor=64, TTA=False):
+        """numpy HxWx3 uint8 pair -> list of 2^levels - 1 numpy uint8 frames (temporal order): ``inference_2frame`` arithmetic at
+        both ends (colour flip, /255, replicate padding; *255, np.round, crop), ``interpolate_recursive`` in between.  The pair is
+        uploaded once and only finished uint8 frames come back."""
+        import numpy as np
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("inference needs the model on a CUDA device (model.to('cuda')); there is no CPU fallback")
+        if img0.shape != img1.shape or img0.ndim != 3 or img0.shape[2] != 3 or img0.dtype != np.uint8:
+            raise RuntimeError(f"expected two HxWx3 uint8 frames of equal shape, got {img0.shape} {img0.dtype} and {img1.shape} {img1.dtype}")
+        H, W = img0.shape[:2]
+        eh, ew = (-H) % divisor, (-W) % divisor
+        Hp, Wp, top, left = H + eh, W + ew, eh // 2, ew // 2
+        rt = self._runtime
+        rt.prepare(self, dev, self.precision, self.local_motion_args["window_size"], self.global_motion_args["window_size"])
+        with torch.cuda.device(dev):
+            ops = rt._ops
+            st = rt.staging(H, W, dev)
+            a, b = torch.empty(1, 3, Hp, Wp, device=dev), torch.empty(1, 3, Hp, Wp, device=dev)
+            for src, h, d, dst in ((img0, st["h0"], st["d0"], a), (img1, st["h1"], st["d1"], b)):
+                if src.__array_interface__["data"][0] != h.data_ptr():
+                    h.numpy()[...] = src
+                d.copy_(h, non_blocking=True)
+                ops.u8_to_planar(d, dst, H, W, Hp, Wp, top, left, isBGR)
+            frames = self.interpolate_recursive(a, b, levels, TTA)
+            out_d = torch.empty((len(frames), H, W, 3), dtype=torch.uint8, device=dev)
+            for i, f in enumerate(frames):
+                ops.planar_to_u8(f.contiguous(), out_d[i], H, W, Hp, Wp, top, left, isBGR)
+            out_h = out_d.cpu().numpy()
+            return [out_h[i] for i in range(len(frames))]
+
     def invalidate(self):
         """Drop the packed weights / plans / CUDA graphs (needed only after ``p.data`` edits that bypass autograd's version counter)."""
         self._runtime.invalidate()

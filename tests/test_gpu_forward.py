@@ -28,10 +28,12 @@ TOL = {("fp32", "default"): dict(img=1e-4, flow=1e-4, mean=1e-5), ("fp32", "stre
        ("tf32", "default"): dict(img=8e-3, flow=2e-4, mean=1e-3), ("tf32", "stress"): dict(img=0.1, flow=0.1, mean=5e-3)}
 # "ensemble" weights = stress gains (x100 on the motion heads) on 8/16-pixel shifts; measured fp32 max-abs 2.1e-3 on I_t_1
 TOL[("fp32", "ensemble")], TOL[("tf32", "ensemble")] = dict(img=5e-3, flow=1e-4, mean=1e-4), TOL[("tf32", "stress")]
-#   fp32x3: 3xTF32 on the tensor cores (hi/lo operand split, three kind::tf32 MMAs per product, fp32 storage): held to the
-#           SAME bounds as the CUDA-core fp32 datapath.
-for _v in ("default", "stress", "ensemble"):
-    TOL[("fp32x3", _v)] = TOL[("fp32", _v)]
+#   fp32x3: 3xTF32 on the tensor cores (hi/lo operand split, three kind::tf32 MMAs per product, fp32 storage).  Operand
+#           rounding is gone (flows agree to 2e-7 px); what is left is the tensor core's TRUNCATING fp32 accumulation
+#           (~1.3e-8 of the sum per K = 8 MMA, see tests/test_gpu_ops_tc.py), which the CUDA-core path does not have.
+TOL[("fp32x3", "default")] = dict(img=2e-4, flow=1e-4, mean=2e-5)
+TOL[("fp32x3", "stress")] = TOL[("fp32", "stress")]
+TOL[("fp32x3", "ensemble")] = TOL[("fp32", "ensemble")]
 
 
 def _net(kind, P):
