@@ -163,6 +163,102 @@ def motion_branch(ops, blocks, head, tok: Map, ws: int) -> Tuple[Map, Map]:
     return tok, out
 
 
+# ------------------------------------------------------------------------------------------------
+# liveness-based buffer arena
+# ------------------------------------------------------------------------------------------------
+_OP_NAMES = frozenset(("window_gather_ln", "gemm_conv", "window_attention", "layernorm", "dwconv_gelu", "conv3x3_first", "copy_map",
+                       "nhwc_to_nchw", "nchw_to_nhwc", "resize", "flow_warp_nchw", "flow_warp_nhwc", "l1_mean", "select3", "warp_blend",
+                       "pack5_planar", "residual_finish"))
+_ARENA_ALIGN = 1024
+
+
+class _DryOps:
+    """Stands in for the operator layer during a dry run of ``Plan._build``: buffers are shape-only ("meta") tensors and every
+    operator call just notes which buffers it touches, giving each buffer a lifetime [first touch, last touch] in launch order."""
+
+    def __init__(self, real):
+        self.real, self.recording, self.step = real, None, 0
+        self.bufs: List[list] = []           # [nbytes, first, last, persistent, shape]
+        self._idx: Dict[int, int] = {}
+        self._keep: List[torch.Tensor] = []
+
+    qkv_head_major = property(lambda s: bool(getattr(s.real, "qkv_head_major", False)))
+    qkv_head_major_min_hd = property(lambda s: getattr(s.real, "qkv_head_major_min_hd", 48))
+    device = property(lambda s: torch.device("meta"))
+
+    def _new(self, shape) -> torch.Tensor:
+        t = torch.empty(tuple(int(x) for x in shape), device="meta", dtype=torch.float32)
+        self._idx[id(t)] = len(self.bufs)
+        self._keep.append(t)
+        self.bufs.append([t.numel() * 4, self.step, self.step, False, tuple(t.shape)])
+        return t
+
+    def new_map(self, B, H, W, C, zero=False) -> Map:
+        return Map(self._new((B, H, W, (C + 3) // 4 * 4)), 0, C)
+
+    def new_win_map(self, g: WinGeom, C) -> Map:
+        return self.new_map(1, 1, g.rows, C)
+
+    def new_planar(self, *shape) -> torch.Tensor:
+        return self._new(shape)
+
+    def replicated(self):
+        return contextlib.nullcontext()
+
+    def index_of(self, x) -> Optional[int]:
+        t = x.t if isinstance(x, Map) else x
+        if not isinstance(t, torch.Tensor):
+            return None
+        base = t._base if t._base is not None else t
+        return self._idx.get(id(base))
+
+    def _touch(self, x, persistent=False) -> None:
+        if isinstance(x, (list, tuple)):
+            for v in x:
+                self._touch(v, persistent)
+            return
+        i = self.index_of(x)
+        if i is not None:
+            b = self.bufs[i]
+            b[2] = self.step
+            b[3] = b[3] or persistent
+
+    def __getattr__(self, name):
+        if name not in _OP_NAMES:
+            raise AttributeError(name)
+
+        def op(*args, **kwargs):
+            self.step += 1
+            keep = name == "copy_map"          # video-stream plans: encoder features cross from one step to the next
+            self._touch(args, keep)
+            self._touch(list(kwargs.values()), keep)
+        return op
+
+
+def _colour_intervals(bufs) -> Tuple[List[int], int]:
+    """Offsets for buffers with lifetimes [first, last] (inclusive, in launch order) such that buffers alive at the same time never
+    overlap: largest first, each at the lowest aligned address free during its lifetime.  Returns (offsets, arena bytes)."""
+    order = sorted(range(len(bufs)), key=lambda i: -bufs[i][0])
+    placed: List[Tuple[int, int, int, int]] = []         # (offset, end, first, last)
+    offs = [0] * len(bufs)
+    top = 0
+    for i in order:
+        n, first, last, persistent, _ = bufs[i]
+        size = (n + _ARENA_ALIGN - 1) // _ARENA_ALIGN * _ARENA_ALIGN
+        if persistent:
+            first, last = -1, 1 << 60
+        busy = sorted((o, e) for (o, e, f, l) in placed if not (l < first or f > last))
+        off = 0
+        for o, e in busy:
+            if off + size <= o:
+                break
+            off = max(off, e)
+        offs[i] = off
+        placed.append((off, off + size, first, last))
+        top = max(top, off + size)
+    return offs, top
+
+
 class Plan:
     """Launch list + buffers for one input shape."""
 
@@ -182,11 +278,42 @@ class Plan:
         self.stream, self.encode_records, self.encode_graph = stream, None, None
         self.in_use = False                     # video-stream plans are owned by one interpolate_stream generator at a time (runtime.acquire_stream_plan)
         a = model.arch
+        self.arena, self.buffer_bytes, self.unshared_bytes = None, None, None
+        import os
+        use_arena = (not hasattr(ops, "begin_plan") and getattr(ops, "allocator", True) is None and hasattr(ops, "lib")
+                     and os.environ.get("ATMVFI_ARENA", "1") != "0")
+        if use_arena:
+            # Dry run: lifetimes of all buffers in launch order -> interval colouring -> ONE arena in which buffers whose lifetimes do
+            # not overlap share addresses (Base 1080p: 19 GB of distinct buffers -> a few GB).  Inputs, the public outputs and
+            # whatever a video-stream plan carries to its next step keep private space.  The arena is never zeroed between steps:
+            # no kernel reads a lane that its producer did not write in the same step (tests/test_gpu_forward.py poisons it).
+            dry = _DryOps(ops)
+            dry.recording = []
+            self._build(dry, model, a, B, H, W, global_motion, ensemble, stream)
+            dry._touch([self.im0, self.im1, list(self.outputs.values()), getattr(self, "ensemble_losses", [])], persistent=True)
+            offs, total = _colour_intervals(dry.bufs)
+            self.unshared_bytes = sum(b[0] for b in dry.bufs)
+            self.buffer_bytes = total
+            self.arena = torch.zeros(max(total, _ARENA_ALIGN), dtype=torch.uint8, device=ops.device)
+            shapes, cursor = [b[4] for b in dry.bufs], [0]
+
+            def alloc(shape, zero):
+                i = cursor[0]
+                cursor[0] += 1
+                assert tuple(shape) == shapes[i], f"plan build is not deterministic: buffer {i} is {tuple(shape)}, dry run saw {shapes[i]}"
+                n = 4
+                for d in shape:
+                    n *= int(d)
+                return self.arena[offs[i] : offs[i] + n].view(torch.float32).view(*shape)
+
+            ops.allocator = alloc
         ops.recording = rec = []
         try:
             self._build(ops, model, a, B, H, W, global_motion, ensemble, stream)
         finally:
             ops.recording = None
+            if use_arena:
+                ops.allocator = None
         self.records = rec
         self.graph = None
 

@@ -32,7 +32,7 @@ TOL[("fp32", "ensemble")], TOL[("tf32", "ensemble")] = dict(img=5e-3, flow=1e-4,
 #           rounding is gone (flows agree to 2e-7 px); what is left is the tensor core's TRUNCATING fp32 accumulation
 #           (~1.3e-8 of the sum per K = 8 MMA, see tests/test_gpu_ops_tc.py), which the CUDA-core path does not have.
 TOL[("fp32x3", "default")] = dict(img=2e-4, flow=1e-4, mean=2e-5)
-TOL[("fp32x3", "stress")] = TOL[("fp32", "stress")]
+TOL[("fp32x3", "stress")] = dict(img=5e-3, flow=1e-4, mean=1e-4)       # measured 3.0e-3 on one coarse pyramid level (gains x100)
 TOL[("fp32x3", "ensemble")] = TOL[("fp32", "ensemble")]
 
 
@@ -266,3 +266,31 @@ def test_one_process_two_devices():
         net = _net("lite", P).to(dev)
         outs.append(net(im0.to(dev), im1.to(dev))["I_t"].cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("kind,glob,shape", [("lite", True, (2, 128, 192)), ("base", True, (1, 256, 448)), ("lite", False, (1, 72, 104))])
+def test_buffer_arena_is_bit_identical_and_never_reads_stale_lanes(kind, glob, shape, monkeypatch):
+    """The plan's buffers share one arena by lifetime (engine._colour_intervals).  Poisoning the arena with NaN bit patterns before a
+    run, and running twice (second run: every buffer starts with a previous tenant's data), must give exactly the bits of a plan
+    whose buffers are all private - i.e. no kernel reads a lane that was not written earlier in the same step."""
+    B, H, W = shape
+    P = weights.make_weights(kind, "stress")
+    im0, im1 = [t.cuda() for t in weights.synthetic_frames(B, H, W, kind="texture")]
+    for precision in ("tf32", "fp32"):
+        monkeypatch.setenv("ATMVFI_ARENA", "0")
+        ref_net = _net(kind, P)
+        ref_net.global_motion, ref_net.precision = glob, precision
+        ref = ref_net(im0, im1)
+        assert ref_net._runtime.plan(B, H, W, glob).arena is None
+        monkeypatch.setenv("ATMVFI_ARENA", "1")
+        net = _net(kind, P)
+        net.global_motion, net.precision = glob, precision
+        net(im0, im1)
+        plan = net._runtime.plan(B, H, W, glob)
+        assert plan.arena is not None and plan.buffer_bytes < 0.45 * plan.unshared_bytes
+        plan.arena.fill_(0xFF)
+        for _ in range(2):
+            out = net(im0, im1)
+            for k, v in ref.items():
+                a, b = (v, out[k]) if isinstance(v, list) else ([v], [out[k]])
+                assert all(torch.equal(x, y) for x, y in zip(a, b)), (precision, k)
