@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libatmvfi_b200.so")
 
 MAX_SRC = 4
-FP32, TF32, TF32X3 = 0, 1, 2
+FP32, TF32, TF32X3, F16 = 0, 1, 2, 3
 OUT_PIXEL, OUT_SHUFFLE2, OUT_WINDOW_REV, OUT_QKV_HEADS = 0, 1, 2, 3
 
 
@@ -46,6 +46,8 @@ class GemmConvDesc(C.Structure):
         ("tma_host", C.c_void_p),
         ("row_begin", C.c_int32), ("row_end", C.c_int32),
         ("qkv_heads", C.c_int32),
+        ("out_f32", C.c_int32),
+        ("head32", C.c_void_p), ("head32_pitch", C.c_int32), ("head32_c0", C.c_int32),
     ]
 
 
@@ -99,6 +101,7 @@ PROTOTYPES = {
     "atmvfi_p2p_exchange": [C.POINTER(P2PPiece), _I, C.POINTER(C.c_void_p), _I, C.POINTER(C.c_void_p), _I, _P, _P, _P, _P],
     "atmvfi_p2p_step_begin": [_P, C.POINTER(C.c_void_p), _I, C.POINTER(C.c_void_p), _I, _P, _P],
     "atmvfi_p2p_set_timeout_ms": [_I],
+    "atmvfi_cast_f32_to_f16": [_P, _I, _P, _I, _L, _I, _I, _P],
 }
 _SPECIAL = {
     "atmvfi_last_error": ([], C.c_char_p),
@@ -108,6 +111,7 @@ _SPECIAL = {
     "atmvfi_l1_mean_scratch_floats": ([C.c_int], C.c_int),
     "atmvfi_attn_prof_read": ([C.POINTER(C.c_uint64)], C.c_int),
     "atmvfi_set_output_rounding": ([C.c_int], None),
+    "atmvfi_set_activation_f16": ([C.c_int], None),
 }
 ALL_SYMBOLS = sorted(list(PROTOTYPES) + list(_SPECIAL))
 
@@ -130,7 +134,7 @@ def load() -> C.CDLL:
     for name, (argt, rest) in _SPECIAL.items():
         fn = getattr(lib, name)
         fn.argtypes, fn.restype = argt, rest
-    if lib.atmvfi_abi_version() != 2:
+    if lib.atmvfi_abi_version() != 3:
         raise AtmvfiError("libatmvfi_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

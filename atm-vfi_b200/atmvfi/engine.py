@@ -103,11 +103,11 @@ def transformer_block(ops, blk, tok: Map, g: WinGeom, motion: Optional[Map] = No
     hidden = blk.fc1.Cout
     xw = ops.new_win_map(g, C)
     ops.window_gather_ln(tok, xw, g, blk.g1, blk.b1)                       # pad + roll + partition + norm1
-    qkv = ops.new_win_map(g, 3 * C)
+    qkv = ops.new_win_map(g, 3 * C, f32=True)       # q | k | v stay fp32 in every mode (the attention MMAs are kind::tf32)
     # head-major q | k | v^T (TMA-fed attention): worth it when the heads are wide.  Measured on B200: Base (hd 48 / 84) +1.3 % end to
     # end; Lite (hd 28 / 44) -5 % because its whole third N tile of the qkv linear is the transposed-V store path.
     hm = bool(getattr(ops, "qkv_head_major", False)) and C // NUM_HEADS >= getattr(ops, "qkv_head_major_min_hd", 48)
-    ops.gemm_conv([xw], blk.qkv, qkv, act=False, qkv_heads=NUM_HEADS if hm else 0)
+    ops.gemm_conv([xw], blk.qkv, qkv, act=False, qkv_heads=NUM_HEADS if hm else 0, out_f32=True)
     ao = ops.new_win_map(g, C)
     if blk.atm and motion is not None:
         scratch = torch.empty(g.rows * NUM_HEADS * 2, device=xw.t.device, dtype=torch.float32)
@@ -150,16 +150,16 @@ def motion_branch(ops, blocks, head, tok: Map, ws: int) -> Tuple[Map, Map]:
     B2, H, W = tok.B, tok.H, tok.W
     B = B2 // 2
     # one 4-channel motion map per block (the two blocks cover different row sets under row slabs)
-    motion = [ops.new_map(B, H, W, 4), ops.new_map(B, H, W, 4)]
+    motion = [ops.new_map(B, H, W, 4, f32=True), ops.new_map(B, H, W, 4, f32=True)]
     for k, shift in enumerate((0, ws // 2)):
         tok = transformer_block(ops, blocks[k], tok, WinGeom(B2, H, W, ws, shift), motion[k])
     h0, h1, h2 = head
     a = ops.new_map(B, H, W, h0.Cout)
-    ops.gemm_conv([motion[0], motion[1], tok.batch(0, B), tok.batch(B, B)], h0, a)
+    ops.gemm_conv([ops.to_act(motion[0]), ops.to_act(motion[1]), tok.batch(0, B), tok.batch(B, B)], h0, a)
     b = ops.new_map(B, H, W, h1.Cout)
     ops.gemm_conv([a], h1, b)
-    out = ops.new_map(B, H, W, MOTION_OUT)
-    ops.gemm_conv([b], h2, out, act=False)
+    out = ops.new_map(B, H, W, MOTION_OUT, f32=True)      # flows + occlusion logit: fp32 in every mode
+    ops.gemm_conv([b], h2, out, act=False, out_f32=True)
     return tok, out
 
 
@@ -186,18 +186,30 @@ class _DryOps:
     qkv_head_major_min_hd = property(lambda s: getattr(s.real, "qkv_head_major_min_hd", 48))
     device = property(lambda s: torch.device("meta"))
 
-    def _new(self, shape) -> torch.Tensor:
-        t = torch.empty(tuple(int(x) for x in shape), device="meta", dtype=torch.float32)
+    act_f16 = property(lambda s: bool(getattr(s.real, "act_f16", False)))
+
+    def _new(self, shape, dtype=torch.float32) -> torch.Tensor:
+        t = torch.empty(tuple(int(x) for x in shape), device="meta", dtype=dtype)
         self._idx[id(t)] = len(self.bufs)
         self._keep.append(t)
-        self.bufs.append([t.numel() * 4, self.step, self.step, False, tuple(t.shape)])
+        self.bufs.append([t.numel() * t.element_size(), self.step, self.step, False, tuple(t.shape)])
         return t
 
-    def new_map(self, B, H, W, C, zero=False) -> Map:
-        return Map(self._new((B, H, W, (C + 3) // 4 * 4)), 0, C)
+    def new_map(self, B, H, W, C, zero=False, f32=False) -> Map:
+        half = self.act_f16 and not f32
+        a = 8 if half else 4
+        return Map(self._new((B, H, W, (C + a - 1) // a * a), torch.float16 if half else torch.float32), 0, C)
 
-    def new_win_map(self, g: WinGeom, C) -> Map:
-        return self.new_map(1, 1, g.rows, C)
+    def new_win_map(self, g: WinGeom, C, f32=False) -> Map:
+        return self.new_map(1, 1, g.rows, C, f32=f32)
+
+    def to_act(self, m: Map) -> Map:
+        if not self.act_f16 or m.half:
+            return m
+        out = self.new_map(m.B, m.H, m.W, m.C)
+        self.step += 1
+        self._touch([m, out])
+        return out
 
     def new_planar(self, *shape) -> torch.Tensor:
         return self._new(shape)
@@ -297,14 +309,15 @@ class Plan:
             self.arena = torch.zeros(max(total, _ARENA_ALIGN), dtype=torch.uint8, device=ops.device)
             shapes, cursor = [b[4] for b in dry.bufs], [0]
 
-            def alloc(shape, zero):
+            def alloc(shape, zero, dtype=torch.float32):
                 i = cursor[0]
                 cursor[0] += 1
                 assert tuple(shape) == shapes[i], f"plan build is not deterministic: buffer {i} is {tuple(shape)}, dry run saw {shapes[i]}"
-                n = 4
+                n = 2 if dtype == torch.float16 else 4
                 for d in shape:
                     n *= int(d)
-                return self.arena[offs[i] : offs[i] + n].view(torch.float32).view(*shape)
+                assert n == dry.bufs[i][0]
+                return self.arena[offs[i] : offs[i] + n].view(dtype).view(*shape)
 
             ops.allocator = alloc
         ops.recording = rec = []
@@ -429,7 +442,7 @@ class Plan:
             f0u, f1u = P(B, 2, h8, w8), P(B, 2, h8, w8)
             with ops.replicated():    # the global flows drive the warps of the whole image pyramid below
                 ops.resize(f0, f0u, 2.0); ops.resize(f1, f1u, 2.0)
-            fl = ops.new_map(2 * B, h8, w8, 2)
+            fl = ops.new_map(2 * B, h8, w8, 2, f32=True)
             ops.nchw_to_nhwc(f0u, fl.batch(0, B), zero_fill_to=fl.pitch)
             ops.nchw_to_nhwc(f1u, fl.batch(B, B), zero_fill_to=fl.pitch)
             tokw = ops.new_map(2 * B, h8, w8, tok.C)
@@ -462,7 +475,8 @@ class Plan:
         ops.flow_warp_nhwc(tok.batch(0, B), lhead, 0, fw.batch(0, B))
         ops.flow_warp_nhwc(tok.batch(B, B), lhead, 2, fw.batch(B, B))
 
-        srcs = [fw.batch(0, B), fw.batch(B, B), lhead]
+        srcs = [fw.batch(0, B), fw.batch(B, B), ops.to_act(lhead)]
+        f16 = bool(getattr(ops, "act_f16", False))
         skips = []
         flow0 = flow1 = occ1 = occ2 = None
         raw = None
@@ -475,8 +489,12 @@ class Plan:
             ops.gemm_conv([u], c1, v)
             raw = ops.new_map(B, h, w, c2.Cout)
             act = ops.new_map(B, h, w, c2.Cout) if nxt is not None else None
-            ops.gemm_conv([v], c2, raw, act=False, out2=act, prelu2=nxt)     # raw level output (+ PReLU'd copy for the next deconv)
-            hd = raw.chan(raw.C - MOTION_OUT, MOTION_OUT)
+            if f16:     # fp16 maps: the level's flows + occlusion logit are also written as an fp32 copy for the warps
+                hd = ops.new_map(B, h, w, MOTION_OUT, f32=True)
+                ops.gemm_conv([v], c2, raw, act=False, out2=act, prelu2=nxt, head32=hd, head32_c0=raw.C - MOTION_OUT)
+            else:
+                ops.gemm_conv([v], c2, raw, act=False, out2=act, prelu2=nxt)     # raw level output (+ PReLU'd copy for the next deconv)
+                hd = raw.chan(raw.C - MOTION_OUT, MOTION_OUT)
             if l:
                 skips.append(raw.chan(0, raw.C - MOTION_OUT))
             a0, a1, it = P(B, 3, h, w), P(B, 3, h, w), P(B, 3, h, w)
@@ -516,8 +534,8 @@ class Plan:
         ops.gemm_conv([u1, r1], m.up3, u0)
         t = ops.new_map(B, H, W, r)
         ops.gemm_conv([u0, r0], m.head[0], t)
-        res = ops.new_map(B, H, W, 3)
-        ops.gemm_conv([t], m.head[1], res)
+        res = ops.new_map(B, H, W, 3, f32=True)
+        ops.gemm_conv([t], m.head[1], res, out_f32=True)
         it_sum, out = P(B, 3, H, W), P(B, 3, H, W)
         ops.residual_finish(res, it, it_sum, out)
         it_list[0] = it_sum      # the reference's in-place ``I_t += residual`` aliases im_t_list[0] (network_base.py:532)
@@ -545,11 +563,16 @@ class Plan:
             self.ops.replay(self.encode_records)               # this call's execution; the graph serves later calls
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=self._capture_stream()):
                 self.ops.replay(self.encode_records)
             self.encode_graph = g
             return
         self.encode_graph.replay()
+
+    def _capture_stream(self) -> torch.cuda.Stream:
+        """A capture stream on THIS plan's device (torch.cuda.graph's default capture stream is created once, on whatever device was
+        current first: a plan on another GPU would capture nothing and later replay an empty graph)."""
+        return torch.cuda.Stream(device=self.ops.device)
 
     def run(self, im0: torch.Tensor, im1: torch.Tensor, use_graph: bool = False) -> Dict[str, object]:
         self.im0.copy_(im0); self.im1.copy_(im1)
@@ -565,7 +588,7 @@ class Plan:
                 self.launch()
                 torch.cuda.current_stream().synchronize()
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with torch.cuda.graph(g, stream=self._capture_stream()):
                     self.launch()
                 self.graph = g
                 return self.outputs

@@ -21,12 +21,12 @@ def round_up(x: int, m: int) -> int:
 
 
 class Map:
-    """NHWC fp32 view: tensor ``t`` of shape [B, H, W, pitch]; this view covers channels [c0, c0+C)."""
+    """NHWC view (fp32, or fp16 in the ATMVFI_F16 mode): tensor ``t`` of shape [B, H, W, pitch]; this view covers channels [c0, c0+C)."""
 
     __slots__ = ("t", "c0", "C")
 
     def __init__(self, t: torch.Tensor, c0: int = 0, C: Optional[int] = None):
-        assert t.dim() == 4 and t.dtype == torch.float32
+        assert t.dim() == 4 and t.dtype in (torch.float32, torch.float16)
         assert t.stride(3) == 1 and t.stride(2) == t.shape[3] and t.stride(1) == t.shape[2] * t.shape[3]
         self.t, self.c0 = t, c0
         self.C = t.shape[3] - c0 if C is None else C
@@ -55,7 +55,15 @@ class Map:
 
     @property
     def ptr(self) -> int:
-        return self.t.data_ptr() + 4 * self.c0
+        return self.t.data_ptr() + self.t.element_size() * self.c0
+
+    @property
+    def esize(self) -> int:
+        return self.t.element_size()
+
+    @property
+    def half(self) -> bool:
+        return self.t.dtype == torch.float16
 
     def view(self) -> torch.Tensor:
         return self.t[..., self.c0 : self.c0 + self.C]
@@ -110,6 +118,7 @@ class PackedGemm:
     prelu: Optional[torch.Tensor]
     wtc: Optional[torch.Tensor] = None   # tcgen05 layout, filled by pack.py when the TF32 path is enabled
     wtc3: Optional[torch.Tensor] = None  # 3xTF32 layout (hi | lo chunk pairs)
+    wtc16: Optional[torch.Tensor] = None  # fp16 layout (64-channel chunks)
     tc_meta: Optional[dict] = None
 
 
@@ -147,22 +156,35 @@ class CudaOps:
         self.allocator: Optional[Callable] = None
         # TF32 mode: the fused q|k|v linear writes the head-major layout that the tcgen05 attention kernel fetches with TMA
         import os
-        self.qkv_head_major = precision == _lib.TF32 and os.environ.get("ATMVFI_QKV_HEADS", "1") != "0"
+        self.qkv_head_major = precision in (_lib.TF32, _lib.F16) and os.environ.get("ATMVFI_QKV_HEADS", "1") != "0"
+        # ATMVFI_F16: channels-last feature maps are stored as fp16 (flows, masks, images, q|k|v and the motion heads stay fp32)
+        self.act_f16 = precision == _lib.F16
         self.qkv_head_major_min_hd = int(os.environ.get("ATMVFI_QKV_HEADS_MIN_HD", "48"))     # see engine.transformer_block
 
     # -- memory -------------------------------------------------------------------------------
-    def _alloc(self, shape, zero: bool) -> torch.Tensor:
+    def _alloc(self, shape, zero: bool, dtype=torch.float32) -> torch.Tensor:
         if self.allocator is not None:
-            return self.allocator(tuple(shape), zero)
-        return (torch.zeros if zero else torch.empty)(tuple(shape), device=self.device, dtype=torch.float32)
+            return self.allocator(tuple(shape), zero, dtype) if dtype != torch.float32 else self.allocator(tuple(shape), zero)
+        return (torch.zeros if zero else torch.empty)(tuple(shape), device=self.device, dtype=dtype)
 
-    def new_map(self, B: int, H: int, W: int, C: int, zero: bool = False) -> Map:
-        pitch = round_up(C, 4)
-        return Map(self._alloc((B, H, W, pitch), zero or pitch != C), 0, C)
+    def new_map(self, B: int, H: int, W: int, C: int, zero: bool = False, f32: bool = False) -> Map:
+        """``f32``: keep this map fp32 in the fp16-activation mode too (flows, motion, q|k|v, final residual)."""
+        half = self.act_f16 and not f32
+        pitch = round_up(C, 8 if half else 4)              # rows start on 16-byte boundaries (TMA strides)
+        return Map(self._alloc((B, H, W, pitch), zero or pitch != C, torch.float16 if half else torch.float32), 0, C)
 
-    def new_win_map(self, g: "WinGeom", C: int) -> Map:
+    def new_win_map(self, g: "WinGeom", C: int, f32: bool = False) -> Map:
         """Window-major token rows [1, 1, B2*Hp*Wp, C] (what window_partition produces, attention.py:8-15)."""
-        return self.new_map(1, 1, g.rows, C)
+        return self.new_map(1, 1, g.rows, C, f32=f32)
+
+    def to_act(self, m: Map) -> Map:
+        """The activation-typed twin of a small fp32 map that is also a GEMM source (per-token motion, 5-channel motion head):
+        the map itself in the fp32-storage modes, an fp16 copy (one cast launch) in the fp16 mode."""
+        if not self.act_f16 or m.half:
+            return m
+        out = self.new_map(m.B, m.H, m.W, m.C)
+        self._emit("atmvfi_cast_f32_to_f16", (m.ptr, m.pitch, out.ptr, out.pitch, m.nrows, m.C, out.pitch), keep=(m, out))
+        return out
 
     def new_planar(self, *shape: int) -> torch.Tensor:
         return self._alloc(shape, False)
@@ -176,8 +198,10 @@ class CudaOps:
     def set_rounding(self) -> None:
         """tcgen05 kind::tf32 truncates its operands: in that mode producers round feature maps to the nearest TF32 value.
         ``round_outputs`` (None = by precision) lets the per-operator tests look at the un-rounded accumulators."""
-        on = self.precision == _lib.TF32 if self.round_outputs is None else bool(self.round_outputs)
+        # (fp16 mode: fp32 side outputs - q|k|v for the tf32 attention MMAs - are rounded too; fp16 stores ignore the flag)
+        on = self.precision in (_lib.TF32, _lib.F16) if self.round_outputs is None else bool(self.round_outputs)
         self.lib.atmvfi_set_output_rounding(1 if on else 0)
+        self.lib.atmvfi_set_activation_f16(1 if self.act_f16 else 0)
 
     def _emit(self, name: str, args: tuple, keep=()):
         fn = getattr(self.lib, name)
@@ -221,7 +245,8 @@ class CudaOps:
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride: int = 1, dil: int = 1,
                   act: bool = True, residual: Optional[Map] = None, out2: Optional[Map] = None,
                   prelu2: Optional[torch.Tensor] = None, win: Optional[WinGeom] = None,
-                  precision: Optional[int] = None, rows: Rows = None, qkv_heads: int = 0):
+                  precision: Optional[int] = None, rows: Rows = None, qkv_heads: int = 0,
+                  out_f32: bool = False, head32: Optional[Map] = None, head32_c0: int = 0):
         assert [s.C for s in srcs] == list(w.split), (w.name, [s.C for s in srcs], w.split)
         s0 = srcs[0]
         for s in srcs:
@@ -265,10 +290,28 @@ class CudaOps:
         prec = self.precision if precision is None else precision
         if prec in (_lib.TF32, _lib.TF32X3) and not self._tc_eligible(srcs, w, out, out2):
             prec = _lib.FP32
+        if prec == _lib.F16:
+            # fp16 storage: there is no CUDA-core fallback for fp16 maps, every GEMM-shaped layer must fit the tensor-core kernel
+            if not self._tc_eligible(srcs, w, out, out2):
+                raise _lib.AtmvfiError(f"gemm_conv({w.name}): layer does not fit the tcgen05 kernel (>= 16 input channels, 16-byte aligned operands) "
+                                       "and fp16 feature maps have no CUDA-core path")
+            assert all(s.half for s in srcs) and (residual is None or residual.half) and (out2 is None or out2.half), w.name
+            assert out.half != bool(out_f32), (w.name, "out dtype does not match out_f32")
+            d.out_f32 = int(bool(out_f32))
+            if head32 is not None:
+                assert not head32.half and head32.nrows == out.nrows and head32.C == w.Cout - head32_c0 and win is None and not w.shuffle
+                d.head32, d.head32_pitch, d.head32_c0 = head32.ptr, head32.pitch, head32_c0
+        else:
+            assert not any(s.half for s in srcs) and not out.half and head32 is None, w.name
         d.precision = prec
         planbuf = None
-        if prec in (_lib.TF32, _lib.TF32X3):
-            if prec == _lib.TF32:
+        if prec in (_lib.TF32, _lib.TF32X3, _lib.F16):
+            if prec == _lib.F16:
+                if w.wtc16 is None:
+                    from .pack import pack_tc_f16
+                    w.wtc16 = pack_tc_f16(w)
+                wt = w.wtc16
+            elif prec == _lib.TF32:
                 if w.wtc is None:
                     from .pack import pack_tc
                     w.wtc = pack_tc(w)
@@ -284,14 +327,15 @@ class CudaOps:
             addr = (C.addressof(planbuf) + 63) & ~63
             _lib.check(self.lib.atmvfi_gemm_conv_plan(C.byref(d), addr), f"gemm_conv_plan({w.name})")
             d.tma_host = addr
-        self._emit("atmvfi_gemm_conv", (C.byref(d),), keep=(d, srcs, w, out, residual, out2, prelu2, planbuf))
+        self._emit("atmvfi_gemm_conv", (C.byref(d),), keep=(d, srcs, w, out, residual, out2, prelu2, planbuf, head32))
 
     @staticmethod
     def _tc_eligible(srcs, w, out, out2) -> bool:
         """Layers the tcgen05 kernel takes: 16-byte aligned operands and enough input channels to fill a K chunk."""
         if sum(w.split) < 16:
             return False
-        if any(s.ptr % 16 for s in srcs) or out.ptr % 16 or (out2 is not None and out2.ptr % 16):
+        oa = lambda m: 8 if m.half else 16             # fp16 outputs are written as 8-byte vectors
+        if any(s.ptr % 16 for s in srcs) or out.ptr % oa(out) or (out2 is not None and out2.ptr % oa(out2)):
             return False
         return True
 
@@ -338,7 +382,8 @@ class CudaOps:
         tail = (m[0], m[1], m[2], m[3], None if motion is None else motion.ptr, 0 if motion is None else motion.pitch, motion_off, _p(scratch)) + _yy(rows) + (int(head_major),)
         head = (qkv.ptr, qkv.pitch, out.ptr, out.pitch, out.C, heads, C.byref(gc), int(cross), _p(rc))
         keep = (qkv, out, gc, rc, mix, motion, scratch)
-        if self.precision == _lib.TF32:
+        if self.precision in (_lib.TF32, _lib.F16):
+            assert not qkv.half and out.half == self.act_f16 and (motion is None or not motion.half)
             self._emit("atmvfi_window_attention_tc", head + (int(rc_closed_form),) + tail, keep=keep)
         else:
             self._emit("atmvfi_window_attention", head + tail, keep=keep)
@@ -417,7 +462,7 @@ class CudaOps:
     def copy_map(self, src: Map, dst: Map):
         """dst <- src for two whole (contiguous) maps of equal shape."""
         assert src.t.shape == dst.t.shape and src.t.is_contiguous() and dst.t.is_contiguous() and src.c0 == dst.c0 == 0
-        self._emit("atmvfi_copy", (dst.t.data_ptr(), src.t.data_ptr(), src.t.numel() * 4), keep=(src, dst))
+        self._emit("atmvfi_copy", (dst.t.data_ptr(), src.t.data_ptr(), src.t.numel() * src.t.element_size()), keep=(src, dst))
 
     def residual_finish(self, res: Map, it, it_sum, it_clamped, rows: Rows = None):
         b, _, h, w = it.shape

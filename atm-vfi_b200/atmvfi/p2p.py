@@ -196,6 +196,8 @@ class SlabSession:
         if not dist.is_initialized():
             raise _lib.AtmvfiError("row slabs need torch.distributed (one process per GPU, launched with torchrun)")
         glob = bool(net.global_motion if global_motion is None else global_motion)
+        if net.precision == "f16":
+            raise _lib.AtmvfiError("row slabs exchange fp32 feature-map rows: use precision 'tf32', 'fp32x3' or 'fp32' (not 'f16')")
         self.device = dev
         with torch.cuda.device(dev):
             self.arena = P2PArena(dev, arena_bytes or default_arena_bytes(net.ARCH.name, B, H, W), group)

@@ -133,3 +133,34 @@ def pack_tc_x3(w: PackedGemm) -> torch.Tensor:
     nk = L["ktc"] // TC_CHUNK
     out = torch.stack([hi.reshape(L["n_pad"], nk, TC_CHUNK), lo.reshape(L["n_pad"], nk, TC_CHUNK)], 2)
     return out.reshape(L["n_pad"], 2 * L["ktc"]).contiguous()
+
+
+TC_CHUNK_F16 = 64      # fp16 elements per K step (one 128-byte swizzle row)
+
+
+def pack_tc_f16(w: PackedGemm) -> torch.Tensor:
+    """fp16 operand of the kind::f16 path: the pack_tc layout with 64-channel chunks, [N_pad][K_tc16] K-major, rounded to fp16
+    (round-to-nearest-even).  Raises if a weight is outside the fp16 range."""
+    L = tc_layout(w.split, w.ksize, w.Cout, w.shuffle)
+    chunks = [-(-c // TC_CHUNK_F16) for c in w.split]
+    ktc = w.ksize * w.ksize * sum(chunks) * TC_CHUNK_F16
+    taps, ctot = w.ksize * w.ksize, sum(w.split)
+    n_true = 4 * w.Cout if w.shuffle else w.Cout
+    src = w.w32[:, :n_true].reshape(taps, ctot, n_true)
+    parts, c0 = [], 0
+    for c, ch in zip(w.split, chunks):
+        blk = src[:, c0 : c0 + c]
+        if ch * TC_CHUNK_F16 != c:
+            blk = torch.nn.functional.pad(blk, (0, 0, 0, ch * TC_CHUNK_F16 - c))
+        parts.append(blk)
+        c0 += c
+    kmat = torch.cat(parts, 1).reshape(ktc, n_true)
+    out = torch.zeros(L["n_pad"], ktc, dtype=torch.float32, device=w.w32.device)
+    if w.shuffle:
+        for q in range(4):
+            out[q * L["cq_pad"] : q * L["cq_pad"] + w.Cout] = kmat[:, q * w.Cout : (q + 1) * w.Cout].t()
+    else:
+        out[: w.Cout] = kmat.t()
+    if float(out.abs().max()) > 6.0e4:
+        raise ValueError(f"{w.name}: weight magnitude {float(out.abs().max()):.3g} does not fit fp16; use precision 'tf32'")
+    return out.to(torch.float16).contiguous()

@@ -11,7 +11,7 @@ from .engine import PackedModel, Plan, clone_outputs
 from .modules import STRUCT_EPOCH
 from .ops import CudaOps
 
-PRECISIONS = {"fp32": _lib.FP32, "tf32": _lib.TF32, "fp32x3": _lib.TF32X3}
+PRECISIONS = {"fp32": _lib.FP32, "tf32": _lib.TF32, "fp32x3": _lib.TF32X3, "f16": _lib.F16}
 
 
 class Runtime:

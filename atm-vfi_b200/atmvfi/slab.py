@@ -196,12 +196,17 @@ class SlabOps:
         self._by_start[t.data_ptr()] = b
         return b
 
-    def new_map(self, B, H, W, C, zero=False) -> Map:
+    act_f16 = False                # row slabs run on fp32 feature maps (tf32 / fp32 / fp32x3)
+
+    def to_act(self, m: Map) -> Map:
+        return m
+
+    def new_map(self, B, H, W, C, zero=False, f32=False) -> Map:
         m = self.backend.new_map(B, H, W, C, zero)
         self._register("nhwc", m.t, B, 1, H)
         return m
 
-    def new_win_map(self, g: WinGeom, C) -> Map:
+    def new_win_map(self, g: WinGeom, C, f32=False) -> Map:
         m = self.backend.new_win_map(g, C)
         self._register("win", m.t, g.B2, 1, g.Hp // g.ws, g)
         return m
@@ -320,7 +325,7 @@ class SlabOps:
 
     # ---- GEMM-shaped layers -----------------------------------------------------------------------
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride=1, dil=1, act=True, residual=None, out2=None,
-                  prelu2=None, win: Optional[WinGeom] = None, precision=None, qkv_heads: int = 0):
+                  prelu2=None, win: Optional[WinGeom] = None, precision=None, qkv_heads: int = 0, out_f32: bool = False):
         ob = self._buf(out)[0]
         sb = self._buf(srcs[0])[0]
         gsrcs = [self._buf(s)[0].grid_map(s) for s in srcs]

@@ -5,7 +5,9 @@
 
 static thread_local char g_err[512] = "";
 static thread_local int g_round = 0;
+static thread_local int g_act_f16 = 0;
 int atmvfi_output_rounding() { return g_round; }
+int atmvfi_act_f16() { return g_act_f16; }
 
 void atmvfi_set_error(const char* fmt, ...) {
   va_list ap;
@@ -22,6 +24,7 @@ extern "C" {
 const char* atmvfi_last_error(void) { return g_err; }
 int atmvfi_abi_version(void) { return ATMVFI_ABI_VERSION; }
 void atmvfi_set_output_rounding(int on) { g_round = on ? 1 : 0; }
+void atmvfi_set_activation_f16(int on) { g_act_f16 = on ? 1 : 0; }
 
 int atmvfi_device_info(int device, char* name, int* cc_major, int* cc_minor) {
   cudaDeviceProp prop;
@@ -62,7 +65,7 @@ int atmvfi_gemm_conv(const atmvfi_gemm_conv_desc* d, void* stream) {
   ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_SHUFFLE2 || (d->ksize == 1 && d->stride == 1), "gemm_conv: SHUFFLE2 needs ksize=1, stride=1");
   ATMVFI_REQUIRE(!d->out2 || d->prelu2, "gemm_conv: out2 needs prelu2 slopes");
   if (d->precision == ATMVFI_FP32) return atmvfi_gemm_conv_simt(d, (cudaStream_t)stream);
-  if (d->precision == ATMVFI_TF32 || d->precision == ATMVFI_TF32X3) return atmvfi_gemm_conv_tc(d, (cudaStream_t)stream);
+  if (d->precision == ATMVFI_TF32 || d->precision == ATMVFI_TF32X3 || d->precision == ATMVFI_F16) return atmvfi_gemm_conv_tc(d, (cudaStream_t)stream);
   atmvfi_set_error("gemm_conv: unknown precision %d", d->precision);
   return 2;
 }

@@ -221,6 +221,8 @@ static int attention_impl(bool tensor_cores, int rc_closed_form, const float* qk
   int rcode = 3;
   if (tensor_cores)
     rcode = atmvfi_window_attention_tc_launch(qkv, qkv_pitch, out, out_pitch, C, heads, g, cross, (want_motion && !rc_closed_form) ? rc : nullptr, raw, wy0, nwy, layout, st);
+  ATMVFI_REQUIRE(!(rcode == 3 && atmvfi_act_f16()), "window_attention: fp16 feature maps need the tcgen05 attention kernel, which does not "
+                 "take this shape (window %d, head dim %d)", g->ws, hd);
   if (rcode == 3)      // shape outside the tcgen05 kernel's envelope (or fp32 requested): CUDA-core kernel
   switch (hd) {
     case 28: rcode = launch_attention<28>(qkv, qkv_pitch, out, out_pitch, C, heads, *g, cross, rc, raw, wy0, nwy, layout, st); break;

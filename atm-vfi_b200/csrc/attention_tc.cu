@@ -24,8 +24,9 @@ constexpr int kThreadsA = 256;     // two threads per query row (they split the 
 struct AttnParams {
   const float* qkv;
   int qkv_pitch;
-  float* out;
+  float* out;                   // fp32, or __half when out_f16 (precision ATMVFI_F16: the attention output feeds an fp16 GEMM)
   int out_pitch;
+  int out_f16;
   int C, heads, hd;
   atmvfi_window_geom g;
   int cross;
@@ -442,12 +443,13 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
     float o[16];
     ld16(tO + lane_addr + c0, o);
     if (row_ok) {
-      float* dst = p.out + grow * p.out_pitch + h * hd + c0;
+      const int64_t off = grow * p.out_pitch + h * hd + c0;
 #pragma unroll
       for (int e = 0; e < 16; e += 4) {
         if (c0 + e < hd) {
           float4 v = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
-          *reinterpret_cast<float4*>(dst + e) = round_tf32_if(v, p.round != 0);
+          if (p.out_f16) Act<__half>::st4(reinterpret_cast<__half*>(p.out) + off + e, v);
+          else *reinterpret_cast<float4*>(p.out + off + e) = round_tf32_if(v, p.round != 0);
         }
       }
     }
@@ -496,6 +498,7 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   AttnParams p;
   p.qkv = qkv; p.qkv_pitch = qkv_pitch; p.out = out; p.out_pitch = out_pitch; p.C = C; p.heads = heads; p.hd = C / heads;
   p.g = *g; p.cross = cross; p.rc = rc; p.motion_raw = motion_raw;
+  p.out_f16 = atmvfi_act_f16();
   p.prof = atmvfi_attn_prof_buffer();
   p.N = g->ws * g->ws;
   if (p.N > 256 || p.hd % 4 != 0 || p.hd > 96) return 3;

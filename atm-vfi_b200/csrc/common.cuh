@@ -1,5 +1,6 @@
 // Shared helpers for the sm_100a kernels of libatmvfi_b200.so.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -9,6 +10,10 @@ void atmvfi_set_error(const char* fmt, ...);
 // 1: producers of channels-last feature maps round their outputs to TF32 (cvt.rna), because tcgen05 kind::tf32
 // TRUNCATES the low 13 mantissa bits of its operands (measured: -2.8e-4 relative magnitude bias per layer).
 int atmvfi_output_rounding();
+
+// 1: channels-last feature maps are stored as fp16 (precision ATMVFI_F16): the entry points that read / write such maps pick their
+// __half instantiation.  Planar images, flows, masks and the 5-channel motion heads stay fp32 in every mode.
+int atmvfi_act_f16();
 
 #define ATMVFI_CHECK_LAUNCH(what)                                                        \
   do {                                                                                   \
@@ -156,3 +161,38 @@ __device__ __forceinline__ float4 round_tf32_if(float4 v, bool on) {
 }
 
 __device__ __forceinline__ float sigmoidf_exact(float x) { return 1.f / (1.f + expf(-x)); }
+
+
+// ---------------------------------------------------------------------------------------------
+// Element access of channels-last feature maps: fp32, or fp16 storage with fp32 arithmetic (ATMVFI_F16).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Act;
+template <>
+struct Act<float> {
+  static constexpr bool kHalf = false;
+  static __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ float4 lds4(const void* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+  static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <>
+struct Act<__half> {
+  static constexpr bool kHalf = true;
+  static __device__ __forceinline__ float4 unpack(uint2 u) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ uint2 pack(float4 v) {
+    uint2 u;
+    *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(v.x, v.y);
+    *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(v.z, v.w);
+    return u;
+  }
+  static __device__ __forceinline__ float4 ld4(const __half* p) { return unpack(__ldg(reinterpret_cast<const uint2*>(p))); }
+  static __device__ __forceinline__ float4 lds4(const void* p) { return unpack(*reinterpret_cast<const uint2*>(p)); }
+  static __device__ __forceinline__ void st4(__half* p, float4 v) { *reinterpret_cast<uint2*>(p) = pack(v); }
+  static __device__ __forceinline__ float ld(const __half* p) { return __half2float(__ldg(p)); }
+  static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+};

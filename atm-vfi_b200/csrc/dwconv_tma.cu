@@ -19,7 +19,7 @@ constexpr int kCc = 64;            // channels per CTA (256 B per pixel in the b
 constexpr int kX = 16;             // output columns per CTA
 constexpr int kStages = 6;
 constexpr int kRowsPerCta = 34;    // output rows per strip
-constexpr int kBoxBytes = kCc * 4 * (kX + 2);
+constexpr int kBoxBytes = kCc * 4 * (kX + 2);       // fp32 maps; fp16 maps fill half of every slot
 constexpr int kThreadsD = 256;
 
 __device__ __forceinline__ uint32_t su32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -42,7 +42,7 @@ __device__ __forceinline__ float gelu_as(float v) {
 
 struct DwParams {
   CUtensorMap map;
-  float* out;
+  void* out;
   const float* w9c;
   const float* bias;
   int B, H, W, C, pitch;
@@ -50,8 +50,9 @@ struct DwParams {
   int cblocks, xblocks, strips;
 };
 
-template <bool kFastErf>
+template <bool kFastErf, typename T = float>
 __global__ void __launch_bounds__(kThreadsD) dwconv_tma_kernel(const __grid_constant__ DwParams p, const bool rnd) {
+  constexpr int kEs = (int)sizeof(T), kBox = kCc * kEs * (kX + 2);
   __shared__ __align__(128) uint8_t ring[kStages][kBoxBytes];
   __shared__ __align__(8) uint64_t full[kStages], empty[kStages];
 
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(kThreadsD) dwconv_tma_kernel(const __grid_cons
 
   auto issue = [&](int i) {                          // input row i of the strip -> slot i % kStages (thread 0 only)
     const int s = i % kStages;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(su32(&full[s])), "r"(kBoxBytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(su32(&full[s])), "r"(kBox) : "memory");
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
                      su32(ring[s])),
                  "l"(&p.map), "r"(su32(&full[s])), "r"(c0), "r"(x0 - 1), "r"(ys - 1 + i), "r"(b)
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kThreadsD) dwconv_tma_kernel(const __grid_cons
 #pragma unroll
   for (int t = 0; t < 9; ++t) k[t] = active ? __ldg(reinterpret_cast<const float4*>(p.w9c + t * p.C + c)) : bz;
   if (active) bz = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-  float* obase = p.out + ((size_t)b * p.H * p.W + x) * p.pitch + c;
+  T* obase = reinterpret_cast<T*>(p.out) + ((size_t)b * p.H * p.W + x) * p.pitch + c;
   const size_t row_stride = (size_t)p.W * p.pitch;
 
   auto fma4 = [](const float4& a, const float4& w, float4& acc) {
@@ -108,10 +109,10 @@ __global__ void __launch_bounds__(kThreadsD) dwconv_tma_kernel(const __grid_cons
   for (int i = 0; i < nin; ++i) {
     const int s = i % kStages;
     wait(&full[s], (uint32_t)(i / kStages) & 1);
-    const uint8_t* rowp = ring[s] + xl * (kCc * 4) + c4 * 16;
-    const float4 l = *reinterpret_cast<const float4*>(rowp);
-    const float4 m = *reinterpret_cast<const float4*>(rowp + kCc * 4);
-    const float4 r = *reinterpret_cast<const float4*>(rowp + 2 * kCc * 4);
+    const uint8_t* rowp = ring[s] + xl * (kCc * kEs) + c4 * (4 * kEs);
+    const float4 l = Act<T>::lds4(rowp);
+    const float4 m = Act<T>::lds4(rowp + kCc * kEs);
+    const float4 r = Act<T>::lds4(rowp + 2 * kCc * kEs);
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(su32(&empty[s])) : "memory");
     if (tid == 0 && i + kStages < nin) {             // refill this slot once all 8 warps have read it
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kThreadsD) dwconv_tma_kernel(const __grid_cons
       float4 o;
       if (kFastErf) o = make_float4(gelu_as(acc0.x), gelu_as(acc0.y), gelu_as(acc0.z), gelu_as(acc0.w));
       else o = make_float4(gelu_erff(acc0.x), gelu_erff(acc0.y), gelu_erff(acc0.z), gelu_erff(acc0.w));
-      *reinterpret_cast<float4*>(obase + (size_t)(ys + i - 2) * row_stride) = round_tf32_if(o, rnd);
+      Act<T>::st4(obase + (size_t)(ys + i - 2) * row_stride, round_tf32_if(o, rnd));
     }
     acc0 = acc1; acc1 = acc2; acc2 = bz;
   }
@@ -149,8 +150,8 @@ EncodeTiledFn dw_get_encode() {
 }  // namespace
 
 // Returns 0 on success, 3 when this kernel does not apply (the caller falls back to the register-ring kernel).
-int atmvfi_dwconv_tma_launch(const float* in, float* out, int B, int H, int W, int C, int pitch, const float* w9c,
-                             const float* bias, int y0, int ny, bool rnd, cudaStream_t st) {
+int atmvfi_dwconv_tma_launch(const void* in, void* out, int B, int H, int W, int C, int pitch, const float* w9c,
+                             const float* bias, int y0, int ny, bool rnd, bool f16, cudaStream_t st) {
   static int enabled = -1;
   if (enabled < 0) { const char* ev = getenv("ATMVFI_DW_TMA"); enabled = ev ? atoi(ev) : 1; }
   if (!enabled) return 3;
@@ -160,10 +161,12 @@ int atmvfi_dwconv_tma_launch(const float* in, float* out, int B, int H, int W, i
   DwParams p;
   memset(&p, 0, sizeof(p));
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t gstr[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * W, (cuuint64_t)pitch * 4 * W * H};
+  const cuuint64_t es = f16 ? 2 : 4;
+  if (f16 && pitch % 8) return 3;                 // TMA strides must be multiples of 16 bytes
+  cuuint64_t gstr[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * es * W, (cuuint64_t)pitch * es * W * H};
   cuuint32_t box[4] = {(cuuint32_t)kCc, (cuuint32_t)(kX + 2), 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&p.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(&p.map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return 3;
   p.out = out; p.w9c = w9c; p.bias = bias;
@@ -175,7 +178,8 @@ int atmvfi_dwconv_tma_launch(const float* in, float* out, int B, int H, int W, i
   const int64_t ctas = (int64_t)p.cblocks * p.xblocks * p.strips * B;
   if (ctas <= 0) return 0;
   if (ctas > 0x7fffffff) return 3;
-  if (rnd) dwconv_tma_kernel<true><<<(unsigned)ctas, kThreadsD, 0, st>>>(p, rnd);
+  if (f16) dwconv_tma_kernel<true, __half><<<(unsigned)ctas, kThreadsD, 0, st>>>(p, false);      // fp16 storage: the fast erf's 2.6e-7 is far below half precision
+  else if (rnd) dwconv_tma_kernel<true><<<(unsigned)ctas, kThreadsD, 0, st>>>(p, rnd);
   else dwconv_tma_kernel<false><<<(unsigned)ctas, kThreadsD, 0, st>>>(p, rnd);
   ATMVFI_CHECK_LAUNCH("dwconv3x3_gelu(tma)");
   return 0;

@@ -5,8 +5,8 @@
 #include <string.h>
 #include "common.cuh"
 
-int atmvfi_dwconv_tma_launch(const float* in, float* out, int B, int H, int W, int C, int pitch, const float* w9c,
-                             const float* bias, int y0, int ny, bool rnd, cudaStream_t st);
+int atmvfi_dwconv_tma_launch(const void* in, void* out, int B, int H, int W, int C, int pitch, const float* w9c,
+                             const float* bias, int y0, int ny, bool rnd, bool f16, cudaStream_t st);
 
 namespace {
 
@@ -19,8 +19,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // One warp normalises one row of C floats (C % 4 == 0); row kept in registers between the passes.
-template <int MAXV>   // float4 per lane
-__device__ __forceinline__ void ln_row(const float* __restrict__ src, float* __restrict__ dst, int C,
+template <int MAXV, typename T>   // 4-channel vectors per lane
+__device__ __forceinline__ void ln_row(const T* __restrict__ src, T* __restrict__ dst, int C,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float eps, int lane, bool rnd) {
   float4 v[MAXV];
@@ -30,7 +30,7 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ src, float* __r
   for (int i = 0; i < MAXV; ++i) {
     int idx = lane + i * 32;
     if (idx < nv) {
-      v[i] = __ldg(reinterpret_cast<const float4*>(src) + idx);
+      v[i] = Act<T>::ld4(src + 4 * idx);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
@@ -56,25 +56,27 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ src, float* __r
       o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z;
       o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      reinterpret_cast<float4*>(dst)[idx] = round_tf32_if(o, rnd);
+      Act<T>::st4(dst + 4 * idx, round_tf32_if(o, rnd));
     }
   }
 }
 
 constexpr int kLnMaxV = 8;   // up to C = 1024
 
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, int in_pitch,
-                                                        float* __restrict__ out, int out_pitch, int64_t rows, int C,
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in, int in_pitch,
+                                                        T* __restrict__ out, int out_pitch, int64_t rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, bool rnd) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps)
-    ln_row<kLnMaxV>(in + r * in_pitch, out + r * out_pitch, C, gamma, beta, eps, lane, rnd);
+    ln_row<kLnMaxV, T>(in + r * in_pitch, out + r * out_pitch, C, gamma, beta, eps, lane, rnd);
 }
 
-__global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __restrict__ tok, int tok_pitch,
-                                                               float* __restrict__ win, int win_pitch, int C,
+template <typename T>
+__global__ void __launch_bounds__(256) window_gather_ln_kernel(const T* __restrict__ tok, int tok_pitch,
+                                                               T* __restrict__ win, int win_pitch, int C,
                                                                atmvfi_window_geom g, int64_t rows, int wy0, int nwy,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, bool rnd) {
@@ -85,14 +87,14 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const float* __re
     const int64_t bi = rr / per_win;
     const int64_t r = bi * per_img + (int64_t)wy0 * g.ws * g.Wp + (rr - bi * per_win);
     WinPos p = win_decode(g, r);
-    float* dst = win + r * win_pitch;
+    T* dst = win + r * win_pitch;
     if (p.real) {
-      const float* src = tok + ((int64_t)(p.b * g.H + p.y) * g.W + p.x) * tok_pitch;
-      ln_row<kLnMaxV>(src, dst, C, gamma, beta, eps, lane, rnd);
+      const T* src = tok + ((int64_t)(p.b * g.H + p.y) * g.W + p.x) * tok_pitch;
+      ln_row<kLnMaxV, T>(src, dst, C, gamma, beta, eps, lane, rnd);
     } else {
       // LayerNorm of an all-zero token: (0-0)*rstd*gamma + beta = beta (attention.py:273,316)
       for (int i = lane; i < (C >> 2); i += 32)
-        reinterpret_cast<float4*>(dst)[i] = round_tf32_if(__ldg(reinterpret_cast<const float4*>(beta) + i), rnd);
+        Act<T>::st4(dst + 4 * i, round_tf32_if(__ldg(reinterpret_cast<const float4*>(beta) + i), rnd));
     }
   }
 }
@@ -133,6 +135,13 @@ struct DwVec {
   float v[V];
 };
 template <int V>
+__device__ __forceinline__ DwVec<V> dw_load(const __half* p) {      // fp16 maps: V == 4 only
+  DwVec<V> r;
+  const float4 t = Act<__half>::ld4(p);
+  r.v[0] = t.x; r.v[1] = t.y; r.v[2 % V] = t.z; r.v[3 % V] = t.w;
+  return r;
+}
+template <int V>
 __device__ __forceinline__ DwVec<V> dw_load(const float* p) {
   DwVec<V> r;
   if (V == 4) {
@@ -145,8 +154,8 @@ __device__ __forceinline__ DwVec<V> dw_load(const float* p) {
   return r;
 }
 
-template <int V, bool kFastErf, int kDepth>
-__global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
+template <int V, bool kFastErf, int kDepth, typename T = float>
+__global__ void __launch_bounds__(256) dwconv_gelu_kernel(const T* __restrict__ in, T* __restrict__ out, int B,
                                                           int H, int W, int C, int pitch,
                                                           const float* __restrict__ w9c, const float* __restrict__ bias,
                                                           int wy0, int wy1, bool rnd) {
@@ -165,19 +174,19 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restric
   for (int t = 0; t < 9; ++t) k[t] = dw_load<V>(w9c + t * C + cg * V);
   const DwVec<V> bz = dw_load<V>(bias + cg * V);
   const bool xl = x > 0, xr = x + 1 < W;
-  const float* base = in + ((size_t)b * H * W + x) * pitch + cg * V;
+  const T* base = in + ((size_t)b * H * W + x) * pitch + cg * V;
   const size_t row_stride = (size_t)W * pitch;
   DwVec<V> zero;
 #pragma unroll
   for (int e = 0; e < V; ++e) zero.v[e] = 0.f;
   auto load_row = [&](int yy, DwVec<V>& l, DwVec<V>& m, DwVec<V>& r) {
     if (yy < 0 || yy >= H) { l = m = r = zero; return; }
-    const float* rowp = base + yy * row_stride;
+    const T* rowp = base + yy * row_stride;
     m = dw_load<V>(rowp);
     l = xl ? dw_load<V>(rowp - pitch) : zero;
     r = xr ? dw_load<V>(rowp + pitch) : zero;
   };
-  float* obase = out + ((size_t)b * H * W + x) * pitch + cg * V;
+  T* obase = out + ((size_t)b * H * W + x) * pitch + cg * V;
   // acc0: output row yy-1 (complete after input row yy), acc1: row yy, acc2: row yy+1
   DwVec<V> acc0 = bz, acc1 = bz, acc2 = bz;
   // register ring of input rows: row (y0 - 1 + i) lives in slot i % (kDepth + 1); kDepth rows are in flight ahead of the
@@ -205,8 +214,8 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restric
       float o[V];
 #pragma unroll
       for (int e = 0; e < V; ++e) o[e] = round_tf32_if(kFastErf ? gelu_fast(acc0.v[e]) : gelu_exact(acc0.v[e]), rnd);
-      float* op = obase + (size_t)(yy - 1) * row_stride;
-      if (V == 4) *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2 % V], o[3 % V]);
+      T* op = obase + (size_t)(yy - 1) * row_stride;
+      if (V == 4) Act<T>::st4(op, make_float4(o[0], o[1], o[2 % V], o[3 % V]));
       else *reinterpret_cast<float2*>(op) = make_float2(o[0], o[1]);
     }
     acc0 = acc1; acc1 = acc2; acc2 = bz;
@@ -215,10 +224,10 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const float* __restric
 
 // First encoder layer: 3x3 conv (pad 1) on a planar 3-channel image + bias + PReLU -> NHWC.  One thread computes all
 // COUT channels of one pixel from 27 cached planar loads; weights/bias/slopes sit in shared memory (broadcast reads).
-template <int COUT>
+template <int COUT, typename T>
 __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wk,
                                                             int ldw, const float* __restrict__ bias,
-                                                            const float* __restrict__ prelu, float* __restrict__ out,
+                                                            const float* __restrict__ prelu, T* __restrict__ out,
                                                             int out_pitch, int B, int H, int W, int wy0, int ny, bool rnd) {
   __shared__ float sw[27 * COUT];
   __shared__ float sb[COUT], sp[COUT];
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restr
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = ok ? __ldg(img + ((int64_t)b * 3 + c) * hw + (int64_t)yy * W + xx) : 0.f;
       }
-    float* o = out + i * out_pitch;
+    T* o = out + i * out_pitch;
 #pragma unroll
     for (int co = 0; co < COUT; co += 4) {
       float a[4] = {0.f, 0.f, 0.f, 0.f};
@@ -257,16 +266,17 @@ __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restr
         t = t > 0.f ? t : t * sp[co + e];
         rp[e] = round_tf32_if(t, rnd);
       }
-      *reinterpret_cast<float4*>(o + co) = r;
+      Act<T>::st4(o + co, r);
     }
   }
 }
 
 // Up to 5 planar 3-channel images -> 15 (+1 zero) consecutive channels of an NHWC buffer in one pass
 // (the image part of torch.cat([feat, im0, I_t_0, im1, I_t_1, I_t], 1), network_base.py:418).
+template <typename T>
 __global__ void __launch_bounds__(256) pack5_planar_kernel(const float* __restrict__ s0, const float* __restrict__ s1,
                                                            const float* __restrict__ s2, const float* __restrict__ s3,
-                                                           const float* __restrict__ s4, float* __restrict__ out,
+                                                           const float* __restrict__ s4, T* __restrict__ out,
                                                            int out_pitch, int B, int H, int W, int wy0, int ny, bool rnd) {
   const int64_t hw = (int64_t)H * W, total = (int64_t)B * ny * W;
   const float* src[5] = {s0, s1, s2, s3, s4};
@@ -280,9 +290,9 @@ __global__ void __launch_bounds__(256) pack5_planar_kernel(const float* __restri
 #pragma unroll
       for (int c = 0; c < 3; ++c) v[j * 3 + c] = round_tf32_if(__ldg(src[j] + ((int64_t)b * 3 + c) * hw + rem), rnd);
     v[15] = 0.f;
-    float4* o = reinterpret_cast<float4*>(out + i * out_pitch);
+    T* o = out + i * out_pitch;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) Act<T>::st4(o + 4 * q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
   }
 }
 
@@ -328,10 +338,10 @@ __global__ void __launch_bounds__(256) flow_warp_nchw_kernel(const float* __rest
 }
 
 // NHWC gather: a group of (C/4) lanes serves one output pixel, each lane moves one float4 per corner.
-template <bool kPeers>
-__global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __restrict__ src, int src_pitch,
+template <bool kPeers, typename T = float>
+__global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T* __restrict__ src, int src_pitch,
                                                              const float* __restrict__ head, int head_pitch, int flow_off,
-                                                             float* __restrict__ out, int out_pitch, int B, int C, int H,
+                                                             T* __restrict__ out, int out_pitch, int B, int C, int H,
                                                              int W, int wy0, int ny, bool rnd, const __grid_constant__ RowOwners own) {
   const int cv = C >> 2;
   const int64_t total = (int64_t)B * ny * W * cv;
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __rest
     float ix = warp_src_coord((float)x, __ldg(hp), W);
     float iy = warp_src_coord((float)y, __ldg(hp + 1), H);
     Bilin s = bilin_setup(ix, iy, W, H);
-    const float* base = src + (int64_t)b * H * W * src_pitch;
+    const T* base = src + (int64_t)b * H * W * src_pitch;
     long long d0 = 0, d1 = 0;
     if (kPeers) {
       if (s.vy0) d0 = owner_delta(own, s.y0);
@@ -352,9 +362,9 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __rest
     }
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     auto corner = [&](int yy, int xx, float w, bool first) {
-      const float* rowp = base + ((int64_t)yy * W + xx) * src_pitch;
-      if (kPeers) rowp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(rowp) + (yy == s.y0 ? d0 : d1));
-      float4 v = __ldg(reinterpret_cast<const float4*>(rowp) + c4);
+      const T* rowp = base + ((int64_t)yy * W + xx) * src_pitch;
+      if (kPeers) rowp = reinterpret_cast<const T*>(reinterpret_cast<const char*>(rowp) + (yy == s.y0 ? d0 : d1));
+      float4 v = Act<T>::ld4(rowp + 4 * c4);
       if (first) {
         o.x = __fmul_rn(v.x, w); o.y = __fmul_rn(v.y, w); o.z = __fmul_rn(v.z, w); o.w = __fmul_rn(v.w, w);
       } else {
@@ -366,7 +376,7 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const float* __rest
     if (s.vy0 && s.vx1) corner(s.y0, s.x0 + 1, s.wne, false);
     if (s.vy1 && s.vx0) corner(s.y0 + 1, s.x0, s.wsw, false);
     if (s.vy1 && s.vx1) corner(s.y0 + 1, s.x0 + 1, s.wse, false);
-    reinterpret_cast<float4*>(out + pix * out_pitch)[c4] = round_tf32_if(o, rnd);
+    Act<T>::st4(out + pix * out_pitch + 4 * c4, round_tf32_if(o, rnd));
   }
 }
 
@@ -565,14 +575,38 @@ inline int grid_for(int64_t work_items, int block) {
 
 }  // namespace
 
+// fp32 rows [rows][C] (pitch in floats) -> fp16 rows (pitch in halves): the tiny fp32 side products (per-token motion, 5-channel
+// motion heads) that also feed an fp16 GEMM as one of its concatenated sources.
+__global__ void __launch_bounds__(256) cast_f32_f16_kernel(const float* __restrict__ in, int in_pitch, __half* __restrict__ out, int out_pitch,
+                                                           int64_t rows, int C, int zero_to) {
+  const int64_t total = rows * zero_to;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / zero_to;
+    const int c = (int)(i - r * zero_to);
+    out[r * out_pitch + c] = c < C ? __float2half_rn(__ldg(in + r * in_pitch + c)) : __float2half_rn(0.f);
+  }
+}
+
 extern "C" {
+
+int atmvfi_cast_f32_to_f16(const float* in, int in_pitch, void* out, int out_pitch, int64_t rows, int C, int zero_fill_to, void* stream) {
+  ATMVFI_REQUIRE(C > 0 && zero_fill_to <= out_pitch && C <= in_pitch, "cast_f32_to_f16: bad channel counts");
+  if (rows <= 0) return 0;
+  const int zt = zero_fill_to > C ? zero_fill_to : C;
+  cast_f32_f16_kernel<<<grid_for(rows * zt, 256), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, reinterpret_cast<__half*>(out), out_pitch, rows, C, zt);
+  ATMVFI_CHECK_LAUNCH("cast_f32_to_f16");
+  return 0;
+}
 
 int atmvfi_layernorm(const float* in, int in_pitch, float* out, int out_pitch, int64_t rows, int C, const float* gamma,
                      const float* beta, float eps, void* stream) {
   ATMVFI_REQUIRE(C % 4 == 0 && C <= kLnMaxV * 128 && in_pitch % 4 == 0 && out_pitch % 4 == 0,
                  "layernorm: C=%d pitches %d/%d unsupported (need C%%4==0, C<=%d)", C, in_pitch, out_pitch, kLnMaxV * 128);
   if (rows <= 0) return 0;
-  layernorm_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, C, gamma, beta, eps, atmvfi_output_rounding() != 0);
+  if (atmvfi_act_f16())
+    layernorm_kernel<__half><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(in), in_pitch, reinterpret_cast<__half*>(out), out_pitch, rows, C, gamma, beta, eps, false);
+  else
+    layernorm_kernel<float><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, C, gamma, beta, eps, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("layernorm");
   return 0;
 }
@@ -585,7 +619,10 @@ int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win
   ATMVFI_REQUIRE(row_window(g->Hp / g->ws, wy0, wy1, &w0, &nwy), "window_gather_ln: bad window-row range [%d,%d)", wy0, wy1);
   int64_t rows = (int64_t)g->B2 * nwy * g->ws * g->Wp;
   if (rows <= 0) return 0;
-  window_gather_ln_kernel<<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(tok, tok_pitch, win, win_pitch, C, *g, rows, w0, nwy, gamma, beta, eps, atmvfi_output_rounding() != 0);
+  if (atmvfi_act_f16())
+    window_gather_ln_kernel<__half><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(tok), tok_pitch, reinterpret_cast<__half*>(win), win_pitch, C, *g, rows, w0, nwy, gamma, beta, eps, false);
+  else
+    window_gather_ln_kernel<float><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(tok, tok_pitch, win, win_pitch, C, *g, rows, w0, nwy, gamma, beta, eps, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("window_gather_ln");
   return 0;
 }
@@ -600,10 +637,21 @@ int atmvfi_conv3x3_first(const float* img, const float* wk, int ldw, const float
   const bool rnd = atmvfi_output_rounding() != 0;
   int grid = grid_for(n, 128);
   cudaStream_t st = (cudaStream_t)stream;
+  const bool f16 = atmvfi_act_f16() != 0;
+  __half* outh = reinterpret_cast<__half*>(out);
   switch (Cout) {
-    case 16: conv3x3_first_kernel<16><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd); break;
-    case 24: conv3x3_first_kernel<24><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd); break;
-    case 32: conv3x3_first_kernel<32><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd); break;
+    case 16:
+      if (f16) conv3x3_first_kernel<16, __half><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, outh, out_pitch, B, H, W, y0, ny, false);
+      else conv3x3_first_kernel<16, float><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd);
+      break;
+    case 24:
+      if (f16) conv3x3_first_kernel<24, __half><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, outh, out_pitch, B, H, W, y0, ny, false);
+      else conv3x3_first_kernel<24, float><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd);
+      break;
+    case 32:
+      if (f16) conv3x3_first_kernel<32, __half><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, outh, out_pitch, B, H, W, y0, ny, false);
+      else conv3x3_first_kernel<32, float><<<grid, 128, 0, st>>>(img, wk, ldw, bias, prelu, out, out_pitch, B, H, W, y0, ny, rnd);
+      break;
     default:
       atmvfi_set_error("conv3x3_first: Cout=%d not instantiated (16, 24, 32)", Cout);
       return 2;
@@ -619,7 +667,10 @@ int atmvfi_pack5_planar(const float* s0, const float* s1, const float* s2, const
   ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "pack5_planar: bad row window [%d,%d)", y0, y1);
   int64_t n = (int64_t)B * ny * W;
   if (n <= 0) return 0;
-  pack5_planar_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s0, s1, s2, s3, s4, out, out_pitch, B, H, W, y0, ny, atmvfi_output_rounding() != 0);
+  if (atmvfi_act_f16())
+    pack5_planar_kernel<__half><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s0, s1, s2, s3, s4, reinterpret_cast<__half*>(out), out_pitch, B, H, W, y0, ny, false);
+  else
+    pack5_planar_kernel<float><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(s0, s1, s2, s3, s4, out, out_pitch, B, H, W, y0, ny, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("pack5_planar");
   return 0;
 }
@@ -632,9 +683,16 @@ int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int 
   if ((int64_t)B * ny * W <= 0) return 0;
   ATMVFI_REQUIRE((int64_t)W * (C / 4) < (1 << 30) && B <= 65535, "dwconv3x3_gelu: shape out of range");
   static_assert(kDwCg * kDwX == 256, "dwconv CTA shape");
+  const bool f16 = atmvfi_act_f16() != 0;
   {   // TMA-fed streaming kernel (dwconv_tma.cu); falls through to the register-ring kernel when it does not apply
-    const int rc = atmvfi_dwconv_tma_launch(in, out, B, H, W, C, pitch, w9c, bias, y0, ny, atmvfi_output_rounding() != 0, (cudaStream_t)stream);
+    const int rc = atmvfi_dwconv_tma_launch(in, out, B, H, W, C, pitch, w9c, bias, y0, ny, !f16 && atmvfi_output_rounding() != 0, f16, (cudaStream_t)stream);
     if (rc != 3) return rc;
+  }
+  if (f16) {      // fp16 maps: register-ring kernel, 4 channels per thread
+    dim3 grid((unsigned)(((C / 4 + kDwCg - 1) / kDwCg) * ((W + kDwX - 1) / kDwX)), (unsigned)((ny + kDwRows - 1) / kDwRows), (unsigned)B);
+    dwconv_gelu_kernel<4, true, 3, __half><<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(in), reinterpret_cast<__half*>(out), B, H, W, C, pitch, w9c, bias, y0, y0 + ny, false);
+    ATMVFI_CHECK_LAUNCH("dwconv3x3_gelu");
+    return 0;
   }
   static int vsel = 0, dsel = 0;
   if (!vsel) { const char* ev = getenv("ATMVFI_DW_V"); vsel = ev ? atoi(ev) : 4; }
@@ -677,11 +735,14 @@ static int flow_warp_nhwc_impl(const float* src, int src_pitch, const float* hea
   memset(&own, 0, sizeof(own));
   const bool rnd = atmvfi_output_rounding() != 0;
   if (owners && owners->nseg > 0) {
+    ATMVFI_REQUIRE(!atmvfi_act_f16(), "flow_warp_nhwc_p2p: the row-slab mode runs on fp32 feature maps (tf32 / fp32 / fp32x3 precision)");
     ATMVFI_REQUIRE(owners->nseg <= ATMVFI_P2P_MAX_PEERS * 2, "flow_warp_nhwc: %d owner segments (max %d)", owners->nseg, ATMVFI_P2P_MAX_PEERS * 2);
     own.nseg = owners->nseg;
     for (int i = 0; i < owners->nseg; ++i) { own.lo[i] = owners->row_lo[i]; own.delta[i] = owners->byte_delta[i]; }
     own.lo[owners->nseg] = owners->row_lo[owners->nseg];
     flow_warp_nhwc_kernel<true><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, ny, rnd, own);
+  } else if (atmvfi_act_f16()) {      // fp16 feature maps (the flows in `head` stay fp32)
+    flow_warp_nhwc_kernel<false, __half><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(src), src_pitch, head, head_pitch, flow_off, reinterpret_cast<__half*>(out), out_pitch, B, C, H, W, y0, ny, false, own);
   } else {
     flow_warp_nhwc_kernel<false><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, head, head_pitch, flow_off, out, out_pitch, B, C, H, W, y0, ny, rnd, own);
   }

@@ -55,9 +55,10 @@ struct TcPlan {                                 // host-side, produced by atmvfi
   int cluster;                                  // CTAs per cluster (B multicast), 1 or 2
   int row0, row1;                               // row window of the GEMM grid: tiles cover output rows [row0, row1)
   int x3;                                       // 1: 3xTF32 (fp32-tolerance) datapath, weights packed as hi | lo chunk pairs
+  int f16, chunk;                               // fp16 operands; elements per 128-byte K row (32 fp32 / 64 fp16)
   uint32_t magic;
 };
-constexpr uint32_t kPlanMagic = 0xA7B20004u;
+constexpr uint32_t kPlanMagic = 0xA7B20005u;
 
 struct TcParams {
   CUtensorMap mapA[ATMVFI_MAX_SRC];
@@ -227,6 +228,35 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (fp16 operands, fp32 accumulate): K = 16 per instruction, i.e. the same 32 bytes of a 128-byte swizzle row as kind::tf32
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <bool kF16, int kCS>
+__device__ __forceinline__ void tc_mma_any(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (kF16) {
+    if (kCS == 2) tc_mma_f16_2cta(tmem_d, adesc, bdesc, idesc, accumulate); else tc_mma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    if (kCS == 2) tc_mma_tf32_2cta(tmem_d, adesc, bdesc, idesc, accumulate); else tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+  }
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -263,6 +293,15 @@ __device__ __forceinline__ uint32_t make_idesc_tf32(int n, int m = kBlockM) {
   return d;
 }
 
+// kind::f16 with fp16 A and B (format code 0), fp32 accumulate
+__device__ __forceinline__ uint32_t make_idesc_f16(int n, int m = kBlockM) {
+  uint32_t d = 0;
+  d |= 1u << 4;                 // D format = F32; A / B format fields stay 0 = F16
+  d |= (uint32_t)(n >> 3) << 17;
+  d |= (uint32_t)(m >> 4) << 24;
+  return d;
+}
+
 // cluster tile -> (n_tile, image, tile origin) for this CTA; m tiles beyond the last one are phantoms whose
 // coordinates fall outside the tensor (TMA zero-fills, the epilogue stores nothing).
 __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs, int rank, int& n_tile, int& b, int& oy0, int& ox0) {
@@ -285,9 +324,14 @@ __device__ __forceinline__ void tile_coords(const TcParams& p, int ctile, int cs
 // host (pack_tc_x3: each 32-channel chunk is a hi row block followed by a lo row block).  Activations stay plain fp32 in HBM: the
 // tensor core itself truncates the raw box to a_hi, and warps 2-3 ("converters") write a_lo = rna_tf32(a - trunc(a)) for every
 // landed box into a second shared-memory ring with the same swizzled layout before the MMA warp may touch the slot.
-template <int kHalo, int kCS, bool kPair, int kEpi, int kEW = 8, bool kX3 = false>
+//
+// kF16 - precision ATMVFI_F16: sources / weights are fp16 (64 channels per 128-byte K row, kind::f16 MMAs, K = 16 each), the
+// epilogue stores fp16 (or fp32 for the few fp32 consumers) and reads fp16 residuals.  Everything byte-based is unchanged.
+template <int kHalo, int kCS, bool kPair, int kEpi, int kEW = 8, bool kX3 = false, bool kF16 = false>
 __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const __grid_constant__ TcParams p) {
   static_assert(!kX3 || (!kPair && kHalo != 2 && kEW == 8), "3xTF32 supports the plain and halo box modes with 8 epilogue warps");
+  static_assert(!(kX3 && kF16), "3xTF32 and fp16 are different datapaths");
+  constexpr int kCh = kF16 ? 2 * kChunk : kChunk;          // elements per 128-byte K row
   constexpr bool kFastEpi = kEpi == 1 || kEpi == 3;
   constexpr bool kQkv = kEpi == 3;
   constexpr bool kResHoist = kEpi == 2;
@@ -373,11 +417,11 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
                 if (elect_one()) {
                   if (kX3) {          // every CTA's box completes on its OWN barrier: its converter warps wait there
                     mbar_expect_tx(&fullA[as_], p.a_bytes);
-                    tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                    tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kCh, ix, iy, b);
                   } else {
                     if (rank == 0) mbar_expect_tx(&fullA[as_], p.a_bytes * cs);          // leader arms for both CTAs' boxes
-                    if (cs == 2) tma_load_4d_2cta(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
-                    else tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kChunk, ix, iy, b);
+                    if (cs == 2) tma_load_4d_2cta(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kCh, ix, iy, b);
+                    else tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kCh, ix, iy, b);
                   }
                 }
                 __syncwarp();
@@ -391,7 +435,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
                     if (elect_one()) {
                       if (rank == 0) mbar_expect_tx(&fullB[bs_], p.block_n * 128);         // both halves of the weight tile
                       uint8_t* dst = ringB + bs_ * p.b_slot_bytes;
-                      const int kcol = (kb * kParts + part) * kChunk;
+                      const int kcol = (kb * kParts + part) * kCh;
                       if (cs == 2)      // this CTA holds columns [rank*N/2, +N/2) of the weight tile
                         tma_load_2d_2cta(dst, &p.mapB, &fullB[bs_], kcol, n_tile * p.block_n + rank * b_rows);
                       else
@@ -523,7 +567,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
   } else if (warp == 1) {
     // ======================================= MMA issuer =========================================
     if (rank == 0) {   // 2-CTA mode: the leader issues M = 256 MMAs that read both CTAs' shared memory
-      const uint32_t idesc = make_idesc_tf32(p.block_n, cs == 2 ? 256 : kBlockM);
+      const uint32_t idesc = kF16 ? make_idesc_f16(p.block_n, cs == 2 ? 256 : kBlockM) : make_idesc_tf32(p.block_n, cs == 2 ? 256 : kBlockM);
       const int groups = (kHalo == 2 ? 1 : (kHalo == 1 ? 3 : p.ntaps)) * p.sum_chunks;
       const uint32_t a_step = kHalo == 1 ? (uint32_t)(p.TW * 128) >> 4 : 0;      // descriptor units of 16 B per vertical tap
       const uint32_t a_sbo = kHalo == 2 ? (uint32_t)((p.TW + 2) * 128) : 1024u;   // full-halo box: tile rows are TW+2 pixels apart
@@ -569,19 +613,13 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
             const uint64_t bdesc = make_smem_desc(smem_u32(ringB + bs_ * p.b_slot_bytes));
             if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)   // up to 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle row
-                if (j < nmma) {
-                  if (cs == 2) tc_mma_tf32_2cta(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
-                  else tc_mma_tf32(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
-                }
+              for (int j = 0; j < 4; ++j)   // up to 4 x (K = 8 tf32 / 16 fp16 = 32 bytes) inside the 128-byte swizzle row
+                if (j < nmma) tc_mma_any<kF16, kCS>(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
               if (kPair) {                  // second 128-pixel tile of the pair: next TH rows of the same box, same weights
                 const uint64_t adesc2 = adesc + (uint64_t)((kBlockM * 128) >> 4);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                  if (j < nmma) {
-                    if (cs == 2) tc_mma_tf32_2cta(tmem_d + 128, adesc2 + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
-                    else tc_mma_tf32(tmem_d + 128, adesc2 + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
-                  }
+                  if (j < nmma) tc_mma_any<kF16, kCS>(tmem_d + 128, adesc2 + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (first && j == 0) ? 0u : 1u);
               }
               if (cs == 2) {
                 tc_commit_2cta(&emptyB[bs_]);
@@ -711,6 +749,10 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
                   v.z = v.z > 0.f ? v.z : v.z * sl4.z; v.w = v.w > 0.f ? v.w : v.w * sl4.w;
                 }
                 const int64_t mrow = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
+                if (kF16 && e.out_half) {         // fp16 map (never the q|k|v layout, which stays fp32)
+                  Act<__half>::st4(reinterpret_cast<__half*>(e.out) + mrow * e.out_pitch + co0 + col, v);
+                  continue;
+                }
                 v = round_tf32_if(v, rnd);
                 if (qkv_v) {
                   const float vv[4] = {v.x, v.y, v.z, v.w};
@@ -741,8 +783,9 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr) {
               const int2 ri = s_row[rr * 4 + rsub];
+              const int64_t roff = (int64_t)ri.y * e.res_pitch + co0 + col;
               res4[rr] = ri.x < 0 ? make_float4(0.f, 0.f, 0.f, 0.f)
-                                  : __ldg(reinterpret_cast<const float4*>(e.residual + (int64_t)ri.y * e.res_pitch + co0 + col));
+                                  : (kF16 ? Act<__half>::ld4(reinterpret_cast<const __half*>(e.residual) + roff) : __ldg(reinterpret_cast<const float4*>(e.residual + roff)));
             }
           }
           auto emit_row = [&](const int rr) {
@@ -752,17 +795,19 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
             const float4 a4 = *reinterpret_cast<const float4*>(&stage[row * kEpiPitch + col]);
             float v[4] = {a4.x + bz[0], a4.y + bz[1], a4.z + bz[2], a4.w + bz[3]};
             if (e.residual) {
-              const float* rs = e.residual + (int64_t)ri.y * e.res_pitch + co0 + col;
+              const int64_t roff = (int64_t)ri.y * e.res_pitch + co0 + col;
+              const float* rs = e.residual + roff;
+              const __half* rsh = reinterpret_cast<const __half*>(e.residual) + roff;
               if (res_vec) {
                 const float4 t = res4[kResHoist ? rr : 0];
                 v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
               } else if (full4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(rs));
+                const float4 t = kF16 ? Act<__half>::ld4(rsh) : __ldg(reinterpret_cast<const float4*>(rs));
                 v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  if (col + k < nvalid) v[k] += __ldg(rs + k);
+                  if (col + k < nvalid) v[k] += kF16 ? Act<__half>::ld(rsh + k) : __ldg(rs + k);
               }
             }
             if (e.prelu) {
@@ -774,6 +819,35 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
 #pragma unroll
               for (int k = 0; k < 4; ++k) w[k] = round_tf32_if(v[k] > 0.f ? v[k] : v[k] * sl2[k], rnd);
             }
+            if (kF16) {
+              if (e.head32) {         // fp32 copy of the motion channels (flows + occlusion logit), before any narrowing
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (col + k < nvalid && co0 + col + k >= e.head32_c0)
+                    e.head32[(int64_t)ri.x * e.head32_pitch + (co0 + col + k - e.head32_c0)] = v[k];
+              }
+              if (e.out_half) {
+                __half* o1 = reinterpret_cast<__half*>(e.out) + (int64_t)ri.x * e.out_pitch + co0 + col;
+                if (full4) {
+                  Act<__half>::st4(o1, make_float4(v[0], v[1], v[2], v[3]));
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (col + k < nvalid) o1[k] = __float2half_rn(v[k]);
+                }
+              }
+              if (e.out2) {
+                __half* o2 = reinterpret_cast<__half*>(e.out2) + (int64_t)ri.x * e.out2_pitch + co0 + col;
+                if (full4) {
+                  Act<__half>::st4(o2, make_float4(w[0], w[1], w[2], w[3]));
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (col + k < nvalid) o2[k] = __float2half_rn(w[k]);
+                }
+              }
+              if (e.out_half) return;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) v[k] = round_tf32_if(v[k], rnd);
             float* o1 = e.out + (int64_t)ri.x * e.out_pitch + co0 + col;
@@ -784,7 +858,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
               for (int k = 0; k < 4; ++k)
                 if (col + k < nvalid) o1[k] = v[k];
             }
-            if (e.out2) {
+            if (e.out2 && !kF16) {
               float* o2 = e.out2 + (int64_t)ri.x * e.out2_pitch + co0 + col;
               if (full4) {
                 *reinterpret_cast<float4*>(o2) = make_float4(w[0], w[1], w[2], w[3]);
@@ -821,6 +895,73 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
+
+// ------------------------------------------------------------------------------------------- kernel tables
+typedef void (*TcKernelFn)(TcParams);
+
+// Instantiations of one operand type.  tbl 0: [fast epilogue][0 plain, 1 halo, 2 full halo, 3 paired halo][cluster]; tbl 1: residual
+// prefetch [cluster]; tbl 2: 16 epilogue warps [fast][0 plain, 1 paired halo][cluster]; tbl 3: head-major q|k|v [16 warps][cluster].
+template <bool kF16>
+struct TcKernels {
+  static TcKernelFn get(int tbl, int a, int b, int c) {
+    static const TcKernelFn table[2][4][2] = {
+        {{gemm_conv_tc_kernel<0, 1, false, 0, 8, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 0, 8, false, kF16>},
+         {gemm_conv_tc_kernel<1, 1, false, 0, 8, false, kF16>, gemm_conv_tc_kernel<1, 2, false, 0, 8, false, kF16>},
+         {gemm_conv_tc_kernel<kF16 ? 1 : 2, 1, false, 0, 8, false, kF16>, gemm_conv_tc_kernel<kF16 ? 1 : 2, 2, false, 0, 8, false, kF16>},
+         {gemm_conv_tc_kernel<1, 1, true, 0, 8, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 0, 8, false, kF16>}},
+        {{gemm_conv_tc_kernel<0, 1, false, 1, 8, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 1, 8, false, kF16>},
+         {gemm_conv_tc_kernel<1, 1, false, 1, 8, false, kF16>, gemm_conv_tc_kernel<1, 2, false, 1, 8, false, kF16>},
+         {gemm_conv_tc_kernel<kF16 ? 1 : 2, 1, false, 1, 8, false, kF16>, gemm_conv_tc_kernel<kF16 ? 1 : 2, 2, false, 1, 8, false, kF16>},
+         {gemm_conv_tc_kernel<1, 1, true, 1, 8, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 1, 8, false, kF16>}}};
+    static const TcKernelFn res_table[2] = {gemm_conv_tc_kernel<0, 1, false, 2, 8, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 2, 8, false, kF16>};
+    static const TcKernelFn table16[2][2][2] = {
+        {{gemm_conv_tc_kernel<0, 1, false, 0, 16, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 0, 16, false, kF16>},
+         {gemm_conv_tc_kernel<1, 1, true, 0, 16, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 0, 16, false, kF16>}},
+        {{gemm_conv_tc_kernel<0, 1, false, 1, 16, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 1, 16, false, kF16>},
+         {gemm_conv_tc_kernel<1, 1, true, 1, 16, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 1, 16, false, kF16>}}};
+    static const TcKernelFn qkv_table[2][2] = {{gemm_conv_tc_kernel<0, 1, false, 3, 8, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 3, 8, false, kF16>},
+                                               {gemm_conv_tc_kernel<0, 1, false, 3, 16, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 3, 16, false, kF16>}};
+    switch (tbl) {
+      case 0: return table[a][b][c];
+      case 1: return res_table[c];
+      case 2: return table16[a][b][c];
+      default: return qkv_table[a][c];
+    }
+  }
+  // opt in to > 48 KB of dynamic shared memory for every instantiation (per device)
+  static cudaError_t configure() {
+    for (int a = 0; a < 2; ++a)
+      for (int c = 0; c < 2; ++c) {
+        for (int b = 0; b < 4; ++b) {
+          cudaError_t e = cudaFuncSetAttribute(get(0, a, b, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8));
+          if (e != cudaSuccess) return e;
+        }
+        for (int b = 0; b < 2; ++b) {
+          cudaError_t e = cudaFuncSetAttribute(get(2, a, b, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
+          if (e != cudaSuccess) return e;
+        }
+        cudaError_t e = cudaFuncSetAttribute(get(3, a, 0, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(a ? 16 : 8));
+        if (e != cudaSuccess) return e;
+        if (a == 0) {
+          e = cudaFuncSetAttribute(get(1, 0, 0, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8));
+          if (e != cudaSuccess) return e;
+        }
+      }
+    return cudaSuccess;
+  }
+};
+
+}  // namespace
+
+#ifdef ATMVFI_TC_F16_TU
+// The fp16 instantiations live in their own translation unit (gemm_conv_tc_f16.cu) so that the two halves compile in parallel.
+TcKernelFn atmvfi_tc_f16_kernel(int tbl, int a, int b, int c) { return TcKernels<true>::get(tbl, a, b, c); }
+cudaError_t atmvfi_tc_f16_configure() { return TcKernels<true>::configure(); }
+#else
+TcKernelFn atmvfi_tc_f16_kernel(int tbl, int a, int b, int c);
+cudaError_t atmvfi_tc_f16_configure();
+
+namespace {
 
 // ------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -869,6 +1010,10 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   static int halo_ok = -1;
   if (halo_ok < 0) { const char* ev = getenv("ATMVFI_TC_HALO"); halo_ok = ev ? atoi(ev) : 1; }
   pl->x3 = d->precision == ATMVFI_TF32X3 ? 1 : 0;
+  pl->f16 = d->precision == ATMVFI_F16 ? 1 : 0;
+  pl->chunk = pl->f16 ? 2 * kChunk : kChunk;
+  const int es = pl->f16 ? 2 : 4;                 // bytes per operand element
+  const int pitch_align = 16 / es;
   pl->halo = (halo_ok && d->ksize == 3 && d->stride == 1 && d->dil == 1) ? (pl->x3 ? 1 : halo_ok) : 0;   // 1: 3 boxes / chunk, 2: one full-halo box
   // pixel tile TW x TH = 128: least padding waste, then squarest.  Element-strided boxes are capped at 256
   // per dimension; halo boxes need TW % 8 == 0 (vertical taps = whole swizzle atoms) and (TH+2)*TW <= 192 rows.
@@ -913,8 +1058,8 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
 
   int ktc = 0;
   for (int s = 0; s < d->nsrc; ++s) {
-    pl->chunks[s] = cdiv(d->src[s].C, kChunk);
-    ktc += pl->chunks[s] * kChunk;
+    pl->chunks[s] = cdiv(d->src[s].C, pl->chunk);
+    ktc += pl->chunks[s] * pl->chunk;
   }
   ktc *= pl->ntaps;
   if (pl->x3) ktc *= 2;                           // every 32-channel chunk is stored as a hi block followed by a lo block
@@ -922,13 +1067,13 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
 
   for (int s = 0; s < d->nsrc; ++s) {
     const atmvfi_src& sr = d->src[s];
-    ATMVFI_REQUIRE(((uintptr_t)sr.ptr & 15) == 0 && sr.pitch % 4 == 0, "gemm_conv(tf32): source %d must be 16-byte aligned with pitch %% 4 == 0", s);
+    ATMVFI_REQUIRE(((uintptr_t)sr.ptr & 15) == 0 && sr.pitch % pitch_align == 0, "gemm_conv(tensor cores): source %d must be 16-byte aligned with a pitch of whole 16-byte units", s);
     cuuint64_t gdim[4] = {(cuuint64_t)sr.C, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->B};
-    cuuint64_t gstr[3] = {(cuuint64_t)sr.pitch * 4, (cuuint64_t)sr.pitch * 4 * d->Win, (cuuint64_t)sr.pitch * 4 * d->Win * d->Hin};
-    cuuint32_t box[4] = {(cuuint32_t)kChunk, (cuuint32_t)((pl->halo == 2 ? pl->TW + 2 : pl->TW) * d->stride),
+    cuuint64_t gstr[3] = {(cuuint64_t)sr.pitch * es, (cuuint64_t)sr.pitch * es * d->Win, (cuuint64_t)sr.pitch * es * d->Win * d->Hin};
+    cuuint32_t box[4] = {(cuuint32_t)pl->chunk, (cuuint32_t)((pl->halo == 2 ? pl->TW + 2 : pl->TW) * d->stride),
                          (cuuint32_t)((pl->halo ? (pl->pair ? 2 : 1) * pl->TH + 2 : pl->TH) * d->stride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
-    CUresult r = enc(&pl->mapA[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sr.ptr), gdim, gstr, box, estr,
+    CUresult r = enc(&pl->mapA[s], pl->f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(sr.ptr), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ATMVFI_REQUIRE(r == CUDA_SUCCESS, "gemm_conv(tf32): cuTensorMapEncodeTiled(A%d) failed with %d (C=%d W=%d H=%d B=%d pitch=%d stride=%d)", s,
@@ -937,16 +1082,18 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   {
     ATMVFI_REQUIRE(((uintptr_t)d->weight & 15) == 0, "gemm_conv(tf32): weights must be 16-byte aligned");
     cuuint64_t gdim[2] = {(cuuint64_t)ktc, (cuuint64_t)n_pad};
-    cuuint64_t gstr[1] = {(cuuint64_t)ktc * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kChunk, (cuuint32_t)(pl->block_n / pl->cluster)};
+    cuuint64_t gstr[1] = {(cuuint64_t)ktc * es};
+    cuuint32_t box[2] = {(cuuint32_t)pl->chunk, (cuuint32_t)(pl->block_n / pl->cluster)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&pl->mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->weight), gdim, gstr, box, estr,
+    CUresult r = enc(&pl->mapB, pl->f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->weight), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     ATMVFI_REQUIRE(r == CUDA_SUCCESS, "gemm_conv(tf32): cuTensorMapEncodeTiled(B) failed with %d", (int)r);
   }
-  ATMVFI_REQUIRE(((uintptr_t)d->out & 15) == 0 && d->out_pitch % 4 == 0, "gemm_conv(tf32): output must be 16-byte aligned with pitch %% 4 == 0");
-  ATMVFI_REQUIRE(!d->out2 || (((uintptr_t)d->out2 & 15) == 0 && d->out2_pitch % 4 == 0), "gemm_conv(tf32): out2 must be 16-byte aligned");
+  ATMVFI_REQUIRE(((uintptr_t)d->out & 7) == 0 && d->out_pitch % 4 == 0 && (pl->f16 || ((uintptr_t)d->out & 15) == 0),
+                 "gemm_conv(tensor cores): output must be 16-byte aligned (fp16 maps: 8-byte) with pitch %% 4 == 0");
+  ATMVFI_REQUIRE(!d->out2 || (((uintptr_t)d->out2 & 7) == 0 && d->out2_pitch % 4 == 0 && (pl->f16 || ((uintptr_t)d->out2 & 15) == 0)),
+                 "gemm_conv(tensor cores): out2 must be 16-byte aligned (fp16 maps: 8-byte)");
   pl->magic = kPlanMagic;
   return 0;
 }
@@ -954,34 +1101,17 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
 int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   const TcPlan* pl = reinterpret_cast<const TcPlan*>(d->tma_host);
   ATMVFI_REQUIRE(pl && pl->magic == kPlanMagic, "gemm_conv(tf32): missing plan (call atmvfi_gemm_conv_plan first)");
-  typedef void (*KernelFn)(TcParams);
-  static const KernelFn table[2][4][2] = {
-      {{gemm_conv_tc_kernel<0, 1, false, 0>, gemm_conv_tc_kernel<0, 2, false, 0>},
-       {gemm_conv_tc_kernel<1, 1, false, 0>, gemm_conv_tc_kernel<1, 2, false, 0>},
-       {gemm_conv_tc_kernel<2, 1, false, 0>, gemm_conv_tc_kernel<2, 2, false, 0>},
-       {gemm_conv_tc_kernel<1, 1, true, 0>, gemm_conv_tc_kernel<1, 2, true, 0>}},
-      {{gemm_conv_tc_kernel<0, 1, false, 1>, gemm_conv_tc_kernel<0, 2, false, 1>},
-       {gemm_conv_tc_kernel<1, 1, false, 1>, gemm_conv_tc_kernel<1, 2, false, 1>},
-       {gemm_conv_tc_kernel<2, 1, false, 1>, gemm_conv_tc_kernel<2, 2, false, 1>},
-       {gemm_conv_tc_kernel<1, 1, true, 1>, gemm_conv_tc_kernel<1, 2, true, 1>}}};
-  // linear layers with a residual (attention proj, Mlp fc2): generic epilogue with the residual rows prefetched
-  static const KernelFn res_table[2] = {gemm_conv_tc_kernel<0, 1, false, 2>, gemm_conv_tc_kernel<0, 2, false, 2>};
-  // fast epilogue: pixel-major output, no residual / second output, whole float4 columns, aligned bias and slopes
-  const bool plain = !d->residual && !d->out2 && d->Cout % 4 == 0 && (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0;
+  typedef TcKernelFn KernelFn;
+  const bool f16 = pl->f16 != 0;
+  // kernel families: TcKernels<false> (tf32, this translation unit), atmvfi_tc_f16_kernel (fp16, gemm_conv_tc_f16.cu), 3xTF32 below
+  auto lookup = [f16](int tbl, int a, int b, int c) -> KernelFn { return f16 ? atmvfi_tc_f16_kernel(tbl, a, b, c) : TcKernels<false>::get(tbl, a, b, c); };
+  // fast epilogue: pixel-major output, no residual / second output / fp32 head copy, whole float4 columns, aligned bias and slopes
+  const bool plain = !d->residual && !d->out2 && !(f16 && d->head32) && d->Cout % 4 == 0 && (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0;
   const int fast = (d->out_mode == ATMVFI_OUT_PIXEL && plain) ? 1 : 0;
   const bool qkv_fast = d->out_mode == ATMVFI_OUT_QKV_HEADS && plain && !pl->halo && !pl->pair;
   ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_QKV_HEADS || qkv_fast,
                  "gemm_conv(tf32): QKV_HEADS needs 16-byte aligned bias and Cout %% 4 == 0 (the generic epilogue does not carry this layout)");
-  // [epilogue warps 8 / 16][cluster]
-  static const KernelFn qkv_table[2][2] = {{gemm_conv_tc_kernel<0, 1, false, 3>, gemm_conv_tc_kernel<0, 2, false, 3>},
-                                           {gemm_conv_tc_kernel<0, 1, false, 3, 16>, gemm_conv_tc_kernel<0, 2, false, 3, 16>}};
-  // 16 epilogue warps for layers whose K loop is shorter than the accumulator drain (tile time = epilogue time):
-  // [epilogue kind][0: no halo, 1: pair mode][cluster]
-  static const KernelFn table16[2][2][2] = {
-      {{gemm_conv_tc_kernel<0, 1, false, 0, 16>, gemm_conv_tc_kernel<0, 2, false, 0, 16>},
-       {gemm_conv_tc_kernel<1, 1, true, 0, 16>, gemm_conv_tc_kernel<1, 2, true, 0, 16>}},
-      {{gemm_conv_tc_kernel<0, 1, false, 1, 16>, gemm_conv_tc_kernel<0, 2, false, 1, 16>},
-       {gemm_conv_tc_kernel<1, 1, true, 1, 16>, gemm_conv_tc_kernel<1, 2, true, 1, 16>}}};
+  ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_QKV_HEADS || !f16 || d->out_f32, "gemm_conv(f16): the head-major q|k|v output is fp32 (set out_f32)");
   // 3xTF32: [epilogue kind 0 generic / 1 fast / 2 residual prefetch][halo][cluster]
   static const KernelFn x3_table[3][2][2] = {
       {{gemm_conv_tc_kernel<0, 1, false, 0, 8, true>, gemm_conv_tc_kernel<0, 2, false, 0, 8, true>},
@@ -991,26 +1121,29 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
       {{gemm_conv_tc_kernel<0, 1, false, 2, 8, true>, gemm_conv_tc_kernel<0, 2, false, 2, 8, true>},
        {gemm_conv_tc_kernel<0, 1, false, 2, 8, true>, gemm_conv_tc_kernel<0, 2, false, 2, 8, true>}}};
   ATMVFI_REQUIRE(!pl->x3 || d->out_mode != ATMVFI_OUT_QKV_HEADS, "gemm_conv(3xtf32): the head-major q|k|v layout belongs to the tf32 attention path");
-  KernelFn kern = table[fast][pl->pair ? 3 : pl->halo][pl->cluster - 1];
+  const int res_align = f16 ? 8 : 4;             // residual rows are read as 4-element vectors: 16 B (fp32) / 8 B (fp16)
+  const bool res_ok = d->residual && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % res_align == 0;
+  KernelFn kern = lookup(0, fast, pl->pair ? 3 : pl->halo, pl->cluster - 1);
   int epi_warps = 8;
   if (pl->x3) {
-    const bool res_hoist = d->residual && !pl->halo && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % 4 == 0;
-    kern = x3_table[res_hoist ? 2 : fast][pl->halo][pl->cluster - 1];
-  } else if (d->residual && !pl->halo && !pl->pair && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % 4 == 0) {
-    kern = res_table[pl->cluster - 1];
+    kern = x3_table[(res_ok && !pl->halo) ? 2 : fast][pl->halo][pl->cluster - 1];
+  } else if (res_ok && !pl->halo && !pl->pair) {
+    // linear layers with a residual (attention proj, Mlp fc2): generic epilogue with the residual rows prefetched
+    kern = lookup(1, 0, 0, pl->cluster - 1);
   } else if (pl->pair || !pl->halo) {
     static int epi16 = -1;                    // ATMVFI_TC_EPI16: 0 never, 1 (default) short-K layers, 2 every eligible layer
     if (epi16 < 0) { const char* ev = getenv("ATMVFI_TC_EPI16"); epi16 = ev ? atoi(ev) : 1; }
     int ktc = 0;
-    for (int s2 = 0; s2 < pl->nsrc; ++s2) ktc += pl->chunks[s2] * kChunk;
+    for (int s2 = 0; s2 < pl->nsrc; ++s2) ktc += pl->chunks[s2] * pl->chunk;
     ktc *= pl->ntaps;
+    // 16 epilogue warps for layers whose K loop is shorter than the accumulator drain (tile time = epilogue time).
     // measured (Base 1080p): k2s2 transposed convs 539->380, 290->190, 277->209, 148->107 us; 3x3 layers lose (fewer
     // activation slots), so only 1x1 / transposed layers take this path by default
     if (epi16 == 2 || (epi16 == 1 && ktc <= 640 && pl->ksize == 1)) {
-      kern = table16[fast][pl->pair ? 1 : 0][pl->cluster - 1];
+      kern = lookup(2, fast, pl->pair ? 1 : 0, pl->cluster - 1);
       epi_warps = 16;
     }
-    if (qkv_fast) kern = qkv_table[epi_warps == 16 ? 1 : 0][pl->cluster - 1];
+    if (qkv_fast) kern = lookup(3, epi_warps == 16 ? 1 : 0, 0, pl->cluster - 1);
   }
   // SM count and the opt-in to > 48 KB of dynamic shared memory are PER DEVICE: a process that runs models on several GPUs
   // (model.to another device, two models) configures each device the first time it launches there.
@@ -1021,16 +1154,13 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   if (!sms_of_device[dev]) {
     int n_sm = 0;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    for (int i = 0; i < 42; ++i) {
-      KernelFn f = i >= 30 ? x3_table[(i - 30) / 4][((i - 30) / 2) % 2][i % 2]
-                 : i < 16 ? table[i / 8][(i / 2) % 4][i % 2]
-                          : (i < 18 ? res_table[i - 16] : (i < 26 ? table16[(i - 18) / 4][((i - 18) / 2) % 2][i % 2] : qkv_table[(i - 26) / 2][i % 2]));
-      const int bytes = (i < 18 || i == 26 || i == 27 || i >= 30) ? smem_bytes(8) : smem_bytes(16);
-      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-      if (e != cudaSuccess) {
-        atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", bytes, cudaGetErrorString(e));
-        return 1;
-      }
+    cudaError_t e = TcKernels<false>::configure();
+    if (e == cudaSuccess) e = atmvfi_tc_f16_configure();
+    for (int i = 0; i < 12 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(x3_table[i / 4][(i / 2) % 2][i % 2], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8));
+    if (e != cudaSuccess) {
+      atmvfi_set_error("gemm_conv(tf32): cannot reserve %d B of shared memory: %s", smem_bytes(16), cudaGetErrorString(e));
+      return 1;
     }
     sms_of_device[dev] = n_sm;
   }
@@ -1043,8 +1173,8 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   for (int s = 0; s < ATMVFI_MAX_SRC; ++s) {
     p.chunks[s] = pl->chunks[s];
     ch += pl->chunks[s];
-    const int rem = s < d->nsrc ? d->src[s].C % kChunk : 0;
-    p.last_mmas[s] = rem ? (rem + 7) / 8 : 4;
+    const int rem = s < d->nsrc ? d->src[s].C % pl->chunk : 0;
+    p.last_mmas[s] = rem ? (f16 ? (rem + 15) / 16 : (rem + 7) / 8) : 4;      // K per MMA: 8 (tf32) / 16 (fp16) elements = 32 bytes
   }
   p.ntaps = pl->ntaps; p.ksize = pl->ksize; p.stride = pl->stride; p.dil = pl->dil; p.pad = pl->pad;
   p.TW = pl->TW; p.TH = pl->TH; p.tiles_x = pl->tiles_x; p.tiles_y = pl->tiles_y; p.B = pl->B;
@@ -1092,3 +1222,5 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   }
   return 0;
 }
+
+#endif  // ATMVFI_TC_F16_TU

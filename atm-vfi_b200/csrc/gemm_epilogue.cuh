@@ -21,6 +21,12 @@ struct EpiParams {
   atmvfi_window_geom win;
   int qkv_heads, qkv_hd, qkv_C;   // ATMVFI_OUT_QKV_HEADS: heads, head dim, C = heads * hd
   int64_t qkv_R;                  // ... rows of the GEMM = B * Hout * Wout
+  // precision ATMVFI_F16: `residual` and `out2` are fp16 maps; `out` is fp16 unless out_half == 0 (q|k|v, motion heads and the final
+  // residual stay fp32); `head32` receives an fp32 copy of output channels [head32_c0, Cout) (the flows + occlusion logit that the
+  // warps consume at full precision while the same tensor feeds the next fp16 GEMM).  Pitches count elements of the map's type.
+  int act_half, out_half;
+  float* head32;
+  int head32_pitch, head32_c0;
 };
 
 // ATMVFI_OUT_QKV_HEADS: float offset of (GEMM row m, output column co in [0, 3C)) - see include/atmvfi.h.
@@ -73,5 +79,9 @@ static inline EpiParams make_epi(const atmvfi_gemm_conv_desc* d) {
   e.qkv_C = d->Cout / 3;
   e.qkv_hd = e.qkv_C / e.qkv_heads;
   e.qkv_R = (int64_t)d->B * d->Hout * d->Wout;
+  e.act_half = d->precision == ATMVFI_F16 ? 1 : 0;
+  e.out_half = (e.act_half && !d->out_f32) ? 1 : 0;
+  e.head32 = e.act_half ? d->head32 : nullptr;
+  e.head32_pitch = d->head32_pitch; e.head32_c0 = d->head32_c0;
   return e;
 }

@@ -415,6 +415,16 @@ def run_ours(args):
         plan = rt.plan(B, Hp, Wp, glob)
     hbm_gbs, bf16_burst, bf16_sust, basis = load_peaks()
     per, tc, fam = measure_kernels(plan, torch)         # BEFORE the 2 s library GEMM below: that one drives the GPU into its power cap
+    # ---------------- the other datapaths on the same workload (N = 1): device-resident value + roofline of their GEMM kernel ----------------
+    extra = {}
+    if world == 1 and not args.no_extra:
+        for prec in ("f16", "fp32x3"):
+            if prec == args.precision:
+                continue
+            try:
+                extra[prec] = measure_precision(kind, B, Hp, Wp, glob, dev, prec, args.steps, (hbm_gbs, bf16_burst, bf16_sust, basis, None), args.workload)
+            except Exception as e:
+                extra[prec] = {"error": f"{type(e).__name__}: {e}"[:300]}
     tf32_meas = measure_matmul_peak(torch, dev, "tf32", local) if args.precision in ("tf32", "fp32x3") else None
     total_ms = sum(v[1] for v in per.values())
     roof, roof_hbm = roofline_records(per, tc, fam, args.workload, (hbm_gbs, bf16_burst, bf16_sust, basis, tf32_meas), total_ms)
@@ -445,9 +455,48 @@ def run_ours(args):
         line["gpu_library_baseline"] = lib_base
     if spatial is not None:
         line["spatial_4k"] = spatial
+    if extra:
+        line["other_precisions"] = extra
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_precision(kind, B, Hp, Wp, glob, dev, precision, steps, peaks, workload):
+    """Device-resident frames/s of the same workload on another datapath ("f16": fp16 feature maps + kind::f16 MMAs; "fp32x3": 3xTF32,
+    the fp32-tolerance tensor-core path), with the roofline of its GEMM kernel.  Tolerances of each mode: tests/test_gpu_forward.py,
+    tests/test_gpu_f16.py."""
+    import torch
+    net = build_net(kind, dev, precision)
+    net.global_motion = glob
+    net.zero_copy_outputs = True
+    g = torch.Generator().manual_seed(1234)
+    im0 = torch.rand(B, 3, Hp, Wp, generator=g).to(dev)
+    im1 = torch.rand(B, 3, Hp, Wp, generator=g).to(dev)
+    for _ in range(3):
+        net(im0, im1)
+    t0 = time.time()
+    while time.time() - t0 < 1.0:
+        net(im0, im1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        net(im0, im1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    plan = net._runtime.plan(B, Hp, Wp, glob)
+    per, tc, fam = measure_kernels(plan, torch)
+    total_ms = sum(v[1] for v in per.values())
+    roof, roof_hbm = roofline_records(per, tc, fam, workload, peaks, total_ms)
+    rec = {"value": round(steps * B / (ms / 1e3), 3), "unit": "frames/s", "ms_per_step": round(ms / steps, 3), "steps": steps, "dtype": precision,
+           "roofline": roof, "roofline_hbm": roof_hbm, "plan_buffer_bytes": getattr(plan, "buffer_bytes", None),
+           "kernels_ms_per_step": {k: {"launches": v[0], "ms": round(v[1], 3)} for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])}}
+    net._runtime._plans.clear()
+    del net, plan
+    torch.cuda.empty_cache()
+    return rec
 
 
 def spatial_measure(args, workload, net, steps, parity):
@@ -653,9 +702,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="base_1080p", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32x3"])
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32", "fp32x3", "f16"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--spatial", action="store_true", help="one pair per step split into row slabs over the N GPUs (NVLink P2P halo exchange)")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the extra precision records (f16, fp32x3) next to the headline line")
     ap.add_argument("--no-spatial", action="store_true", help="N > 1: skip the embedded 4K row-slab leg (spatial_4k)")
     ap.add_argument("--no-parity", action="store_true", help="--spatial: skip the slab-vs-single-GPU bit-exactness check")
     args = ap.parse_args()

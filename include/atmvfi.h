@@ -20,6 +20,11 @@
  *     ATMVFI_TF32X3 = "3xTF32": fp32-tolerance products on the same tensor cores, each a*b issued as
  *     a_hi*b_lo + a_lo*b_hi + a_hi*b_hi (x_hi = tf32(x), x_lo = tf32(x - x_hi)); weights packed as hi|lo chunk pairs
  *     (pack.pack_tc_x3), activations split on the fly in shared memory; feature maps are stored un-rounded.
+ *     ATMVFI_F16 = fp16 STORAGE of the channels-last feature maps + tcgen05.mma kind::f16 (fp32 accumulate): same 10-bit
+ *     mantissa as TF32 at half the bytes and twice the MMA rate.  The mode is thread-local (atmvfi_set_activation_f16): while
+ *     it is on, every `float*` that names a channels-last feature map in layernorm / window_gather_ln / dwconv3x3_gelu /
+ *     flow_warp_nhwc (src, out) / conv3x3_first (out) / pack5_planar (out) / window_attention_tc (out) points to __half
+ *     elements and its pitch counts halves.  Planar images, flows, masks, q|k|v and the 5-channel motion heads stay fp32.
  *
  * There is no CPU fallback behind any of these symbols.
  */
@@ -33,10 +38,10 @@
 extern "C" {
 #endif
 
-#define ATMVFI_ABI_VERSION 2
+#define ATMVFI_ABI_VERSION 3
 #define ATMVFI_MAX_SRC 4
 
-enum { ATMVFI_FP32 = 0, ATMVFI_TF32 = 1, ATMVFI_TF32X3 = 2 };
+enum { ATMVFI_FP32 = 0, ATMVFI_TF32 = 1, ATMVFI_TF32X3 = 2, ATMVFI_F16 = 3 };
 
 /* output row mapping of atmvfi_gemm_conv */
 enum {
@@ -100,6 +105,11 @@ typedef struct {
   int32_t row_begin, row_end;    /* row window on the GEMM grid [B][Hout][Wout] (window-major sources: rows of windows,
                                     i.e. Hout = B2-images x window rows); row_end == 0: all rows */
   int32_t qkv_heads;             /* ATMVFI_OUT_QKV_HEADS: number of attention heads */
+  /* ATMVFI_F16 only: sources, residual and out2 are fp16 maps (pitches in halves, pitch % 8 == 0); `out` is fp16 unless out_f32;
+   * head32 (optional) receives an fp32 copy of output channels [head32_c0, Cout) - the flows / occlusion logit of a motion head */
+  int32_t out_f32;
+  float* head32;
+  int32_t head32_pitch, head32_c0;
 } atmvfi_gemm_conv_desc;
 
 const char* atmvfi_last_error(void);
@@ -108,6 +118,11 @@ int atmvfi_abi_version(void);
  * maps round their outputs to the nearest TF32 value (the tcgen05 tf32 datapath truncates operands otherwise).
  * The host runtime turns it on for precision ATMVFI_TF32 and off for ATMVFI_FP32 / ATMVFI_TF32X3. */
 void atmvfi_set_output_rounding(int on);
+/* Thread-local: channels-last feature maps are fp16 (see ATMVFI_F16 above).  The host runtime sets it per launch sequence. */
+void atmvfi_set_activation_f16(int on);
+/* fp32 rows [rows][C] -> fp16 rows, zero-filling channels [C, zero_fill_to): small fp32 side products (per-token motion, motion
+ * heads) that are also a source of an fp16 GEMM. */
+int atmvfi_cast_f32_to_f16(const float* in, int in_pitch, void* out, int out_pitch, int64_t rows, int C, int zero_fill_to, void* stream);
 /* Fills name[] (<=255 chars) with the device name and returns the SM count, or -1 without a usable sm_100 device. */
 int atmvfi_device_info(int device, char* name, int* cc_major, int* cc_minor);
 

