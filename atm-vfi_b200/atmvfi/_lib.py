@@ -48,6 +48,7 @@ class GemmConvDesc(C.Structure):
         ("qkv_heads", C.c_int32),
         ("out_f32", C.c_int32),
         ("head32", C.c_void_p), ("head32_pitch", C.c_int32), ("head32_c0", C.c_int32),
+        ("pad_stores", C.c_int32), ("param_pad", C.c_int32),
     ]
 
 

@@ -264,13 +264,23 @@ class CudaOps:
         d.weight, d.ldw = w.w32.data_ptr(), w.w32.shape[1]
         d.bias = _p(w.bias)
         d.prelu = _p(w.prelu) if act else None
+        pad4 = None
+        tc_prec = (self.precision if precision is None else precision) in (_lib.TF32, _lib.TF32X3, _lib.F16)
+        if tc_prec and win is None and not qkv_heads:
+            # Tensor-core epilogues read bias / slopes in whole vectors: hand them over padded to a multiple of 32 floats (cached per
+            # layer).  Odd channel counts (101, 197, 389, 5, 3 ...) on a map that owns its pad lanes (c0 == 0) may additionally be
+            # stored as whole 4-channel vectors (pad_stores) when the layer takes the non-TMA vector epilogue.
+            pad4 = self._padded(w, prelu2)
+            d.bias, d.prelu, d.param_pad = _p(pad4[0]), (_p(pad4[1]) if act else None), 32
+            if w.Cout % 4 and not w.shuffle and out.c0 == 0 and (out2 is None or out2.c0 == 0):
+                d.pad_stores = 1
         if residual is not None:
             assert residual.C == w.Cout
             d.residual, d.res_pitch = residual.ptr, residual.pitch
         d.out, d.out_pitch = out.ptr, out.pitch
         assert out.C == w.Cout, (w.name, out.C, w.Cout)
         if out2 is not None:
-            d.out2, d.prelu2, d.out2_pitch = out2.ptr, prelu2.data_ptr(), out2.pitch
+            d.out2, d.prelu2, d.out2_pitch = out2.ptr, (prelu2 if pad4 is None else pad4[2]).data_ptr(), out2.pitch
         if win is not None:
             d.out_mode, d.win = _lib.OUT_WINDOW_REV, win.c()
             assert s0.nrows == win.rows and out.nrows == win.B2 * win.H * win.W
@@ -327,7 +337,24 @@ class CudaOps:
             addr = (C.addressof(planbuf) + 63) & ~63
             _lib.check(self.lib.atmvfi_gemm_conv_plan(C.byref(d), addr), f"gemm_conv_plan({w.name})")
             d.tma_host = addr
-        self._emit("atmvfi_gemm_conv", (C.byref(d),), keep=(d, srcs, w, out, residual, out2, prelu2, planbuf, head32))
+        self._emit("atmvfi_gemm_conv", (C.byref(d),), keep=(d, srcs, w, out, residual, out2, prelu2, planbuf, head32, pad4))
+
+    @staticmethod
+    def _padded(w: PackedGemm, prelu2: Optional[torch.Tensor]):
+        """(bias, prelu, prelu2) of a layer padded to round_up(Cout, 32) + 32 floats (zeros / ones), cached on the packed layer."""
+        cache = w.__dict__.setdefault("_pad4", {})
+        key = None if prelu2 is None else prelu2.data_ptr()
+        if key not in cache:
+            n4 = round_up(w.Cout, 32) + 32
+
+            def pad(t, fill):
+                if t is None:
+                    return None
+                o = torch.full((n4,), fill, dtype=torch.float32, device=t.device)
+                o[: w.Cout] = t.reshape(-1)[: w.Cout]
+                return o
+            cache[key] = (pad(w.bias, 0.0), pad(w.prelu, 1.0), pad(prelu2, 1.0))
+        return cache[key]
 
     @staticmethod
     def _tc_eligible(srcs, w, out, out2) -> bool:

@@ -195,4 +195,19 @@ struct Act<__half> {
   static __device__ __forceinline__ void st4(__half* p, float4 v) { *reinterpret_cast<uint2*>(p) = pack(v); }
   static __device__ __forceinline__ float ld(const __half* p) { return __half2float(__ldg(p)); }
   static __device__ __forceinline__ void st(__half* p, float v) { *p = __float2half_rn(v); }
+  // 8 channels = 16 bytes per access: what the streaming kernels need to keep as many bytes in flight as their fp32 versions
+  static __device__ __forceinline__ void ld8(const __half* p, float4& a, float4& b) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    a = unpack(make_uint2(u.x, u.y));
+    b = unpack(make_uint2(u.z, u.w));
+  }
+  static __device__ __forceinline__ void lds8(const void* p, float4& a, float4& b) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    a = unpack(make_uint2(u.x, u.y));
+    b = unpack(make_uint2(u.z, u.w));
+  }
+  static __device__ __forceinline__ void st8(__half* p, float4 a, float4 b) {
+    const uint2 x = pack(a), y = pack(b);
+    *reinterpret_cast<uint4*>(p) = make_uint4(x.x, x.y, y.x, y.y);
+  }
 };

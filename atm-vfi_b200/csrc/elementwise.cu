@@ -61,7 +61,62 @@ __device__ __forceinline__ void ln_row(const T* __restrict__ src, T* __restrict_
   }
 }
 
+// fp16 rows with C % 8 == 0: 8 channels (16 bytes) per lane and step, same structure
+template <int MAXV>
+__device__ __forceinline__ void ln_row8(const __half* __restrict__ src, __half* __restrict__ dst, int C, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float eps, int lane) {
+  float4 a[MAXV], b[MAXV];
+  const int nv = C >> 3;
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      Act<__half>::ld8(src + 8 * idx, a[i], b[i]);
+      s += ((a[i].x + a[i].y) + (a[i].z + a[i].w)) + ((b[i].x + b[i].y) + (b[i].z + b[i].w));
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float d0 = a[i].x - mean, d1 = a[i].y - mean, d2 = a[i].z - mean, d3 = a[i].w - mean;
+      const float d4 = b[i].x - mean, d5 = b[i].y - mean, d6 = b[i].z - mean, d7 = b[i].w - mean;
+      q += ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * idx + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * idx), b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * idx + 1);
+      float4 o0, o1;
+      o0.x = (a[i].x - mean) * rstd * g0.x + b0.x; o0.y = (a[i].y - mean) * rstd * g0.y + b0.y;
+      o0.z = (a[i].z - mean) * rstd * g0.z + b0.z; o0.w = (a[i].w - mean) * rstd * g0.w + b0.w;
+      o1.x = (b[i].x - mean) * rstd * g1.x + b1.x; o1.y = (b[i].y - mean) * rstd * g1.y + b1.y;
+      o1.z = (b[i].z - mean) * rstd * g1.z + b1.z; o1.w = (b[i].w - mean) * rstd * g1.w + b1.w;
+      Act<__half>::st8(dst + 8 * idx, o0, o1);
+    }
+  }
+}
+
 constexpr int kLnMaxV = 8;   // up to C = 1024
+
+template <typename T>
+__device__ __forceinline__ void ln_any(const T* __restrict__ src, T* __restrict__ dst, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, int lane, bool rnd) {
+  ln_row<kLnMaxV, T>(src, dst, C, gamma, beta, eps, lane, rnd);
+}
+template <>
+__device__ __forceinline__ void ln_any<__half>(const __half* __restrict__ src, __half* __restrict__ dst, int C, const float* __restrict__ gamma,
+                                               const float* __restrict__ beta, float eps, int lane, bool rnd) {
+  if ((C & 7) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) ln_row8<kLnMaxV / 2>(src, dst, C, gamma, beta, eps, lane);
+  else ln_row<kLnMaxV, __half>(src, dst, C, gamma, beta, eps, lane, rnd);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in, int in_pitch,
@@ -71,7 +126,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps)
-    ln_row<kLnMaxV, T>(in + r * in_pitch, out + r * out_pitch, C, gamma, beta, eps, lane, rnd);
+    ln_any<T>(in + r * in_pitch, out + r * out_pitch, C, gamma, beta, eps, lane, rnd);
 }
 
 template <typename T>
@@ -90,7 +145,7 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const T* __restri
     T* dst = win + r * win_pitch;
     if (p.real) {
       const T* src = tok + ((int64_t)(p.b * g.H + p.y) * g.W + p.x) * tok_pitch;
-      ln_row<kLnMaxV, T>(src, dst, C, gamma, beta, eps, lane, rnd);
+      ln_any<T>(src, dst, C, gamma, beta, eps, lane, rnd);
     } else {
       // LayerNorm of an all-zero token: (0-0)*rstd*gamma + beta = beta (attention.py:273,316)
       for (int i = lane; i < (C >> 2); i += 32)

@@ -32,13 +32,17 @@ constexpr int kMaxASlots = 4;
 constexpr int kMaxBSlots = 12;
 constexpr int kMaxBlockN = 256;
 constexpr int kDataBytes = 184 * 1024;          // A ring + B ring, carved per layer (see atmvfi_gemm_conv_tc)
-constexpr int kDataBytes16 = 150 * 1024;        // ... when 16 epilogue warps need twice the staging area
+constexpr int kDataBytes16 = 146 * 1024;        // ... when 16 epilogue warps need twice the staging area
 constexpr int kMaxABoxBytes = 24 * 1024;        // up to 192 rows of 128 B (halo box; 320 rows = 40 KB in pair mode), 128 rows otherwise
 // Epilogue warps: 8 (two per TMEM lane quarter, alternating column chunks) or, for layers whose K is so short that the
 // accumulator drain + global stores bound the tile time (k2s2 transposed convs, 1x1 and 24/48-channel 3x3 layers), 16.
 constexpr int kEpiPitch = 36;                                 // floats per staged row: 16-byte aligned, conflict-free for 128-bit access
-constexpr int kEpiWarpBytes = 32 * kEpiPitch * 4 + 32 * 8;    // per epilogue warp: 32 x 36 floats staging + 32 x int2 row info
-constexpr int smem_bytes(int epi_warps) { return (epi_warps == 16 ? kDataBytes16 : kDataBytes) + 512 + epi_warps * kEpiWarpBytes; }
+// per epilogue warp: 32 x 36 floats staging + 32 x int2 row info, rounded up to 5 KB so that every warp's region starts on a 1024-byte
+// boundary (the TMA-store epilogue stages 32 rows x <= 128 B there in the SWIZZLE_128B / 64B / 32B layouts of its tensor maps)
+constexpr int kEpiWarpBytes = 5 * 1024;
+static_assert(32 * kEpiPitch * 4 + 32 * 8 <= kEpiWarpBytes, "epilogue staging region");
+// shared memory: [A / B rings][epilogue staging, one region per warp][barriers, 512 B]
+constexpr int smem_bytes(int epi_warps) { return (epi_warps == 16 ? kDataBytes16 : kDataBytes) + epi_warps * kEpiWarpBytes + 512; }
 constexpr int threads_for(int epi_warps) { return 128 + 32 * epi_warps; }
 
 struct TcPlan {                                 // host-side, produced by atmvfi_gemm_conv_plan
@@ -56,9 +60,12 @@ struct TcPlan {                                 // host-side, produced by atmvfi
   int row0, row1;                               // row window of the GEMM grid: tiles cover output rows [row0, row1)
   int x3;                                       // 1: 3xTF32 (fp32-tolerance) datapath, weights packed as hi | lo chunk pairs
   int f16, chunk;                               // fp16 operands; elements per 128-byte K row (32 fp32 / 64 fp16)
+  // TMA-store epilogue: output tensor maps (32-channel boxes + the 16-channel tail of block_n), one pair per destination
+  CUtensorMap mapOut, mapOutTail, mapOut2, mapOut2Tail;
+  int st_ok, st_bx, st_by, st_shuffle;
   uint32_t magic;
 };
-constexpr uint32_t kPlanMagic = 0xA7B20005u;
+constexpr uint32_t kPlanMagic = 0xA7B20006u;
 
 struct TcParams {
   CUtensorMap mapA[ATMVFI_MAX_SRC];
@@ -73,7 +80,13 @@ struct TcParams {
   int th_super;                                 // rows of output covered by one CTA tile (TH, or 2*TH in pair mode)
   int a_slots, a_slot_bytes, b_slots, b_slot_bytes;   // smem rings: A at offset 0, (3xTF32: the A-lo ring,) B right after
   int a_lo_off, b_off;                          // byte offsets of the A-lo ring (3xTF32 only) and of the B ring
-  int bar_off;                                  // barriers behind the data rings, epilogue staging 512 B further
+  int bar_off;                                  // barriers: behind the data rings and the epilogue staging regions
+  int epi_off;                                  // epilogue staging regions (1024-byte aligned), right behind the data rings
+  // TMA-store epilogue (kEpi == 4): the stored tile of one warp and one 32-column chunk is a box {st_w channels, st_bx, st_by} of the output
+  CUtensorMap mapOut, mapOutTail, mapOut2, mapOut2Tail;
+  int st_bx, st_by;                             // pixels of a warp's 32 rows along x / y (st_bx * st_by == 32)
+  int st_shuffle;                               // 1: ConvTranspose k2 s2 - the box walks the output with element stride 2 from (2x + dx, 2y + dy)
+  int dbg;                                      // ATMVFI_TC_DEBUG_EPI (timing experiments only): 1 no TMA store, 2 no staging either, 3 no accumulator read
   int total_ctiles;                             // cluster tiles: ceil(m_tiles / cluster) * n_tiles
   int row0, row1;                               // output rows [row0, row1) of every image (row window)
   EpiParams epi;
@@ -142,6 +155,16 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
+// bulk tensor store shared -> global (the epilogue's output path): clipped to the tensor's extent by the TMA unit
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // smem may be reused
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // stores are complete
+
 // cta_group::2 variants: the two CTAs of a cluster drive one M = 256 MMA.  TMA completions of BOTH CTAs are counted on
 // the LEADER's mbarrier (shared::cluster address with the peer bit cleared), commits are multicast to both CTAs.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
@@ -339,7 +362,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
   extern __shared__ __align__(1024) uint8_t smem[];      // SWIZZLE_128B atoms need a 1024-byte aligned base
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.bar_off);
-  const int kEpiOff = p.bar_off + 512;
+  const int kEpiOff = p.epi_off;
   uint64_t* fullA = bars;                                  // [kMaxASlots]
   uint64_t* emptyA = fullA + kMaxASlots;                   // [kMaxASlots]
   uint64_t* fullB = emptyA + kMaxASlots;                   // [kMaxBSlots]
@@ -671,6 +694,106 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
       int last_q = -1, last_t = -1;
       int64_t m = 0;
       bool row_ok = false;
+      if (kEpi == 4) {
+        // ---------------- TMA-store epilogue ----------------
+        // A TMEM lane is an output pixel, so after tcgen05.ld every lane holds 32 consecutive channels of ITS pixel: bias / PReLU /
+        // narrowing happen in registers, the lane writes its 32-channel row into the warp's staging tile (swizzled like the
+        // output tensor map: conflict-free 16-byte stores) and one elected lane hands the 32-pixel x 32-channel box to the TMA
+        // unit.  No per-element address arithmetic, no bounds checks (the TMA unit clips the box to the tensor: image border,
+        // row window, channels beyond Cout, phantom tiles), no global store instructions.  ConvTranspose k2 s2: the same box
+        // walks the output with element stride 2.
+        uint8_t* const sbuf = smem + kEpiOff + ew * kEpiWarpBytes;
+        const int es = (kF16 && e.out_half) ? 2 : 4;
+        const int qx = (q * 32) % p.TW, qy = (q * 32) / p.TW;          // where this warp's 32 pixels sit inside the 128-pixel tile
+        for (int u = half; u < nunits; u += kSeq) {
+          const int t = kPair ? u / nchunks : 0;
+          const int c0 = (kPair ? u - t * nchunks : u) * 32;
+          const int n0 = n_tile * p.block_n + c0;
+          int sq = 0, co0 = n0;
+          if (p.st_shuffle) { sq = n0 / p.cq_pad; co0 = n0 - sq * p.cq_pad; }
+          if (co0 >= e.Cout || sq > 3) continue;
+          const int width = min(32, p.block_n - c0);                    // 32, or a 16-column tail (block_n is a multiple of 16)
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + as * kMaxBlockN + t * 128;
+          uint32_t r[32];
+          __syncwarp();
+          if (p.dbg >= 3) continue;
+          tc_ld32(trow + c0, r);
+          tc_wait_ld();
+          int cx = ox0 + qx, cy = oy0 + t * p.TH + qy;
+          if (p.st_shuffle) { cx = 2 * cx + (sq & 1); cy = 2 * cy + (sq >> 1); }
+          float v[32];
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {          // bias / slope arrays are padded to a multiple of 32 floats by the caller
+            const float4 bz = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + co0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[c] = __uint_as_float(r[c]) + bz.x; v[c + 1] = __uint_as_float(r[c + 1]) + bz.y;
+            v[c + 2] = __uint_as_float(r[c + 2]) + bz.z; v[c + 3] = __uint_as_float(r[c + 3]) + bz.w;
+            if (e.prelu) {
+              const float4 sl = __ldg(reinterpret_cast<const float4*>(e.prelu + co0 + c));
+              v[c] = v[c] > 0.f ? v[c] : v[c] * sl.x; v[c + 1] = v[c + 1] > 0.f ? v[c + 1] : v[c + 1] * sl.y;
+              v[c + 2] = v[c + 2] > 0.f ? v[c + 2] : v[c + 2] * sl.z; v[c + 3] = v[c + 3] > 0.f ? v[c + 3] : v[c + 3] * sl.w;
+            }
+          }
+          if (kF16 && e.head32 && co0 + 31 >= e.head32_c0) {             // fp32 copy of the motion channels: a handful of scalars per pixel
+            const int oy = oy0 + t * p.TH + th, ox = ox0 + tw;
+            if (b < p.B && oy < p.row1 && ox < e.Wout) {
+              float* hp = e.head32 + (((int64_t)b * e.Hout + oy) * e.Wout + ox) * e.head32_pitch;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (co0 + j >= e.head32_c0 && co0 + j < e.Cout) hp[co0 + j - e.head32_c0] = v[j];
+            }
+          }
+          // one pass per destination: the output, then the PReLU'd second output of the decoder levels
+          const int npass = e.out2 ? 2 : 1;
+          for (int pass = 0; pass < npass; ++pass) {
+            if (pass == 1) {
+#pragma unroll
+              for (int c = 0; c < 32; c += 4) {
+                const float4 sl = __ldg(reinterpret_cast<const float4*>(e.prelu2 + co0 + c));
+                v[c] = v[c] > 0.f ? v[c] : v[c] * sl.x; v[c + 1] = v[c + 1] > 0.f ? v[c + 1] : v[c + 1] * sl.y;
+                v[c + 2] = v[c + 2] > 0.f ? v[c + 2] : v[c + 2] * sl.z; v[c + 3] = v[c + 3] > 0.f ? v[c + 3] : v[c + 3] * sl.w;
+              }
+            }
+            const int pes = (pass == 1 && kF16) ? 2 : es;                 // out2 is always an activation map
+            const int rb = width * pes;                                   // bytes per staged row: 128 / 64 / 32
+            const uint32_t swz = (uint32_t)((lane * rb) >> 7) & (uint32_t)((rb >> 4) - 1);   // SWIZZLE_<rb>B: 16-byte chunk index ^ address bits [7, ..)
+            if (p.dbg >= 2) { if (v[0] == 1.2345e-30f) sbuf[lane] = 1; continue; }
+            if (lane == 0) tma_store_wait_read();                         // the previous box has left the staging tile
+            __syncwarp();
+            uint8_t* rowp = sbuf + lane * rb;
+            if (pes == 2) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c * 8 < width) {
+                  uint4 w;
+                  *reinterpret_cast<__half2*>(&w.x) = __floats2half2_rn(v[8 * c], v[8 * c + 1]);
+                  *reinterpret_cast<__half2*>(&w.y) = __floats2half2_rn(v[8 * c + 2], v[8 * c + 3]);
+                  *reinterpret_cast<__half2*>(&w.z) = __floats2half2_rn(v[8 * c + 4], v[8 * c + 5]);
+                  *reinterpret_cast<__half2*>(&w.w) = __floats2half2_rn(v[8 * c + 6], v[8 * c + 7]);
+                  *reinterpret_cast<uint4*>(rowp + (((uint32_t)c ^ swz) << 4)) = w;
+                }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                if (c * 4 < width)
+                  *reinterpret_cast<float4*>(rowp + (((uint32_t)c ^ swz) << 4)) =
+                      round_tf32_if(make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]), rnd);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && p.dbg < 1) {
+              const CUtensorMap* mp = pass == 0 ? (width == 32 ? &p.mapOut : &p.mapOutTail) : (width == 32 ? &p.mapOut2 : &p.mapOut2Tail);
+              tma_store_4d(mp, sbuf, co0, cx, cy, b);
+              tma_store_commit();
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (cs == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]);
+        }
+        continue;
+      }
       for (int u = half; u < nunits; u += kSeq) {
         const int t = kPair ? u / nchunks : 0;                // sub-tile of the pair (warp-uniform)
         const int c0 = (kPair ? u - t * nchunks : u) * 32;
@@ -685,7 +808,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
         const int n0 = n_tile * p.block_n + c0;               // first GEMM column of this chunk (warp-uniform)
         int sq = 0, co0 = n0;
         if (e.out_mode == ATMVFI_OUT_SHUFFLE2) { sq = n0 / p.cq_pad; co0 = n0 - sq * p.cq_pad; }
-        if (co0 >= e.Cout || sq > 3) continue;                // padding columns: nothing to store (uniform branch)
+        if (co0 >= (kFastEpi ? e.cout4 : e.Cout) || sq > 3) continue;                // padding columns: nothing to store (uniform branch)
         uint32_t r[32];
         __syncwarp();
         tc_ld32(trow + c0, r);
@@ -722,13 +845,18 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
         const int nvalid = min(min(32, p.block_n - c0), e.Cout - co0);   // block_n may end inside this 32-column chunk
         const bool full4 = col + 4 <= nvalid;
         if (kFastEpi) {
-          // plain layers (pixel-major output, no residual, no second output, Cout % 4 == 0): rows are addressed
-          // arithmetically (TW is a power of two), nothing but the accumulator tile is read from shared memory
-          if (col < nvalid) {
-            float4 bz4 = make_float4(0.f, 0.f, 0.f, 0.f), sl4 = make_float4(1.f, 1.f, 1.f, 1.f);
+          // layers without residual and with pixel-major output: rows are addressed arithmetically (TW is a power of two), nothing
+          // but the accumulator tile is read from shared memory.  Channel counts that are not multiples of 4 (101, 197, 389 ...)
+          // are stored as whole 4-channel vectors up to e.cout4: the pad lanes of the map receive zeros (zero weight rows, zero-
+          // padded bias).  Optional second PReLU'd output and (fp16 mode) fp32 copy of the motion channels.
+          const int nvalid_f = min(min(32, p.block_n - c0), e.cout4 - co0);
+          if (col < nvalid_f) {
+            float4 bz4 = make_float4(0.f, 0.f, 0.f, 0.f), sl4 = make_float4(1.f, 1.f, 1.f, 1.f), sl24 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (e.bias) bz4 = __ldg(reinterpret_cast<const float4*>(e.bias + co0 + col));
             const bool act = e.prelu != nullptr;
             if (act) sl4 = __ldg(reinterpret_cast<const float4*>(e.prelu + co0 + col));
+            const bool dual = !kQkv && e.out2 != nullptr;
+            if (dual) sl24 = __ldg(reinterpret_cast<const float4*>(e.prelu2 + co0 + col));
             const int tw_mask = p.TW - 1, tw_shift = 31 - __clz(p.TW);
             const int oyb = oy0 + (kPair ? t * p.TH : 0);
             // QKV_HEADS (q / k columns; whole-v chunks never get here): row pitch = head dim, column offset = head plane.
@@ -737,6 +865,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
             const bool qkv_v = qkv && co0 + col >= 2 * e.qkv_C;
             float* obase = qkv ? e.out + (qkv_v ? 0 : epi_qkv_offset(e, 0, co0 + col)) : e.out + co0 + col;
             const int64_t opitch = qkv ? e.qkv_hd : e.out_pitch;
+            const bool head = kF16 && !kQkv && e.head32 != nullptr && co0 + col + 3 >= e.head32_c0;
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr) {
               const int row = rr * 4 + rsub, ml = q * 32 + row;
@@ -749,6 +878,20 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
                   v.z = v.z > 0.f ? v.z : v.z * sl4.z; v.w = v.w > 0.f ? v.w : v.w * sl4.w;
                 }
                 const int64_t mrow = ((int64_t)b * e.Hout + oy) * e.Wout + ox;
+                if (head) {            // fp32 copy of the motion channels, before any narrowing
+                  const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const int co = co0 + col + k;
+                    if (co >= e.head32_c0 && co < e.Cout) e.head32[mrow * e.head32_pitch + (co - e.head32_c0)] = vv[k];
+                  }
+                }
+                if (dual) {
+                  float4 w2 = make_float4(v.x > 0.f ? v.x : v.x * sl24.x, v.y > 0.f ? v.y : v.y * sl24.y,
+                                          v.z > 0.f ? v.z : v.z * sl24.z, v.w > 0.f ? v.w : v.w * sl24.w);
+                  if (kF16) Act<__half>::st4(reinterpret_cast<__half*>(e.out2) + mrow * e.out2_pitch + co0 + col, w2);
+                  else *reinterpret_cast<float4*>(e.out2 + mrow * e.out2_pitch + co0 + col) = round_tf32_if(w2, rnd);
+                }
                 if (kF16 && e.out_half) {         // fp16 map (never the q|k|v layout, which stays fp32)
                   Act<__half>::st4(reinterpret_cast<__half*>(e.out) + mrow * e.out_pitch + co0 + col, v);
                   continue;
@@ -884,6 +1027,7 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
         if (cs == 2) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]);
       }
     }
+    if (kEpi == 4 && lane == 0) tma_store_wait_all();          // bulk stores of this warp are complete before the CTA may exit
   }
 
   tc_fence_before();
@@ -914,6 +1058,7 @@ struct TcKernels {
          {gemm_conv_tc_kernel<kF16 ? 1 : 2, 1, false, 1, 8, false, kF16>, gemm_conv_tc_kernel<kF16 ? 1 : 2, 2, false, 1, 8, false, kF16>},
          {gemm_conv_tc_kernel<1, 1, true, 1, 8, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 1, 8, false, kF16>}}};
     static const TcKernelFn res_table[2] = {gemm_conv_tc_kernel<0, 1, false, 2, 8, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 2, 8, false, kF16>};
+    static const TcKernelFn res_table16[2] = {gemm_conv_tc_kernel<0, 1, false, 2, 16, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 2, 16, false, kF16>};
     static const TcKernelFn table16[2][2][2] = {
         {{gemm_conv_tc_kernel<0, 1, false, 0, 16, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 0, 16, false, kF16>},
          {gemm_conv_tc_kernel<1, 1, true, 0, 16, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 0, 16, false, kF16>}},
@@ -921,10 +1066,21 @@ struct TcKernels {
          {gemm_conv_tc_kernel<1, 1, true, 1, 16, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 1, 16, false, kF16>}}};
     static const TcKernelFn qkv_table[2][2] = {{gemm_conv_tc_kernel<0, 1, false, 3, 8, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 3, 8, false, kF16>},
                                                {gemm_conv_tc_kernel<0, 1, false, 3, 16, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 3, 16, false, kF16>}};
+    // TMA-store epilogue: tbl 5 [0 plain, 1 halo, 2 paired halo][cluster] with 8 warps, tbl 6 [0 plain, 1 paired halo][cluster] with 16
+    static const TcKernelFn st_table[3][2] = {
+        {gemm_conv_tc_kernel<0, 1, false, 4, 8, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 4, 8, false, kF16>},
+        {gemm_conv_tc_kernel<1, 1, false, 4, 8, false, kF16>, gemm_conv_tc_kernel<1, 2, false, 4, 8, false, kF16>},
+        {gemm_conv_tc_kernel<1, 1, true, 4, 8, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 4, 8, false, kF16>}};
+    static const TcKernelFn st_table16[2][2] = {
+        {gemm_conv_tc_kernel<0, 1, false, 4, 16, false, kF16>, gemm_conv_tc_kernel<0, 2, false, 4, 16, false, kF16>},
+        {gemm_conv_tc_kernel<1, 1, true, 4, 16, false, kF16>, gemm_conv_tc_kernel<1, 2, true, 4, 16, false, kF16>}};
     switch (tbl) {
+      case 5: return st_table[a][c];
+      case 6: return st_table16[a][c];
       case 0: return table[a][b][c];
       case 1: return res_table[c];
       case 2: return table16[a][b][c];
+      case 4: return res_table16[c];
       default: return qkv_table[a][c];
     }
   }
@@ -942,8 +1098,16 @@ struct TcKernels {
         }
         cudaError_t e = cudaFuncSetAttribute(get(3, a, 0, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(a ? 16 : 8));
         if (e != cudaSuccess) return e;
+        for (int v = 0; v < 3; ++v) {
+          e = cudaFuncSetAttribute(get(5, v, 0, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8));
+          if (e != cudaSuccess) return e;
+          if (v < 2) e = cudaFuncSetAttribute(get(6, v, 0, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
+          if (e != cudaSuccess) return e;
+        }
         if (a == 0) {
           e = cudaFuncSetAttribute(get(1, 0, 0, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(8));
+          if (e != cudaSuccess) return e;
+          e = cudaFuncSetAttribute(get(4, 0, 0, c), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(16));
           if (e != cudaSuccess) return e;
         }
       }
@@ -1094,6 +1258,36 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
                  "gemm_conv(tensor cores): output must be 16-byte aligned (fp16 maps: 8-byte) with pitch %% 4 == 0");
   ATMVFI_REQUIRE(!d->out2 || (((uintptr_t)d->out2 & 7) == 0 && d->out2_pitch % 4 == 0 && (pl->f16 || ((uintptr_t)d->out2 & 15) == 0)),
                  "gemm_conv(tensor cores): out2 must be 16-byte aligned (fp16 maps: 8-byte)");
+  {
+    // TMA-store epilogue (see the kernel): layers without residual whose output is pixel-major or a k2 s2 ConvTranspose
+    static int tma_store = -1;
+    if (tma_store < 0) { const char* ev = getenv("ATMVFI_TC_TMASTORE"); tma_store = ev ? atoi(ev) : 1; }
+    const bool shuf = d->out_mode == ATMVFI_OUT_SHUFFLE2;
+    const int es_out = (pl->f16 && !d->out_f32) ? 2 : 4, es_out2 = pl->f16 ? 2 : 4;
+    pl->st_ok = 0;
+    if (tma_store && !pl->x3 && (d->out_mode == ATMVFI_OUT_PIXEL || shuf) && !d->residual && d->param_pad >= 32 &&
+        ((uintptr_t)d->out & 15) == 0 && (d->out_pitch * es_out) % 16 == 0 &&
+        (!d->out2 || (((uintptr_t)d->out2 & 15) == 0 && (d->out2_pitch * es_out2) % 16 == 0))) {
+      pl->st_bx = pl->TW < 32 ? pl->TW : 32;
+      pl->st_by = 32 / pl->st_bx;
+      pl->st_shuffle = shuf ? 1 : 0;
+      const int sc = shuf ? 2 : 1;
+      auto encode_out = [&](CUtensorMap* map, void* ptr, int es, int pitch, int boxw) -> bool {
+        cuuint64_t gdim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wout * sc, (cuuint64_t)pl->row1 * sc, (cuuint64_t)d->B};
+        cuuint64_t gstr[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * es * d->Wout * sc, (cuuint64_t)pitch * es * d->Wout * sc * d->Hout * sc};
+        cuuint32_t box[4] = {(cuuint32_t)boxw, (cuuint32_t)(pl->st_bx * sc), (cuuint32_t)(pl->st_by * sc), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)sc, (cuuint32_t)sc, 1};
+        const int rb = boxw * es;
+        const CUtensorMapSwizzle sw = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        return enc(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ptr, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+      };
+      const bool tail = pl->block_n % 32 != 0;
+      bool ok = encode_out(&pl->mapOut, d->out, es_out, d->out_pitch, 32) && (!tail || encode_out(&pl->mapOutTail, d->out, es_out, d->out_pitch, 16));
+      if (ok && d->out2) ok = encode_out(&pl->mapOut2, d->out2, es_out2, d->out2_pitch, 32) && (!tail || encode_out(&pl->mapOut2Tail, d->out2, es_out2, d->out2_pitch, 16));
+      pl->st_ok = ok ? 1 : 0;
+    }
+  }
   pl->magic = kPlanMagic;
   return 0;
 }
@@ -1106,8 +1300,11 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   // kernel families: TcKernels<false> (tf32, this translation unit), atmvfi_tc_f16_kernel (fp16, gemm_conv_tc_f16.cu), 3xTF32 below
   auto lookup = [f16](int tbl, int a, int b, int c) -> KernelFn { return f16 ? atmvfi_tc_f16_kernel(tbl, a, b, c) : TcKernels<false>::get(tbl, a, b, c); };
   // fast epilogue: pixel-major output, no residual / second output / fp32 head copy, whole float4 columns, aligned bias and slopes
-  const bool plain = !d->residual && !d->out2 && !(f16 && d->head32) && d->Cout % 4 == 0 && (((uintptr_t)d->bias | (uintptr_t)d->prelu) & 15) == 0;
-  const int fast = (d->out_mode == ATMVFI_OUT_PIXEL && plain) ? 1 : 0;
+  // (channel counts that are not multiples of 4 qualify when the caller allows whole-vector stores into the map's pad lanes and passes
+  // bias / slope arrays padded to a multiple of 4: pad_stores)
+  const bool vec_ok = (d->Cout % 4 == 0 || d->pad_stores) && (((uintptr_t)d->bias | (uintptr_t)d->prelu | (uintptr_t)d->prelu2) & 15) == 0;
+  const bool plain = !d->residual && !d->out2 && !(f16 && d->head32) && d->Cout % 4 == 0 && vec_ok;
+  const int fast = (d->out_mode == ATMVFI_OUT_PIXEL && !d->residual && vec_ok) ? 1 : 0;
   const bool qkv_fast = d->out_mode == ATMVFI_OUT_QKV_HEADS && plain && !pl->halo && !pl->pair;
   ATMVFI_REQUIRE(d->out_mode != ATMVFI_OUT_QKV_HEADS || qkv_fast,
                  "gemm_conv(tf32): QKV_HEADS needs 16-byte aligned bias and Cout %% 4 == 0 (the generic epilogue does not carry this layout)");
@@ -1125,11 +1322,30 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   const bool res_ok = d->residual && d->Cout % 4 == 0 && ((uintptr_t)d->residual & 15) == 0 && d->res_pitch % res_align == 0;
   KernelFn kern = lookup(0, fast, pl->pair ? 3 : pl->halo, pl->cluster - 1);
   int epi_warps = 8;
-  if (pl->x3) {
+  if (pl->st_ok && pl->halo != 2) {
+    // TMA-store epilogue; 16 warps for the layers whose tile time is the accumulator drain (short K, 1x1 / transposed)
+    static int epi16 = -1;
+    if (epi16 < 0) { const char* ev = getenv("ATMVFI_TC_EPI16"); epi16 = ev ? atoi(ev) : 1; }
+    int ktc = 0;
+    for (int s2 = 0; s2 < pl->nsrc; ++s2) ktc += pl->chunks[s2] * pl->chunk;
+    ktc *= pl->ntaps;
+    const bool can16 = pl->pair || !pl->halo;
+    if (can16 && (epi16 == 2 || (epi16 == 1 && ktc <= 640 && pl->ksize == 1))) {
+      kern = lookup(6, pl->pair ? 1 : 0, 0, pl->cluster - 1);
+      epi_warps = 16;
+    } else {
+      kern = lookup(5, pl->pair ? 2 : pl->halo, 0, pl->cluster - 1);
+    }
+  } else if (pl->x3) {
     kern = x3_table[(res_ok && !pl->halo) ? 2 : fast][pl->halo][pl->cluster - 1];
   } else if (res_ok && !pl->halo && !pl->pair) {
-    // linear layers with a residual (attention proj, Mlp fc2): generic epilogue with the residual rows prefetched
-    kern = lookup(1, 0, 0, pl->cluster - 1);
+    // linear layers with a residual (attention proj, Mlp fc2): generic epilogue with the residual rows prefetched.  Their tile
+    // time is the epilogue (accumulator drain + residual reads + stores at memory latency), so 16 epilogue warps double the
+    // loads / stores in flight per SM (ATMVFI_TC_RES16=0: 8 warps)
+    static int res16 = -1;
+    if (res16 < 0) { const char* ev = getenv("ATMVFI_TC_RES16"); res16 = ev ? atoi(ev) : 1; }
+    if (res16) { kern = lookup(4, 0, 0, pl->cluster - 1); epi_warps = 16; }
+    else kern = lookup(1, 0, 0, pl->cluster - 1);
   } else if (pl->pair || !pl->halo) {
     static int epi16 = -1;                    // ATMVFI_TC_EPI16: 0 never, 1 (default) short-K layers, 2 every eligible layer
     if (epi16 < 0) { const char* ev = getenv("ATMVFI_TC_EPI16"); epi16 = ev ? atoi(ev) : 1; }
@@ -1184,7 +1400,16 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   p.th_super = pl->TH * (pl->pair ? 2 : 1);
   p.sum_chunks = ch;
   const int data_bytes = epi_warps == 16 ? kDataBytes16 : kDataBytes;
-  p.bar_off = data_bytes;
+  p.epi_off = data_bytes;
+  p.bar_off = data_bytes + epi_warps * kEpiWarpBytes;
+  memcpy(&p.mapOut, &pl->mapOut, sizeof(CUtensorMap)); memcpy(&p.mapOutTail, &pl->mapOutTail, sizeof(CUtensorMap));
+  memcpy(&p.mapOut2, &pl->mapOut2, sizeof(CUtensorMap)); memcpy(&p.mapOut2Tail, &pl->mapOut2Tail, sizeof(CUtensorMap));
+  p.st_bx = pl->st_bx; p.st_by = pl->st_by; p.st_shuffle = pl->st_shuffle;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* ev = getenv("ATMVFI_TC_DEBUG_EPI"); dbg = ev ? atoi(ev) : 0; }
+    p.dbg = dbg;
+  }
   p.a_slots = pl->halo ? (epi_warps == 16 ? 2 : 3) : 4;     // 16-warp layers have short K loops: two (large, paired) boxes suffice
   if (pl->x3) p.a_slots = pl->halo ? 2 : 3;                 // every slot exists twice (raw box + its a_lo copy)
   p.a_slot_bytes = (p.a_bytes + 1023) / 1024 * 1024;

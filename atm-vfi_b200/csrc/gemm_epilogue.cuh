@@ -24,6 +24,7 @@ struct EpiParams {
   // precision ATMVFI_F16: `residual` and `out2` are fp16 maps; `out` is fp16 unless out_half == 0 (q|k|v, motion heads and the final
   // residual stay fp32); `head32` receives an fp32 copy of output channels [head32_c0, Cout) (the flows + occlusion logit that the
   // warps consume at full precision while the same tensor feeds the next fp16 GEMM).  Pitches count elements of the map's type.
+  int cout4;                      // Cout rounded up to 4 when whole-vector stores into the pad lanes are allowed (pad_stores), else Cout
   int act_half, out_half;
   float* head32;
   int head32_pitch, head32_c0;
@@ -79,6 +80,7 @@ static inline EpiParams make_epi(const atmvfi_gemm_conv_desc* d) {
   e.qkv_C = d->Cout / 3;
   e.qkv_hd = e.qkv_C / e.qkv_heads;
   e.qkv_R = (int64_t)d->B * d->Hout * d->Wout;
+  e.cout4 = d->pad_stores ? (d->Cout + 3) / 4 * 4 : d->Cout;
   e.act_half = d->precision == ATMVFI_F16 ? 1 : 0;
   e.out_half = (e.act_half && !d->out_f32) ? 1 : 0;
   e.head32 = e.act_half ? d->head32 : nullptr;

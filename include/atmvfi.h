@@ -110,6 +110,13 @@ typedef struct {
   int32_t out_f32;
   float* head32;
   int32_t head32_pitch, head32_c0;
+  /* Tensor-core paths, Cout % 4 != 0: the caller owns the pad lanes [Cout, round_up(Cout, 4)) of every output row (out, out2) and
+   * passes bias / prelu / prelu2 arrays padded to round_up(Cout, 4) floats; the kernel may then store whole 4-channel vectors (the
+   * pad lanes receive zeros).  Lets layers with 101 / 197 / 389 channels use the vectorised epilogue. */
+  int32_t pad_stores;
+  /* bias / prelu / prelu2 point to arrays padded (zeros / ones) to a multiple of this many floats (0: exactly Cout).  >= 32 lets the
+   * tensor-core kernel take its TMA-store epilogue, which reads parameters in whole 32-channel chunks. */
+  int32_t param_pad;
 } atmvfi_gemm_conv_desc;
 
 const char* atmvfi_last_error(void);
