@@ -63,9 +63,10 @@ struct TcPlan {                                 // host-side, produced by atmvfi
   // TMA-store epilogue: output tensor maps (32-channel boxes + the 16-channel tail of block_n), one pair per destination
   CUtensorMap mapOut, mapOutTail, mapOut2, mapOut2Tail;
   int st_ok, st_bx, st_by, st_shuffle;
+  int grp;                                      // grouped main loop: 0 off, 1 halo (3 vertical taps per weight slot), 2 chunk pairs
   uint32_t magic;
 };
-constexpr uint32_t kPlanMagic = 0xA7B20006u;
+constexpr uint32_t kPlanMagic = 0xA7B20007u;
 
 struct TcParams {
   CUtensorMap mapA[ATMVFI_MAX_SRC];
@@ -86,6 +87,11 @@ struct TcParams {
   CUtensorMap mapOut, mapOutTail, mapOut2, mapOut2Tail;
   int st_bx, st_by;                             // pixels of a warp's 32 rows along x / y (st_bx * st_by == 32)
   int st_shuffle;                               // 1: ConvTranspose k2 s2 - the box walks the output with element stride 2 from (2x + dx, 2y + dy)
+  // Grouped main loop (fewer, larger pipeline steps: the MMA warp pays ~0.35 us of barrier / commit latency per step, which
+  // bounded every layer with few MMAs per step).  grp 1 (3x3 stride-1 halo layers): one weight slot holds the 3 vertical taps of a
+  // (chunk, kx) group, fetched by ONE 3-D TMA box.  grp 2 (1x1 / strided layers): a step covers TWO K chunks - two activation
+  // boxes in one slot, their two weight tiles fetched by one 3-D box.  0: one weight tile per step (3xTF32, full-halo mode).
+  int grp;
   int dbg;                                      // ATMVFI_TC_DEBUG_EPI (timing experiments only): 1 no TMA store, 2 no staging either, 3 no accumulator read
   int total_ctiles;                             // cluster tiles: ceil(m_tiles / cluster) * n_tiles
   int row0, row1;                               // output rows [row0, row1) of every image (row window)
@@ -165,6 +171,12 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // smem may be reused
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }         // stores are complete
 
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 // cta_group::2 variants: the two CTAs of a cluster drive one M = 256 MMA.  TMA completions of BOTH CTAs are counted on
 // the LEADER's mbarrier (shared::cluster address with the peer bit cleared), commits are multicast to both CTAs.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
@@ -179,6 +191,13 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -411,7 +430,71 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
   uint8_t* const ringAlo = smem + p.a_lo_off;
   uint8_t* const ringB = smem + p.b_off;
 
-  if (warp == 0) {
+  if (warp == 0 && !kX3 && kHalo != 2 && p.grp) {
+    // ======================================= TMA producer, grouped steps =========================
+    int as_ = 0, bs_ = 0;
+    uint32_t aph_ = 0, bph_ = 0;
+    const int grp_tiles = kHalo == 1 ? 3 : 2;                              // weight tiles per slot
+    for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters) {
+      int n_tile, b, oy0, ox0;
+      tile_coords(p, ct, cs, rank, n_tile, b, oy0, ox0);
+      const int n0 = n_tile * p.block_n + rank * b_rows;
+      auto load_b = [&](int k0, int k2) {                                  // 3-D box {chunk, b_rows, grp_tiles} -> slot bs_
+        mbar_wait(&emptyB[bs_], bph_ ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(&fullB[bs_], p.block_n * 128 * grp_tiles);
+          uint8_t* dst = ringB + bs_ * p.b_slot_bytes;
+          if (cs == 2) tma_load_3d_2cta(dst, &p.mapB, &fullB[bs_], k0, n0, k2);
+          else tma_load_3d(dst, &p.mapB, &fullB[bs_], k0, n0, k2);
+        }
+        __syncwarp();
+        if (++bs_ == kBSlots) { bs_ = 0; bph_ ^= 1; }
+      };
+      if (kHalo == 1) {
+        int cbase = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const CUtensorMap* mapA = s == 0 ? &p.mapA[0] : (s == 1 ? &p.mapA[1] : (s == 2 ? &p.mapA[2] : &p.mapA[3]));
+          for (int c = 0; c < p.chunks[s]; ++c)
+            for (int kx_i = 0; kx_i < 3; ++kx_i) {
+              mbar_wait(&emptyA[as_], aph_ ^ 1);
+              if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(&fullA[as_], p.a_bytes * cs);
+                if (cs == 2) tma_load_4d_2cta(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kCh, ox0 + kx_i - 1, oy0 - 1, b);
+                else tma_load_4d(ringA + as_ * p.a_slot_bytes, mapA, &fullA[as_], c * kCh, ox0 + kx_i - 1, oy0 - 1, b);
+              }
+              __syncwarp();
+              if (++as_ == kASlots) { as_ = 0; aph_ ^= 1; }
+              load_b((kx_i * p.sum_chunks + cbase + c) * kCh, 0);          // the three vertical taps of (chunk, kx)
+            }
+          cbase += p.chunks[s];
+        }
+      } else {
+        for (int tap_o = 0; tap_o < p.ntaps; ++tap_o) {
+          const int ky = p.ksize == 3 ? tap_o / 3 : 0, kx = p.ksize == 3 ? tap_o % 3 : 0;
+          const int iy = oy0 * p.stride + ky * p.dil - p.pad, ix = ox0 * p.stride + kx * p.dil - p.pad;
+          int s = 0, c = 0;
+          for (int gc = 0; gc < p.sum_chunks; gc += 2) {
+            const int npair = min(2, p.sum_chunks - gc);
+            mbar_wait(&emptyA[as_], aph_ ^ 1);
+            if (elect_one() && rank == 0) mbar_expect_tx(&fullA[as_], p.a_bytes * cs * npair);
+            __syncwarp();
+            for (int j = 0; j < npair; ++j) {
+              const CUtensorMap* mapA = s == 0 ? &p.mapA[0] : (s == 1 ? &p.mapA[1] : (s == 2 ? &p.mapA[2] : &p.mapA[3]));
+              if (elect_one()) {
+                uint8_t* dst = ringA + as_ * p.a_slot_bytes + j * p.a_bytes;
+                if (cs == 2) tma_load_4d_2cta(dst, mapA, &fullA[as_], c * kCh, ix, iy, b);
+                else tma_load_4d(dst, mapA, &fullA[as_], c * kCh, ix, iy, b);
+              }
+              __syncwarp();
+              if (++c == p.chunks[s]) { c = 0; ++s; }
+            }
+            if (++as_ == kASlots) { as_ = 0; aph_ ^= 1; }
+            load_b(0, tap_o * p.sum_chunks + gc);                          // the weight tiles of the two chunks
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ======================================= TMA producer =======================================
     {
       int as_ = 0, bs_ = 0;
@@ -585,6 +668,88 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
           if (cs == 2) mbar_arrive_leader(&convA[as_]); else mbar_arrive(&convA[as_]);
         }
         if (++as_ == kASlots) { as_ = 0; aph_ ^= 1; }
+      }
+    }
+  } else if (warp == 1 && !kX3 && kHalo != 2 && p.grp) {
+    // ======================================= MMA issuer, grouped steps ===========================
+    if (rank == 0) {
+      const uint32_t idesc = kF16 ? make_idesc_f16(p.block_n, cs == 2 ? 256 : kBlockM) : make_idesc_tf32(p.block_n, cs == 2 ? 256 : kBlockM);
+      const uint32_t a_step = kHalo == 1 ? (uint32_t)(p.TW * 128) >> 4 : (uint32_t)p.a_bytes >> 4;   // next vertical tap / next chunk's box
+      const uint32_t b_step = (uint32_t)(b_rows * 128) >> 4;                                          // next weight tile of the slot
+      const int ngroups = kHalo == 1 ? 3 * p.sum_chunks : p.ntaps * ((p.sum_chunks + 1) >> 1);
+      uint32_t tcount = 0;
+      int as_ = 0, bs_ = 0;
+      uint32_t aph_ = 0, bph_ = 0;
+      for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
+        const uint32_t as = tcount & 1, aph = (tcount >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kMaxBlockN;
+        mbar_wait(&fullA[as_], aph_);
+        mbar_wait(&fullB[bs_], bph_);
+        int s = 0, c = 0, sub = 0;                 // running (source, chunk); halo: sub = kx of the group
+        for (int g = 0; g < ngroups; ++g) {
+          int nm0, nm1 = 0, nparts;
+          if (kHalo == 1) {
+            nm0 = (c == p.chunks[s] - 1) ? p.last_mmas[s] : 4;
+            nparts = 3;
+          } else {
+            nm0 = (c == p.chunks[s] - 1) ? p.last_mmas[s] : 4;
+            int s1 = s, c1 = c + 1;
+            if (c1 == p.chunks[s1]) { c1 = 0; ++s1; }
+            const int gc = g % ((p.sum_chunks + 1) >> 1);
+            nparts = (2 * gc + 1 < p.sum_chunks) ? 2 : 1;
+            if (nparts == 2) nm1 = (c1 == p.chunks[s1] - 1) ? p.last_mmas[s1] : 4;
+          }
+          int as_n = as_ + 1, bs_n = bs_ + 1;
+          uint32_t aph_n = aph_, bph_n = bph_;
+          if (as_n == kASlots) { as_n = 0; aph_n ^= 1; }
+          if (bs_n == kBSlots) { bs_n = 0; bph_n ^= 1; }
+          const bool last = g == ngroups - 1;
+          uint32_t okA = 1, okB = 1;
+          if (!last) { okA = mbar_test_wait(&fullA[as_n], aph_n); okB = mbar_test_wait(&fullB[bs_n], bph_n); }
+          tc_fence_after();
+          const uint64_t adesc0 = make_smem_desc(smem_u32(ringA + as_ * p.a_slot_bytes));
+          const uint64_t bdesc0 = make_smem_desc(smem_u32(ringB + bs_ * p.b_slot_bytes));
+          if (elect_one()) {
+#pragma unroll
+            for (int part = 0; part < 3; ++part)
+              if (part < nparts) {
+                const int nm = (kHalo == 1 || part == 0) ? nm0 : nm1;
+                const uint64_t adesc = adesc0 + (uint64_t)(part * a_step), bdesc = bdesc0 + (uint64_t)(part * b_step);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  if (j < nm) tc_mma_any<kF16, kCS>(tmem_d, adesc + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (g == 0 && part == 0 && j == 0) ? 0u : 1u);
+                if (kPair) {
+                  const uint64_t adesc2 = adesc + (uint64_t)((kBlockM * 128) >> 4);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (j < nm) tc_mma_any<kF16, kCS>(tmem_d + 128, adesc2 + (uint64_t)(j * 2), bdesc + (uint64_t)(j * 2), idesc, (g == 0 && part == 0 && j == 0) ? 0u : 1u);
+                }
+              }
+            if (cs == 2) {
+              tc_commit_2cta(&emptyB[bs_]);
+              tc_commit_2cta(&emptyA[as_]);
+              if (last) tc_commit_2cta(&tfull[as]);
+            } else {
+              tc_commit(&emptyB[bs_]);
+              tc_commit(&emptyA[as_]);
+              if (last) tc_commit(&tfull[as]);
+            }
+          }
+          __syncwarp();
+          // advance the running chunk
+          if (kHalo == 1) {
+            if (++sub == 3) { sub = 0; if (++c == p.chunks[s]) { c = 0; ++s; } }
+          } else {
+            for (int j = 0; j < nparts; ++j)
+              if (++c == p.chunks[s]) { c = 0; ++s; }
+            if (s >= p.nsrc) { s = 0; c = 0; }     // next tap walks the sources again
+          }
+          as_ = as_n; aph_ = aph_n; bs_ = bs_n; bph_ = bph_n;
+          if (!okA) mbar_wait(&fullA[as_], aph_);
+          if (!okB) mbar_wait(&fullB[bs_], bph_);
+        }
       }
     }
   } else if (warp == 1) {
@@ -1245,14 +1410,51 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
   }
   {
     ATMVFI_REQUIRE(((uintptr_t)d->weight & 15) == 0, "gemm_conv(tf32): weights must be 16-byte aligned");
-    cuuint64_t gdim[2] = {(cuuint64_t)ktc, (cuuint64_t)n_pad};
-    cuuint64_t gstr[1] = {(cuuint64_t)ktc * es};
-    cuuint32_t box[2] = {(cuuint32_t)pl->chunk, (cuuint32_t)(pl->block_n / pl->cluster)};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&pl->mapB, pl->f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->weight), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ATMVFI_REQUIRE(r == CUDA_SUCCESS, "gemm_conv(tf32): cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+    // Grouped main loop (see TcParams::grp): decided here because it fixes the shape of the weight tensor map.  The weight ring
+    // must still hold two slots next to the activation ring in the smaller (16-epilogue-warp) shared-memory budget.
+    static int grp_ok = -1;
+    if (grp_ok < 0) { const char* ev = getenv("ATMVFI_TC_GROUP"); grp_ok = ev ? atoi(ev) : 1; }
+    pl->grp = 0;
+    const int sum_chunks = ktc / (pl->ntaps * pl->chunk * (pl->x3 ? 2 : 1));
+    const int tile_bytes = (pl->block_n / pl->cluster) * 128;
+    if (grp_ok && !pl->x3 && pl->halo == 1) {
+      const int a_bytes = ((pl->pair ? 2 : 1) * pl->TH + 2) * pl->TW * 128;
+      const int a_ring = 3 * ((a_bytes + 1023) / 1024 * 1024);
+      if ((kDataBytes - a_ring) / (3 * tile_bytes) >= 2) pl->grp = 1;
+    } else if (grp_ok >= 2 && !pl->x3 && pl->halo == 0 && sum_chunks >= 2) {
+      // (measured on B200: chunk pairs do NOT pay for the 1x1 layers - fc1 92 -> 103 us, qkv 126 -> 130 us: the shallower activation
+      // ring costs more than the saved barrier round trips; kept behind ATMVFI_TC_GROUP=2)
+      const int a_ring = 2 * (2 * kBlockM * 128);              // two slots of two boxes (the 16-warp budget)
+      if ((kDataBytes16 - a_ring) / (2 * tile_bytes) >= 2) pl->grp = 2;
+    }
+    const CUtensorMapDataType dt = pl->f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    CUresult r;
+    if (pl->grp == 1) {
+      // [N_pad][K_tc] seen as {K inside one ky plane (kx, chunk, channel), n, ky}: box {chunk, rows, 3} = the vertical taps of (chunk, kx)
+      const cuuint64_t S = (cuuint64_t)sum_chunks * pl->chunk;
+      cuuint64_t gdim[3] = {3 * S, (cuuint64_t)n_pad, 3};
+      cuuint64_t gstr[2] = {(cuuint64_t)ktc * es, 3 * S * es};
+      cuuint32_t box[3] = {(cuuint32_t)pl->chunk, (cuuint32_t)(pl->block_n / pl->cluster), 3};
+      cuuint32_t estr[3] = {1, 1, 1};
+      r = enc(&pl->mapB, dt, 3, const_cast<float*>(d->weight), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (pl->grp == 2) {
+      // {channel inside a chunk, n, chunk index over the whole K}: box {chunk, rows, 2} = the weight tiles of two consecutive chunks
+      cuuint64_t gdim[3] = {(cuuint64_t)pl->chunk, (cuuint64_t)n_pad, (cuuint64_t)(ktc / pl->chunk)};
+      cuuint64_t gstr[2] = {(cuuint64_t)ktc * es, (cuuint64_t)pl->chunk * es};
+      cuuint32_t box[3] = {(cuuint32_t)pl->chunk, (cuuint32_t)(pl->block_n / pl->cluster), 2};
+      cuuint32_t estr[3] = {1, 1, 1};
+      r = enc(&pl->mapB, dt, 3, const_cast<float*>(d->weight), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim[2] = {(cuuint64_t)ktc, (cuuint64_t)n_pad};
+      cuuint64_t gstr[1] = {(cuuint64_t)ktc * es};
+      cuuint32_t box[2] = {(cuuint32_t)pl->chunk, (cuuint32_t)(pl->block_n / pl->cluster)};
+      cuuint32_t estr[2] = {1, 1};
+      r = enc(&pl->mapB, dt, 2, const_cast<float*>(d->weight), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    ATMVFI_REQUIRE(r == CUDA_SUCCESS, "gemm_conv(tf32): cuTensorMapEncodeTiled(B, group mode %d) failed with %d", pl->grp, (int)r);
   }
   ATMVFI_REQUIRE(((uintptr_t)d->out & 7) == 0 && d->out_pitch % 4 == 0 && (pl->f16 || ((uintptr_t)d->out & 15) == 0),
                  "gemm_conv(tensor cores): output must be 16-byte aligned (fp16 maps: 8-byte) with pitch %% 4 == 0");
@@ -1412,10 +1614,14 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   }
   p.a_slots = pl->halo ? (epi_warps == 16 ? 2 : 3) : 4;     // 16-warp layers have short K loops: two (large, paired) boxes suffice
   if (pl->x3) p.a_slots = pl->halo ? 2 : 3;                 // every slot exists twice (raw box + its a_lo copy)
+  p.grp = pl->grp;
   p.a_slot_bytes = (p.a_bytes + 1023) / 1024 * 1024;
+  if (p.grp == 2) { p.a_slot_bytes = 2 * p.a_bytes; p.a_slots = epi_warps == 16 ? 2 : 3; }   // a slot = the boxes of two chunks
   p.a_lo_off = p.a_slots * p.a_slot_bytes;
   p.b_off = (pl->x3 ? 2 : 1) * p.a_slots * p.a_slot_bytes;
   p.b_slot_bytes = (pl->block_n / pl->cluster) * 128;        // 2-CTA mode: each CTA holds half of the weight tile
+  if (p.grp == 1) p.b_slot_bytes *= 3;                       // a slot = the three vertical taps of (chunk, kx)
+  if (p.grp == 2) p.b_slot_bytes *= 2;                       // ... the tiles of two chunks
   p.b_slots = (data_bytes - p.b_off) / p.b_slot_bytes;
   if (p.b_slots > kMaxBSlots) p.b_slots = kMaxBSlots;
   ATMVFI_REQUIRE(p.b_slots >= 2, "gemm_conv(tf32): shared memory rings too small (%d weight slots)", p.b_slots);
