@@ -93,6 +93,7 @@ PROTOTYPES = {
     "atmvfi_residual_finish": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_u8_to_planar": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_planar_to_u8": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "atmvfi_u8_to_planar_rows": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     # NVLink row exchange (spatial row-slab mode)
     "atmvfi_arena_alloc": [C.c_size_t, C.POINTER(C.c_void_p)],
     "atmvfi_arena_free": [_P],

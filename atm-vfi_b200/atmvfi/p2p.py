@@ -18,8 +18,9 @@ from .ops import CudaOps
 from .slab import Push, SlabOps
 
 CTRL_BYTES = 1 << 20            # control block at the start of every arena
-OFF_EPOCH, OFF_ERROR, OFF_READY, OFF_COUNTERS, OFF_FLAGS = 0, 16, 64, 4096, 65536
+OFF_EPOCH, OFF_ERROR, OFF_EPOCH_IN, OFF_READY, OFF_READY_IN, OFF_COUNTERS, OFF_FLAGS = 0, 16, 32, 64, 128, 4096, 65536
 MAX_SITES = 8192
+INPUT_SITE = MAX_SITES - 1      # exchange site of the input-frame all-gather (its flags count the input epoch OFF_EPOCH_IN)
 ALIGN = 1024
 
 
@@ -130,6 +131,7 @@ class P2PTransport:
                                 keep=(sig, wait))
 
     remote_reads = True            # kernels may dereference peer-mapped addresses (flow_warp_nhwc_p2p)
+    split_sites = True             # SlabOps issues push and wait of an exchange site separately (push early, wait late)
 
     def byte_delta(self, rank: int) -> int:
         """Distance from a local arena address to the same buffer in ``rank``'s arena (peer-mapped address space)."""
@@ -147,11 +149,50 @@ class P2PTransport:
         self.slab.backend._emit("atmvfi_p2p_exchange", (arr, 0, sig, len(others), wait, len(others), a.ctrl(me, OFF_EPOCH),
                                                         a.ctrl(me, OFF_COUNTERS + 4 * site), a.ctrl(me, OFF_ERROR)), keep=(arr, sig, wait))
 
+    def push(self, site: int, outgoing: List[Push]) -> None:
+        """First half of a split site: copy my rows into the consumers' buffers and raise their flags; waits for nobody."""
+        self.exchange(site, outgoing, [])
+
+    def wait(self, site: int, incoming: List[Push]) -> None:
+        """Second half: spin (on the device) until every producer of my incoming rows has raised this site's flag."""
+        self.exchange(site, [], incoming)
+
+    def gather_inputs(self, frames: List[torch.Tensor], bounds: List[int]) -> None:
+        """All-gather of the input frames over NVLink: every rank holds rows [bounds[r], bounds[r+1]) of each planar frame
+        [1, C, H, W] (it converted them from ITS share of the uploaded uint8 rows) and pushes them to every peer.  A barrier on a
+        second epoch word comes first: a peer may still be reading the previous pair's frames.  Launched eagerly, in front of the
+        captured plan; flags of the input site carry the input epoch."""
+        a, me = self.arena, self.rank
+        others = [r for r in range(self.world) if r != me]
+        if not others:
+            return
+        emit = self.slab.backend._emit
+        sig = self._ptr_array([a.ctrl(r, OFF_READY_IN + 4 * me) for r in others])
+        wait = self._ptr_array([a.ctrl(me, OFF_READY_IN + 4 * r) for r in others])
+        emit("atmvfi_p2p_step_begin", (a.ctrl(me, OFF_EPOCH_IN), sig, len(others), wait, len(others), a.ctrl(me, OFF_ERROR)), keep=(sig, wait))
+        lo, hi = bounds[me], bounds[me + 1]
+        pieces = []
+        for t in frames:
+            _, c, h, w = t.shape
+            start = t.data_ptr() + lo * w * 4
+            for d in others:
+                pieces.append(_lib.P2PPiece(start, a.peer(d, start), (hi - lo) * w * 4, h * w * 4, c, 0))
+        site = INPUT_SITE
+        sig = self._ptr_array([a.ctrl(d, OFF_FLAGS + 4 * (site * _lib.P2P_MAX_PEERS + me)) for d in others])
+        wait = self._ptr_array([a.ctrl(me, OFF_FLAGS + 4 * (site * _lib.P2P_MAX_PEERS + s)) for s in others])
+        n = _lib.P2P_MAX_PIECES
+        groups = [pieces[i : i + n] for i in range(0, len(pieces), n)]
+        for gi, grp in enumerate(groups):
+            arr = (_lib.P2PPiece * len(grp))(*grp)
+            last = gi == len(groups) - 1
+            emit("atmvfi_p2p_exchange", (arr, len(grp), sig, len(others) if last else 0, wait, len(others) if last else 0, a.ctrl(me, OFF_EPOCH_IN),
+                                         a.ctrl(me, OFF_COUNTERS + 4 * site), a.ctrl(me, OFF_ERROR)), keep=(arr, sig, wait))
+
     def exchange(self, site: int, outgoing: List[Push], incoming: List[Push]) -> None:
         if not outgoing and not incoming:
             return
-        if site >= MAX_SITES:
-            raise _lib.AtmvfiError(f"more than {MAX_SITES} exchange sites in one plan")
+        if site >= INPUT_SITE:
+            raise _lib.AtmvfiError(f"more than {INPUT_SITE} exchange sites in one plan")
         a, me = self.arena, self.rank
         pieces = []
         for ps in outgoing:
@@ -188,6 +229,8 @@ class SlabSession:
                  arena_bytes: Optional[int] = None, timeout_ms: Optional[int] = None):
         from .runtime import PRECISIONS
         self._failed = False
+        import os
+        self.sliced_upload = os.environ.get("ATMVFI_SLAB_SLICED_UPLOAD", "1") != "0"
         if timeout_ms is not None:          # peer-wait time-out of the exchange kernels (default 4 s / ATMVFI_P2P_TIMEOUT_MS)
             _lib.check(_lib.load().atmvfi_p2p_set_timeout_ms(int(timeout_ms)), "p2p_set_timeout_ms")
         dev = next(net.parameters()).device
@@ -258,12 +301,27 @@ class SlabSession:
         self._usable()
         with torch.cuda.device(self.device):
             st = self._stage(H, W)
-            for src, h, d in ((img0, st["h0"], st["d0"]), (img1, st["h1"], st["d1"])):
-                if src.__array_interface__["data"][0] != h.data_ptr():      # not already in the pinned buffers
-                    h.numpy()[...] = src
-                d.copy_(h, non_blocking=True)
-            self.ops.u8_to_planar(st["d0"], self.plan.im0, H, W, Hp, Wp, top, left, isBGR)
-            self.ops.u8_to_planar(st["d1"], self.plan.im1, H, W, Hp, Wp, top, left, isBGR)
+            if self.sliced_upload and self.world > 1:
+                # every rank uploads only the uint8 rows behind ITS slab of the padded frame (1/N of the PCIe traffic), converts
+                # them, and the fp32 planar rows are all-gathered over NVLink (P2PTransport.gather_inputs)
+                b = self.slab.bounds
+                y0, y1 = b[self.rank], b[self.rank + 1]
+                s0, s1 = min(max(y0 - top, 0), H - 1), min(max(y1 - 1 - top, 0), H - 1) + 1
+                for src, h, d, dst in ((img0, st["h0"], st["d0"], self.plan.im0), (img1, st["h1"], st["d1"], self.plan.im1)):
+                    if src.__array_interface__["data"][0] != h.data_ptr():
+                        h.numpy()[s0:s1] = src[s0:s1]
+                    d[s0:s1].copy_(h[s0:s1], non_blocking=True)
+                    self.ops._emit("atmvfi_u8_to_planar_rows", (d.data_ptr(), dst.data_ptr(), H, W, Hp, Wp, top, left, int(isBGR), y0, y1), keep=(d, dst))
+                self.transport.gather_inputs([self.plan.im0, self.plan.im1], b)
+                self.h2d_bytes_this_rank = 2 * (s1 - s0) * W * 3
+            else:
+                for src, h, d in ((img0, st["h0"], st["d0"]), (img1, st["h1"], st["d1"])):
+                    if src.__array_interface__["data"][0] != h.data_ptr():      # not already in the pinned buffers
+                        h.numpy()[...] = src
+                    d.copy_(h, non_blocking=True)
+                self.ops.u8_to_planar(st["d0"], self.plan.im0, H, W, Hp, Wp, top, left, isBGR)
+                self.ops.u8_to_planar(st["d1"], self.plan.im1, H, W, Hp, Wp, top, left, isBGR)
+                self.h2d_bytes_this_rank = 2 * H * W * 3
             out = self.plan.run_inplace(use_graph=True)
             if self.rank == 0:
                 self.ops.planar_to_u8(out["I_t"], st["dout"], H, W, Hp, Wp, top, left, isBGR)

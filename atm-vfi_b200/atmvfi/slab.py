@@ -103,6 +103,9 @@ class BufInfo:
         # (the frames): every rank holds all of it.
         self.external = True
         self.have: List[List[RowSet]] = [[[] for _ in range(images)] for _ in range(world)]
+        # order key (SlabOps._keys) of the last launch on THIS rank after which rows of the buffer became valid here: a push of
+        # such rows may be issued right behind that launch
+        self.ready_key = 0.0
 
     def grid_map(self, like: Map) -> Map:
         """``like`` (any reshaped view of this buffer, e.g. ``Map.rows()``) on the buffer's native [B,H,W,pitch] grid."""
@@ -150,10 +153,40 @@ class SlabOps:
         self.H = 0
         self.site = 0
         self.stats = {"sites": 0, "pushed_bytes": 0, "received_bytes": 0}
+        self._keys: List[float] = []
+        self._next_key = 0.0
         transport.attach(self)
 
     # ---- plumbing shared with the backend -------------------------------------------------------
-    recording = property(lambda s: s.backend.recording, lambda s, v: setattr(s.backend, "recording", v))
+    def _set_recording(self, v):
+        self.backend.recording = v
+        self._keys, self._next_key = [], 0.0          # order keys of the records of the list being built (see _run)
+
+    recording = property(lambda s: s.backend.recording, _set_recording)
+
+    def _sync_keys(self, key: Optional[float] = None) -> float:
+        """Give every record appended since the last call its order key: the next integer, or ``key`` (a push that is to be
+        issued right behind the launch that produced its rows).  Returns the key of the newest record."""
+        rec = self.backend.recording
+        if rec is None:
+            return 0.0
+        while len(self._keys) < len(rec):
+            if key is None:
+                self._next_key += 1.0
+                self._keys.append(self._next_key)
+            else:
+                self._keys.append(key)
+        return self._keys[-1] if self._keys else 0.0
+
+    def _reorder(self) -> None:
+        """Move every early push to its place (stable sort by order key); called once, at the end of a plan build."""
+        rec = self.backend.recording
+        if rec is None or not getattr(self.transport, "split_sites", False):
+            return
+        self._sync_keys()
+        order = sorted(range(len(rec)), key=lambda i: self._keys[i])
+        rec[:] = [rec[i] for i in order]
+        self._keys = [self._keys[i] for i in order]
     launches = property(lambda s: s.backend.launches)
     lib = property(lambda s: s.backend.lib)
     device = property(lambda s: s.backend.device)
@@ -284,15 +317,33 @@ class SlabOps:
             self.stats["sites"] += 1
             self.stats["pushed_bytes"] += sum(ps.nbytes() for ps in mine_out)
             self.stats["received_bytes"] += sum(ps.nbytes() for ps in mine_in)
-            self.transport.exchange(self.site, mine_out, mine_in)
+            if getattr(self.transport, "split_sites", False) and self.backend.recording is not None:
+                # Split site: the PUSH (copy my rows into the consumers' buffers + raise their flags) is issued right behind the
+                # launch that produced the rows - it then overlaps whatever this rank computes next - and only the WAIT for my
+                # own incoming rows stays in front of the consumer.  Records carry order keys; _reorder() sorts them once.
+                self._sync_keys()
+                if mine_out:
+                    self.transport.push(self.site, mine_out)
+                    self._sync_keys(max(ps.buf.ready_key for ps in mine_out) + 0.5)
+                if mine_in:
+                    self.transport.wait(self.site, mine_in)
+                    k = self._sync_keys()
+                    for ps in mine_in:
+                        ps.buf.ready_key = max(ps.buf.ready_key, k)
+            else:
+                self.transport.exchange(self.site, mine_out, mine_in)
             self.site += 1
+        self._sync_keys()
         launch()
+        k_launch = self._sync_keys()
         for p in range(self.world):
             for view, rows in writes[p]:
                 if not rows:
                     continue
                 b, i0, ni = self._buf(view)
                 b.external = False
+                if p == self.rank:
+                    b.ready_key = max(b.ready_key, k_launch)
                 for img in range(i0, i0 + ni):
                     b.have[p][img] = rs_union(b.have[p][img], rows)
 
@@ -560,3 +611,4 @@ class SlabOps:
                     tensors.append(t)
         reads = [[(t, self._all(t)) for t in tensors] if p == 0 else [] for p in range(self.world)]
         self._run(reads, [[] for _ in range(self.world)], lambda: None)
+        self._reorder()

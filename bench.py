@@ -568,9 +568,12 @@ def spatial_measure(args, workload, net, steps, parity):
     torch.cuda.synchronize()
     t = torch.tensor([time.perf_counter() - t0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    h2d = getattr(sess, "h2d_bytes_per_step", world * 2 * H * W * 3)
+    hb = torch.tensor([float(getattr(sess, "h2d_bytes_this_rank", 2 * H * W * 3))], device=dev)
+    dist.all_reduce(hb, op=dist.ReduceOp.SUM)
+    h2d = int(hb.item())
     e2e = {"value": steps / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": H * W * 3,
-           "api": "atmvfi.p2p.SlabSession.interpolate_u8 (inference_2frame arithmetic; uint8 frames in pinned host memory, rank 0 downloads the frame)"}
+           "api": "atmvfi.p2p.SlabSession.interpolate_u8 (inference_2frame arithmetic; uint8 frames in pinned host memory: every rank uploads the rows of its "
+                  "slab, the converted rows are all-gathered over NVLink; rank 0 downloads the frame)"}
     barrier()
     per, tc, fam = measure_kernels(sess.plan, torch)      # all ranks replay in lockstep (exchange sites need the peers)
     barrier()

@@ -254,6 +254,10 @@ int atmvfi_u8_to_planar(const uint8_t* in, float* out, int H, int W, int Hp, int
                         int bgr, void* stream);
 int atmvfi_planar_to_u8(const float* in, uint8_t* out, int H, int W, int Hp, int Wp, int top, int left,
                         int bgr, void* stream);
+/* atmvfi_u8_to_planar restricted to rows [y0, y1) of the PADDED frame: only source rows clamp(y - top, 0, H-1) of `in` are read, so a
+ * rank of the row-slab mode uploads just its share of the uint8 frame (the planar rows then travel to the peers over NVLink). */
+int atmvfi_u8_to_planar_rows(const uint8_t* in, float* out, int H, int W, int Hp, int Wp, int top, int left,
+                             int bgr, int y0, int y1, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Spatial row-slab mode over NVLink (BASELINE.json configs[3]: one 4096x2160 pair on 2/4/8 GPUs).

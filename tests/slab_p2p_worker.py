@@ -58,6 +58,28 @@ def main():
                       f"launches={sess.plan.num_launches()}", flush=True)
             sess.close()
             dist.barrier()
+    # uint8 front end: every rank uploads only the rows of its slab, the planar rows are all-gathered over NVLink; two different
+    # pairs in a row (the second one must not see rows of the first) against the single-GPU inference_2frame arithmetic
+    import numpy as np
+    for kind, H, W in (("lite", 200, 300), ("base", 250, 180)):
+        P = weights.make_weights(kind, "default")
+        net = (Base if kind == "base" else Lite)()
+        net.load_state_dict(P, strict=True)
+        net = net.to(f"cuda:{local}").eval()
+        rng = np.random.default_rng(7)                         # same frames on every rank
+        frames = [rng.integers(0, 256, (H, W, 3), dtype=np.uint8) for _ in range(3)]
+        Hp, Wp = H + (-H) % 64, W + (-W) % 64
+        sess = SlabSession(net, 1, Hp, Wp, gather="I_t")
+        for a, b in ((frames[0], frames[1]), (frames[1], frames[2]), (frames[2], frames[0])):
+            got = sess.interpolate_u8(a, b, copy=True)
+            if rank == 0:
+                want = net.interpolate_u8(a, b)
+                same = np.array_equal(got, want)
+                ok = ok and same
+                print(f"[slab p2p u8] {kind} {H}x{W} world={world} sliced upload: {'identical' if same else 'MISMATCH'} "
+                      f"(this rank uploads {sess.h2d_bytes_this_rank} of {2 * H * W * 3} bytes)", flush=True)
+        sess.close()
+        dist.barrier()
     if rank == 0:
         print("SLAB_P2P_OK" if ok else "SLAB_P2P_FAILED", flush=True)
     dist.destroy_process_group()
