@@ -85,6 +85,7 @@ PROTOTYPES = {
     "atmvfi_warp_blend": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_warp_blend_p2p": [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.POINTER(RowOwners), _P],
     "atmvfi_resize_bilinear_ac": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _I, _P],
+    "atmvfi_pyramid_warp": [_P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_nchw_to_nhwc": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_nhwc_to_nchw": [_P, _I, _P, _I, _I, _I, _I, _P],
     "atmvfi_l1_mean": [_P, _P, _P, _P, _I, _L, _P],

@@ -168,7 +168,7 @@ def motion_branch(ops, blocks, head, tok: Map, ws: int) -> Tuple[Map, Map]:
 # ------------------------------------------------------------------------------------------------
 _OP_NAMES = frozenset(("window_gather_ln", "gemm_conv", "window_attention", "layernorm", "dwconv_gelu", "conv3x3_first", "copy_map",
                        "nhwc_to_nchw", "nchw_to_nhwc", "resize", "flow_warp_nchw", "flow_warp_nhwc", "l1_mean", "select3", "warp_blend",
-                       "pack5_planar", "residual_finish"))
+                       "pack5_planar", "residual_finish", "pyramid_warp"))
 _ARENA_ALIGN = 1024
 
 
@@ -236,7 +236,7 @@ class _DryOps:
             b[3] = b[3] or persistent
 
     def __getattr__(self, name):
-        if name not in _OP_NAMES:
+        if name not in _OP_NAMES or (name == "pyramid_warp" and not hasattr(self.real, name)):
             raise AttributeError(name)
 
         def op(*args, **kwargs):
@@ -453,15 +453,27 @@ class Plan:
             # Row slabs: the un-warped pyramid is whole on every rank, so each rank warps only its own rows; the later
             # warp_blend launches read the warped levels in place from their owners.  The flows stay replicated down to 1/2
             # resolution (cheap) so that no up-sampling step needs halo rows from a neighbour.
-            for l in (3, 2, 1, 0):
-                n0, n1 = P(*pyr0[l].shape), P(*pyr1[l].shape)
-                ops.flow_warp_nchw(pyr0[l], f0, n0); ops.flow_warp_nchw(pyr1[l], f1, n1)
-                pyr0[l], pyr1[l] = n0, n1
-                if l:
-                    g0, g1 = P(B, 2, H >> (l - 1), W >> (l - 1)), P(B, 2, H >> (l - 1), W >> (l - 1))
-                    with (ops.replicated() if l > 1 else contextlib.nullcontext()):
-                        ops.resize(f0, g0, 2.0); ops.resize(f1, g1, 2.0)
-                    f0, f1 = g0, g1
+            if hasattr(ops, "pyramid_warp"):
+                # fused: one launch per level warps both frames and (levels 2..0) up-samples the coarser level's flows on the fly
+                for l in (3, 2, 1, 0):
+                    n0, n1 = P(*pyr0[l].shape), P(*pyr1[l].shape)
+                    if l == 3:
+                        ops.pyramid_warp(pyr0[l], pyr1[l], f0, f1, False, n0, n1)
+                    else:
+                        g0, g1 = (P(B, 2, H >> l, W >> l), P(B, 2, H >> l, W >> l)) if l else (None, None)
+                        ops.pyramid_warp(pyr0[l], pyr1[l], f0, f1, True, n0, n1, g0, g1)
+                        f0, f1 = g0, g1
+                    pyr0[l], pyr1[l] = n0, n1
+            else:
+                for l in (3, 2, 1, 0):
+                    n0, n1 = P(*pyr0[l].shape), P(*pyr1[l].shape)
+                    ops.flow_warp_nchw(pyr0[l], f0, n0); ops.flow_warp_nchw(pyr1[l], f1, n1)
+                    pyr0[l], pyr1[l] = n0, n1
+                    if l:
+                        g0, g1 = P(B, 2, H >> (l - 1), W >> (l - 1)), P(B, 2, H >> (l - 1), W >> (l - 1))
+                        with (ops.replicated() if l > 1 else contextlib.nullcontext()):
+                            ops.resize(f0, g0, 2.0); ops.resize(f1, g1, 2.0)
+                        f0, f1 = g0, g1
 
         tok, lhead = motion_branch(ops, m.local_blocks, m.local_head, tok, m.local_ws)
         for k, shift in enumerate((0, ENHANCE_WINDOW // 2)):

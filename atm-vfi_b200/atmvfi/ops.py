@@ -426,6 +426,19 @@ class CudaOps:
         assert flow.shape == (b, 2, h, w) and img.is_contiguous() and flow.is_contiguous() and out.is_contiguous()
         self._emit("atmvfi_flow_warp_nchw", (img.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w) + _yy(rows), keep=(img, flow, out))
 
+    def pyramid_warp(self, im0: torch.Tensor, im1: torch.Tensor, flow0: torch.Tensor, flow1: torch.Tensor, upsample: bool,
+                     out0: torch.Tensor, out1: torch.Tensor, flow0_out: Optional[torch.Tensor] = None, flow1_out: Optional[torch.Tensor] = None,
+                     rows: Rows = None):
+        """One level of the global-motion pyramid warp for both frames (include/atmvfi.h atmvfi_pyramid_warp): optional x2 flow
+        up-sampling fused into the two backward warps."""
+        b, c, h, w = im0.shape
+        fs = (b, 2, h // 2, w // 2) if upsample else (b, 2, h, w)
+        assert c == 3 and im1.shape == im0.shape == out0.shape == out1.shape and tuple(flow0.shape) == fs == tuple(flow1.shape)
+        assert all(t is None or (tuple(t.shape) == (b, 2, h, w) and t.is_contiguous()) for t in (flow0_out, flow1_out))
+        self._emit("atmvfi_pyramid_warp", (im0.data_ptr(), im1.data_ptr(), flow0.data_ptr(), flow1.data_ptr(), int(bool(upsample)), out0.data_ptr(),
+                                           out1.data_ptr(), _p(flow0_out), _p(flow1_out), b, h, w) + _yy(rows),
+                   keep=(im0, im1, flow0, flow1, out0, out1, flow0_out, flow1_out))
+
     @staticmethod
     def _row_owners(owners, H: int):
         """[(row_lo, row_hi, byte_delta)] covering [0, H) -> the C struct (rows held by other GPUs, read in place over NVLink)."""

@@ -484,6 +484,119 @@ __global__ void __launch_bounds__(256) warp_blend_kernel(const float* __restrict
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// One level of the global-motion pyramid warp (network_base.py:480-485) in ONE launch: for both frames, (optionally) the x2
+// align_corners up-sampling of the coarser level's flow with doubled values (upsample_flow, network_base.py:11-18) fused into
+// the backward warp that consumes it (flow_warp.py:50-60).  Replaces 2 resize + 2 warp launches per level.
+// A CTA produces a 32 x 8 pixel tile of BOTH frames.  The flows of a tile are smooth (they come from the 1/16 grid), so the
+// footprint of the tile in the source image is the tile shifted by its flow plus a small apron: the CTA stages that source
+// window (3 channels, zero outside the image = grid_sample's zero padding) in shared memory with coalesced row reads and every
+// bilinear tap becomes a shared-memory read.  A tile whose footprint does not fit the window (very divergent flows) falls back
+// to the direct global gather.  The arithmetic (coordinate round trip, tap weights, accumulation order) is that of
+// resize_ac_kernel / flow_warp_nchw_kernel, operation by operation: the outputs are bit-identical to the unfused launches.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kPwTx = 32, kPwTy = 8, kPwApron = 7;
+constexpr int kPwSw = kPwTx + 2 * kPwApron + 2, kPwSh = kPwTy + 2 * kPwApron + 2;     // staged source window (48 x 24)
+
+__device__ __forceinline__ float upsample2_ac(const float* __restrict__ src, int Hin, int Win, float sh, float sw, int y, int x) {
+  float fy = __fmul_rn(sh, (float)y), fx = __fmul_rn(sw, (float)x);
+  int y0 = (int)fy, x0 = (int)fx;
+  int y1 = y0 + (y0 < Hin - 1 ? 1 : 0), x1 = x0 + (x0 < Win - 1 ? 1 : 0);
+  float ly = __fsub_rn(fy, (float)y0), lx = __fsub_rn(fx, (float)x0);
+  float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+  float v00 = __ldg(src + (int64_t)y0 * Win + x0), v01 = __ldg(src + (int64_t)y0 * Win + x1);
+  float v10 = __ldg(src + (int64_t)y1 * Win + x0), v11 = __ldg(src + (int64_t)y1 * Win + x1);
+  float top = __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01));
+  float bot = __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11));
+  return __fmul_rn(__fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot)), 2.f);
+}
+
+__global__ void __launch_bounds__(kPwTx * kPwTy) pyramid_warp_kernel(const float* __restrict__ im0, const float* __restrict__ im1,
+                                                                     const float* __restrict__ fin0, const float* __restrict__ fin1, int up,
+                                                                     float* __restrict__ out0, float* __restrict__ out1,
+                                                                     float* __restrict__ fout0, float* __restrict__ fout1, int B, int H, int W,
+                                                                     float sh, float sw, int wy0, int ny) {
+  __shared__ float tile[2][3][kPwSh][kPwSw];
+  __shared__ int s_box[2][4];                       // per frame: min x0, min y0, max x0, max y0 of the taps' top-left corners
+  const int tx = threadIdx.x % kPwTx, ty = threadIdx.x / kPwTx;
+  const int tiles_x = (W + kPwTx - 1) / kPwTx, tiles_y = (ny + kPwTy - 1) / kPwTy;
+  const int64_t ntiles = (int64_t)B * tiles_y * tiles_x, hw = (int64_t)H * W;
+  const int Hc = H >> 1, Wc = W >> 1;
+  for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int bx = (int)(t % tiles_x), by = (int)((t / tiles_x) % tiles_y), b = (int)(t / ((int64_t)tiles_x * tiles_y));
+    const int x = bx * kPwTx + tx, y = wy0 + by * kPwTy + ty;
+    const bool in_img = x < W && y < wy0 + ny;
+    if (threadIdx.x < 8) s_box[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 2) ? -(1 << 30) : (1 << 30);
+    __syncthreads();
+    Bilin sm[2];
+    bool finite[2] = {false, false};
+    if (in_img) {
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const float* fin = f ? fin1 : fin0;
+        float fx, fy;
+        if (up) {
+          fx = upsample2_ac(fin + (int64_t)b * 2 * Hc * Wc, Hc, Wc, sh, sw, y, x);
+          fy = upsample2_ac(fin + ((int64_t)b * 2 + 1) * Hc * Wc, Hc, Wc, sh, sw, y, x);
+          float* fo = f ? fout1 : fout0;
+          if (fo) { fo[(int64_t)b * 2 * hw + (int64_t)y * W + x] = fx; fo[((int64_t)b * 2 + 1) * hw + (int64_t)y * W + x] = fy; }
+        } else {
+          fx = __ldg(fin + (int64_t)b * 2 * hw + (int64_t)y * W + x);
+          fy = __ldg(fin + ((int64_t)b * 2 + 1) * hw + (int64_t)y * W + x);
+        }
+        const float ix = warp_src_coord((float)x, fx, W), iy = warp_src_coord((float)y, fy, H);
+        sm[f] = bilin_setup(ix, iy, W, H);
+        finite[f] = (ix > -2.0e9f && ix < 2.0e9f) && (iy > -2.0e9f && iy < 2.0e9f);
+        if (finite[f] && (sm[f].vx0 || sm[f].vx1) && (sm[f].vy0 || sm[f].vy1)) {      // samples that touch the image define the footprint
+          atomicMin(&s_box[f][0], sm[f].x0); atomicMin(&s_box[f][1], sm[f].y0);
+          atomicMax(&s_box[f][2], sm[f].x0); atomicMax(&s_box[f][3], sm[f].y0);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      const float* img = (f ? im1 : im0) + (int64_t)b * 3 * hw;
+      float* out = (f ? out1 : out0) + (int64_t)b * 3 * hw;
+      const int bx0 = s_box[f][0], by0 = s_box[f][1], bx1 = s_box[f][2], by1 = s_box[f][3];
+      const bool any = bx1 >= bx0;
+      const bool staged = any && (bx1 - bx0 + 2 <= kPwSw) && (by1 - by0 + 2 <= kPwSh);
+      if (staged) {
+        const int wx = bx1 - bx0 + 2, wy = by1 - by0 + 2;          // window that holds every tap: [bx0, bx0 + wx) x [by0, by0 + wy)
+        for (int i = threadIdx.x; i < 3 * wy * wx; i += kPwTx * kPwTy) {
+          const int c = i / (wy * wx), r = (i / wx) % wy, q = i % wx;
+          const int sy = by0 + r, sx = bx0 + q;
+          tile[f][c][r][q] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? __ldg(img + (int64_t)c * hw + (int64_t)sy * W + sx) : 0.f;
+        }
+      }
+      __syncthreads();
+      if (in_img) {
+        const Bilin& s = sm[f];
+        const int64_t rem = (int64_t)y * W + x;
+        const bool touches = finite[f] && (s.vx0 || s.vx1) && (s.vy0 || s.vy1);
+        if (staged && touches) {
+          const int r = s.y0 - by0, q = s.x0 - bx0;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            // same accumulation as sample_plane: invalid taps are skipped there and read a staged 0 here (x + 0 = x)
+            float o = 0.f;
+            if (s.vy0 && s.vx0) o = __fmul_rn(tile[f][c][r][q], s.wnw);
+            if (s.vy0 && s.vx1) o = __fadd_rn(o, __fmul_rn(tile[f][c][r][q + 1], s.wne));
+            if (s.vy1 && s.vx0) o = __fadd_rn(o, __fmul_rn(tile[f][c][r + 1][q], s.wsw));
+            if (s.vy1 && s.vx1) o = __fadd_rn(o, __fmul_rn(tile[f][c][r + 1][q + 1], s.wse));
+            out[(int64_t)c * hw + rem] = o;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) out[(int64_t)c * hw + rem] = sample_plane(img + (int64_t)c * hw, s, W);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // F.interpolate(bilinear, align_corners=True): src = dst * (in-1)/(out-1); ATen's weights w1 = src - floor, w0 = 1 - w1.
 __global__ void __launch_bounds__(256) resize_ac_kernel(const float* __restrict__ in, float* __restrict__ out, int planes,
                                                         int Hin, int Win, int Hout, int Wout, float sh, float sw,
@@ -861,6 +974,23 @@ int atmvfi_resize_bilinear_ac(const float* in, float* out, int planes, int Hin, 
   float sw = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
   resize_ac_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, planes, Hin, Win, Hout, Wout, sh, sw, scale, y0, ny);
   ATMVFI_CHECK_LAUNCH("resize_bilinear_ac");
+  return 0;
+}
+
+int atmvfi_pyramid_warp(const float* im0, const float* im1, const float* flow0, const float* flow1, int upsample, float* out0, float* out1,
+                        float* flow0_out, float* flow1_out, int B, int H, int W, int y0, int y1, void* stream) {
+  ATMVFI_REQUIRE(im0 && im1 && flow0 && flow1 && out0 && out1, "pyramid_warp: null argument");
+  ATMVFI_REQUIRE(!upsample || (H % 2 == 0 && W % 2 == 0), "pyramid_warp: the x2 flow up-sampling needs even H, W (got %dx%d)", H, W);
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "pyramid_warp: bad row window [%d,%d)", y0, y1);
+  const int64_t tiles = (int64_t)B * ((ny + kPwTy - 1) / kPwTy) * ((W + kPwTx - 1) / kPwTx);
+  if (tiles <= 0) return 0;
+  const int Hc = H / 2, Wc = W / 2;
+  const float sh = H > 1 ? (float)(Hc - 1) / (float)(H - 1) : 0.f, sw = W > 1 ? (float)(Wc - 1) / (float)(W - 1) : 0.f;
+  const int grid = (int)(tiles < (int64_t)kSMs * 8 ? tiles : (int64_t)kSMs * 8);
+  pyramid_warp_kernel<<<grid, kPwTx * kPwTy, 0, (cudaStream_t)stream>>>(im0, im1, flow0, flow1, upsample, out0, out1, flow0_out, flow1_out, B, H, W, sh,
+                                                                        sw, y0, ny);
+  ATMVFI_CHECK_LAUNCH("pyramid_warp");
   return 0;
 }
 

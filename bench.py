@@ -186,6 +186,11 @@ def algorithmic_bytes(name, args, keep):
     if name == "atmvfi_flow_warp_nchw":
         b, c, h, w, y0, y1 = args[3:9]
         return "flow_warp", b * _rows(y0, y1, h) * w * (2 * c * 4 + 8)
+    if name == "atmvfi_pyramid_warp":
+        up, b, h, w, y0, y1 = args[4], args[9], args[10], args[11], args[12], args[13]
+        px = b * _rows(y0, y1, h) * w
+        flows = (2 * 2 * 4 / 4 if up else 2 * 2 * 4) + sum(8 for a in args[7:9] if a is not None)
+        return "flow_warp", int(px * (2 * (3 + 3) * 4 + flows))
     if name in ("atmvfi_warp_blend", "atmvfi_warp_blend_p2p"):
         b, h, w, y0, y1 = args[12:17]
         extra = sum(8 if a is not None else 0 for a in args[8:10]) + sum(4 if a is not None else 0 for a in args[10:12])

@@ -247,6 +247,14 @@ int atmvfi_copy(void* dst, const void* src, size_t bytes, void* stream);
 int atmvfi_residual_finish(const float* res, int res_pitch, const float* it, float* it_sum, float* it_clamped,
                            int B, int H, int W, int y0, int y1, void* stream);
 
+/* One level of the global-motion pyramid warp (network_base.py:480-485) for both frames in one launch: the x2 align_corners
+ * up-sampling of the coarser level's flows with doubled values (upsample_flow, network_base.py:11-18; `upsample` = 1: flow0 / flow1 are
+ * [B,2,H/2,W/2] and the up-sampled flows are also written to flow*_out when non-null) fused into the backward warps of im0 / im1
+ * ([B,3,H,W] planar) that consume them (flow_warp.py:50-60).  Source tiles are staged in shared memory; results are bit-identical to
+ * atmvfi_resize_bilinear_ac + atmvfi_flow_warp_nchw. */
+int atmvfi_pyramid_warp(const float* im0, const float* im1, const float* flow0, const float* flow1, int upsample, float* out0,
+                        float* out1, float* flow0_out, float* flow1_out, int B, int H, int W, int y0, int y1, void* stream);
+
 /* demo_2x.inference_2frame host arithmetic on the device (demo_2x.py:64-75, 79-85):
  * uint8 HWC (optionally BGR) -> fp32 planar RGB / 255, replicate-padded by (left, top) to Hp x Wp, and back
  * with round-half-even (np.round) and clipping to [0,255]. */

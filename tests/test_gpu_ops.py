@@ -372,3 +372,41 @@ def test_window_attention_head_major(B2, H, W, ws, shift, hd, precision):
     tol = 2e-4 if precision == _lib.FP32 else 6e-3
     assert max_err(og, out) < tol
     assert max_err(mg, mo) < (1e-3 if precision == _lib.FP32 else 5e-2)
+
+
+@pytest.mark.parametrize("H,W,mag,smooth", [(34, 60, 3.0, True), (68, 120, 25.0, True), (136, 240, 60.0, False), (40, 56, 400.0, False)])
+def test_pyramid_warp_equals_resize_plus_warp(ops, H, W, mag, smooth):
+    """The fused level of the global-motion pyramid (x2 flow up-sampling + both backward warps, source tiles staged in shared memory)
+    must give the bits of the unfused launches: smooth flows (staged path), divergent flows (global fallback), flows that leave
+    the frame, NaN flows."""
+    cu, _ = ops
+    g = gen(17)
+    B = 2
+    im0, im1 = torch.rand(B, 3, H, W, generator=g).cuda(), torch.rand(B, 3, H, W, generator=g).cuda()
+    for up in (False, True):
+        fh, fw = (H // 2, W // 2) if up else (H, W)
+        if smooth:      # a coarse field blown up: what the 1/16-grid global flows look like
+            lo = torch.randn(B, 2, 5, 7, generator=g) * mag
+            mk = lambda: torch.nn.functional.interpolate(lo + torch.randn(B, 2, 5, 7, generator=g), size=(fh, fw), mode="bilinear", align_corners=True).contiguous().cuda()
+        else:
+            mk = lambda: (torch.randn(B, 2, fh, fw, generator=g) * mag).cuda()
+        f0, f1 = mk(), mk()
+        f1[0, :, 3, 4] = float("nan")
+        # unfused reference launches
+        if up:
+            u0, u1 = torch.empty(B, 2, H, W, device="cuda"), torch.empty(B, 2, H, W, device="cuda")
+            cu.resize(f0, u0, 2.0); cu.resize(f1, u1, 2.0)
+        else:
+            u0, u1 = f0, f1
+        r0, r1 = torch.empty_like(im0), torch.empty_like(im1)
+        cu.flow_warp_nchw(im0, u0, r0); cu.flow_warp_nchw(im1, u1, r1)
+        o0, o1 = torch.full_like(im0, -7.0), torch.full_like(im1, -7.0)
+        g0, g1 = (torch.empty(B, 2, H, W, device="cuda"), torch.empty(B, 2, H, W, device="cuda")) if up else (None, None)
+        cu.pyramid_warp(im0, im1, f0, f1, up, o0, o1, g0, g1)
+        assert torch.equal(o0, r0) and torch.equal(o1, r1), (up, (o0 - r0).abs().max().item(), (o1 - r1).abs().max().item())
+        if up:
+            assert torch.equal(g0, u0) and torch.equal(torch.nan_to_num(g1), torch.nan_to_num(u1))
+        # row window
+        w0, w1 = torch.full_like(im0, -7.0), torch.full_like(im1, -7.0)
+        cu.pyramid_warp(im0, im1, f0, f1, up, w0, w1, None, None, rows=(5, H - 3))
+        assert torch.equal(w0[:, :, 5 : H - 3], r0[:, :, 5 : H - 3]) and float(w0[:, :, :5].max()) == -7.0 and float(w1[:, :, H - 3 :].max()) == -7.0
