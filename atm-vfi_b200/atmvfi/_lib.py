@@ -79,6 +79,7 @@ PROTOTYPES = {
     "atmvfi_pack5_planar": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_window_attention_tc": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P],
     "atmvfi_dwconv3x3_gelu": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
+    "atmvfi_mlp_tail": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _P],
     "atmvfi_flow_warp_nchw": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_flow_warp_nhwc": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_flow_warp_nhwc_p2p": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(RowOwners), _P],
@@ -113,6 +114,7 @@ _SPECIAL = {
     "atmvfi_gemm_conv_plan_bytes": ([], C.c_int),
     "atmvfi_l1_mean_scratch_floats": ([C.c_int], C.c_int),
     "atmvfi_attn_prof_read": ([C.POINTER(C.c_uint64)], C.c_int),
+    "atmvfi_mlp_tail_prof_read": ([C.POINTER(C.c_uint64)], C.c_int),
     "atmvfi_set_output_rounding": ([C.c_int], None),
     "atmvfi_set_activation_f16": ([C.c_int], None),
 }

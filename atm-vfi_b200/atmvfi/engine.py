@@ -121,9 +121,14 @@ def transformer_block(ops, blk, tok: Map, g: WinGeom, motion: Optional[Map] = No
     ops.layernorm(t2, t3, blk.g2, blk.b2)
     h1 = ops.new_map(tok.B, tok.H, tok.W, hidden)
     ops.gemm_conv([t3.rows()], blk.fc1, h1.rows(), act=False)
+    out = ops.new_map(tok.B, tok.H, tok.W, C)
+    ok = getattr(ops, "mlp_tail_ok", None)
+    if ok is not None and ok(h1, blk.fc2, t2, out):
+        # DWConv + GELU produced in shared memory as the A operand of fc2: the activated hidden map never reaches HBM
+        ops.mlp_tail(h1, blk.dw_w, blk.dw_b, blk.fc2, t2, out)
+        return out
     h2 = ops.new_map(tok.B, tok.H, tok.W, hidden)
     ops.dwconv_gelu(h1, h2, blk.dw_w, blk.dw_b)
-    out = ops.new_map(tok.B, tok.H, tok.W, C)
     ops.gemm_conv([h2.rows()], blk.fc2, out.rows(), act=False, residual=t2.rows())
     return out
 
@@ -168,7 +173,7 @@ def motion_branch(ops, blocks, head, tok: Map, ws: int) -> Tuple[Map, Map]:
 # ------------------------------------------------------------------------------------------------
 _OP_NAMES = frozenset(("window_gather_ln", "gemm_conv", "window_attention", "layernorm", "dwconv_gelu", "conv3x3_first", "copy_map",
                        "nhwc_to_nchw", "nchw_to_nhwc", "resize", "flow_warp_nchw", "flow_warp_nhwc", "l1_mean", "select3", "warp_blend",
-                       "pack5_planar", "residual_finish", "pyramid_warp"))
+                       "pack5_planar", "residual_finish", "pyramid_warp", "mlp_tail"))
 _ARENA_ALIGN = 1024
 
 
@@ -216,6 +221,10 @@ class _DryOps:
 
     def replicated(self):
         return contextlib.nullcontext()
+
+    def mlp_tail_ok(self, *a) -> bool:
+        f = getattr(self.real, "mlp_tail_ok", None)
+        return bool(f and f(*a))
 
     def index_of(self, x) -> Optional[int]:
         t = x.t if isinstance(x, Map) else x

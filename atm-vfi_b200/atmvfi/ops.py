@@ -420,6 +420,45 @@ class CudaOps:
         self._emit("atmvfi_dwconv3x3_gelu", (x.ptr, out.ptr, x.B, x.H, x.W, x.C, x.pitch, w9c.data_ptr(), bias.data_ptr()) + _yy(rows),
                    keep=(x, out, w9c, bias))
 
+    def mlp_tail_ok(self, hidden: Map, fc2: PackedGemm, residual: Map, out: Map) -> bool:
+        """Shapes the fused Mlp tail (atmvfi_mlp_tail) takes; everything else runs dwconv_gelu + gemm_conv."""
+        import os
+        if self.precision not in (_lib.TF32, _lib.F16) or os.environ.get("ATMVFI_MLP_TAIL", "0") == "0":
+            return False
+        chunk = 64 if self.act_f16 else 32
+        maps = (hidden, residual, out)
+        return (hidden.C % chunk == 0 and fc2.Cout % 32 == 0 and fc2.ksize == 1 and list(fc2.split) == [hidden.C]
+                and all(m.c0 == 0 and (m.pitch * m.esize) % 16 == 0 and m.half == self.act_f16 for m in maps))
+
+    def mlp_tail(self, hidden: Map, dw_w: torch.Tensor, dw_b: torch.Tensor, fc2: PackedGemm, residual: Map, out: Map):
+        """out = residual + fc2(GELU(DWConv3x3(hidden) + dw_b)) + b_fc2 in one launch (include/atmvfi.h atmvfi_mlp_tail)."""
+        assert self.mlp_tail_ok(hidden, fc2, residual, out) and all(m.ptr % 16 == 0 for m in (hidden, residual, out))
+        assert (hidden.B, hidden.H, hidden.W) == (residual.B, residual.H, residual.W) == (out.B, out.H, out.W) and residual.C == out.C == fc2.Cout
+        cache = fc2.__dict__.setdefault("_mlp_tail", {})
+        key = (dw_w.data_ptr(), dw_b.data_ptr())
+        if key not in cache:
+            w10 = torch.cat([dw_w.reshape(9, -1), dw_b.reshape(1, -1)], 0).contiguous().float()
+            nb = round_up(fc2.Cout, 32) + 384
+            bias = torch.zeros(nb, dtype=torch.float32, device=w10.device)
+            if fc2.bias is not None:
+                bias[: fc2.Cout] = fc2.bias.reshape(-1)
+            cache[key] = (w10, bias)
+        w10, bias = cache[key]
+        if self.act_f16:
+            if fc2.wtc16 is None:
+                from .pack import pack_tc_f16
+                fc2.wtc16 = pack_tc_f16(fc2)
+            wt = fc2.wtc16
+        else:
+            if fc2.wtc is None:
+                from .pack import pack_tc
+                fc2.wtc = pack_tc(fc2)
+            wt = fc2.wtc
+        assert wt.shape[1] == hidden.C and wt.shape[0] >= fc2.Cout
+        self._emit("atmvfi_mlp_tail", (hidden.ptr, hidden.pitch, hidden.B, hidden.H, hidden.W, hidden.C, w10.data_ptr(), wt.data_ptr(), wt.shape[0],
+                                       bias.data_ptr(), residual.ptr, residual.pitch, out.ptr, out.pitch, fc2.Cout, int(self.precision)),
+                   keep=(hidden, w10, bias, wt, fc2, residual, out))
+
     # -- warps, resampling, layout ------------------------------------------------------------
     def flow_warp_nchw(self, img: torch.Tensor, flow: torch.Tensor, out: torch.Tensor, rows: Rows = None):
         b, c, h, w = img.shape

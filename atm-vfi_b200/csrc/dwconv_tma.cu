@@ -24,22 +24,6 @@ constexpr int kThreadsD = 256;
 
 __device__ __forceinline__ uint32_t su32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ float gelu_erff(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
-// same branch-free erf as elementwise.cu (TF32 mode only; see the comment there)
-__device__ __forceinline__ float gelu_as(float v) {
-  const float x = v * 0.70710678118654752440f;
-  const float ax = fabsf(x);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = __expf(-ax * ax);
-  const float r = copysignf(fmaf(-p, e, 1.f), x);
-  return 0.5f * v * (1.f + r);
-}
-
 struct DwParams {
   CUtensorMap map;
   void* out;
@@ -125,7 +109,7 @@ __global__ void __launch_bounds__(kThreadsD) dwconv_tma_kernel(const __grid_cons
     fma4(l, k[0], acc2); fma4(m, k[1], acc2); fma4(r, k[2], acc2);
     if (i >= 2 && active) {
       float4 o;
-      if (kFastErf) o = make_float4(gelu_as(acc0.x), gelu_as(acc0.y), gelu_as(acc0.z), gelu_as(acc0.w));
+      if (kFastErf) o = make_float4(gelu_fast(acc0.x), gelu_fast(acc0.y), gelu_fast(acc0.z), gelu_fast(acc0.w));
       else o = make_float4(gelu_erff(acc0.x), gelu_erff(acc0.y), gelu_erff(acc0.z), gelu_erff(acc0.w));
       Act<T>::st4(obase + (size_t)(ys + i - 2) * row_stride, round_tf32_if(o, rnd));
     }

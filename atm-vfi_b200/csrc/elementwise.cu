@@ -166,25 +166,7 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const T* __restri
 constexpr int kDwRows = 8;
 constexpr int kDwCg = 32, kDwX = 8;          // 256 threads
 __device__ __forceinline__ float gelu_exact(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f)); }
-// TF32 mode only (the result is rounded to a 10-bit mantissa right after): erf by Abramowitz-Stegun 7.1.26,
-// 1 - (a1 t + ... + a5 t^5) exp(-x^2), t = 1 / (1 + p |x|): branch-free, 2 MUFU + ~14 FP32 instructions instead of the
-// ~45 predicated instructions of erff, which made this kernel issue-bound (333 us per launch at 802 MB, 37 % of the HBM
-// roofline).  |erf error| <= 6e-7, |GELU error| <= 2.6e-7 (measured over [-8.5, 8.5] against float64), i.e. three orders of
-// magnitude below the TF32 rounding step.  The FP32 mode keeps erff.
-__device__ __forceinline__ float gelu_fast(float v) {
-  const float x = v * 0.70710678118654752440f;
-  const float ax = fabsf(x);
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = __expf(-ax * ax);
-  const float r = copysignf(fmaf(-p, e, 1.f), x);
-  return 0.5f * v * (1.f + r);
-}
+// (TF32 / fp16 modes: gelu_fast of common.cuh; the FP32 mode keeps erff)
 
 template <int V>
 struct DwVec {

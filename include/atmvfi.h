@@ -188,6 +188,20 @@ int atmvfi_attn_prof_read(unsigned long long* out6_host);
 int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int C, int pitch,
                           const float* w9c /* [9][C] */, const float* bias, int y0, int y1, void* stream);
 
+/* Fused Mlp tail (attention.py:74-85, 118-123 and the block residual at attention.py:333, 494):
+ *     out = residual + fc2( GELU( DWConv3x3(hidden) + b_dw ) ) + b_fc2
+ * on the tensor cores, without ever storing the activated hidden map: it is produced tile by tile in shared memory as the A operand
+ * of a tcgen05 GEMM (csrc/mlp_tail_tc.cu).  Same arithmetic as atmvfi_dwconv3x3_gelu followed by atmvfi_gemm_conv with a residual.
+ * hidden [B][H][W][hid_pitch] (Ch channels), residual / out [B][H][W][pitch] (C channels): fp32 maps for ATMVFI_TF32, fp16 maps for
+ * ATMVFI_F16.  w10: [10][Ch] fp32 = the nine depth-wise taps (row ky*3+kx) followed by the depth-wise bias.  w_fc2: the packed
+ * tensor-core operand of fc2, [w_rows][Ch] K-major (fp32 values pre-rounded to TF32, or fp16), w_rows >= C.  bias_fc2: padded with
+ * zeros to a multiple of 32 floats past C + 352.  Requires Ch % 32 == 0 (fp16: % 64), C % 32 == 0, 16-byte aligned operands. */
+int atmvfi_mlp_tail(const void* hidden, int hid_pitch, int B, int H, int W, int Ch, const float* w10, const void* w_fc2, int w_rows,
+                    const float* bias_fc2, const void* residual, int res_pitch, void* out, int out_pitch, int C, int precision,
+                    void* stream);
+/* Debug aid (ATMVFI_MT_PROF=1): per-role cycle counters of CTA 0 of atmvfi_mlp_tail (csrc/mlp_tail_tc.cu); reads and clears them. */
+int atmvfi_mlp_tail_prof_read(unsigned long long* out16_host);
+
 /* First encoder layer (feat_extracts.0.0, network_base.py:103): Conv2d(3 -> Cout, k3, p1) + PReLU read straight from
  * the planar frame, written channels-last.  wk: [27][ldw] with row = (ky*3+kx)*3 + c (the FP32 packing of atmvfi_gemm_conv). */
 int atmvfi_conv3x3_first(const float* img, const float* wk, int ldw, const float* bias, const float* prelu, float* out,
