@@ -423,7 +423,7 @@ class CudaOps:
     def mlp_tail_ok(self, hidden: Map, fc2: PackedGemm, residual: Map, out: Map) -> bool:
         """Shapes the fused Mlp tail (atmvfi_mlp_tail) takes; everything else runs dwconv_gelu + gemm_conv."""
         import os
-        if self.precision not in (_lib.TF32, _lib.F16) or os.environ.get("ATMVFI_MLP_TAIL", "0") == "0":
+        if self.precision not in (_lib.TF32, _lib.F16) or os.environ.get("ATMVFI_MLP_TAIL", "1") == "0":
             return False
         chunk = 64 if self.act_f16 else 32
         maps = (hidden, residual, out)

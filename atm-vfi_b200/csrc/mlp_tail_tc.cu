@@ -6,18 +6,23 @@
 // K-major SWIZZLE_128B layout of the A operand of a tcgen05 GEMM, by CUDA-core "converter" warps that sit between the TMA
 // producer and the MMA issuer.  Per 128-pixel tile (16 x 8 pixels) and per K chunk (32 fp32 / 64 fp16 hidden channels):
 //
-//   warp 0       TMA: hidden box {chunk, 18, 10} with a one-pixel halo (zero-filled outside the image = the conv's padding) plus the
-//                ten rows {chunk, 10} of the depth-wise taps and bias -> raw ring (3 slots); fc2 weight tile -> B ring (2 slots);
-//                L2 prefetch of the boxes a few steps ahead, so that the short rings only have to cover the L2 latency
-//   warps 4-11   converters: 3x3 depth-wise taps (fp32 FMAs in the order of the stand-alone kernel), bias, GELU, rounding to the
-//                operand type, 16-byte stores into the swizzled A slot (2 slots), fence.proxy.async, arrive
+//   warp 3       TMA: hidden box {chunk, 18, 10} with a one-pixel halo (zero-filled outside the image = the conv's padding, SWIZZLE_128B)
+//                plus the ten rows {chunk, 10} of the depth-wise taps and bias -> raw ring (3 slots); L2 prefetch of the boxes five
+//                steps ahead, so that the short ring only has to cover the L2 latency
+//   warp 0       TMA: this CTA's half of the fc2 weight tile -> B ring (2 slots)
+//   warps 4-19   workers in two groups of eight that take alternate steps: 3x3 depth-wise taps (packed fp32 FFMA2, in the order of
+//                the stand-alone kernel), bias, GELU, rounding to the operand type, 16-byte stores into the swizzled A slot (3 slots),
+//                fence.proxy.async, arrive.  The first twelve also run the epilogue of the previous tile right after their group's
+//                first conversion of the next one: residual box by TMA into the warp's staging tile, accumulators from TMEM (+ bias
+//                + residual) written back in place and handed to a TMA store
 //   warp 1       (leader CTA) tcgen05.mma cta_group::2, M = 256 (both CTAs' pixel tiles), N = the WHOLE fc2 width (<= 384, issued
 //                as 256 + rest) - so the hidden map is converted exactly once per pixel; each CTA holds half of the weight tile
-//   warps 12-19  epilogue: residual box prefetched by TMA into the warp's staging tile, accumulators from TMEM (+ bias + residual),
-//                written back in place and handed to a TMA store
 //
-// One accumulator stage (N columns of the 512): the epilogue of a tile is exposed, but the converters run ahead into the rings
-// meanwhile and they are the bottleneck of this kernel (24 instructions per hidden element on the CUDA cores).
+// One accumulator stage (N columns of the 512): the epilogue of a tile is exposed.  The conversion (20 instructions per hidden
+// element on the CUDA cores, 2 MUFU) bounds the kernel, not the tensor pipe or HBM.  History on B200, Base 1080p local grid
+// (2 x 136 x 240 tokens, 384 <- 1536), tf32: the two stand-alone launches 177 + 225 us; first fused version 435 us (cluster-scope
+// release / acquire on every step: ~1000 cycles each); 316 us without them; 224 us with two converter groups, three A slots and the
+// raw slot handed back before the GELU half of a step (ncu: no pipe above 50 %, the converters were latency-bound at 0.45 IPC).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,18 +34,19 @@ constexpr int kTW = 16, kTH = 8;                         // pixel tile = 128 GEM
 constexpr int kHaloW = kTW + 2, kHaloH = kTH + 2;
 constexpr int kRawBoxBytes = kHaloW * kHaloH * 128;      // 23040
 constexpr int kRawSlotBytes = kRawBoxBytes + 10 * 256;   // + taps / bias rows (fp32: 128 B per row for 32 channels, 256 B for 64)
-constexpr int kRawSlots = 3, kASlots = 2, kBSlots = 2;
+constexpr int kRawSlots = 3, kASlots = 3, kBSlots = 2;
 constexpr int kABytes = 128 * 128;
 constexpr int kMaxBSlotBytes = 192 * 128;                // half of a 384-row weight tile
-constexpr int kEpiWarps = 8, kConvWarps = 8;
+constexpr int kWorkerWarps = 16, kGroupWarps = 8;        // two groups of converter warps
+constexpr int kEpiWarps = 12;                            // the first twelve workers also run the epilogue (one 4 KB staging tile each)
 constexpr int kEpiBufBytes = 4096;
 constexpr int kOffA = 0;
-constexpr int kOffB = kOffA + kASlots * kABytes;                       // 32768
-constexpr int kOffEpi = kOffB + kBSlots * kMaxBSlotBytes;              // 81920
-constexpr int kOffRaw = kOffEpi + kEpiWarps * 2 * kEpiBufBytes;        // 147456
+constexpr int kOffB = kOffA + kASlots * kABytes;                       // 49152
+constexpr int kOffEpi = kOffB + kBSlots * kMaxBSlotBytes;              // 98304
+constexpr int kOffRaw = kOffEpi + kEpiWarps * kEpiBufBytes;            // 147456
 constexpr int kOffBar = kOffRaw + kRawSlots * kRawSlotBytes;           // 224256
 constexpr int kSmemBytes = kOffBar + 512;                              // 224768 of the 232448 available
-constexpr int kThreads = 128 + 32 * (kConvWarps + kEpiWarps);          // 640
+constexpr int kThreads = 128 + 32 * kWorkerWarps;                      // 640
 constexpr int kPrefetchAhead = 5;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 static_assert(kRawSlotBytes % 1024 == 0 && kOffRaw % 1024 == 0, "the swizzled hidden boxes start on 1024-byte boundaries");
@@ -230,21 +236,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tail_kernel(const __grid_cons
   uint64_t* bEmpty = bFull + kBSlots;          // [2]
   uint64_t* tFull = bEmpty + kBSlots;          // [1]
   uint64_t* tEmpty = tFull + 1;                // [1]  leader's: both CTAs' epilogues
-  uint64_t* resFull = tEmpty + 1;              // [8 warps][2 buffers]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resFull + 2 * kEpiWarps);
+  uint64_t* resFull = tEmpty + 1;              // [16 warps]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resFull + kWorkerWarps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)cta_rank();
   const int num_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
-  const bool prof_on = p.prof != nullptr && (int)blockIdx.x == p.prof_cta && lane == 0 && (warp < 4 || warp == 4 || warp == 4 + kConvWarps);
+  unsigned long long gt0 = 0;
+  if (p.prof && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+  const bool prof_on = p.prof != nullptr && (int)blockIdx.x == p.prof_cta && lane == 0 && warp <= 4;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kRawSlots; ++s) { bar_init(&rawFull[s], 1); bar_init(&rawEmpty[s], kConvWarps); }
-    for (int s = 0; s < kASlots; ++s) { bar_init(&aFull[s], 2 * kConvWarps); bar_init(&aEmpty[s], 1); }
+    for (int s = 0; s < kRawSlots; ++s) { bar_init(&rawFull[s], 1); bar_init(&rawEmpty[s], kGroupWarps); }
+    for (int s = 0; s < kASlots; ++s) { bar_init(&aFull[s], 2 * kGroupWarps); bar_init(&aEmpty[s], 1); }
     for (int s = 0; s < kBSlots; ++s) { bar_init(&bFull[s], 1); bar_init(&bEmpty[s], 1); }
     bar_init(tFull, 1);
     bar_init(tEmpty, 2 * kEpiWarps);
-    for (int s = 0; s < 2 * kEpiWarps; ++s) bar_init(&resFull[s], 1);
+    for (int s = 0; s < kWorkerWarps; ++s) bar_init(&resFull[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -350,111 +358,60 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tail_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp >= 4 && warp < 4 + kConvWarps) {
-    // ======================================= converters =========================================
-    // A warp owns one 4-channel group of the chunk (fp16: two), its lanes are 16 columns x 2 row halves: the taps are one broadcast
-    // read for the whole warp, and with the SWIZZLE_128B layout of the box (16-byte unit ^ pixel index) the 16 pixels a half-warp
-    // touches sit in different bank groups.
-    const int cq = warp - 4, x = lane & 15, yh = lane >> 4;
-    int rs = 0, as = 0;
-    uint32_t rph = 0, aph = 0;
-    for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters) {
-      for (int g = 0; g < p.nk; ++g) {
-        { MT_T0(); bar_wait(&rawFull[rs], rph); MT_ADD(6); }
-        { MT_T0(); bar_wait(&aEmpty[as], aph ^ 1); MT_ADD(7); }
-        MT_T0();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint8_t* raw = smem + kOffRaw + rs * kRawSlotBytes;
-        const float* w10 = reinterpret_cast<const float*>(raw + kRawBoxBytes);
-        uint8_t* at = smem + kOffA + as * kABytes;
-#pragma unroll
-        for (int sub = 0; sub < kSub; ++sub) {
-          const int q = cq + 8 * sub;                                     // 4-channel group inside the chunk
-          const int unit = kF16 ? (q >> 1) : q, inner = kF16 ? ((q & 1) << 3) : 0;      // 16-byte unit of a 128-byte pixel row, offset inside it
-          F4 k[9], bz;
-#pragma unroll
-          for (int t = 0; t < 9; ++t) k[t] = f4_of(*reinterpret_cast<const float4*>(w10 + t * kCh + 4 * q));
-          bz = f4_of(*reinterpret_cast<const float4*>(w10 + 9 * kCh + 4 * q));
-          F4 acc[4] = {bz, bz, bz, bz};
-          auto px = [&](int pi) -> F4 { return f4_of(Act<T>::lds4(raw + pi * 128 + ((unit ^ (pi & 7)) << 4) + inner)); };
-          const int pi0 = (4 * yh) * kHaloW + x;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {                                   // input rows 4 yh + i of the halo box
-            const F4 l = px(pi0 + i * kHaloW), m = px(pi0 + i * kHaloW + 1), r = px(pi0 + i * kHaloW + 2);
-            // taps in row-major order per output row (bias, top row, middle row, bottom row): the order of the stand-alone kernel
-            if (i >= 2) { fma4p(l, k[6], acc[i - 2]); fma4p(m, k[7], acc[i - 2]); fma4p(r, k[8], acc[i - 2]); }
-            if (i >= 1 && i <= 4) { fma4p(l, k[3], acc[i - 1]); fma4p(m, k[4], acc[i - 1]); fma4p(r, k[5], acc[i - 1]); }
-            if (i <= 3) { fma4p(l, k[0], acc[i]); fma4p(m, k[1], acc[i]); fma4p(r, k[2], acc[i]); }
-          }
-#pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            const int row = (4 * yh + o) * kTW + x;
-            float4 v;
-            upk2(gelu_fast2(acc[o].lo), v.x, v.y);
-            upk2(gelu_fast2(acc[o].hi), v.z, v.w);
-            uint8_t* dst = at + row * 128 + ((unit ^ (row & 7)) << 4) + inner;
-            if (kF16) *reinterpret_cast<uint2*>(dst) = Act<__half>::pack(v);
-            else *reinterpret_cast<float4*>(dst) = round_tf32_if(v, p.round != 0);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
-        __syncwarp();
-        if (lane == 0) {
-          if (rank == 0) bar_arrive(&aFull[as]); else bar_arrive_leader(&aFull[as]);
-          bar_arrive(&rawEmpty[rs]);
-        }
-        MT_ADD(8);
-        if (++rs == kRawSlots) { rs = 0; rph ^= 1; }
-        if (++as == kASlots) { as = 0; aph ^= 1; }
-      }
-    }
-  } else if (warp >= 4 + kConvWarps) {
-    // ======================================= epilogue ===========================================
-    const int ew = warp - (4 + kConvWarps);                 // 0..7
-    const int q = warp & 3;                                 // TMEM lane quarter = tile rows 2q, 2q + 1
-    const int half = ew >> 2;
-    uint8_t* const buf0 = smem + kOffEpi + ew * 2 * kEpiBufBytes;
-    uint64_t* const rbar = resFull + 2 * ew;
+  } else if (warp >= 4) {
+    // ======================================= workers: converters + epilogue ======================
+    // Sixteen warps in two groups of eight; group (s & 1) converts step s of the CTA's running step count into A slot (s % 3), so
+    // that four converter warps per scheduler hide each other's latencies (two were latency-bound at 0.45 instructions per cycle).
+    // In a group a warp owns one 4-channel set of the chunk (fp16: two), its lanes are 16 columns x 2 row halves: the taps are one
+    // broadcast read for the warp, and with the SWIZZLE_128B layout of the box (16-byte unit ^ pixel index) the 16 pixels a half-
+    // warp touches sit in different bank groups.  The epilogue of a tile is shared by all sixteen warps (TMEM lane quarter warp & 3,
+    // every fourth 32-column chunk) and runs right after the group's first conversion of the NEXT tile, whose MMAs are waiting for
+    // the accumulator anyway.
+    const int wk = warp - 4;
+    const int grp = wk >> 3, cq = wk & 7, x = lane & 15, yh = lane >> 4;
+    const int q = warp & 3, eidx = wk >> 2;                 // epilogue (wk < 12): TMEM lane quarter (tile rows 2q, 2q + 1), chunks eidx, eidx + 3, ...
+    const bool epi_warp = wk < kEpiWarps;
+    uint8_t* const ebuf = smem + kOffEpi + wk * kEpiBufBytes;
+    uint64_t* const rbar = resFull + wk;
     constexpr int es = (int)sizeof(T);
     constexpr int rb = 32 * es;                             // bytes per staged row: 128 (fp32) / 64 (fp16)
     const uint32_t swz = (uint32_t)((lane * rb) >> 7) & (uint32_t)((rb >> 4) - 1);
-    uint32_t rpar[2] = {0, 0};
-    uint32_t tcount = 0;
-    for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
-      int n_tile, b, oy0, ox0;
-      tile_of(p, ct, rank, n_tile, b, oy0, ox0);
-      const int n0 = n_tile * p.block_n;
-      int nch = (min(p.block_n, p.C - n0) + 31) >> 5;       // 32-column chunks of this tile that hold real channels
-      if (nch < 0) nch = 0;
-      const int cy = oy0 + 2 * q;
-      const int mine = nch > half ? (nch - half + 1) >> 1 : 0;           // chunks u = half, half + 2, ...
-      auto load_res = [&](int i) {                          // chunk i of this warp -> buffer i & 1 (lane 0)
-        const int u = half + 2 * i;
-        bar_expect(&rbar[i & 1], (uint32_t)(32 * rb));
-        tma4(buf0 + (i & 1) * kEpiBufBytes, &p.mapRes, &rbar[i & 1], n0 + u * 32, ox0, cy, b);
-      };
-      if (lane == 0 && mine > 0) {
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's stores have left the staging tiles
+    uint32_t rpar = 0;
+
+    // epilogue state of the tile whose accumulators are pending
+    int e_n0 = 0, e_b = 0, e_cy = 0, e_ox0 = 0, e_mine = 0;
+    auto load_res = [&](int j) {                            // j-th chunk of this warp -> the staging tile (lane 0)
+      bar_expect(rbar, (uint32_t)(32 * rb));
+      tma4(ebuf, &p.mapRes, rbar, e_n0 + (eidx + 3 * j) * 32, e_ox0, e_cy, e_b);
+    };
+    auto epilogue_begin = [&](int ct) {                     // tile ct just finished its conversions: set up, prefetch the first residual box
+      int n_tile, oy0;
+      tile_of(p, ct, rank, n_tile, e_b, oy0, e_ox0);
+      e_n0 = n_tile * p.block_n;
+      int nch = (min(p.block_n, p.C - e_n0) + 31) >> 5;     // 32-column chunks of this tile that hold real channels
+      e_mine = (epi_warp && nch > eidx) ? (nch - eidx + 2) / 3 : 0;
+      e_cy = oy0 + 2 * q;
+      if (lane == 0 && e_mine > 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's stores have left the staging tile
         load_res(0);
+        for (int j = 1; j < e_mine; ++j)                                   // later boxes: into L2 now, into the tile when it is free
+          if (e_b < p.B) tma_prefetch4(&p.mapRes, e_n0 + (eidx + 3 * j) * 32, e_ox0, e_cy, e_b);
       }
       __syncwarp();
+    };
+    auto epilogue_run = [&](uint32_t tcount) {
+      if (!epi_warp) return;
       { MT_T0(); bar_wait(tFull, tcount & 1); MT_ADD(9); }
       MT_T0();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int i = 0; i < mine; ++i) {
-        const int u = half + 2 * i;
-        const int co0 = n0 + u * 32;
-        uint8_t* buf = buf0 + (i & 1) * kEpiBufBytes;
-        if (lane == 0 && i + 1 < mine) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // chunk i - 1 (same buffer as chunk i + 1) has been read
-          load_res(i + 1);
-        }
-        __syncwarp();
+      for (int j = 0; j < e_mine; ++j) {
+        const int u = eidx + 3 * j;
+        const int co0 = e_n0 + u * 32;
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 32), r);
-        bar_wait(&rbar[i & 1], rpar[i & 1]);
-        rpar[i & 1] ^= 1;
-        uint8_t* rowp = buf + lane * rb;
+        bar_wait(rbar, rpar);
+        rpar ^= 1;
+        uint8_t* rowp = ebuf + lane * rb;
         if (kF16) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -483,9 +440,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tail_kernel(const __grid_cons
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          tma_store4(&p.mapOut, buf, co0, ox0, cy, b);
+          tma_store4(&p.mapOut, ebuf, co0, e_ox0, e_cy, e_b);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (j + 1 < e_mine) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the box has left the staging tile
+            load_res(j + 1);
+          }
         }
+        __syncwarp();
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -493,7 +455,76 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tail_kernel(const __grid_cons
         if (rank == 0) bar_arrive(tEmpty); else bar_arrive_leader(tEmpty);
       }
       MT_ADD(10);
+    };
+
+    int rs = 0, as = 0;
+    uint32_t rph = 0, aph = 0, gs = 0, tcount = 0;
+    int prev_ct = -1;
+    for (int ct = cluster_id; ct < p.total_ctiles; ct += num_clusters, ++tcount) {
+      bool first = true;                                    // this group's first conversion of the tile is still to come
+      for (int g = 0; g < p.nk; ++g, ++gs) {
+        if ((int)(gs & 1) == grp) {
+          { MT_T0(); bar_wait(&rawFull[rs], rph); MT_ADD(6); }
+          { MT_T0(); bar_wait(&aEmpty[as], aph ^ 1); MT_ADD(7); }
+          MT_T0();
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint8_t* raw = smem + kOffRaw + rs * kRawSlotBytes;
+          const float* w10 = reinterpret_cast<const float*>(raw + kRawBoxBytes);
+          uint8_t* at = smem + kOffA + as * kABytes;
+#pragma unroll
+          for (int sub = 0; sub < kSub; ++sub) {
+            const int cg = cq + 8 * sub;                                    // 4-channel group inside the chunk
+            const int unit = kF16 ? (cg >> 1) : cg, inner = kF16 ? ((cg & 1) << 3) : 0;   // 16-byte unit of a 128-byte pixel row, offset inside it
+            F4 k[9], bz;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) k[t] = f4_of(*reinterpret_cast<const float4*>(w10 + t * kCh + 4 * cg));
+            bz = f4_of(*reinterpret_cast<const float4*>(w10 + 9 * kCh + 4 * cg));
+            F4 acc[4] = {bz, bz, bz, bz};
+            auto px = [&](int pi) -> F4 { return f4_of(Act<T>::lds4(raw + pi * 128 + ((unit ^ (pi & 7)) << 4) + inner)); };
+            const int pi0 = (4 * yh) * kHaloW + x;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {                                   // input rows 4 yh + i of the halo box
+              const F4 l = px(pi0 + i * kHaloW), m = px(pi0 + i * kHaloW + 1), r = px(pi0 + i * kHaloW + 2);
+              // taps in row-major order per output row (bias, top row, middle row, bottom row): the order of the stand-alone kernel
+              if (i >= 2) { fma4p(l, k[6], acc[i - 2]); fma4p(m, k[7], acc[i - 2]); fma4p(r, k[8], acc[i - 2]); }
+              if (i >= 1 && i <= 4) { fma4p(l, k[3], acc[i - 1]); fma4p(m, k[4], acc[i - 1]); fma4p(r, k[5], acc[i - 1]); }
+              if (i <= 3) { fma4p(l, k[0], acc[i]); fma4p(m, k[1], acc[i]); fma4p(r, k[2], acc[i]); }
+            }
+            if (sub == kSub - 1) {
+              // every value of the raw slot this warp needs is in registers: hand the slot back before the GELU half of the step
+              // (two groups hold two of the three slots otherwise, leaving a single load in flight)
+              __syncwarp();
+              if (lane == 0) bar_arrive(&rawEmpty[rs]);
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              const int row = (4 * yh + o) * kTW + x;
+              float4 v;
+              upk2(gelu_fast2(acc[o].lo), v.x, v.y);
+              upk2(gelu_fast2(acc[o].hi), v.z, v.w);
+              uint8_t* dst = at + row * 128 + ((unit ^ (row & 7)) << 4) + inner;
+              if (kF16) *reinterpret_cast<uint2*>(dst) = Act<__half>::pack(v);
+              else *reinterpret_cast<float4*>(dst) = round_tf32_if(v, p.round != 0);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) bar_arrive(&aFull[as]); else bar_arrive_leader(&aFull[as]);
+          }
+          MT_ADD(8);
+          if (first) {
+            first = false;
+            if (prev_ct >= 0) epilogue_run(tcount - 1);     // the previous tile's accumulators: the MMAs of this tile wait for them
+          }
+        }
+        if (++rs == kRawSlots) { rs = 0; rph ^= 1; }
+        if (++as == kASlots) { as = 0; aph ^= 1; }
+      }
+      epilogue_begin(ct);
+      prev_ct = ct;
     }
+    if (prev_ct >= 0) epilogue_run(tcount - 1);
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA may exit
   }
 
@@ -503,6 +534,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tail_kernel(const __grid_cons
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+  if (p.prof && threadIdx.x == 0 && blockIdx.x < 160) {
+    unsigned long long gt1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+    p.prof[16 + 2 * blockIdx.x] = gt0;
+    p.prof[17 + 2 * blockIdx.x] = gt1;
   }
 }
 
@@ -529,7 +566,7 @@ unsigned long long* g_mt_prof = nullptr;
 // accumulator, [10] epilogue.  Reads and clears the counters; non-zero when profiling is off.
 extern "C" int atmvfi_mlp_tail_prof_read(unsigned long long* out16) {
   if (!g_mt_prof) return 1;
-  cudaMemcpy(out16, g_mt_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(out16, g_mt_prof, 336 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);      // [16 + 2 i], [17 + 2 i]: globaltimer at the start / end of CTA i (last launch)
   cudaMemset(g_mt_prof, 0, 16 * sizeof(unsigned long long));
   return 0;
 }
@@ -606,7 +643,7 @@ extern "C" int atmvfi_mlp_tail(const void* hidden, int hid_pitch, int B, int H, 
     if (prof < 0) {
       const char* ev = getenv("ATMVFI_MT_PROF");
       prof = ev && atoi(ev) > 0 ? atoi(ev) : 0;
-      if (prof) { cudaMalloc(&g_mt_prof, 16 * sizeof(unsigned long long)); cudaMemset(g_mt_prof, 0, 16 * sizeof(unsigned long long)); }
+      if (prof) { cudaMalloc(&g_mt_prof, 336 * sizeof(unsigned long long)); cudaMemset(g_mt_prof, 0, 336 * sizeof(unsigned long long)); }
     }
     p.prof = prof ? g_mt_prof : nullptr;
     p.prof_cta = prof - 1;

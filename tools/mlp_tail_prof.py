@@ -24,7 +24,7 @@ for (B, H, W, C, hid) in ((2, 136, 240, 384, 1536), (2, 68, 120, 672, 2688)):
     out = cu.new_map(B, H, W, C)
     for _ in range(3): cu.mlp_tail(h, dw_w.cuda(), dw_b.cuda(), fc2, x, out)
     torch.cuda.synchronize()
-    buf = (ctypes.c_uint64 * 16)()
+    buf = (ctypes.c_uint64 * 336)()
     cu.lib.atmvfi_mlp_tail_prof_read(buf)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     R = 10
@@ -34,3 +34,7 @@ for (B, H, W, C, hid) in ((2, 136, 240, 384, 1536), (2, 68, 120, 672, 2688)):
     print(f"{prec} {B}x{H}x{W} C={C} hid={hid}: {e0.elapsed_time(e1) / R * 1000:.1f} us per launch")
     if cu.lib.atmvfi_mlp_tail_prof_read(buf) == 0:
         for i, n in enumerate(NAMES): print(f"   {n:22s} {buf[i] / R / 1000:10.1f} kcycles per launch")
+        st = [buf[16 + 2 * i] for i in range(148)]; en = [buf[17 + 2 * i] for i in range(148)]
+        t0 = min(st)
+        print('   CTA start offsets (us):', sorted(set(round((v - t0) / 1000) for v in st)))
+        print('   CTA durations (us): min %.1f max %.1f; last end %.1f' % (min(e - b for b, e in zip(st, en)) / 1000, max(e - b for b, e in zip(st, en)) / 1000, (max(en) - t0) / 1000))
