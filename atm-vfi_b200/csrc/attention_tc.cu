@@ -45,6 +45,10 @@ struct AttnParams {
   // UMMA layouts: mapQ / mapK = 3-D {hd, R, 2*heads} (box 32 x rows x 1), mapV = 2-D {R, C} (box 32 keys x HP channels)
   int layout, qrows;
   CUtensorMap mapQ, mapK, mapV;
+  // output through shared memory + TMA store: mapO = 3-D {hd, heads, R} over `out`, box {hd + o_pad, 1, o_rows}; the box is wider than a
+  // head on purpose - the staging rows are padded to a conflict-free pitch and the TMA unit clips the columns beyond hd
+  int o_tma, o_pad, o_rows;
+  CUtensorMap mapO;
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,8 +126,6 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   uint64_t* tbar = bars + 4;                  // TMA completion (head-major layout)
 
   const int tid = threadIdx.x & (kRows - 1), part = threadIdx.x >> 7, warp = (threadIdx.x >> 5) & 3;
-  const int N = p.N, hd = kHD ? kHD : p.hd;
-  const int HP = kHD ? (kHD + 15) / 16 * 16 : p.HP;
   float* sRed = reinterpret_cast<float*>(smem + p.offBar + 64);      // [4][2][128] partial max / sum / motion x / motion y
   // work item
   int item = blockIdx.x;
@@ -134,13 +136,49 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   const int64_t total_win = p.total_windows;
   const int64_t win0 = (int64_t)wg * p.wpi;
 
+  const int N = p.N, hd = kHD ? kHD : p.hd;
+  const int HP = kHD ? (kHD + 15) / 16 * 16 : p.HP;
+  const int nwx = p.g.Wp / p.g.ws;
+  // virtual window index v (dense over the row window) -> window id in the full window-major tensor
+  auto actual = [&](int64_t v) -> int64_t { const int vi = (int)v, bi = vi / p.per_img; return (int64_t)bi * p.nW + p.wy0 * nwx + (vi - bi * p.per_img); };
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(&bars[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(&bars[1])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s_u32(tbar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (p.layout == 1) {
+      // Head-major operands: this thread issues a handful of TMA boxes per window right away - they land in the swizzled K-major
+      // layouts of the two MMAs (Q, K: rows = tokens; V^T: rows = channels) while the CTA builds its row / key tables.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int nkc = (N + 31) >> 5;                               // 32-key chunks of V^T per window
+      uint32_t bytes = 0;
+      for (int wl = 0; wl < p.wpi; ++wl)
+        if (win0 + wl < p.virt_windows) bytes += (uint32_t)(p.chunksH * p.qrows * 128 + p.chunksH * N * 128 + nkc * HP * 128);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(tbar)), "r"(bytes) : "memory");
+      for (int wl = 0; wl < p.wpi; ++wl) {
+        if (win0 + wl >= p.virt_windows) continue;
+        const int64_t w = actual(win0 + wl);
+        const int64_t wk = p.cross ? (w + total_win / 2) % total_win : w;       // the other frame's copy of the window (attention.py:318)
+        const int qrow0 = (int)(w * N) + mt * kRows, krow0 = (int)(wk * N);
+        for (int c = 0; c < p.chunksH; ++c) {
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                           s_u32(sQ + c * (kRows * 128) + wl * N * 128)),
+                       "l"(&p.mapQ), "r"(s_u32(tbar)), "r"(c * 32), "r"(qrow0), "r"(h)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                           s_u32(sK + c * (p.KP * 128) + wl * N * 128)),
+                       "l"(&p.mapK), "r"(s_u32(tbar)), "r"(c * 32), "r"(krow0), "r"(p.heads + h)
+                       : "memory");
+        }
+        for (int kc = 0; kc < nkc; ++kc)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                           s_u32(sV + (((wl * N) >> 5) + kc) * (HP * 128))),
+                       "l"(&p.mapV), "r"(s_u32(tbar)), "r"(krow0 + kc * 32), "r"(h * hd)
+                       : "memory");
+      }
+    }
   }
-  if (threadIdx.x < 32) {
+  if (threadIdx.x >= 32 && threadIdx.x < 64) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -150,11 +188,8 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   const int nslH = (hd + 7) >> 3;             // K = 8 slices of the head dimension
   const int hd_pad = nslH * 8;
   const bool masked = (p.g.shift != 0) || p.g.Hp != p.g.H || p.g.Wp != p.g.W;
-  const int nwx = p.g.Wp / p.g.ws;
   const int ws = p.g.ws;
   // (window-local index, token) of row / key `r`; window < 0: padding row of the tile
-  // virtual window index v (dense over the row window) -> window id in the full window-major tensor
-  auto actual = [&](int64_t v) -> int64_t { const int vi = (int)v, bi = vi / p.per_img; return (int64_t)bi * p.nW + p.wy0 * nwx + (vi - bi * p.per_img); };
   auto locate = [&](int r, int base_tok, int& wl, int& tok) -> int64_t {
     if (p.wpi == 1) { wl = 0; tok = base_tok + r; return tok < N ? actual(win0) : -1; }
     wl = r / N;
@@ -192,42 +227,12 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   }
   __syncthreads();
   if (p.layout == 1) {
-    // Head-major operands: one elected thread issues a handful of TMA boxes per window; they land in the swizzled K-major
-    // layouts of the two MMAs (Q, K: rows = tokens; V^T: rows = channels) with no thread touching the data.
-    const int nkc = (N + 31) >> 5;                               // 32-key chunks of V^T per window
+    // (operands were requested by thread 0 at the top of the kernel)
+    const int nkc = (N + 31) >> 5;
     for (int wl = 0; wl < p.wpi; ++wl) {                         // windows of the group that do not exist: zero their V^T columns
       if (win0 + wl < p.virt_windows) continue;                  // (P is zero there, but 0 x garbage could be NaN)
       uint8_t* z = sV + ((wl * N) >> 5) * (HP * 128);
       for (int i = threadIdx.x * 16; i < nkc * HP * 128; i += kThreadsA * 16) *reinterpret_cast<float4*>(z + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t bytes = 0;
-      for (int wl = 0; wl < p.wpi; ++wl)
-        if (win0 + wl < p.virt_windows) bytes += (uint32_t)(p.chunksH * p.qrows * 128 + p.chunksH * N * 128 + nkc * HP * 128);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(tbar)), "r"(bytes) : "memory");
-      for (int wl = 0; wl < p.wpi; ++wl) {
-        if (win0 + wl >= p.virt_windows) continue;
-        const int64_t w = actual(win0 + wl);
-        const int64_t wk = p.cross ? (w + total_win / 2) % total_win : w;       // the other frame's copy of the window (attention.py:318)
-        const int qrow0 = (int)(w * N) + mt * kRows, krow0 = (int)(wk * N);
-        for (int c = 0; c < p.chunksH; ++c) {
-          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                           s_u32(sQ + c * (kRows * 128) + wl * N * 128)),
-                       "l"(&p.mapQ), "r"(s_u32(tbar)), "r"(c * 32), "r"(qrow0), "r"(h)
-                       : "memory");
-          asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                           s_u32(sK + c * (p.KP * 128) + wl * N * 128)),
-                       "l"(&p.mapK), "r"(s_u32(tbar)), "r"(c * 32), "r"(krow0), "r"(p.heads + h)
-                       : "memory");
-        }
-        for (int kc = 0; kc < nkc; ++kc)
-          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-                           s_u32(sV + (((wl * N) >> 5) + kc) * (HP * 128))),
-                       "l"(&p.mapV), "r"(s_u32(tbar)), "r"(krow0 + kc * 32), "r"(h * hd)
-                       : "memory");
-      }
     }
     bar_wait(tbar, 0);
   } else {
@@ -438,6 +443,50 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   mvy = sRed[6 * kRows + tid] + sRed[7 * kRows + tid];
   const float inv = row_ok ? 1.0f / l : 0.f;
   const int64_t grow = row_ok ? win_i * N + tok_i : 0;
+  if (p.o_tma) {
+    // Output through shared memory: every thread drops its 16-channel pieces into a [128][hd + pad] tile in the (now free) Q / P
+    // region - the pad makes the row pitch an odd number of 16-byte units, so the stores of a quarter-warp hit different banks -
+    // and thread 0 hands one box per window (or per 16 rows of a large window) to the TMA unit, which clips the pad columns.
+    const int es = p.out_f16 ? 2 : 4;
+    const int pitch_b = (hd + p.o_pad) * es;
+    uint8_t* so = sQ + tid * pitch_b;
+#pragma unroll
+    for (int c0 = part * 16; c0 < HP; c0 += 32) {
+      float o[16];
+      ld16(tO + lane_addr + c0, o);
+#pragma unroll
+      for (int e = 0; e < 16; e += 8) {
+        if (c0 + e < hd) {
+          const float4 v0 = make_float4(o[e] * inv, o[e + 1] * inv, o[e + 2] * inv, o[e + 3] * inv);
+          const float4 v1 = make_float4(o[e + 4] * inv, o[e + 5] * inv, o[e + 6] * inv, o[e + 7] * inv);
+          if (p.out_f16) {
+            const uint2 a = Act<__half>::pack(v0), b = Act<__half>::pack(v1);
+            if (c0 + e + 4 < hd) *reinterpret_cast<uint4*>(so + (c0 + e) * 2) = make_uint4(a.x, a.y, b.x, b.y);
+            else *reinterpret_cast<uint2*>(so + (c0 + e) * 2) = a;
+          } else {
+            *reinterpret_cast<float4*>(so + (c0 + e) * 4) = round_tf32_if(v0, p.round != 0);
+            if (c0 + e + 4 < hd) *reinterpret_cast<float4*>(so + (c0 + e + 4) * 4) = round_tf32_if(v1, p.round != 0);
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int wl = 0; wl < p.wpi; ++wl) {
+        if (win0 + wl >= p.virt_windows) continue;
+        const int64_t w = actual(win0 + wl);
+        const int nrows = p.wpi > 1 ? N : min(kRows, N - mt * kRows);           // real rows of this window in the tile
+        const int row_g = (int)(w * N) + mt * kRows, row_s = p.wpi > 1 ? wl * N : 0;
+        for (int r0 = 0; r0 < nrows; r0 += p.o_rows)
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(&p.mapO),
+                       "r"(s_u32(sQ + (row_s + r0) * pitch_b)), "r"(0), "r"(h), "r"(row_g + r0)
+                       : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  } else {
 #pragma unroll
   for (int c0 = part * 16; c0 < HP; c0 += 32) {
     float o[16];
@@ -454,6 +503,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
       }
     }
   }
+  }
   if (row_ok && p.motion_raw && part == 0) {
     p.motion_raw[(grow * p.heads + h) * 2 + 0] = mvx * inv;
     p.motion_raw[(grow * p.heads + h) * 2 + 1] = mvy * inv;
@@ -461,10 +511,11 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[5], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
-  if (threadIdx.x < 32) {
+  if (threadIdx.x >= 32 && threadIdx.x < 64) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
   }
+  if (p.o_tma && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // the staging tile lives until the boxes have left it
 }
 
 inline int rup(int x, int m) { return (x + m - 1) / m * m; }
@@ -552,6 +603,38 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
     CUresult r3 = enc(&p.mapV, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(qkv) + 2 * (size_t)C * R, vdim, vstr, boxv, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS) return 3;
+  }
+  {
+    // output staging + TMA store: needs 16-byte aligned head slices and whole 16-row boxes for windows larger than the tile rows
+    static int o_tma_on = -1;
+    if (o_tma_on < 0) { const char* ev = getenv("ATMVFI_ATTN_TMASTORE"); o_tma_on = ev ? atoi(ev) : 1; }
+    const int es = p.out_f16 ? 2 : 4;
+    p.o_tma = 0;
+    p.o_pad = p.out_f16 ? 8 : (((p.hd + 4) % 8 == 4) ? 4 : 8);            // row pitch = odd number of 16-byte units
+    p.o_rows = p.N <= 64 ? p.N : 16;
+    const int pitch_b = (p.hd + p.o_pad) * es;
+    if (o_tma_on && ((uintptr_t)out & 15) == 0 && (p.hd * es) % 16 == 0 && (out_pitch * es) % 16 == 0 && (p.N <= 64 || p.N % 16 == 0) &&
+        pitch_b % 16 == 0 && (pitch_b / 16) % 2 == 1 && p.hd + p.o_pad <= 256 && (p.o_rows * pitch_b) % 128 == 0 && kRows * pitch_b <= (bytesQ + bytesK > bytesP ? bytesQ + bytesK : bytesP)) {
+      typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+      static EncodeTiledFn enc_o = nullptr;
+      if (!enc_o) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+          enc_o = reinterpret_cast<EncodeTiledFn>(fp);
+      }
+      if (enc_o) {
+        const cuuint64_t R = (cuuint64_t)p.total_windows * p.N;
+        cuuint64_t odim[3] = {(cuuint64_t)p.hd, (cuuint64_t)heads, R};
+        cuuint64_t ostr[2] = {(cuuint64_t)p.hd * es, (cuuint64_t)out_pitch * es};
+        cuuint32_t obox[3] = {(cuuint32_t)(p.hd + p.o_pad), 1, (cuuint32_t)p.o_rows};
+        cuuint32_t oestr[3] = {1, 1, 1};
+        if (enc_o(&p.mapO, p.out_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, odim, ostr, obox, oestr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+          p.o_tma = 1;
+      }
+    }
   }
   const int smem = p.offBar + 64 + 8 * kRows * 4 + (kRows + 256) * 4;      // + row / key source tables
   if (smem > 227 * 1024) return 3;
