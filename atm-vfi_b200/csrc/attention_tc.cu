@@ -19,7 +19,7 @@
 namespace {
 
 constexpr int kRows = 128;
-constexpr int kThreadsA = 256;     // two threads per query row (they split the key chunks); warps w and w+4 share TMEM lanes
+constexpr int kMaxParts = 4;       // kP threads per query row split the 16-key chunks (2 or 4); warps w, w+4, ... share TMEM lanes
 
 struct AttnParams {
   const float* qkv;
@@ -114,8 +114,8 @@ __device__ __forceinline__ float tf32r(float v) {
 
 // kHD > 0: head dimension known at compile time - the Q / K / V staging loops unroll and their global loads are issued
 // back to back (with a run-time bound every 16-byte load waited for the previous one: ~18k of the ~46k cycles of a CTA).
-template <int kHD>
-__global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __grid_constant__ AttnParams p) {
+template <int kHD, int kP>
+__global__ void __launch_bounds__(128 * kP) window_attention_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;                         // chunksH x [128 x 128 B]; later P: chunksK x [128 x 128 B]
   uint8_t* sK = smem + p.offK;                // chunksH x [KP x 128 B]
@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   uint64_t* tbar = bars + 4;                  // TMA completion (head-major layout)
 
+  constexpr int kThreadsA = kRows * kP;
   const int tid = threadIdx.x & (kRows - 1), part = threadIdx.x >> 7, warp = (threadIdx.x >> 5) & 3;
   float* sRed = reinterpret_cast<float*>(smem + p.offBar + 64);      // [4][2][128] partial max / sum / motion x / motion y
   // work item
@@ -209,8 +210,10 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   int wl_i, tok_i;
   const int64_t win_i = locate(tid, mt * kRows, wl_i, tok_i);
   const bool row_ok = win_i >= 0;
-  int* sRowSrc = reinterpret_cast<int*>(sRed + 8 * kRows);      // [128] global row of each query row, -1 = padding row
+  int* sRowSrc = reinterpret_cast<int*>(sRed + 4 * kMaxParts * kRows);      // [128] global row of each query row, -1 = padding row
   int* sKeySrc = sRowSrc + kRows;                               // [KP]  global row of each key (other frame's window if cross)
+  float* sKx = reinterpret_cast<float*>(sKeySrc + 256);         // [KP]  window coordinates of each key as floats (closed-form motion)
+  float* sKy = sKx + 256;
   if (part == 0) sRowSrc[tid] = row_ok ? (int)(win_i * N + tok_i) : -1;
   for (int kk = threadIdx.x; kk < p.KP; kk += kThreadsA) {
     int wl, tok;
@@ -224,7 +227,39 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
     sKeySrc[kk] = src;
     // key meta: bits [0,12) mask label, [12,16) window-local index, [16,24) x, [24,32) y; -1 = excluded key
     sLab[kk] = ok ? (mask_label(w, tok) | (wl << 12) | ((tok % ws) << 16) | ((tok / ws) << 24)) : -1;
+    sKx[kk] = (float)(tok % ws);
+    sKy[kk] = (float)(tok / ws);
   }
+  // row constants of the softmax, computed while the operands are in flight
+  const int lab_i = row_ok ? (mask_label(win_i, tok_i) | (wl_i << 12)) : 0;
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const float sc2 = p.scale * 1.4426950408889634f;              // logits are kept in the log2 domain: exp(x) = exp2(x*log2e)
+  const float mask2 = -100.0f * 1.4426950408889634f;
+  auto logit2 = [&](float s, int meta) -> float {               // -inf: excluded; else (scaled logit + additive mask) * log2(e)
+    if (meta < 0 || ((meta ^ lab_i) & 0xF000)) return -INFINITY; // padding key, or a key of another window of the group
+    float x = s * sc2;
+    if ((meta ^ lab_i) & 0xFFF) x += mask2;
+    return x;
+  };
+  // the two threads of a row take alternate 16-key chunks; chunks that belong entirely to another window of the group
+  // (N % 16 == 0) are never read: their probabilities are exactly zero
+  // (decided per WARP - tcgen05.ld is .aligned - from the first and last row of the warp; rows are window-ordered)
+  const bool skip_foreign = p.wpi > 1;
+  const int own_lo = __shfl_sync(0xffffffffu, wl_i * N, 0), own_hi = __shfl_sync(0xffffffffu, wl_i * N + N, 31);
+  // this thread's chunks: c0 = first + 32 j < lim.  With at most two of them (8x8 windows: 64 keys per row, two threads per
+  // row) S stays in registers between the two passes and both tcgen05.ld are in flight together; larger windows re-read
+  // S from TMEM in the second pass (keeping 5 chunks live cost more in register pressure than the reload).
+  constexpr int kMaxOwn = 2;
+  constexpr int kStep = 16 * kP;                                // distance between two chunks of one thread
+  int first = part * 16, lim = p.KP;
+  if (skip_foreign) {
+    int ci = own_lo >> 4;
+    ci += (part - ci) & (kP - 1);                     // first chunk index >= ci that is congruent to part
+    first = ci * 16;
+    lim = min(own_hi, p.KP);
+  }
+  const bool keep = first + kStep * kMaxOwn >= lim;             // warp-uniform
+  const int xi = tok_i % ws, yi = tok_i / ws;
   __syncthreads();
   if (p.layout == 1) {
     // (operands were requested by thread 0 at the top of the kernel)
@@ -298,98 +333,109 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
   // ---- softmax + motion, row per thread ---------------------------------------------------------------------
-  const int lab_i = row_ok ? (mask_label(win_i, tok_i) | (wl_i << 12)) : 0;
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-  const float sc2 = p.scale * 1.4426950408889634f;              // logits are kept in the log2 domain: exp(x) = exp2(x*log2e)
-  const float mask2 = -100.0f * 1.4426950408889634f;
-  auto logit2 = [&](float s, int meta) -> float {               // -inf: excluded; else (scaled logit + additive mask) * log2(e)
-    if (meta < 0 || ((meta ^ lab_i) & 0xF000)) return -INFINITY; // padding key, or a key of another window of the group
-    float x = s * sc2;
-    if ((meta ^ lab_i) & 0xFFF) x += mask2;
-    return x;
-  };
-  // the two threads of a row take alternate 16-key chunks; chunks that belong entirely to another window of the group
-  // (N % 16 == 0) are never read: their probabilities are exactly zero
-  // (decided per WARP - tcgen05.ld is .aligned - from the first and last row of the warp; rows are window-ordered)
-  const bool skip_foreign = p.wpi > 1;
-  const int own_lo = __shfl_sync(0xffffffffu, wl_i * N, 0), own_hi = __shfl_sync(0xffffffffu, wl_i * N + N, 31);
-  // this thread's chunks: c0 = first + 32 j < lim.  With at most two of them (8x8 windows: 64 keys per row, two threads per
-  // row) S stays in registers between the two passes and both tcgen05.ld are in flight together; larger windows re-read
-  // S from TMEM in the second pass (keeping 5 chunks live cost more in register pressure than the reload).
-  constexpr int kMaxOwn = 2;
-  int first = part * 16, lim = p.KP;
-  if (skip_foreign) {
-    int ci = own_lo >> 4;
-    if ((ci & 1) != part) ++ci;
-    first = ci * 16;
-    lim = min(own_hi, p.KP);
-  }
-  const bool keep = first + 32 * kMaxOwn >= lim;                // warp-uniform
   uint32_t sraw[kMaxOwn][16];
   float mx = -INFINITY;
+  float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // four independent chains
   if (keep) {
 #pragma unroll
     for (int j = 0; j < kMaxOwn; ++j)
-      if (first + 32 * j < lim) ld16_issue(tS + lane_addr + first + 32 * j, sraw[j]);
+      if (first + kStep * j < lim) ld16_issue(tS + lane_addr + first + kStep * j, sraw[j]);
     ld_wait();
 #pragma unroll
     for (int j = 0; j < kMaxOwn; ++j) {
-      const int c0 = first + 32 * j;
+      const int c0 = first + kStep * j;
       if (c0 < lim) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float x = logit2(__uint_as_float(sraw[j][e]), sLab[c0 + e]);
-          sraw[j][e] = __float_as_uint(x);
-          mx = fmaxf(mx, x);
+        for (int e = 0; e < 16; e += 4) {
+          const int4 m4 = *reinterpret_cast<const int4*>(sLab + c0 + e);          // one broadcast read for four keys
+          const int mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float x = logit2(__uint_as_float(sraw[j][e + k]), mm[k]);
+            sraw[j][e + k] = __float_as_uint(x);
+            mx4[k] = fmaxf(mx4[k], x);
+          }
         }
       }
     }
   } else {
-    for (int c0 = first; c0 < lim; c0 += 32) {
-      float sv[16];
-      ld16(tS + lane_addr + c0, sv);
+    // larger windows: two chunks in flight per step, labels four at a time
+    for (int c0 = first; c0 < lim; c0 += 2 * kStep) {
+      uint32_t ra[16], rb[16];
+      const bool two = c0 + kStep < lim;
+      ld16_issue(tS + lane_addr + c0, ra);
+      if (two) ld16_issue(tS + lane_addr + c0 + kStep, rb);
+      ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) mx = fmaxf(mx, logit2(sv[e], sLab[c0 + e]));
+      for (int e = 0; e < 16; e += 4) {
+        const int4 m4 = *reinterpret_cast<const int4*>(sLab + c0 + e);
+        const int mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mx4[k] = fmaxf(mx4[k], logit2(__uint_as_float(ra[e + k]), mm[k]));
+      }
+      if (two) {
+#pragma unroll
+        for (int e = 0; e < 16; e += 4) {
+          const int4 m4 = *reinterpret_cast<const int4*>(sLab + c0 + kStep + e);
+          const int mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mx4[k] = fmaxf(mx4[k], logit2(__uint_as_float(rb[e + k]), mm[k]));
+        }
+      }
     }
   }
+  mx = fmaxf(fmaxf(mx, mx4[0]), fmaxf(fmaxf(mx4[1], mx4[2]), mx4[3]));
   sRed[part * kRows + tid] = mx;
   __syncthreads();
   if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[2], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
-  mx = fmaxf(sRed[tid], sRed[kRows + tid]);
+  mx = sRed[tid];
+#pragma unroll
+  for (int k = 1; k < kP; ++k) mx = fmaxf(mx, sRed[k * kRows + tid]);
   // P may overwrite the Q/K area now: the MMA that read it has retired (bars[0]) and S lives in TMEM / registers
   float l = 0.f, mvx = 0.f, mvy = 0.f;
-  const int xi = tok_i % ws, yi = tok_i / ws;
   const bool want_motion = p.motion_raw != nullptr;
   // chunks of this thread that are not its own (another window of the group, or beyond KP): P = 0
-  for (int c0 = part * 16; c0 < p.chunksK * 32; c0 += 32) {
+  for (int c0 = part * 16; c0 < p.chunksK * 32; c0 += kStep) {
     if (c0 >= first && c0 < lim) continue;
     uint8_t* prow = sQ + (c0 >> 5) * (kRows * 128);
 #pragma unroll
     for (int e = 0; e < 16; e += 4) *reinterpret_cast<float4*>(prow + swz(tid, (c0 & 31) + e)) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  const float mxs = mx > -INFINITY ? mx : 0.f;                   // (a row without any admissible key: 2^(-inf - 0) = 0, not NaN)
   auto emit_chunk = [&](const int c0, const float (&x16)[16]) {      // x16: masked logits (log2 domain) of 16 keys
     uint8_t* prow = sQ + (c0 >> 5) * (kRows * 128);
     float pv[16];
+    if (want_motion && p.rc) {          // relative_coord table given explicitly (not the reference's own buffer): per-entry loads
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int meta = sLab[c0 + e];
-      const float x = x16[e];
-      const float pe = (row_ok && x > -INFINITY) ? exp2f(x - mx) : 0.f;
-      l += pe;
-      if (want_motion) {
-        float dx, dy;
-        if (p.rc) {
-          const int tj = ((meta >> 24) & 0xFF) * ws + ((meta >> 16) & 0xFF);
-          dx = pe != 0.f ? __ldg(p.rc + (int64_t)tok_i * N + tj) : 0.f;
-          dy = pe != 0.f ? __ldg(p.rc + (int64_t)N * N + (int64_t)tok_i * N + tj) : 0.f;
-        } else {
-          dx = (float)(((meta >> 16) & 0xFF) - xi);
-          dy = (float)(((meta >> 24) & 0xFF) - yi);
-        }
+      for (int e = 0; e < 16; ++e) {
+        const int meta = sLab[c0 + e];
+        const float x = x16[e];
+        const float pe = (row_ok && x > -INFINITY) ? exp2f(x - mx) : 0.f;
+        l += pe;
+        const int tj = ((meta >> 24) & 0xFF) * ws + ((meta >> 16) & 0xFF);
+        const float dx = pe != 0.f ? __ldg(p.rc + (int64_t)tok_i * N + tj) : 0.f;
+        const float dy = pe != 0.f ? __ldg(p.rc + (int64_t)N * N + (int64_t)tok_i * N + tj) : 0.f;
         mvx = fmaf(pe, dx, mvx);
         mvy = fmaf(pe, dy, mvy);
+        pv[e] = tf32r(pe);
       }
-      pv[e] = tf32r(pe);
+    } else {
+      // closed form: sum_j p_j (k_j - q) = sum_j p_j k_j - q l; the key coordinates come from shared memory four at a time
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const float4 kx4 = *reinterpret_cast<const float4*>(sKx + c0 + e), ky4 = *reinterpret_cast<const float4*>(sKy + c0 + e);
+        const float kx[4] = {kx4.x, kx4.y, kx4.z, kx4.w}, ky[4] = {ky4.x, ky4.y, ky4.z, ky4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float pe;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pe) : "f"(x16[e + k] - mxs));
+          pe = row_ok ? pe : 0.f;                                                            // padding rows of the tile contribute nothing
+          l += pe;
+          mvx = fmaf(pe, kx[k], mvx);
+          mvy = fmaf(pe, ky[k], mvy);
+          pv[e + k] = __uint_as_float((__float_as_uint(pe) + 0x1000u) & 0xFFFFE000u);      // cvt.rna.tf32 of a finite non-negative value
+        }
+      }
     }
 #pragma unroll
     for (int e = 0; e < 16; e += 4)
@@ -398,7 +444,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   if (keep) {
 #pragma unroll
     for (int j = 0; j < kMaxOwn; ++j) {
-      const int c0 = first + 32 * j;
+      const int c0 = first + kStep * j;
       if (c0 < lim) {
         float x16[16];
 #pragma unroll
@@ -407,17 +453,26 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
       }
     }
   } else {
-    for (int c0 = first; c0 < lim; c0 += 32) {
-      float sv[16], x16[16];
-      ld16(tS + lane_addr + c0, sv);
+    uint32_t rn[16];
+    ld16_issue(tS + lane_addr + first, rn);
+    for (int c0 = first; c0 < lim; c0 += kStep) {
+      float x16[16];
+      ld_wait();
 #pragma unroll
-      for (int e = 0; e < 16; ++e) x16[e] = logit2(sv[e], sLab[c0 + e]);
+      for (int e = 0; e < 16; e += 4) {
+        const int4 m4 = *reinterpret_cast<const int4*>(sLab + c0 + e);
+        const int mm[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x16[e + k] = logit2(__uint_as_float(rn[e + k]), mm[k]);
+      }
+      if (c0 + kStep < lim) ld16_issue(tS + lane_addr + c0 + kStep, rn);        // next chunk's accumulators while this one is exponentiated
       emit_chunk(c0, x16);
     }
   }
-  sRed[(2 + part) * kRows + tid] = l;
-  sRed[(4 + part) * kRows + tid] = mvx;
-  sRed[(6 + part) * kRows + tid] = mvy;
+  if (!p.rc) { mvx = fmaf(-(float)xi, l, mvx); mvy = fmaf(-(float)yi, l, mvy); }
+  sRed[(kMaxParts + part) * kRows + tid] = l;
+  sRed[(2 * kMaxParts + part) * kRows + tid] = mvx;
+  sRed[(3 * kMaxParts + part) * kRows + tid] = mvy;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -438,9 +493,13 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
   if (p.prof && threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&p.prof[4], (unsigned long long)(t_ - t_prev)); t_prev = t_; }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  l = sRed[2 * kRows + tid] + sRed[3 * kRows + tid];
-  mvx = sRed[4 * kRows + tid] + sRed[5 * kRows + tid];
-  mvy = sRed[6 * kRows + tid] + sRed[7 * kRows + tid];
+  l = 0.f; mvx = 0.f; mvy = 0.f;
+#pragma unroll
+  for (int k = 0; k < kP; ++k) {
+    l += sRed[(kMaxParts + k) * kRows + tid];
+    mvx += sRed[(2 * kMaxParts + k) * kRows + tid];
+    mvy += sRed[(3 * kMaxParts + k) * kRows + tid];
+  }
   const float inv = row_ok ? 1.0f / l : 0.f;
   const int64_t grow = row_ok ? win_i * N + tok_i : 0;
   if (p.o_tma) {
@@ -451,7 +510,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
     const int pitch_b = (hd + p.o_pad) * es;
     uint8_t* so = sQ + tid * pitch_b;
 #pragma unroll
-    for (int c0 = part * 16; c0 < HP; c0 += 32) {
+    for (int c0 = part * 16; c0 < HP; c0 += kStep) {
       float o[16];
       ld16(tO + lane_addr + c0, o);
 #pragma unroll
@@ -488,7 +547,7 @@ __global__ void __launch_bounds__(kThreadsA) window_attention_tc_kernel(const __
     }
   } else {
 #pragma unroll
-  for (int c0 = part * 16; c0 < HP; c0 += 32) {
+  for (int c0 = part * 16; c0 < HP; c0 += kStep) {
     float o[16];
     ld16(tO + lane_addr + c0, o);
     if (row_ok) {
@@ -636,11 +695,22 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
       }
     }
   }
-  const int smem = p.offBar + 64 + 8 * kRows * 4 + (kRows + 256) * 4;      // + row / key source tables
+  const int smem = p.offBar + 64 + 4 * kMaxParts * kRows * 4 + (kRows + 256) * 4 + 2 * 256 * 4;      // + row / key source tables, key coordinates
   if (smem > 227 * 1024) return 3;
   typedef void (*KernFn)(AttnParams);
-  static const KernFn kerns[5] = {window_attention_tc_kernel<0>, window_attention_tc_kernel<48>, window_attention_tc_kernel<84>,
-                                  window_attention_tc_kernel<28>, window_attention_tc_kernel<44>};
+  // [threads per row: 2, 4][head dim]
+  static const KernFn kerns[2][5] = {
+      {window_attention_tc_kernel<0, 2>, window_attention_tc_kernel<48, 2>, window_attention_tc_kernel<84, 2>, window_attention_tc_kernel<28, 2>,
+       window_attention_tc_kernel<44, 2>},
+      {window_attention_tc_kernel<0, 4>, window_attention_tc_kernel<48, 4>, window_attention_tc_kernel<84, 4>, window_attention_tc_kernel<28, 4>,
+       window_attention_tc_kernel<44, 4>}};
+  // four threads per row for windows larger than the 64 keys of an 8x8 window: their single resident CTA per SM (165 KB of operands)
+  // needs the extra warps to hide its latencies (measured, Base 1080p: 12x12 global launch 214 -> 185 us; the 8x8 local launch, two
+  // CTAs per SM, is 7 % slower with four); ATMVFI_ATTN_PARTS overrides
+  static int parts_env = -1;
+  if (parts_env < 0) { const char* ev = getenv("ATMVFI_ATTN_PARTS"); parts_env = ev ? atoi(ev) : 0; }
+  const int parts = parts_env == 2 || parts_env == 4 ? parts_env : (p.N > 64 ? 4 : 2);
+  const int pi = parts == 4 ? 1 : 0;
   const int ki = p.hd == 48 ? 1 : (p.hd == 84 ? 2 : (p.hd == 28 ? 3 : (p.hd == 44 ? 4 : 0)));
   static int configured_of_device[ATMVFI_MAX_DEVICES] = {0};      // function attributes are per device
   int dev = 0;
@@ -649,8 +719,8 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   int& configured = configured_of_device[dev];
   if (configured < smem) {
     const int want = smem > 100 * 1024 ? 227 * 1024 : 100 * 1024;
-    for (int i = 0; i < 5; ++i) {
-      cudaError_t e = cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, want);
+    for (int i = 0; i < 10; ++i) {
+      cudaError_t e = cudaFuncSetAttribute(kerns[i / 5][i % 5], cudaFuncAttributeMaxDynamicSharedMemorySize, want);
       if (e != cudaSuccess) {
         atmvfi_set_error("window_attention(tf32): cannot reserve shared memory: %s", cudaGetErrorString(e));
         return 1;
@@ -663,7 +733,7 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   const int64_t wgroups = (p.virt_windows + p.wpi - 1) / p.wpi;
   const int64_t items = wgroups * heads * p.mtiles;
   if (items <= 0) return 0;
-  kerns[ki]<<<(unsigned)items, kThreadsA, smem, st>>>(p);
+  kerns[pi][ki]<<<(unsigned)items, kRows * parts, smem, st>>>(p);
   ATMVFI_CHECK_LAUNCH("window_attention(tf32)");
   return 0;
 }
