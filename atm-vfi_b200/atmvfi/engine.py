@@ -104,9 +104,10 @@ def transformer_block(ops, blk, tok: Map, g: WinGeom, motion: Optional[Map] = No
     xw = ops.new_win_map(g, C)
     ops.window_gather_ln(tok, xw, g, blk.g1, blk.b1)                       # pad + roll + partition + norm1
     qkv = ops.new_win_map(g, 3 * C, f32=True)       # q | k | v stay fp32 in every mode (the attention MMAs are kind::tf32)
-    # head-major q | k | v^T (TMA-fed attention): worth it when the heads are wide.  Measured on B200: Base (hd 48 / 84) +1.3 % end to
-    # end; Lite (hd 28 / 44) -5 % because its whole third N tile of the qkv linear is the transposed-V store path.
-    hm = bool(getattr(ops, "qkv_head_major", False)) and C // NUM_HEADS >= getattr(ops, "qkv_head_major_min_hd", 48)
+    # head-major q | k | v^T (TMA-fed attention).  Measured on B200 at 1080p: Base (hd 48 / 84) +1.3 % end to end; Lite (hd 28 / 44) was
+    # -5 % with the first TMA-fed kernel (its whole third N tile of the qkv linear is the transposed-V store path) and is +1.3 % since the
+    # attention kernel requests its operands at the top of the CTA - so every head dim takes it (ATMVFI_QKV_HEADS_MIN_HD restores a floor).
+    hm = bool(getattr(ops, "qkv_head_major", False)) and C // NUM_HEADS >= getattr(ops, "qkv_head_major_min_hd", 0)
     ops.gemm_conv([xw], blk.qkv, qkv, act=False, qkv_heads=NUM_HEADS if hm else 0, out_f32=True)
     ao = ops.new_win_map(g, C)
     if blk.atm and motion is not None:

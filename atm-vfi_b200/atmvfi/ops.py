@@ -159,7 +159,7 @@ class CudaOps:
         self.qkv_head_major = precision in (_lib.TF32, _lib.F16) and os.environ.get("ATMVFI_QKV_HEADS", "1") != "0"
         # ATMVFI_F16: channels-last feature maps are stored as fp16 (flows, masks, images, q|k|v and the motion heads stay fp32)
         self.act_f16 = precision == _lib.F16
-        self.qkv_head_major_min_hd = int(os.environ.get("ATMVFI_QKV_HEADS_MIN_HD", "48"))     # see engine.transformer_block
+        self.qkv_head_major_min_hd = int(os.environ.get("ATMVFI_QKV_HEADS_MIN_HD", "0"))      # see engine.transformer_block
 
     # -- memory -------------------------------------------------------------------------------
     def _alloc(self, shape, zero: bool, dtype=torch.float32) -> torch.Tensor:
