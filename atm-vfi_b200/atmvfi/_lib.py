@@ -79,7 +79,7 @@ PROTOTYPES = {
     "atmvfi_pack5_planar": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_window_attention_tc": [_P, _I, _P, _I, _I, _I, _GP, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _P],
     "atmvfi_dwconv3x3_gelu": [_P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P],
-    "atmvfi_mlp_tail": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _P],
+    "atmvfi_mlp_tail": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "atmvfi_flow_warp_nchw": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_flow_warp_nhwc": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "atmvfi_flow_warp_nhwc_p2p": [_P, _I, _P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(RowOwners), _P],

@@ -430,7 +430,7 @@ class CudaOps:
         return (hidden.C % chunk == 0 and fc2.Cout % 32 == 0 and fc2.ksize == 1 and list(fc2.split) == [hidden.C]
                 and all(m.c0 == 0 and (m.pitch * m.esize) % 16 == 0 and m.half == self.act_f16 for m in maps))
 
-    def mlp_tail(self, hidden: Map, dw_w: torch.Tensor, dw_b: torch.Tensor, fc2: PackedGemm, residual: Map, out: Map):
+    def mlp_tail(self, hidden: Map, dw_w: torch.Tensor, dw_b: torch.Tensor, fc2: PackedGemm, residual: Map, out: Map, rows: Rows = None):
         """out = residual + fc2(GELU(DWConv3x3(hidden) + dw_b)) + b_fc2 in one launch (include/atmvfi.h atmvfi_mlp_tail)."""
         assert self.mlp_tail_ok(hidden, fc2, residual, out) and all(m.ptr % 16 == 0 for m in (hidden, residual, out))
         assert (hidden.B, hidden.H, hidden.W) == (residual.B, residual.H, residual.W) == (out.B, out.H, out.W) and residual.C == out.C == fc2.Cout
@@ -456,7 +456,7 @@ class CudaOps:
             wt = fc2.wtc
         assert wt.shape[1] == hidden.C and wt.shape[0] >= fc2.Cout
         self._emit("atmvfi_mlp_tail", (hidden.ptr, hidden.pitch, hidden.B, hidden.H, hidden.W, hidden.C, w10.data_ptr(), wt.data_ptr(), wt.shape[0],
-                                       bias.data_ptr(), residual.ptr, residual.pitch, out.ptr, out.pitch, fc2.Cout, int(self.precision)),
+                                       bias.data_ptr(), residual.ptr, residual.pitch, out.ptr, out.pitch, fc2.Cout, int(self.precision)) + _yy(rows),
                    keep=(hidden, w10, bias, wt, fc2, residual, out))
 
     # -- warps, resampling, layout ------------------------------------------------------------

@@ -514,6 +514,24 @@ class SlabOps:
         mine = self.own(ob, self.rank)
         self._run(reads, writes, lambda: self.backend.dwconv_gelu(x, out, w9c, bias, rows=mine) if mine[1] > mine[0] else None)
 
+    def mlp_tail_ok(self, *a) -> bool:
+        f = getattr(self.backend, "mlp_tail_ok", None)
+        return bool(f and f(*a))
+
+    def mlp_tail(self, hidden: Map, dw_w, dw_b, fc2, residual: Map, out: Map):
+        """Fused DWConv + GELU + fc2 + residual: the depth-wise taps reach one hidden row beyond the slab on either side."""
+        ob = self._buf(out)[0]
+
+        def deps(p):
+            a, b = self.own(ob, p)
+            if b <= a:
+                return [], []
+            return [(hidden, [(max(0, a - 1), min(ob.H, b + 1))]), (residual, [(a, b)])], [(out, [(a, b)])]
+
+        reads, writes = self._per_rank(deps)
+        mine = self.own(ob, self.rank)
+        self._run(reads, writes, lambda: self.backend.mlp_tail(hidden, dw_w, dw_b, fc2, residual, out, rows=mine) if mine[1] > mine[0] else None)
+
     # ---- warps, resampling, layout ------------------------------------------------------------------
     def flow_warp_nchw(self, img, flow, out):
         self._same_rows([out], [flow], lambda rows: self.backend.flow_warp_nchw(img, flow, out, rows=rows), all_rows_in=[img])

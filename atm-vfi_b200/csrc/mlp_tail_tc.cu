@@ -58,6 +58,7 @@ struct MtParams {
   int nk;                              // K steps = hidden channels / chunk
   int tiles_x, tiles_y, m_tiles, n_tiles, total_ctiles;
   int block_n, n1, n2;                 // columns per CTA tile; MMA split n1 (<= 256) + n2
+  int row0;                            // first output row of every image (row window, include/atmvfi.h "ROW WINDOWS")
   int round;                           // tf32: round the produced operand / the output to TF32
   unsigned long long* prof;            // debug (ATMVFI_MT_PROF = 1 + CTA index): cycle counters of one CTA, see atmvfi_mlp_tail_prof_read
   int prof_cta;
@@ -212,7 +213,7 @@ __device__ __forceinline__ void tile_of(const MtParams& p, int ct, int rank, int
   mt /= p.tiles_x;
   const int ty = mt % p.tiles_y;
   b = mt / p.tiles_y;                        // >= B for the phantom tile of an odd tile count: TMA zero-fills / clips everything
-  oy0 = ty * kTH;
+  oy0 = p.row0 + ty * kTH;
   ox0 = tx * kTW;
 }
 
@@ -573,7 +574,7 @@ extern "C" int atmvfi_mlp_tail_prof_read(unsigned long long* out16) {
 
 extern "C" int atmvfi_mlp_tail(const void* hidden, int hid_pitch, int B, int H, int W, int Ch, const float* w10, const void* w_fc2, int w_rows,
                                const float* bias_fc2, const void* residual, int res_pitch, void* out, int out_pitch, int C, int precision,
-                               void* stream) {
+                               int y0, int y1, void* stream) {
   ATMVFI_REQUIRE(precision == ATMVFI_TF32 || precision == ATMVFI_F16, "mlp_tail: precision must be ATMVFI_TF32 or ATMVFI_F16");
   const bool f16 = precision == ATMVFI_F16;
   const int es = f16 ? 2 : 4, chunk = f16 ? 64 : 32;
@@ -583,6 +584,9 @@ extern "C" int atmvfi_mlp_tail(const void* hidden, int hid_pitch, int B, int H, 
   ATMVFI_REQUIRE((((uintptr_t)hidden | (uintptr_t)w10 | (uintptr_t)w_fc2 | (uintptr_t)bias_fc2 | (uintptr_t)residual | (uintptr_t)out) & 15) == 0 &&
                      (hid_pitch * es) % 16 == 0 && (res_pitch * es) % 16 == 0 && (out_pitch * es) % 16 == 0,
                  "mlp_tail: operands must be 16-byte aligned with pitches of whole 16-byte units");
+  int ny;
+  ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "mlp_tail: bad row window [%d,%d) for H=%d", y0, y1, H);
+  if (ny <= 0) return 0;
   EncodeTiledFn enc = mt_get_encode();
   ATMVFI_REQUIRE(enc != nullptr, "mlp_tail: cuTensorMapEncodeTiled not available");
   MtParams p;
@@ -623,7 +627,8 @@ extern "C" int atmvfi_mlp_tail(const void* hidden, int hid_pitch, int B, int H, 
   for (int which = 0; which < 2; ++which) {
     const void* ptr = which == 0 ? residual : out;
     const int pitch = which == 0 ? res_pitch : out_pitch;
-    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    // y extent = end of the row window: the tiles of the last tile row hang over it and the TMA unit clips them (strides keep H)
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)(y0 + ny), (cuuint64_t)B};
     cuuint64_t gstr[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * es * W, (cuuint64_t)pitch * es * W * H};
     cuuint32_t box[4] = {32, (cuuint32_t)kTW, 2, 1};
     CUresult r = enc(which == 0 ? &p.mapRes : &p.mapOut, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, one4, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -634,7 +639,8 @@ extern "C" int atmvfi_mlp_tail(const void* hidden, int hid_pitch, int B, int H, 
   p.bias = bias_fc2;
   p.B = B; p.H = H; p.W = W; p.C = C;
   p.nk = Ch / chunk;
-  p.tiles_x = cdiv(W, kTW); p.tiles_y = cdiv(H, kTH);
+  p.row0 = y0;
+  p.tiles_x = cdiv(W, kTW); p.tiles_y = cdiv(ny, kTH);
   p.m_tiles = p.tiles_x * p.tiles_y * B;
   p.total_ctiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
   p.round = (!f16 && atmvfi_output_rounding()) ? 1 : 0;

@@ -183,9 +183,9 @@ def algorithmic_bytes(name, args, keep):
     if name == "atmvfi_mlp_tail":
         # fused DWConv + GELU + fc2 + residual: hidden map read once, residual read, output written (the activated hidden map that the
         # two stand-alone launches wrote and re-read - another 2 x hidden bytes - never exists)
-        B, H, W, Ch, C, prec = args[2], args[3], args[4], args[5], args[14], args[15]
+        B, H, W, Ch, C, prec, y0, y1 = args[2], args[3], args[4], args[5], args[14], args[15], args[16], args[17]
         e = 2 if prec == 3 else 4
-        return "mlp_tail (dwconv+gelu+fc2+res)", B * H * W * (Ch + 2 * C) * e
+        return "mlp_tail (dwconv+gelu+fc2+res)", B * _rows(y0, y1, H) * W * (Ch + 2 * C) * e
     if name in ("atmvfi_flow_warp_nhwc", "atmvfi_flow_warp_nhwc_p2p"):
         B, C, H, W, y0, y1 = args[7:13]
         return "flow_warp", B * _rows(y0, y1, H) * W * (2 * C * es + 8)

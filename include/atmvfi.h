@@ -195,10 +195,11 @@ int atmvfi_dwconv3x3_gelu(const float* in, float* out, int B, int H, int W, int 
  * hidden [B][H][W][hid_pitch] (Ch channels), residual / out [B][H][W][pitch] (C channels): fp32 maps for ATMVFI_TF32, fp16 maps for
  * ATMVFI_F16.  w10: [10][Ch] fp32 = the nine depth-wise taps (row ky*3+kx) followed by the depth-wise bias.  w_fc2: the packed
  * tensor-core operand of fc2, [w_rows][Ch] K-major (fp32 values pre-rounded to TF32, or fp16), w_rows >= C.  bias_fc2: padded with
- * zeros to a multiple of 32 floats past C + 352.  Requires Ch % 32 == 0 (fp16: % 64), C % 32 == 0, 16-byte aligned operands. */
+ * zeros to a multiple of 32 floats past C + 352.  Requires Ch % 32 == 0 (fp16: % 64), C % 32 == 0, 16-byte aligned operands.
+ * [y0, y1): row window of the output (it reads hidden rows y0 - 1 .. y1). */
 int atmvfi_mlp_tail(const void* hidden, int hid_pitch, int B, int H, int W, int Ch, const float* w10, const void* w_fc2, int w_rows,
                     const float* bias_fc2, const void* residual, int res_pitch, void* out, int out_pitch, int C, int precision,
-                    void* stream);
+                    int y0, int y1, void* stream);
 /* Debug aid (ATMVFI_MT_PROF=1): per-role cycle counters of CTA 0 of atmvfi_mlp_tail (csrc/mlp_tail_tc.cu); reads and clears them. */
 int atmvfi_mlp_tail_prof_read(unsigned long long* out16_host);
 

@@ -316,6 +316,15 @@ class EmulOps:
             _put(out.view(), F.gelu(y).permute(0, 2, 3, 1), rows)
         self._emit(run)
 
+    def mlp_tail_ok(self, hidden: Map, fc2: PackedGemm, residual: Map, out: Map) -> bool:
+        return fc2.ksize == 1 and list(fc2.split) == [hidden.C] and fc2.Cout % 32 == 0 and hidden.C % 32 == 0
+
+    def mlp_tail(self, hidden: Map, dw_w, dw_b, fc2: PackedGemm, residual: Map, out: Map, rows=None):
+        """Contract of atmvfi_mlp_tail = atmvfi_dwconv3x3_gelu followed by the fc2 gemm_conv with the block residual."""
+        h2 = self.new_map(hidden.B, hidden.H, hidden.W, hidden.C)
+        self.dwconv_gelu(hidden, h2, dw_w, dw_b, rows=rows)
+        self.gemm_conv([h2], fc2, out, act=False, residual=residual, rows=rows)
+
     def flow_warp_nchw(self, img, flow, out, rows=None):
         self._emit(lambda: _put(out, _warp(img, flow), rows, 2))
 

@@ -86,3 +86,31 @@ def test_mlp_tail_matches_unfused_and_emulation(B, H, W, C, hid, precision):
     # outputs are O(1): same operand bits and K order as the unfused launches (fp16 stores: one ulp of 2^-10 at |v| <= 4)
     assert e_unfused <= (4e-3 if f16 else 2e-5), e_unfused
     assert e_emul <= (8e-3 if f16 else 4e-3), e_emul       # + the TF32 rounding of the stored output (2^-11 relative)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "f16"])
+def test_mlp_tail_row_window(precision):
+    """Row window (row-slab mode): the rows of the window equal the full launch bit for bit, rows outside it are not touched, and
+    hidden rows beyond the window's one-row halo are never needed (they are poisoned with NaN here)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(9)
+    f16 = precision == "f16"
+    B, H, W, C, hid = 2, 29, 40, 384, 1536
+    cu = CudaOps(dev, _lib.F16 if f16 else _lib.TF32)
+    fc2, (dw_w, dw_b) = _weights(C, hid, g)
+    dt = torch.float16 if f16 else torch.float32
+    h = (torch.randn(B, H, W, hid, generator=g).half().float() if f16 else round_tf32(torch.randn(B, H, W, hid, generator=g))).to(dev, dt)
+    x = (torch.randn(B, H, W, C, generator=g).half().float() if f16 else round_tf32(torch.randn(B, H, W, C, generator=g))).to(dev, dt)
+    fc2g, dw_wg, dw_bg = _pg_to_gpu(fc2), dw_w.cuda(), dw_b.cuda()
+    full = cu.new_map(B, H, W, C)
+    cu.mlp_tail(Map(h, 0, hid), dw_wg, dw_bg, fc2g, Map(x, 0, C), full)
+    for y0, y1 in ((0, 9), (9, 21), (21, 29), (5, 6)):
+        hp = h.clone()
+        hp[:, : max(0, y0 - 1)] = float("nan")
+        hp[:, y1 + 1 :] = float("nan")
+        part = cu.new_map(B, H, W, C)
+        part.t.fill_(7.0)
+        cu.mlp_tail(Map(hp, 0, hid), dw_wg, dw_bg, fc2g, Map(x, 0, C), part, rows=(y0, y1))
+        torch.cuda.synchronize()
+        assert torch.equal(part.t[:, y0:y1], full.t[:, y0:y1]), (y0, y1)
+        assert (part.t[:, :y0] == 7.0).all() and (part.t[:, y1:] == 7.0).all(), (y0, y1)
