@@ -383,12 +383,15 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T* __restrict
                                                              const float* __restrict__ head, int head_pitch, int flow_off,
                                                              T* __restrict__ out, int out_pitch, int B, int C, int H,
                                                              int W, int wy0, int ny, bool rnd, const __grid_constant__ RowOwners own) {
+  // One warp per pixel, lanes over its 4-channel groups: the index decode, the coordinate round trip and the tap weights (the
+  // bulk of the instructions: four fp32 divisions) are evaluated once per pixel instead of once per channel group, and the four
+  // corner reads of a warp are contiguous 512-byte pieces of the source rows.
   const int cv = C >> 2;
-  const int64_t total = (int64_t)B * ny * W * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int c4 = (int)(i % cv);
+  const int lane = threadIdx.x & 31;
+  const int64_t npix = (int64_t)B * ny * W, warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t pi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; pi < npix; pi += warps) {
     int b, y, x;
-    rw_decode(i / cv, W, wy0, ny, b, y, x);
+    rw_decode(pi, W, wy0, ny, b, y, x);
     const int64_t pix = ((int64_t)b * H + y) * W + x;
     const float* hp = head + pix * head_pitch + flow_off;
     float ix = warp_src_coord((float)x, __ldg(hp), W);
@@ -400,6 +403,7 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T* __restrict
       if (s.vy0) d0 = owner_delta(own, s.y0);
       if (s.vy1) d1 = owner_delta(own, s.y0 + 1);
     }
+    for (int c4 = lane; c4 < cv; c4 += 32) {
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     auto corner = [&](int yy, int xx, float w, bool first) {
       const T* rowp = base + ((int64_t)yy * W + xx) * src_pitch;
@@ -417,6 +421,7 @@ __global__ void __launch_bounds__(256) flow_warp_nhwc_kernel(const T* __restrict
     if (s.vy1 && s.vx0) corner(s.y0 + 1, s.x0, s.wsw, false);
     if (s.vy1 && s.vx1) corner(s.y0 + 1, s.x0 + 1, s.wse, false);
     Act<T>::st4(out + pix * out_pitch + 4 * c4, round_tf32_if(o, rnd));
+    }
   }
 }
 
@@ -560,10 +565,18 @@ __global__ void __launch_bounds__(kPwTx * kPwTy) pyramid_warp_kernel(const float
       const bool staged = any && (bx1 - bx0 + 2 <= kPwSw) && (by1 - by0 + 2 <= kPwSh);
       if (staged) {
         const int wx = bx1 - bx0 + 2, wy = by1 - by0 + 2;          // window that holds every tap: [bx0, bx0 + wx) x [by0, by0 + wy)
-        for (int i = threadIdx.x; i < 3 * wy * wx; i += kPwTx * kPwTy) {
-          const int c = i / (wy * wx), r = (i / wx) % wy, q = i % wx;
-          const int sy = by0 + r, sx = bx0 + q;
-          tile[f][c][r][q] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? __ldg(img + (int64_t)c * hw + (int64_t)sy * W + sx) : 0.f;
+        // one warp per source row, lanes along it: coalesced reads and no index divisions (the flat loop with its three runtime
+        // divisions per element cost ten times the warp arithmetic itself: 140 us for the full-resolution level)
+        for (int r = threadIdx.x >> 5; r < wy; r += (kPwTx * kPwTy) >> 5) {
+          const int sy = by0 + r;
+          const bool rok = sy >= 0 && sy < H;
+          for (int q = threadIdx.x & 31; q < wx; q += 32) {
+            const int sx = bx0 + q;
+            const bool ok = rok && sx >= 0 && sx < W;
+            const int64_t off = (int64_t)sy * W + sx;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) tile[f][c][r][q] = ok ? __ldg(img + (int64_t)c * hw + off) : 0.f;
+          }
         }
       }
       __syncthreads();
@@ -894,7 +907,7 @@ static int flow_warp_nhwc_impl(const float* src, int src_pitch, const float* hea
   ATMVFI_REQUIRE(C % 4 == 0 && src_pitch % 4 == 0 && out_pitch % 4 == 0, "flow_warp_nhwc: C=%d must be a multiple of 4", C);
   int ny;
   ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "flow_warp_nhwc: bad row window [%d,%d)", y0, y1);
-  int64_t n = (int64_t)B * ny * W * (C / 4);
+  int64_t n = (int64_t)B * ny * W * 32;          // one warp per pixel
   if (n <= 0) return 0;
   RowOwners own;
   memset(&own, 0, sizeof(own));
