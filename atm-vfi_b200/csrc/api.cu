@@ -1,5 +1,6 @@
 // C-ABI plumbing of libatmvfi_b200.so: error reporting, device probe, precision dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -8,6 +9,11 @@ static thread_local int g_round = 0;
 static thread_local int g_act_f16 = 0;
 int atmvfi_output_rounding() { return g_round; }
 int atmvfi_act_f16() { return g_act_f16; }
+int atmvfi_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* ev = getenv("ATMVFI_PDL"); on = ev ? (atoi(ev) != 0) : 1; }
+  return on;
+}
 
 void atmvfi_set_error(const char* fmt, ...) {
   va_list ap;

@@ -14,6 +14,7 @@
 // the per-head outputs and two floats per (token, head) ever reach HBM.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace {
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(128 * kP) window_attention_tc_kernel(const __g
   const int64_t total_win = p.total_windows;
   const int64_t win0 = (int64_t)wg * p.wpi;
 
+  pdl_wait();                                 // programmatic dependent launch (common.cuh): q | k | v come from the previous kernel
   const int N = p.N, hd = kHD ? kHD : p.hd;
   const int HP = kHD ? (kHD + 15) / 16 * 16 : p.HP;
   const int nwx = p.g.Wp / p.g.ws;
@@ -733,7 +735,23 @@ int atmvfi_window_attention_tc_launch(const float* qkv, int qkv_pitch, float* ou
   const int64_t wgroups = (p.virt_windows + p.wpi - 1) / p.wpi;
   const int64_t items = wgroups * heads * p.mtiles;
   if (items <= 0) return 0;
-  kerns[pi][ki]<<<(unsigned)items, kRows * parts, smem, st>>>(p);
-  ATMVFI_CHECK_LAUNCH("window_attention(tf32)");
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)items);
+    cfg.blockDim = dim3(kRows * parts);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = atmvfi_pdl_enabled() ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kerns[pi][ki], p);
+    if (le != cudaSuccess) {
+      atmvfi_set_error("window_attention(tf32): launch failed: %s", cudaGetErrorString(le));
+      return 1;
+    }
+  }
   return 0;
 }

@@ -34,6 +34,20 @@ int atmvfi_act_f16();
 
 constexpr int ATMVFI_MAX_DEVICES = 64;      // per-device launch configuration caches are indexed by the CUDA device ordinal
 
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (ATMVFI_PDL, default on): the tensor-core kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so their CTAs may become resident - and run their prologue (barrier init,
+// TMEM allocation, tensor-map fetch) - while the previous kernel of the stream drains its last tiles.  pdl_wait() is the point
+// before which such a kernel touches no global memory: it returns once the previous kernel has completed and its writes are
+// visible.  The persistent kernels (one CTA per SM, all resident) call pdl_launch_dependents() at their start, which lets the
+// NEXT kernel's CTAs take over SMs as this kernel's CTAs exit; it does not weaken that kernel's own pdl_wait().  Both are no-ops
+// in a launch without the attribute.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+int atmvfi_pdl_enabled();          // api.cu: ATMVFI_PDL environment switch (default 1)
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // Row window [y0, y1) of every image of a [B][H][W] grid (include/atmvfi.h "ROW WINDOWS"); y1 == 0 means all rows.

@@ -419,6 +419,9 @@ __global__ void __launch_bounds__(threads_for(kEW), 1) gemm_conv_tc_kernel(const
   if (cs > 1) cluster_sync_all();          // peers' barriers must exist before any multicast arrives
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch (common.cuh): everything above touched no global memory
+  pdl_launch_dependents();
+  pdl_wait();
 
   // K is walked as "A groups" (one activation box in smem) x "steps" (one weight tile, 4 MMAs each):
   //   halo mode : group = (source, chunk, kx), steps ky = 0..2 reuse the box at row offset ky*TW
@@ -1639,13 +1642,15 @@ int atmvfi_gemm_conv_tc(const atmvfi_gemm_conv_desc* d, cudaStream_t st) {
   cfg.blockDim = dim3(threads_for(epi_warps));
   cfg.dynamicSmemBytes = smem_bytes(epi_warps);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = atmvfi_pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
   if (le != cudaSuccess) {
     atmvfi_set_error("gemm_conv(tf32): launch failed: %s", cudaGetErrorString(le));

@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tail_kernel(const __grid_cons
   cluster_sync();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();                // programmatic dependent launch (common.cuh): nothing above touched global memory
+  pdl_wait();
 
   const int b_rows1 = p.n1 >> 1, b_rows2 = p.n2 >> 1;       // weight rows of the two MMAs held by one CTA
   const uint32_t b_tx = (uint32_t)p.block_n * 128u;         // both halves
@@ -681,13 +683,15 @@ extern "C" int atmvfi_mlp_tail(const void* hidden, int hid_pitch, int B, int H, 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = atmvfi_pdl_enabled() ? 2 : 1;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, p);
   if (le != cudaSuccess) {
     atmvfi_set_error("mlp_tail: launch failed: %s", cudaGetErrorString(le));
