@@ -94,6 +94,31 @@ __device__ __forceinline__ WinPos win_decode(const atmvfi_window_geom& g, int64_
   return p;
 }
 
+// 32-bit flavour for the kernels that decode one row per warp (64-bit divisions cost ~100 instructions each, as much as the
+// LayerNorm of the row itself); the caller guarantees r < 2^31.
+__device__ __forceinline__ WinPos win_decode32(const atmvfi_window_geom& g, int r) {
+  const int N = g.ws * g.ws;
+  const int nwx = g.Wp / g.ws, nwy = g.Hp / g.ws;
+  int w = r / N;
+  const int n = r - w * N;
+  const int ty = n / g.ws, tx = n - ty * g.ws;
+  int q = w / nwx;
+  const int wx = w - q * nwx;
+  WinPos p;
+  p.b = q / nwy;
+  const int wy = q - p.b * nwy;
+  p.yr = wy * g.ws + ty;
+  p.xr = wx * g.ws + tx;
+  int yp = p.yr + g.shift;
+  if (yp >= g.Hp) yp -= g.Hp;
+  int xp = p.xr + g.shift;
+  if (xp >= g.Wp) xp -= g.Wp;
+  p.y = yp - g.pad_top;
+  p.x = xp - g.pad_left;
+  p.real = (p.y >= 0) && (p.y < g.H) && (p.x >= 0) && (p.x < g.W);
+  return p;
+}
+
 // Region labels of the two additive -100 masks.  The reference builds the centre-padding mask on the
 // UN-rolled padded frame and applies it to the rolled windows (attention.py:273-303), so the padding
 // label is a function of the window-frame coordinates, not of where the token came from.

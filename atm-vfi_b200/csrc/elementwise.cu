@@ -139,10 +139,20 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const T* __restri
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t per_img = (int64_t)g.Hp * g.Wp, per_win = (int64_t)nwy * g.ws * g.Wp;   // tokens per image: all / in the row window
+  const bool small = (int64_t)g.B2 * per_img < (1ll << 31);
   for (int64_t rr = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); rr < rows; rr += warps) {
-    const int64_t bi = rr / per_win;
-    const int64_t r = bi * per_img + (int64_t)wy0 * g.ws * g.Wp + (rr - bi * per_win);
-    WinPos p = win_decode(g, r);
+    int64_t r;
+    WinPos p;
+    if (small) {
+      const int bi = (int)rr / (int)per_win;
+      const int r32 = bi * (int)per_img + wy0 * g.ws * g.Wp + ((int)rr - bi * (int)per_win);
+      r = r32;
+      p = win_decode32(g, r32);
+    } else {
+      const int64_t bi = rr / per_win;
+      r = bi * per_img + (int64_t)wy0 * g.ws * g.Wp + (rr - bi * per_win);
+      p = win_decode(g, r);
+    }
     T* dst = win + r * win_pitch;
     if (p.real) {
       const T* src = tok + ((int64_t)(p.b * g.H + p.y) * g.W + p.x) * tok_pitch;
@@ -263,13 +273,14 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const T* __restrict__ 
 // First encoder layer: 3x3 conv (pad 1) on a planar 3-channel image + bias + PReLU -> NHWC.  One thread computes all
 // COUT channels of one pixel from 27 cached planar loads; weights/bias/slopes sit in shared memory (broadcast reads).
 // (Tried: four adjacent pixels per thread - a quarter of the weight reads, float4 image loads - measured 25 % SLOWER on B200: the
-// 384-byte lane stride of its stores costs more than the shared-memory reads it saves.)
+// 384-byte lane stride of its stores costs more than the shared-memory reads it saves.  Packed FFMA2 arithmetic: no change - the kernel
+// is bound by its 96-byte-stride stores, not by instruction issue.)
 template <int COUT, typename T>
 __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wk,
                                                             int ldw, const float* __restrict__ bias,
                                                             const float* __restrict__ prelu, T* __restrict__ out,
                                                             int out_pitch, int B, int H, int W, int wy0, int ny, bool rnd) {
-  __shared__ float sw[27 * COUT];
+  __shared__ __align__(16) float sw[27 * COUT];
   __shared__ float sb[COUT], sp[COUT];
   for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = wk[(i / COUT) * ldw + (i % COUT)];
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) { sb[i] = bias[i]; sp[i] = prelu ? prelu[i] : 1.f; }
