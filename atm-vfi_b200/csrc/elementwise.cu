@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(256) dwconv_gelu_kernel(const T* __restrict__ 
 // First encoder layer: 3x3 conv (pad 1) on a planar 3-channel image + bias + PReLU -> NHWC.  One thread computes all
 // COUT channels of one pixel from 27 cached planar loads; weights/bias/slopes sit in shared memory (broadcast reads).
 // (Tried: four adjacent pixels per thread - a quarter of the weight reads, float4 image loads - measured 25 % SLOWER on B200: the
-// 384-byte lane stride of its stores costs more than the shared-memory reads it saves.  Packed FFMA2 arithmetic: no change - the kernel
-// is bound by its 96-byte-stride stores, not by instruction issue.)
+// 384-byte lane stride of its stores costs more than the shared-memory reads it saves.  Packed FFMA2 arithmetic, and staging a warp's 3 KB output block in shared memory
+// for fully coalesced stores: no change either - neither instruction issue nor the 96-byte-stride stores bound it.)
 template <int COUT, typename T>
 __global__ void __launch_bounds__(128) conv3x3_first_kernel(const float* __restrict__ img, const float* __restrict__ wk,
                                                             int ldw, const float* __restrict__ bias,
