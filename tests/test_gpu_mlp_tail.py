@@ -114,3 +114,32 @@ def test_mlp_tail_row_window(precision):
         torch.cuda.synchronize()
         assert torch.equal(part.t[:, y0:y1], full.t[:, y0:y1]), (y0, y1)
         assert (part.t[:, :y0] == 7.0).all() and (part.t[:, y1:] == 7.0).all(), (y0, y1)
+
+
+@pytest.mark.parametrize("kind,precision", [("base", "tf32"), ("lite", "tf32"), ("base", "f16")])
+def test_forward_is_bit_identical_with_and_without_the_fused_tail(kind, precision, monkeypatch):
+    """Whole forward (six transformer blocks, local + global branch): the plan with atmvfi_mlp_tail and the plan with the two
+    stand-alone launches (ATMVFI_MLP_TAIL=0) produce the same bits in every output."""
+    import weights
+    from test_gpu_forward import _net
+    P = weights.make_weights(kind, "stress")
+    im0, im1 = weights.synthetic_frames(1, 192, 256, kind="texture")
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ATMVFI_MLP_TAIL", flag)
+        net = _net(kind, P)
+        net.precision = precision
+        o = net(im0.cuda(), im1.cuda())
+        torch.cuda.synchronize()
+        names = {r[0] for r in next(iter(net._runtime._plans.values())).records}
+        assert ("atmvfi_mlp_tail" in names) == (flag == "1") and ("atmvfi_dwconv3x3_gelu" in names) == (flag == "0")
+        flat = {}
+        for k, v in o.items():
+            for j, t in enumerate(v if isinstance(v, (list, tuple)) else [v]):
+                if isinstance(t, torch.Tensor):
+                    flat[f"{k}[{j}]"] = t.clone()
+        outs.append(flat)
+        del net
+    assert len(outs[0]) >= 10 and outs[0].keys() == outs[1].keys()
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
