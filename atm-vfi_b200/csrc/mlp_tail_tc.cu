@@ -217,6 +217,89 @@ __device__ __forceinline__ void tile_of(const MtParams& p, int ct, int rank, int
   ox0 = tx * kTW;
 }
 
+// One K step of the conversion for one warp: DWConv 3x3 + bias + GELU of its 4-channel group(s) over the 16 x 8 pixel tile, from the
+// swizzled halo box `raw` (followed by the ten tap / bias rows) into the K-major SWIZZLE_128B A tile `at`.  The raw slot is handed
+// back (one arrival per warp on `raw_empty`) as soon as its values are in registers, before the GELU half of the step.
+template <typename T>
+__device__ __forceinline__ void convert_step(const uint8_t* raw, uint8_t* at, int cq, int x, int yh, int lane, bool rnd, uint64_t* raw_empty) {
+  constexpr bool kF16 = Act<T>::kHalf;
+  constexpr int kCh = kF16 ? 64 : 32;
+  constexpr int kSub = kF16 ? 2 : 1;
+  const float* w10 = reinterpret_cast<const float*>(raw + kRawBoxBytes);
+#pragma unroll
+  for (int sub = 0; sub < kSub; ++sub) {
+    const int cg = cq + 8 * sub;                                    // 4-channel group inside the chunk
+    const int unit = kF16 ? (cg >> 1) : cg, inner = kF16 ? ((cg & 1) << 3) : 0;   // 16-byte unit of a 128-byte pixel row, offset inside it
+    F4 k[9], bz;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t] = f4_of(*reinterpret_cast<const float4*>(w10 + t * kCh + 4 * cg));
+    bz = f4_of(*reinterpret_cast<const float4*>(w10 + 9 * kCh + 4 * cg));
+    F4 acc[4] = {bz, bz, bz, bz};
+    auto px = [&](int pi) -> F4 { return f4_of(Act<T>::lds4(raw + pi * 128 + ((unit ^ (pi & 7)) << 4) + inner)); };
+    const int pi0 = (4 * yh) * kHaloW + x;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {                                   // input rows 4 yh + i of the halo box
+      const F4 l = px(pi0 + i * kHaloW), m = px(pi0 + i * kHaloW + 1), r = px(pi0 + i * kHaloW + 2);
+      // taps in row-major order per output row (bias, top row, middle row, bottom row): the order of the stand-alone kernel
+      if (i >= 2) { fma4p(l, k[6], acc[i - 2]); fma4p(m, k[7], acc[i - 2]); fma4p(r, k[8], acc[i - 2]); }
+      if (i >= 1 && i <= 4) { fma4p(l, k[3], acc[i - 1]); fma4p(m, k[4], acc[i - 1]); fma4p(r, k[5], acc[i - 1]); }
+      if (i <= 3) { fma4p(l, k[0], acc[i]); fma4p(m, k[1], acc[i]); fma4p(r, k[2], acc[i]); }
+    }
+    if (sub == kSub - 1) {
+      // every value of the raw slot this warp needs is in registers: hand the slot back before the GELU half of the step
+      // (two groups hold two of the three slots otherwise, leaving a single load in flight)
+      __syncwarp();
+      if (lane == 0) bar_arrive(raw_empty);
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int row = (4 * yh + o) * kTW + x;
+      float4 v;
+      upk2(gelu_fast2(acc[o].lo), v.x, v.y);
+      upk2(gelu_fast2(acc[o].hi), v.z, v.w);
+      uint8_t* dst = at + row * 128 + ((unit ^ (row & 7)) << 4) + inner;
+      if (kF16) *reinterpret_cast<uint2*>(dst) = Act<__half>::pack(v);
+      else *reinterpret_cast<float4*>(dst) = round_tf32_if(v, rnd);
+    }
+  }
+}
+
+// Epilogue arithmetic of one 32-column chunk for one warp: lane = output pixel; its residual row sits in the staging tile `ebuf`
+// (swizzled like the tensor map: SWIZZLE_128B for fp32 rows, SWIZZLE_64B for fp16 rows) and is replaced in place by
+// accumulator + bias + residual, ready for the TMA store.
+template <typename T>
+__device__ __forceinline__ void epi_chunk(uint8_t* ebuf, const uint32_t (&r)[32], const float* bias, int lane, bool rnd) {
+  constexpr bool kF16 = Act<T>::kHalf;
+  constexpr int rb = 32 * (int)sizeof(T);
+  const uint32_t swz = (uint32_t)((lane * rb) >> 7) & (uint32_t)((rb >> 4) - 1);
+  uint8_t* rowp = ebuf + lane * rb;
+  if (kF16) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4* cell = reinterpret_cast<uint4*>(rowp + (((uint32_t)c ^ swz) << 4));
+      const uint4 rv = *cell;
+      const float4 bz0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * c)), bz1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * c + 4));
+      const float4 ra = Act<__half>::unpack(make_uint2(rv.x, rv.y)), rb4 = Act<__half>::unpack(make_uint2(rv.z, rv.w));
+      const float4 va = make_float4(__uint_as_float(r[8 * c]) + bz0.x + ra.x, __uint_as_float(r[8 * c + 1]) + bz0.y + ra.y,
+                                    __uint_as_float(r[8 * c + 2]) + bz0.z + ra.z, __uint_as_float(r[8 * c + 3]) + bz0.w + ra.w);
+      const float4 vb = make_float4(__uint_as_float(r[8 * c + 4]) + bz1.x + rb4.x, __uint_as_float(r[8 * c + 5]) + bz1.y + rb4.y,
+                                    __uint_as_float(r[8 * c + 6]) + bz1.z + rb4.z, __uint_as_float(r[8 * c + 7]) + bz1.w + rb4.w);
+      const uint2 pa = Act<__half>::pack(va), pb = Act<__half>::pack(vb);
+      *cell = make_uint4(pa.x, pa.y, pb.x, pb.y);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4* cell = reinterpret_cast<float4*>(rowp + (((uint32_t)c ^ swz) << 4));
+      const float4 rv = *cell;
+      const float4 bz = __ldg(reinterpret_cast<const float4*>(bias + 4 * c));
+      *cell = round_tf32_if(make_float4(__uint_as_float(r[4 * c]) + bz.x + rv.x, __uint_as_float(r[4 * c + 1]) + bz.y + rv.y,
+                                        __uint_as_float(r[4 * c + 2]) + bz.z + rv.z, __uint_as_float(r[4 * c + 3]) + bz.w + rv.w),
+                            rnd);
+    }
+  }
+}
+
 // debug timers: CTA 0 only, one thread per role
 #define MT_T0() const long long t0__ = prof_on ? clock64() : 0
 #define MT_ADD(slot) do { if (prof_on) atomicAdd(&p.prof[slot], (unsigned long long)(clock64() - t0__)); } while (0)
@@ -414,32 +497,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tail_kernel(const __grid_cons
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(u * 32), r);
         bar_wait(rbar, rpar);
         rpar ^= 1;
-        uint8_t* rowp = ebuf + lane * rb;
-        if (kF16) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint4* cell = reinterpret_cast<uint4*>(rowp + (((uint32_t)c ^ swz) << 4));
-            const uint4 rv = *cell;
-            const float4 bz0 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + 8 * c)), bz1 = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + 8 * c + 4));
-            const float4 ra = Act<__half>::unpack(make_uint2(rv.x, rv.y)), rb4 = Act<__half>::unpack(make_uint2(rv.z, rv.w));
-            const float4 va = make_float4(__uint_as_float(r[8 * c]) + bz0.x + ra.x, __uint_as_float(r[8 * c + 1]) + bz0.y + ra.y,
-                                          __uint_as_float(r[8 * c + 2]) + bz0.z + ra.z, __uint_as_float(r[8 * c + 3]) + bz0.w + ra.w);
-            const float4 vb = make_float4(__uint_as_float(r[8 * c + 4]) + bz1.x + rb4.x, __uint_as_float(r[8 * c + 5]) + bz1.y + rb4.y,
-                                          __uint_as_float(r[8 * c + 6]) + bz1.z + rb4.z, __uint_as_float(r[8 * c + 7]) + bz1.w + rb4.w);
-            const uint2 pa = Act<__half>::pack(va), pb = Act<__half>::pack(vb);
-            *cell = make_uint4(pa.x, pa.y, pb.x, pb.y);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4* cell = reinterpret_cast<float4*>(rowp + (((uint32_t)c ^ swz) << 4));
-            const float4 rv = *cell;
-            const float4 bz = __ldg(reinterpret_cast<const float4*>(p.bias + co0 + 4 * c));
-            *cell = round_tf32_if(make_float4(__uint_as_float(r[4 * c]) + bz.x + rv.x, __uint_as_float(r[4 * c + 1]) + bz.y + rv.y,
-                                              __uint_as_float(r[4 * c + 2]) + bz.z + rv.z, __uint_as_float(r[4 * c + 3]) + bz.w + rv.w),
-                                  p.round != 0);
-          }
-        }
+        epi_chunk<T>(ebuf, r, p.bias + co0, lane, p.round != 0);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -471,45 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_tail_kernel(const __grid_cons
           { MT_T0(); bar_wait(&aEmpty[as], aph ^ 1); MT_ADD(7); }
           MT_T0();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint8_t* raw = smem + kOffRaw + rs * kRawSlotBytes;
-          const float* w10 = reinterpret_cast<const float*>(raw + kRawBoxBytes);
-          uint8_t* at = smem + kOffA + as * kABytes;
-#pragma unroll
-          for (int sub = 0; sub < kSub; ++sub) {
-            const int cg = cq + 8 * sub;                                    // 4-channel group inside the chunk
-            const int unit = kF16 ? (cg >> 1) : cg, inner = kF16 ? ((cg & 1) << 3) : 0;   // 16-byte unit of a 128-byte pixel row, offset inside it
-            F4 k[9], bz;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) k[t] = f4_of(*reinterpret_cast<const float4*>(w10 + t * kCh + 4 * cg));
-            bz = f4_of(*reinterpret_cast<const float4*>(w10 + 9 * kCh + 4 * cg));
-            F4 acc[4] = {bz, bz, bz, bz};
-            auto px = [&](int pi) -> F4 { return f4_of(Act<T>::lds4(raw + pi * 128 + ((unit ^ (pi & 7)) << 4) + inner)); };
-            const int pi0 = (4 * yh) * kHaloW + x;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {                                   // input rows 4 yh + i of the halo box
-              const F4 l = px(pi0 + i * kHaloW), m = px(pi0 + i * kHaloW + 1), r = px(pi0 + i * kHaloW + 2);
-              // taps in row-major order per output row (bias, top row, middle row, bottom row): the order of the stand-alone kernel
-              if (i >= 2) { fma4p(l, k[6], acc[i - 2]); fma4p(m, k[7], acc[i - 2]); fma4p(r, k[8], acc[i - 2]); }
-              if (i >= 1 && i <= 4) { fma4p(l, k[3], acc[i - 1]); fma4p(m, k[4], acc[i - 1]); fma4p(r, k[5], acc[i - 1]); }
-              if (i <= 3) { fma4p(l, k[0], acc[i]); fma4p(m, k[1], acc[i]); fma4p(r, k[2], acc[i]); }
-            }
-            if (sub == kSub - 1) {
-              // every value of the raw slot this warp needs is in registers: hand the slot back before the GELU half of the step
-              // (two groups hold two of the three slots otherwise, leaving a single load in flight)
-              __syncwarp();
-              if (lane == 0) bar_arrive(&rawEmpty[rs]);
-            }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              const int row = (4 * yh + o) * kTW + x;
-              float4 v;
-              upk2(gelu_fast2(acc[o].lo), v.x, v.y);
-              upk2(gelu_fast2(acc[o].hi), v.z, v.w);
-              uint8_t* dst = at + row * 128 + ((unit ^ (row & 7)) << 4) + inner;
-              if (kF16) *reinterpret_cast<uint2*>(dst) = Act<__half>::pack(v);
-              else *reinterpret_cast<float4*>(dst) = round_tf32_if(v, p.round != 0);
-            }
-          }
+          convert_step<T>(smem + kOffRaw + rs * kRawSlotBytes, smem + kOffA + as * kABytes, cq, x, yh, lane, p.round != 0, &rawEmpty[rs]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
           __syncwarp();
           if (lane == 0) {
