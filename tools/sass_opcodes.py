@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "atm-vfi_b200", "atmvfi", "libatmvfi_b200.so")
-OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "UTCATOMSWS", "ELECT", "HMMA", "FFMA", "LDG", "STG", "LDS", "STS"]
+OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAPF", "UTCBAR", "SYNCS", "UTCATOMSWS", "ELECT", "HMMA", "FFMA", "FFMA2", "LDG", "STG", "LDS", "STS"]
 
 
 def main():
@@ -24,7 +24,7 @@ def main():
             continue
         if cur is None:
             continue
-        m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
+        m = re.search(r"/\*[0-9a-f]{4,5}\*/\s+(?:@!?U?P(?:\d+|T)\s+)?([A-Z][A-Z0-9_]*)((?:\.[A-Z0-9_]+)*)", line)
         if m:
             op, mods = m.group(1), m.group(2)
             cur[op] += 1
