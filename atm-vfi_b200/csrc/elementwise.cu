@@ -524,7 +524,8 @@ __global__ void __launch_bounds__(kPwTx * kPwTy) pyramid_warp_kernel(const float
   const int64_t ntiles = (int64_t)B * tiles_y * tiles_x, hw = (int64_t)H * W;
   const int Hc = H >> 1, Wc = W >> 1;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int bx = (int)(t % tiles_x), by = (int)((t / tiles_x) % tiles_y), b = (int)(t / ((int64_t)tiles_x * tiles_y));
+    // (32-bit decode: ntiles < 2^31 is checked by the launcher; 64-bit divisions cost ~100 instructions each)
+    const int t32 = (int)t, trow = t32 / tiles_x, bx = t32 - trow * tiles_x, b = trow / tiles_y, by = trow - b * tiles_y;
     const int x = bx * kPwTx + tx, y = wy0 + by * kPwTy + ty;
     const bool in_img = x < W && y < wy0 + ny;
     if (threadIdx.x < 8) s_box[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 2) ? -(1 << 30) : (1 << 30);
@@ -1005,6 +1006,7 @@ int atmvfi_pyramid_warp(const float* im0, const float* im1, const float* flow0, 
   ATMVFI_REQUIRE(row_window(H, y0, y1, &y0, &ny), "pyramid_warp: bad row window [%d,%d)", y0, y1);
   const int64_t tiles = (int64_t)B * ((ny + kPwTy - 1) / kPwTy) * ((W + kPwTx - 1) / kPwTx);
   if (tiles <= 0) return 0;
+  ATMVFI_REQUIRE(tiles < (1ll << 31), "pyramid_warp: shape out of range");
   const int Hc = H / 2, Wc = W / 2;
   const float sh = H > 1 ? (float)(Hc - 1) / (float)(H - 1) : 0.f, sw = W > 1 ? (float)(Wc - 1) / (float)(W - 1) : 0.f;
   const int grid = (int)(tiles < (int64_t)kSMs * 8 ? tiles : (int64_t)kSMs * 8);
