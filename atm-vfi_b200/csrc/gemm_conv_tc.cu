@@ -1375,6 +1375,34 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     if (pair_ok < 0) { const char* ev = getenv("ATMVFI_TC_PAIR"); pair_ok = ev ? atoi(ev) : 1; }
     pl->pair = (pair_ok && !pl->x3 && pl->halo == 1 && pl->block_n <= 128 && Hwin > pl->TH && (2 * pl->TH + 2) * pl->TW * 128 <= 40 * 1024) ? 1 : 0;
   }
+  {
+    // Wave balance of small grids (the 1/8- and 1/16-resolution layers): the kernel is persistent, one CTA per SM in clusters of two,
+    // so a layer with few (M tile, N tile) pairs runs ceil(tiles / 74) rounds and the last one can be mostly empty (the global motion
+    // head: 96 cluster tiles = 2 rounds at 65 %).  Halving the N tile (the packed weight layout does not change: the same rows, twice
+    // the tiles) doubles the tiles; it is taken when the rounds x tile-width product drops by more than the cost of the doubled
+    // activation traffic.  ATMVFI_TC_BALANCE=0 disables it.
+    static int balance = -1;
+    if (balance < 0) { const char* ev = getenv("ATMVFI_TC_BALANCE"); balance = ev ? atoi(ev) : 1; }
+    static int sms_cached = 0;
+    if (!sms_cached) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&sms_cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_cached <= 0) sms_cached = 148;
+    }
+    if (balance && !shuffle && !pl->x3 && pl->block_n % 32 == 0 && pl->block_n >= 128 && d->out_mode != ATMVFI_OUT_QKV_HEADS) {
+      const int clusters = sms_cached / 2;
+      const int64_t mt_now = (int64_t)cdiv(d->Wout, pl->TW) * cdiv(Hwin, pl->TH * (pl->pair ? 2 : 1)) * d->B;
+      const int64_t mt_half = (int64_t)cdiv(d->Wout, pl->TW) * cdiv(Hwin, pl->TH) * d->B;           // the halved tile never pairs
+      const int64_t ct_now = (mt_now + 1) / 2 * pl->n_tiles, ct_half = (mt_half + 1) / 2 * (2 * pl->n_tiles);
+      const double cost_now = (double)cdiv(ct_now, clusters) * pl->block_n * (pl->pair ? 2 : 1);
+      const double cost_half = (double)cdiv(ct_half, clusters) * (pl->block_n / 2) * 1.12;
+      if (ct_now <= 8 * clusters && cost_half < 0.92 * cost_now) {
+        pl->block_n /= 2;
+        pl->n_tiles *= 2;
+        pl->pair = 0;
+      }
+    }
+  }
   pl->tiles_x = cdiv(d->Wout, pl->TW);
   pl->tiles_y = cdiv(Hwin, pl->TH * (pl->pair ? 2 : 1));
   {
