@@ -1380,7 +1380,9 @@ extern "C" int atmvfi_gemm_conv_plan(const atmvfi_gemm_conv_desc* d, void* plan_
     // so a layer with few (M tile, N tile) pairs runs ceil(tiles / 74) rounds and the last one can be mostly empty (the global motion
     // head: 96 cluster tiles = 2 rounds at 65 %).  Halving the N tile (the packed weight layout does not change: the same rows, twice
     // the tiles) doubles the tiles; it is taken when the rounds x tile-width product drops by more than the cost of the doubled
-    // activation traffic.  ATMVFI_TC_BALANCE=0 disables it.
+    // activation traffic.  The margin matters: taking every halving that merely ties on rounds x width made local_motion_mlp 20 % and
+    // the 128-channel U-Net layers 50 % slower (half-width tiles lose pairing and re-read every activation box).
+    // ATMVFI_TC_BALANCE=0 disables it.
     static int balance = -1;
     if (balance < 0) { const char* ev = getenv("ATMVFI_TC_BALANCE"); balance = ev ? atoi(ev) : 1; }
     static int sms_cached = 0;
