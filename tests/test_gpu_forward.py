@@ -298,3 +298,26 @@ def test_buffer_arena_is_bit_identical_and_never_reads_stale_lanes(kind, glob, s
             for k, v in ref.items():
                 a, b = (v, out[k]) if isinstance(v, list) else ([v], [out[k]])
                 assert all(torch.equal(x, y) for x, y in zip(a, b)), (precision, k)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "f16"])
+def test_graph_replays_are_bit_identical(precision):
+    """Race detector of last resort: the kernels overlap through programmatic dependent launch and share one liveness-coloured
+    arena, so any missing dependency shows up as a run-to-run difference.  60 replays of one CUDA graph (Base, 384x640, stress
+    weights) must reproduce the first one bit for bit (tools/replay_consistency.py does 300 at 1080p)."""
+    P = weights.make_weights("base", "stress")
+    net = _net("base", P)
+    net.precision = precision
+    im0, im1 = [t.cuda() for t in weights.synthetic_frames(1, 384, 640, kind="texture")]
+    keys = ("I_t", "opt_flow_0", "opt_flow_1", "occ_mask1")
+    first = None
+    for i in range(60):
+        out = net(im0, im1)
+        torch.cuda.synchronize()
+        cur = {k: out[k].clone() for k in keys}
+        if first is None:
+            first = cur
+            assert all(torch.isfinite(v).all() for v in cur.values())
+        else:
+            for k in keys:
+                assert torch.equal(first[k], cur[k]), (i, k)
