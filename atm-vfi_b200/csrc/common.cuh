@@ -48,6 +48,23 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 int atmvfi_pdl_enabled();          // api.cu: ATMVFI_PDL environment switch (default 1)
 
+// <<<grid, block, 0, stream>>> with the programmatic-stream-serialization attribute (when ATMVFI_PDL is on): for the small kernels
+// that sit between two tensor-core launches of a transformer block.  The kernel must call pdl_wait() before its first global access.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = atmvfi_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // Row window [y0, y1) of every image of a [B][H][W] grid (include/atmvfi.h "ROW WINDOWS"); y1 == 0 means all rows.

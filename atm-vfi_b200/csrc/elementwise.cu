@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in
                                                         T* __restrict__ out, int out_pitch, int64_t rows, int C,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, bool rnd) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps)
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(256) window_gather_ln_kernel(const T* __restri
                                                                atmvfi_window_geom g, int64_t rows, int wy0, int nwy,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float eps, bool rnd) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
   const int64_t per_img = (int64_t)g.Hp * g.Wp, per_win = (int64_t)nwy * g.ws * g.Wp;   // tokens per image: all / in the row window
@@ -794,9 +796,9 @@ int atmvfi_layernorm(const float* in, int in_pitch, float* out, int out_pitch, i
                  "layernorm: C=%d pitches %d/%d unsupported (need C%%4==0, C<=%d)", C, in_pitch, out_pitch, kLnMaxV * 128);
   if (rows <= 0) return 0;
   if (atmvfi_act_f16())
-    layernorm_kernel<__half><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(in), in_pitch, reinterpret_cast<__half*>(out), out_pitch, rows, C, gamma, beta, eps, false);
+    launch_pdl(layernorm_kernel<__half>, grid_for(rows, 8), 256, (cudaStream_t)stream, reinterpret_cast<const __half*>(in), in_pitch, reinterpret_cast<__half*>(out), out_pitch, rows, C, gamma, beta, eps, false);
   else
-    layernorm_kernel<float><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(in, in_pitch, out, out_pitch, rows, C, gamma, beta, eps, atmvfi_output_rounding() != 0);
+    launch_pdl(layernorm_kernel<float>, grid_for(rows, 8), 256, (cudaStream_t)stream, in, in_pitch, out, out_pitch, rows, C, gamma, beta, eps, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("layernorm");
   return 0;
 }
@@ -810,9 +812,9 @@ int atmvfi_window_gather_ln(const float* tok, int tok_pitch, float* win, int win
   int64_t rows = (int64_t)g->B2 * nwy * g->ws * g->Wp;
   if (rows <= 0) return 0;
   if (atmvfi_act_f16())
-    window_gather_ln_kernel<__half><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(tok), tok_pitch, reinterpret_cast<__half*>(win), win_pitch, C, *g, rows, w0, nwy, gamma, beta, eps, false);
+    launch_pdl(window_gather_ln_kernel<__half>, grid_for(rows, 8), 256, (cudaStream_t)stream, reinterpret_cast<const __half*>(tok), tok_pitch, reinterpret_cast<__half*>(win), win_pitch, C, *g, rows, w0, nwy, gamma, beta, eps, false);
   else
-    window_gather_ln_kernel<float><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(tok, tok_pitch, win, win_pitch, C, *g, rows, w0, nwy, gamma, beta, eps, atmvfi_output_rounding() != 0);
+    launch_pdl(window_gather_ln_kernel<float>, grid_for(rows, 8), 256, (cudaStream_t)stream, tok, tok_pitch, win, win_pitch, C, *g, rows, w0, nwy, gamma, beta, eps, atmvfi_output_rounding() != 0);
   ATMVFI_CHECK_LAUNCH("window_gather_ln");
   return 0;
 }
