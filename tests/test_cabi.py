@@ -47,3 +47,26 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "atmvfi_oracle" not in text and "import oracle" not in text and "emul_ops" not in text, f
+
+
+def test_binding_argument_counts_match_header():
+    """Every ctypes prototype in atmvfi/_lib.py takes as many arguments as the declaration in include/atmvfi.h (a count that
+    drifts makes ctypes push garbage into the trailing parameters without any error)."""
+    from atmvfi import _lib
+    src = open(os.path.join(ROOT, "include", "atmvfi.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    decl = {}
+    for m in re.finditer(r"\b(atmvfi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    checked = 0
+    for name, argt in _lib.PROTOTYPES.items():
+        assert name in decl, name
+        assert len(argt) == decl[name], f"{name}: binding has {len(argt)} arguments, header declares {decl[name]}"
+        checked += 1
+    for name, (argt, _) in _lib._SPECIAL.items():
+        assert name in decl, name
+        assert len(argt) == decl[name], f"{name}: binding has {len(argt)} arguments, header declares {decl[name]}"
+        checked += 1
+    assert checked >= 40
